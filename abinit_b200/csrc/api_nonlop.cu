@@ -1,0 +1,334 @@
+// C-ABI entry points: gemm_nonlop life cycle + apply, Hamiltonian handle, fused getghc, Gram matrices.
+// See include/abinit_b200.h for the reference interfaces replaced.
+#include "../../include/abinit_b200.h"
+#include "context.cuh"
+#include "fourwf.cuh"
+#include "nonlop.cuh"
+#include <map>
+#include <memory>
+
+using namespace abi;
+
+namespace abi {
+void nonlop_release_workspace();
+
+struct NonlopSlot { Projectors P; };
+static std::map<int, std::unique_ptr<NonlopSlot>> g_slots;
+static int g_cur_slot = 1;
+static NonlopAtoms g_call_atoms; static uint64_t g_call_atoms_key = 0;
+static NonlopEnl g_call_enl;
+
+static uint64_t hash_ints(const int* p, size_t n, uint64_t h = 1469598103934665603ULL) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n * sizeof(int); i++) { h ^= b[i]; h *= 1099511628211ULL; }
+  return h;
+}
+static const NonlopAtoms& call_atoms(int natom, int ntypat, int lmnmax, const int* indlmn, const int* nattyp, const int* atindx1) {
+  uint64_t k = hash_ints(indlmn, (size_t)6 * lmnmax * ntypat);
+  k = hash_ints(nattyp, ntypat, k);
+  if (atindx1) k = hash_ints(atindx1, natom, k);
+  int meta[3] = {natom, ntypat, lmnmax};
+  k = hash_ints(meta, 3, k);
+  if (k != g_call_atoms_key || g_call_atoms.d_proj_typ == nullptr) {
+    std::vector<int> ident(natom);
+    for (int i = 0; i < natom; i++) ident[i] = i + 1;
+    g_call_atoms.build(natom, ntypat, lmnmax, indlmn, nattyp, atindx1 ? atindx1 : ident.data());
+    g_call_atoms_key = k;
+  }
+  return g_call_atoms;
+}
+
+void nonlop_release_all() {
+  for (auto& kv : g_slots) kv.second->P.release();
+  g_slots.clear();
+  g_call_atoms.release(); g_call_atoms_key = 0;
+  g_call_enl.release();
+  nonlop_release_workspace();
+}
+
+#ifndef ABI_EMU
+// ghc = (kinpw < huge*1e-11) ? ghc + kinpw*cwavef + gvnlxc : 0 ; gsc zeroed likewise (m_getghc.F90:1266-1280)
+__global__ void k_assemble(double2* __restrict__ ghc, double2* __restrict__ gsc, const double* __restrict__ kinpw,
+                           const double2* __restrict__ cwavef, const double2* __restrict__ gvnlxc, int npw, int ndat,
+                           double kin_filter) {
+  const long long total = (long long)npw * ndat;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ig = (int)(i % npw);
+    const double k = kinpw[ig];
+    double2 v = make_double2(0.0, 0.0);
+    if (k < kin_filter) {
+      v = ghc[i];
+      const double2 c = cwavef[i];
+      v.x = v.x + k * c.x; v.y = v.y + k * c.y;
+      if (gvnlxc) { v.x += gvnlxc[i].x; v.y += gvnlxc[i].y; }
+    } else if (gsc) {
+      gsc[i] = make_double2(0.0, 0.0);
+    }
+    ghc[i] = v;
+  }
+}
+__global__ void k_filter_only(double2* __restrict__ ghc, const double* __restrict__ kinpw, int npw, int ndat, double kin_filter) {
+  const long long total = (long long)npw * ndat;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    if (kinpw[i % npw] > kin_filter) ghc[i] = make_double2(0.0, 0.0);
+}
+#endif
+}  // namespace abi
+
+struct abi_b200_ham {
+  int ngfft[18];
+  int natom, ntypat, lmnmax, usepaw;
+  double ucvol;
+  NonlopAtoms atoms;
+  NonlopEnl enl;
+  Projectors P;
+  VlocDev vloc;
+  int istwf_k = 1, npw = 0, me_g0 = 1;
+  std::vector<int> kg;
+  double* d_kinpw = nullptr;
+  FourwfPlan* plan = nullptr;
+  double* d_gvnlxc = nullptr; size_t gvnlxc_cap = 0;
+};
+
+extern "C" {
+
+void abi_b200_init_gemm_nonlop_(int* nkpt) { (void)nkpt; ensure_init(); }
+void abi_b200_destroy_gemm_nonlop_(void) { nonlop_release_all(); }
+void abi_b200_set_gemm_nonlop_ikpt_(int* ikpt) { g_cur_slot = *ikpt; }
+long long abi_b200_nonlop_counter(void) { return ctx().nonlop_counter; }
+
+static NonlopSlot& slot(int ikpt) {
+  auto& s = g_slots[ikpt];
+  if (!s) s = std::make_unique<NonlopSlot>();
+  return *s;
+}
+
+void abi_b200_prep_projectors_(int* ikpt, int* npw, int* lmnmax, int* ntypat, int* indlmn, int* nattyp, int* istwf_k,
+                               double* ucvol, double* ffnl, double* ph3d, int* dimffnl, int* matblk) {
+  ensure_init();
+  Context& c = ctx();
+  int natom = 0;
+  for (int t = 0; t < *ntypat; t++) natom += nattyp[t];
+  const NonlopAtoms& at = call_atoms(natom, *ntypat, *lmnmax, indlmn, nattyp, nullptr);
+  NonlopSlot& s = slot(*ikpt);
+  s.P.alloc(*npw, at.nprojs, *istwf_k);
+  DevArg a_ffnl(6, ffnl, sizeof(double) * (size_t)(*npw) * (*dimffnl) * (*lmnmax) * (*ntypat), true);
+  DevArg a_ph3d(7, ph3d, sizeof(double) * 2 * (size_t)(*npw) * (*matblk), true);
+  prep_projectors_device(s.P, at, a_ffnl.as<double>(), *dimffnl, a_ph3d.as<double>(), *matblk, *ucvol, c.stream);
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  g_cur_slot = *ikpt;
+}
+
+void abi_b200_set_projectors_(int* ikpt, int* npw, int* nprojs, int* istwf_k, double* projs) {
+  ensure_init();
+  Context& c = ctx();
+  NonlopSlot& s = slot(*ikpt);
+  s.P.alloc(*npw, *nprojs, *istwf_k);
+  CUDA_CHECK(cudaMemcpyAsync(s.P.d_p, projs, sizeof(double) * 2 * (size_t)(*npw) * (*nprojs), cudaMemcpyDefault, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  g_cur_slot = *ikpt;
+}
+
+void abi_b200_gemm_nonlop_(int* atindx1, int* choice, int* cpopt, double* vectproj, int* dimenl1, int* dimenl2, int* dimekbq,
+                           double* enl, int* indlmn, int* istwf_k, double* lambda, int* lmnmax, int* natom, int* nattyp,
+                           int* ndat, int* nnlout, int* npwin, int* npwout, int* nspinor, int* nspinortot, int* ntypat,
+                           int* paw_opt, double* sij, double* svectout, int* useylm, double* vectin, double* vectout,
+                           int* signs) {
+  (void)nnlout;
+  ensure_init();
+  Context& c = ctx();
+  c.nonlop_counter += *ndat;                               // m_nonlop.F90:389-392
+  ABI_CHECK(*signs == 2, "gemm_nonlop: only signs=2 is on the getghc path (signs=1 contractions are out of scope)");
+  ABI_CHECK(*useylm == 1, "gemm_nonlop requires useylm=1 (m_invars2.F90:2829)");
+  ABI_CHECK(*nspinor == 1 && *nspinortot == 1, "gemm_nonlop: nspinor=2 is not implemented in this build");
+  ABI_CHECK(*dimekbq == 1, "gemm_nonlop: dimekbq=2 (q-dependent D_ij) is not implemented");
+  ABI_CHECK(*npwin == *npwout, "gemm_nonlop: k/=k' is not implemented");
+  auto it = g_slots.find(g_cur_slot);
+  ABI_CHECK(it != g_slots.end() && it->second->P.d_p != nullptr, "gemm_nonlop: projectors not prepared for the current ikpt");
+  const Projectors& P = it->second->P;
+  ABI_CHECK(P.npw == *npwin, "gemm_nonlop: npw differs from the prepared projectors");
+  ABI_CHECK(P.istwf_k == *istwf_k, "gemm_nonlop: istwf_k differs from the prepared projectors");
+  const NonlopAtoms& at = call_atoms(*natom, *ntypat, *lmnmax, indlmn, nattyp, atindx1);
+  if (*choice != 0 && *choice != 7) {
+    ABI_CHECK(enl != nullptr, "gemm_nonlop: enl is required");
+    g_call_enl.load(enl, *dimenl1, *dimenl2, (*paw_opt >= 2) ? sij : nullptr, *ntypat, c.stream);
+  }
+  const int cplex = (*istwf_k == 1) ? 2 : 1;
+  const size_t nv = sizeof(double) * 2 * (size_t)P.npw * (*ndat);
+  const size_t np = sizeof(double) * (size_t)cplex * P.nprojs * (*ndat);
+  DevArg a_in(0, vectin, nv, true);
+  DevArg a_out(1, vectout, nv, false);
+  DevArg a_sout(2, svectout, nv, false);
+  DevArg a_proj(3, vectproj, np, *cpopt >= 2);
+  DevArg a_lam(4, lambda, sizeof(double) * (*ndat), true);
+  gemm_nonlop_device(P, at, g_call_enl, *choice, *cpopt, *paw_opt, c.me_g0, a_lam.as<double>(), *ndat, a_in.as<double>(),
+                     a_out.as<double>(), a_sout.as<double>(), a_proj.as<double>(), c.stream);
+  const bool want_v = *choice == 1 && (*paw_opt == 0 || *paw_opt == 1 || *paw_opt == 2 || *paw_opt == 4);
+  const bool want_s = *choice == 7 || (*choice == 1 && (*paw_opt == 3 || *paw_opt == 4));
+  if (want_v) a_out.copy_back();
+  if (want_s) a_sout.copy_back();
+  if ((*cpopt >= 0 && *cpopt < 2) || *choice == 0) a_proj.copy_back();
+  if (!c.async || a_in.staged || a_out.staged || a_sout.staged || a_proj.staged) CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Hamiltonian handle + getghc
+// ---------------------------------------------------------------------------------------------------------
+abi_b200_ham_t* abi_b200_ham_create(const int* ngfft, int natom, int ntypat, int lmnmax, const int* indlmn, const int* nattyp,
+                                    const int* atindx1, int usepaw, double ucvol) {
+  ensure_init();
+  auto* h = new abi_b200_ham();
+  memcpy(h->ngfft, ngfft, sizeof(int) * 18);
+  h->natom = natom; h->ntypat = ntypat; h->lmnmax = lmnmax; h->usepaw = usepaw; h->ucvol = ucvol;
+  h->atoms.build(natom, ntypat, lmnmax, indlmn, nattyp, atindx1);
+  for (int i = 0; i < 3; i++) fft_tables(ngfft[i]);
+  return h;
+}
+
+void abi_b200_ham_destroy(abi_b200_ham_t* h) {
+  if (!h) return;
+  if (ctx().initialized) CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+  h->atoms.release(); h->enl.release(); h->P.release();
+  if (h->vloc.d_v) cudaFree(h->vloc.d_v);
+  if (h->vloc.d_vT) cudaFree(h->vloc.d_vT);
+  if (h->d_kinpw) cudaFree(h->d_kinpw);
+  if (h->d_gvnlxc) cudaFree(h->d_gvnlxc);
+  delete h;
+}
+
+void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_vloc, int n4, int n5, int n6) {
+  ensure_init();
+  ABI_CHECK(n4 == h->ngfft[0] && n5 == h->ngfft[1] && n6 == h->ngfft[2],
+            "FFT SIZE ERROR: when gpu mode is on the fft grid must not be augmented (n4,n5,n6 must equal n1,n2,n3)");
+  ABI_CHECK(cplex_vloc == 1 || cplex_vloc == 2, "vlocal must be real (cplex=1) or complex (cplex=2)");
+  vloc_upload(h->vloc, vlocal, is_device_ptr(vlocal), cplex_vloc, n4, n5, n6, ctx().stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+}
+
+void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, const double* sij) {
+  ensure_init();
+  h->enl.load(enl, dimenl1, dimenl2, sij, h->ntypat, ctx().stream);
+}
+
+void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw, const double* ffnl,
+                         int dimffnl, const double* ph3d, int matblk, int me_g0) {
+  ensure_init();
+  Context& c = ctx();
+  ABI_CHECK(!is_device_ptr(kg_k), "kg_k must be a host array");
+  h->istwf_k = istwf_k; h->npw = npw; h->me_g0 = me_g0;
+  h->kg.assign(kg_k, kg_k + (size_t)3 * npw);
+  h->plan = fourwf_get_plan(h->kg.data(), npw, h->kg.data(), npw, h->ngfft, istwf_k, me_g0);
+  if (h->d_kinpw) cudaFree(h->d_kinpw);
+  CUDA_CHECK(cudaMalloc(&h->d_kinpw, sizeof(double) * std::max(1, npw)));
+  CUDA_CHECK(cudaMemcpyAsync(h->d_kinpw, kinpw, sizeof(double) * npw, cudaMemcpyDefault, c.stream));
+  if (ffnl && ph3d) {
+    h->P.alloc(npw, h->atoms.nprojs, istwf_k);
+    DevArg a_ffnl(6, ffnl, sizeof(double) * (size_t)npw * dimffnl * h->lmnmax * h->ntypat, true);
+    DevArg a_ph3d(7, ph3d, sizeof(double) * 2 * (size_t)npw * matblk, true);
+    prep_projectors_device(h->P, h->atoms, a_ffnl.as<double>(), dimffnl, a_ph3d.as<double>(), matblk, h->ucvol, c.stream);
+  } else {
+    h->P.npw = npw; h->P.istwf_k = istwf_k;     // projectors to be installed with abi_b200_ham_set_projectors
+  }
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+void abi_b200_ham_set_projectors(abi_b200_ham_t* h, const double* projs, int nprojs) {
+  ensure_init();
+  ABI_CHECK(nprojs == h->atoms.nprojs, "set_projectors: nprojs differs from sum(nlmn*nattyp)");
+  h->P.alloc(h->npw, nprojs, h->istwf_k);
+  CUDA_CHECK(cudaMemcpyAsync(h->P.d_p, projs, sizeof(double) * 2 * (size_t)h->npw * nprojs, cudaMemcpyDefault, ctx().stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+}
+
+int abi_b200_ham_nprojs(const abi_b200_ham_t* h) { return h->atoms.nprojs; }
+
+void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc, double* gsc, abi_b200_ham_t** gs_ham,
+                      double* gvnlxc, double* lambda, int* ndat, int* prtvol, int* sij_opt, int* tim_getghc, int* type_calc) {
+  (void)prtvol; (void)tim_getghc;
+  ensure_init();
+  Context& c = ctx();
+  abi_b200_ham* h = *gs_ham;
+  const int tc = *type_calc, nd = *ndat, npw = h->npw;
+  ABI_CHECK(tc >= 0 && tc <= 3, "getghc: type_calc must be 0, 1, 2 or 3");
+  ABI_CHECK(h->plan != nullptr, "getghc: load_k has not been called");
+  ABI_CHECK(!(*sij_opt != 0 && h->usepaw == 0), "getghc: sij_opt/=0 requires PAW");   // m_getghc.F90:333-336
+  const bool local = (tc == 0 || tc == 1 || tc == 3), nonlocal = (tc == 0 || tc == 2);
+  if (local) ABI_CHECK(h->vloc.d_v != nullptr, "We need vlocal in gs_ham!");             // m_getghc.F90:404
+  const size_t nv = sizeof(double) * 2 * (size_t)npw * nd;
+  const int cplex = (h->istwf_k == 1) ? 2 : 1;
+  DevArg a_c(0, cwavef, nv, true);
+  DevArg a_ghc(1, ghc, nv, tc == 2);
+  DevArg a_gsc(2, (*sij_opt == 1) ? gsc : nullptr, nv, false);
+  DevArg a_gv(3, gvnlxc, nv, false);
+  const int cpopt_here = (h->usepaw == 1) ? *cpopt : -1;                                 // m_getghc.F90:1046
+  DevArg a_prj(4, (cpopt_here >= 0) ? cwaveprj : nullptr, sizeof(double) * (size_t)cplex * h->atoms.nprojs * nd, cpopt_here >= 2);
+  DevArg a_lam(5, lambda, sizeof(double) * nd, true);
+  double* d_gv = a_gv.as<double>();
+  if (nonlocal && d_gv == nullptr) {
+    if (h->gvnlxc_cap < nv) { if (h->d_gvnlxc) cudaFree(h->d_gvnlxc); CUDA_CHECK(cudaMalloc(&h->d_gvnlxc, nv)); h->gvnlxc_cap = nv; }
+    d_gv = h->d_gvnlxc;
+  }
+  const double kin_filter = 1.7976931348623157e308 * 1.0e-11;
+#ifndef ABI_EMU
+  if (nonlocal) {
+    ABI_CHECK(h->P.d_p != nullptr || h->atoms.nprojs == 0, "getghc: projectors not loaded (load_k with ffnl/ph3d or set_projectors)");
+    int paw_opt = h->usepaw; if (*sij_opt != 0) paw_opt = *sij_opt + 3;                  // m_getghc.F90:1067
+    c.nonlop_counter += nd;
+    gemm_nonlop_device(h->P, h->atoms, h->enl, 1, cpopt_here, paw_opt, h->me_g0, a_lam.as<double>(), nd, a_c.as<double>(), d_gv,
+                       a_gsc.as<double>(), a_prj.as<double>(), c.stream);
+  } else if (tc == 3 && a_gv.dev) {
+    CUDA_CHECK(cudaMemsetAsync(a_gv.dev, 0, nv, c.stream));                              // m_getghc.F90:1148-1154
+  }
+#endif
+  if (local) {
+    c.fourwf_counter += 2 * nd;
+    FourwfEpilogue epi;
+    if (tc == 1) { epi.mode = 2; epi.kinpw = h->d_kinpw; }
+    else { epi.mode = 1; epi.kinpw = h->d_kinpw; epi.cwavef = a_c.as<double2>(); epi.gvnlxc = nonlocal ? (const double2*)d_gv : nullptr;
+           epi.gsc = a_gsc.as<double2>(); }
+    if (h->plan->fused_ok && c.fourwf_impl != 1) {
+      fourwf_fused_opt2(*h->plan, h->vloc, a_c.as<double2>(), a_ghc.as<double2>(), nd, epi, c.stream);
+    } else {
+#ifndef ABI_EMU
+      fourwf_generic(*h->plan, 2, h->vloc.cplex, h->vloc.d_v, a_c.as<double2>(), a_ghc.as<double2>(), nullptr, nd, nullptr, nullptr, c.stream);
+      const int blocks = std::min(kNumSM * 8, (int)ceil_div<long long>((long long)npw * nd, 256));
+      if (tc == 1) k_filter_only<<<blocks, 256, 0, c.stream>>>(a_ghc.as<double2>(), h->d_kinpw, npw, nd, kin_filter);
+      else k_assemble<<<blocks, 256, 0, c.stream>>>(a_ghc.as<double2>(), a_gsc.as<double2>(), h->d_kinpw, a_c.as<double2>(),
+                                                    nonlocal ? (const double2*)d_gv : nullptr, npw, nd, kin_filter);
+      CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+#endif
+    }
+  } else {
+#ifndef ABI_EMU
+    // type_calc == 2: non-local + kinetic added to the existing ghc (m_getghc.F90:152)
+    const int blocks = std::min(kNumSM * 8, (int)ceil_div<long long>((long long)npw * nd, 256));
+    k_assemble<<<blocks, 256, 0, c.stream>>>(a_ghc.as<double2>(), a_gsc.as<double2>(), h->d_kinpw, a_c.as<double2>(),
+                                             (const double2*)d_gv, npw, nd, kin_filter);
+    CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+#endif
+  }
+  a_ghc.copy_back();
+  if (*sij_opt == 1) a_gsc.copy_back();
+  if (tc != 1) a_gv.copy_back();
+  if (cpopt_here >= 0 && cpopt_here < 2) a_prj.copy_back();
+  if (!c.async || a_c.staged || a_ghc.staged || a_gsc.staged || a_gv.staged || a_prj.staged)
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+void abi_b200_xg_gram_(int* space, int* rows, int* ncols_a, int* ncols_b, double* a, int* lda, double* b, int* ldb, double* cmat,
+                       int* ldc, int* me_g0) {
+  ensure_init();
+  Context& c = ctx();
+  ABI_CHECK(*space == 2, "xg_gram: only SPACE_CR (istwfk>=2 real view) is implemented in this round");
+  ABI_CHECK(is_device_ptr(a) && is_device_ptr(b) && is_device_ptr(cmat), "xg_gram: device pointers required");
+  (void)me_g0;
+#ifndef ABI_EMU
+  // SPACE_CR: rows counts complex coefficients; the real view has 2*rows rows (m_xg.F90:1802-1882).
+  dgemm_tn(*ncols_a, *ncols_b, 2 * (*rows), a, 2LL * (*lda), b, 2LL * (*ldb), cmat, *ldc, 2.0, c.stream);
+#endif
+  if (!c.async) CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+}  // extern "C"

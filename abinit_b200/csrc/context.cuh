@@ -1,0 +1,41 @@
+// Process-wide state of the library: device, stream, staging buffers for host-resident arguments.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace abi {
+
+struct Staging {             // grow-only device buffer used to mirror one host argument
+  void* d = nullptr; size_t cap = 0;
+  void* get(size_t bytes);
+  void release();
+};
+
+struct Context {
+  bool initialized = false;
+  int device = 0;
+  cudaStream_t stream = 0;
+  bool own_stream = false;
+  bool async = false;
+  int me_g0 = 1;
+  int fourwf_impl = 0;          // 0 auto, 1 generic, 2 fused
+  long long fourwf_counter = 0; // m_fft.F90:2333-2336
+  long long nonlop_counter = 0; // m_nonlop.F90:389-392
+  Staging stage[16];
+};
+Context& ctx();
+void ensure_init();
+
+bool is_device_ptr(const void* p);
+
+// Mirror of one argument on the device: if `p` is a host pointer, a staging buffer is used (copied in when
+// `in`), and copy_back() copies results to the host; if `p` is already a device pointer it is used as is.
+struct DevArg {
+  void* host = nullptr; void* dev = nullptr; size_t bytes = 0; bool staged = false;
+  DevArg() {}
+  DevArg(int slot, const void* p, size_t bytes, bool in);
+  void copy_back();
+  template <typename T> T* as() const { return reinterpret_cast<T*>(dev); }
+};
+
+}  // namespace abi

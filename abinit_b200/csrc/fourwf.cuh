@@ -1,0 +1,88 @@
+// fourwf on sm_100a: plans, tables and kernel entry points (internal header).
+// Reference semantics: src/53_ffts/m_fft.F90:2290-2940 (fourwf), src/46_ghc_omp/m_ompgpu_fourwf.F90:179-585.
+#pragma once
+#include "common.cuh"
+#include "fft_engine.cuh"
+#include <vector>
+
+namespace abi {
+
+// device-resident tables for one FFT length
+struct FftTables {
+  Fft1d plan;                                  // device pointers inside
+  std::vector<unsigned short> pos_of_idx;      // host copies (used by the planners)
+  std::vector<unsigned short> idx_of_pos;
+};
+const FftTables& fft_tables(int n);            // cached; aborts if n has a prime factor > 7 or n > kMaxFftLen
+bool fft_length_supported(int n);
+void fft_tables_clear();
+
+// Epilogue fused into the last pass of option 2 when called from getghc (m_getghc.F90:1266-1280):
+//   out = (kinpw < huge*1e-11) ? fourwf + kinpw*cwavef + gvnlxc : 0
+struct FourwfEpilogue {
+  int mode = 0;                  // 0: plain fourwf; 1: + kinetic + nonlocal with filter; 2: filter only (type_calc=1)
+  const double* kinpw = nullptr; // device, npw_out
+  const double2* cwavef = nullptr;  // device, ndat*npw_out
+  const double2* gvnlxc = nullptr;  // device or null
+  double2* gsc = nullptr;        // device or null: zeroed where filtered (sij_opt==1)
+};
+
+struct FourwfPlan {
+  int n1 = 0, n2 = 0, n3 = 0, istwf_k = 1, me_g0 = 1;
+  int npw_in = 0, npw_out = 0;
+  uint64_t key = 0;
+  // ---- generic path (options 0,1,3 and fallback shapes) ----
+  int nent_in = 0;
+  int* d_in_src = nullptr;       // ipw | conj<<31 | zero_imag<<30
+  int* d_in_box = nullptr;       // linear box index
+  int* d_out_box = nullptr;      // npw_out
+  // ---- fused option-2 path ----
+  bool fused_ok = false;
+  int nlin = 0, nlout = 0, nU = 0;
+  int2* d_in_ent = nullptr;      // sorted by in-line: {src, (line<<10)|pos1}
+  int* d_lin_estart = nullptr;   // nlin+1
+  int* d_lin_u = nullptr;        // nlin
+  unsigned short* d_lin_pos2 = nullptr;  // nlin: DIT input position of the line's i2
+  int* d_inpl_start = nullptr;   // nU+1
+  int2* d_out_ent = nullptr;     // sorted by out-line: {ipw, (line<<10)|pos1}
+  int* d_lout_estart = nullptr;  // nlout+1
+  int* d_lout_u = nullptr;
+  unsigned short* d_lout_pos2 = nullptr;
+  int* d_outpl_start = nullptr;  // nU+1
+  unsigned short* d_u_i3 = nullptr;      // nU
+  unsigned char* d_u_flags = nullptr;    // bit0: has input lines, bit1: has output lines
+  std::vector<void*> owned;      // device allocations to free
+  void release();
+};
+
+// Build (or fetch from the cache) the plan for (kg_in, kg_out). kg arrays are HOST pointers, Fortran layout kg(3,npw).
+FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int npw_out, const int* ngfft,
+                            int istwf_k, int me_g0);
+void fourwf_clear_plans();
+
+// V_loc on the device: natural layout [i3][i2][i1] (cplex doubles per point) and the x-slowest transpose
+// [i1][i3][i2] used by the fused z pass (built once per load_spin).
+struct VlocDev {
+  int cplex = 1, n1 = 0, n2 = 0, n3 = 0;
+  double* d_v = nullptr;
+  double* d_vT = nullptr;
+  uint64_t stamp = 0;
+};
+void vloc_upload(VlocDev& v, const double* denpot, bool on_device, int cplex, int n1, int n2, int n3,
+                 cudaStream_t st);
+
+// All pointers below are DEVICE pointers.
+void fourwf_generic(const FourwfPlan& pl, int option, int cplex, double* d_denpot, const double2* d_fofgin,
+                    double2* d_fofgout, double2* d_fofr, int ndat, const double* d_wr, const double* d_wi,
+                    cudaStream_t st);
+void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_fofgin, double2* d_fofgout,
+                       int ndat, const FourwfEpilogue& epi, cudaStream_t st);
+
+// tuning knobs (env ABI_B200_* override), reported by bench.py
+struct FourwfTuning { int cluster = 0; int lines_x = 32; int smem_kb_mid = 0; int band_chunk = 0; };
+FourwfTuning& fourwf_tuning();
+
+// launch counter for bench.py's gpu_launches
+extern long long g_kernel_launches;
+
+}  // namespace abi

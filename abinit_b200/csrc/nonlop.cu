@@ -1,0 +1,615 @@
+// gemm_nonlop for sm_100a: projector overlaps P^H psi, D_ij/S_ij application, P.z back-accumulation.
+//
+// Reference semantics (not code): src/66_nonlocal/m_gemm_nonlop.F90:191-1242 (driver),
+// m_gemm_nonlop_projectors.F90:792-1038 (prep_projectors), m_opernla_gemm.F90:361-712 (P^H psi),
+// m_opernlc_ylm_allwf.F90:308-447,1253-1295 (D/S), m_opernlb_gemm.F90:353-837 (P z).
+//
+// Design: P is kept as ONE real matrix, the real view of P(2,npw,nprojs): (2 npw) x nprojs, column-major.
+//  * istwf_k>=2 (real projections): gx = 2 (P_r^T psi_r + P_i^T psi_i) is a single real GEMM with K = 2 npw on
+//    the interleaved data -- no de-interleave pass (the reference splits into P_r/P_i and psi_r/psi_i,
+//    m_opernla_gemm.F90:569-689); the istwf_k=2 G=0 correction is a rank-1 fix-up in the reduction epilogue.
+//  * istwf_k==1 (complex): P^H psi is the same real GEMM on 2 ndat columns, the odd ones being (-i psi), which
+//    is formed while loading B fragments from shared memory (swap + sign), never materialised.
+//    P z is a real GEMM with K = 2 nprojs whose odd k are (i P), formed while loading A fragments.
+//  * The GEMM kernels issue FP64 tensor-core MMAs (mma.sync m8n8k4 f64 = DMMA.8x8x4 in SASS; tcgen05 has no
+//    f64 kind) from a 4-stage cp.async pipeline; 16 warps x (32x32) warp tiles per 128x128 CTA tile.
+//  * opernla is K-long and output-small: split-K across CTAs with deterministic partial buffers; the reduction
+//    kernel fuses the x2 / G=0 fix-up, the projections store and the NC ekb scaling (opernlc).
+#include "nonlop.cuh"
+#include "fourwf.cuh"   // g_kernel_launches
+#include <algorithm>
+
+namespace abi {
+
+#ifndef ABI_EMU
+// ---------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kBM = 128, kBN = 128, kBK = 16, kThreads = 512, kStages = 4;
+constexpr int kPitchM = kBM + 8;       // M-contiguous tile pitch (doubles): 1088 B = 64 mod 128 -> 2 wavefronts/LDS.64
+
+ABI_DEV int swz(int r) { return ((r & 3) << 1) | ((r >> 2) & 1); }
+ABI_DEV int addr_k(int row, int k) { return row * kBK + ((((k >> 1) ^ swz(row)) << 1) | (k & 1)); }
+
+ABI_DEV void cp_async16(double* smem_dst, const double* gsrc, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int bytes = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(bytes));
+}
+ABI_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> ABI_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+ABI_DEV void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TN: part[z][n][m] = sum_{k in split z} A[k + m lda] * Beff[k][n]
+//   CPLX: Beff columns are (psi_j, -i psi_j) pairs read from one smem row per band
+// ---------------------------------------------------------------------------------------------------------
+struct TnParams {
+  int M, N, K;                 // N = effective columns (2*ndat when CPLX)
+  const double* A; long long lda;
+  const double* B; long long ldb;
+  double* part;                // [nsplit][N][M]
+  int nsplit, kchunk, tiles_m, tiles_n;
+};
+
+template <bool CPLX>
+__global__ void __launch_bounds__(kThreads, 1) k_dgemm_tn(TnParams p) {
+  extern __shared__ __align__(16) double smem_d[];
+  constexpr int BROWS = CPLX ? kBN / 2 : kBN;
+  double* As = smem_d;                                  // [stages][128*16]
+  double* Bs = smem_d + kStages * kBM * kBK;            // [stages][BROWS*16]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
+  int bid = blockIdx.x;
+  const int tn = bid % p.tiles_n; bid /= p.tiles_n;
+  const int tm = bid % p.tiles_m; const int z = bid / p.tiles_m;
+  const int m0 = tm * kBM, n0 = tn * kBN;
+  const int k_begin = z * p.kchunk, k_end = min(p.K, k_begin + p.kchunk);
+  const int nkt = (k_end - k_begin + kBK - 1) / kBK;
+  const int brow0 = CPLX ? n0 / 2 : n0;
+  const int nrows_b = CPLX ? p.N / 2 : p.N;
+
+  auto load_stage = [&](int s, int kt) {
+    const int k0 = k_begin + kt * kBK;
+    double* as = As + s * kBM * kBK;
+    double* bs = Bs + s * BROWS * kBK;
+#pragma unroll
+    for (int c = tid; c < kBM * 8; c += kThreads) {
+      const int row = c >> 3, ch = c & 7;
+      const int gm = m0 + row, gk = k0 + ch * 2;
+      const bool ok = gm < p.M && gk < k_end;
+      cp_async16(as + row * kBK + ((ch ^ swz(row)) << 1), ok ? p.A + (long long)gm * p.lda + gk : p.A, ok);
+    }
+#pragma unroll
+    for (int c = tid; c < BROWS * 8; c += kThreads) {
+      const int row = c >> 3, ch = c & 7;
+      const int gn = brow0 + row, gk = k0 + ch * 2;
+      const bool ok = gn < nrows_b && gk < k_end;
+      cp_async16(bs + row * kBK + ((ch ^ swz(row)) << 1), ok ? p.B + (long long)gn * p.ldb + gk : p.B, ok);
+    }
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int s = 0; s < kStages - 1; s++) { if (s < nkt) load_stage(s, s); cp_async_commit(); }
+  for (int kt = 0; kt < nkt; kt++) {
+    cp_async_wait<kStages - 2>();
+    __syncthreads();
+    { const int nx = kt + kStages - 1; if (nx < nkt) load_stage(nx % kStages, nx); cp_async_commit(); }
+    const double* as = As + (kt % kStages) * kBM * kBK;
+    const double* bs = Bs + (kt % kStages) * BROWS * kBK;
+#pragma unroll
+    for (int kk = 0; kk < kBK / 4; kk++) {
+      const int k = kk * 4 + t;
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = as[addr_k(wm + 8 * i + g, k)];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (CPLX) {
+          const int n = wn + 8 * j + g;          // effective column inside the tile
+          const int row = n >> 1;
+          if (n & 1) { const double v = bs[addr_k(row, k ^ 1)]; b[j] = (k & 1) ? -v : v; }
+          else b[j] = bs[addr_k(row, k)];
+        } else {
+          b[j] = bs[addr_k(wn + 8 * j + g, k)];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+  double* out = p.part + (size_t)z * p.N * p.M;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int m = m0 + wm + 8 * i + g;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int n = n0 + wn + 8 * j + 2 * t;
+      if (n < p.N) out[(size_t)n * p.M + m] = acc[i][j][0];
+      if (n + 1 < p.N) out[(size_t)(n + 1) * p.M + m] = acc[i][j][1];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NN: C[m + n ldc] = sum_k Aeff[m][k] * B[k + n ldb]   (+ add[m + n ldc])
+//   A is M-contiguous (P real view). CPLX: k = 2p+c, Aeff[m][2p] = A[m][p], Aeff[m][2p+1] = (iP)[m][p]
+// ---------------------------------------------------------------------------------------------------------
+struct NnParams {
+  int M, N, K;                 // K = number of A columns (nprojs)
+  const double* A; long long lda;
+  const double* B; long long ldb;   // K-contiguous columns: real: K doubles, CPLX: 2K doubles
+  double* C; long long ldc;
+  const double* add;           // optional, same layout as C
+  int tiles_m, tiles_n;
+};
+
+template <bool CPLX>
+__global__ void __launch_bounds__(kThreads, 1) k_dgemm_nn(NnParams p) {
+  extern __shared__ __align__(16) double smem_d[];
+  constexpr int AROWS = CPLX ? kBK / 2 : kBK;           // A columns (p) per stage
+  double* As = smem_d;                                  // [stages][AROWS*kPitchM]
+  double* Bs = smem_d + kStages * AROWS * kPitchM;      // [stages][128*16]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
+  const int tn = blockIdx.x % p.tiles_n, tm = blockIdx.x / p.tiles_n;
+  const int m0 = tm * kBM, n0 = tn * kBN;
+  const int nkt = (p.K + AROWS - 1) / AROWS;
+  const int kb_len = CPLX ? 2 * p.K : p.K;              // length of a B column in doubles
+
+  auto load_stage = [&](int s, int kt) {
+    const int p0 = kt * AROWS;
+    double* as = As + s * AROWS * kPitchM;
+    double* bs = Bs + s * kBN * kBK;
+#pragma unroll
+    for (int c = tid; c < AROWS * (kBM / 2); c += kThreads) {
+      const int krow = c / (kBM / 2), ch = c % (kBM / 2);
+      const int gk = p0 + krow, gm = m0 + ch * 2;
+      const bool ok = gk < p.K && gm < p.M;
+      cp_async16(as + krow * kPitchM + ch * 2, ok ? p.A + (long long)gk * p.lda + gm : p.A, ok);
+    }
+    const int q0 = kt * kBK;
+#pragma unroll
+    for (int c = tid; c < kBN * 8; c += kThreads) {
+      const int row = c >> 3, ch = c & 7;
+      const int gn = n0 + row, gq = q0 + ch * 2;
+      const bool ok = gn < p.N && gq < kb_len;
+      cp_async16(bs + row * kBK + ((ch ^ swz(row)) << 1), ok ? p.B + (long long)gn * p.ldb + gq : p.B, ok);
+    }
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int s = 0; s < kStages - 1; s++) { if (s < nkt) load_stage(s, s); cp_async_commit(); }
+  for (int kt = 0; kt < nkt; kt++) {
+    cp_async_wait<kStages - 2>();
+    __syncthreads();
+    { const int nx = kt + kStages - 1; if (nx < nkt) load_stage(nx % kStages, nx); cp_async_commit(); }
+    const double* as = As + (kt % kStages) * AROWS * kPitchM;
+    const double* bs = Bs + (kt % kStages) * kBN * kBK;
+#pragma unroll
+    for (int kk = 0; kk < kBK / 4; kk++) {
+      const int k = kk * 4 + t;
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int m = wm + 8 * i + g;
+        if (CPLX) {
+          const int pr = k >> 1;
+          if (k & 1) { const double v = as[pr * kPitchM + (m ^ 1)]; a[i] = (m & 1) ? v : -v; }
+          else a[i] = as[pr * kPitchM + m];
+        } else {
+          a[i] = as[k * kPitchM + m];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = bs[addr_k(wn + 8 * j + g, k)];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int m = m0 + wm + 8 * i + g;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int n = n0 + wn + 8 * j + 2 * t;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        if (n + h < p.N) {
+          const size_t o = (size_t)(n + h) * p.ldc + m;
+          double v = acc[i][j][h];
+          if (p.add) v += p.add[o];
+          p.C[o] = v;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// reduction of the split-K partials + opernla post-processing + NC opernlc
+// ---------------------------------------------------------------------------------------------------------
+struct ReduceParams {
+  int M, ndat, cplex, nsplit, neff;      // M = nprojs, neff = cplex*ndat
+  const double* part;                    // [nsplit][neff][M]
+  double scale;                          // 2 for istwf_k>=2 (m_opernla_gemm.F90:681-689), 1 otherwise
+  int g0fix;                             // istwf_k==2 && me_g0
+  const double* A; long long lda;        // P real view (rows 0,1 = G=0)
+  const double* B; long long ldb;        // psi real view
+  double* gx; long long ldg;             // internal gx [ndat][ldg] (cplex interleaved)
+  double* proj_out;                      // caller's projections(cplex,nprojs,ndat) or null
+  // NC opernlc fused: gxfac = ekb(iln,itypat) * gx (m_opernlc_ylm_allwf.F90:318-331)
+  double* gxfac; const double* ekb; int dimenl1; const int* proj_typ; const int* proj_iln;
+};
+
+__global__ void k_reduce_proj(ReduceParams r) {
+  const long long total = (long long)r.M * r.ndat;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx % r.M), n = (int)(idx / r.M);
+    double v[2] = {0.0, 0.0};
+    for (int c = 0; c < r.cplex; c++) {
+      const int ne = r.cplex * n + c;
+      double s = 0.0;
+      for (int z = 0; z < r.nsplit; z++) s += r.part[((size_t)z * r.neff + ne) * r.M + m];
+      v[c] = s * r.scale;
+    }
+    if (r.g0fix) {
+      const double a0 = r.A[(long long)m * r.lda], a1 = r.A[(long long)m * r.lda + 1];
+      const double b0 = r.B[(long long)n * r.ldb], b1 = r.B[(long long)n * r.ldb + 1];
+      v[0] -= a0 * b0 + 2.0 * a1 * b1;
+    }
+    double e = 1.0;
+    if (r.gxfac && r.ekb) e = r.ekb[r.proj_iln[m] + r.dimenl1 * r.proj_typ[m]];
+    for (int c = 0; c < r.cplex; c++) {
+      const size_t o = (size_t)n * r.ldg + (size_t)r.cplex * m + c;
+      r.gx[o] = v[c];
+      if (r.proj_out) r.proj_out[((size_t)n * r.M + m) * r.cplex + c] = v[c];
+      if (r.gxfac && r.ekb) r.gxfac[o] = e * v[c];
+    }
+  }
+}
+
+__global__ void k_load_proj(const double* __restrict__ proj, double* __restrict__ gx, long long ldg, int M, int ndat, int cplex) {
+  const long long total = (long long)M * ndat * cplex;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / ((long long)M * cplex), r = idx % ((long long)M * cplex);
+    gx[n * ldg + r] = proj[idx];
+  }
+}
+
+__global__ void k_nc_scale(const double* __restrict__ gx, double* __restrict__ gxfac, long long ldg, int M, int ndat,
+                           int cplex, const double* __restrict__ ekb, int dimenl1, const int* __restrict__ proj_typ,
+                           const int* __restrict__ proj_iln) {
+  const long long total = (long long)M * ndat;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx % M); const long long n = idx / M;
+    const double e = ekb[proj_iln[m] + dimenl1 * proj_typ[m]];
+    for (int c = 0; c < cplex; c++) gxfac[n * ldg + (long long)cplex * m + c] = e * gx[n * ldg + (long long)cplex * m + c];
+  }
+}
+
+// PAW: per (sorted atom, band): gxfac = D_ij gx (packed symmetric, real), optional -lambda S_ij, gxs = S_ij gx
+// (m_opernlc_ylm_allwf.F90:336-447, 1253-1295)
+__global__ void k_paw_opernlc(const double* __restrict__ gx, double* __restrict__ gxfac, double* __restrict__ gxs,
+                              long long ldg, int cplex, const int* __restrict__ atom_first, const int* __restrict__ atom_typ,
+                              const int* __restrict__ atom_enl, const double* __restrict__ enl, const double* __restrict__ sij,
+                              int dimenl1, int paw_opt, const double* __restrict__ lambda) {
+  const int a = blockIdx.x, n = blockIdx.y;
+  const int first = atom_first[a], nlmn = atom_first[a + 1] - first;
+  const double* D = enl + (size_t)dimenl1 * atom_enl[a];
+  const double* S = sij ? sij + (size_t)dimenl1 * atom_typ[a] : nullptr;
+  const double lam = (paw_opt == 2) ? lambda[n] : 0.0;
+  const double* x = gx + (size_t)n * ldg + (size_t)cplex * first;
+  for (int w = threadIdx.x; w < nlmn * cplex; w += blockDim.x) {
+    const int j = w / cplex, c = w - j * cplex;
+    double sd = 0.0, ss = 0.0;
+    for (int i = 0; i < nlmn; i++) {
+      const int hi = max(i, j), lo = min(i, j);
+      const int pk = hi * (hi + 1) / 2 + lo;
+      const double xv = x[i * cplex + c];
+      if (paw_opt == 1 || paw_opt == 2 || paw_opt == 4) sd += (D[pk] - (paw_opt == 2 ? lam * S[pk] : 0.0)) * xv;
+      if (paw_opt == 3 || paw_opt == 4) ss += S[pk] * xv;
+    }
+    const size_t o = (size_t)n * ldg + (size_t)cplex * (first + j) + c;
+    if (gxfac && (paw_opt == 1 || paw_opt == 2 || paw_opt == 4)) gxfac[o] = sd;
+    if (gxs && (paw_opt == 3 || paw_opt == 4)) gxs[o] = ss;
+  }
+}
+
+// prep_projectors: P = 4 pi / sqrt(ucvol) * ffnl(:,1,ilmn,itypat) * (-i)^l * conj(ph3d(:,ia))
+__global__ void k_prep_projectors(double2* __restrict__ P, int npw, int nprojs, const double* __restrict__ ffnl, int dimffnl,
+                                  int lmnmax, const double2* __restrict__ ph3d, const int* __restrict__ proj_typ,
+                                  const int* __restrict__ proj_lmn, const int* __restrict__ proj_atom,
+                                  const int* __restrict__ proj_l, double wt) {
+  const int ip = blockIdx.y;
+  const int typ = proj_typ[ip], lmn = proj_lmn[ip], ia = proj_atom[ip], il = proj_l[ip] & 3;
+  const double* f = ffnl + (size_t)npw * ((size_t)dimffnl * (lmn + (size_t)lmnmax * typ));
+  const double2* ph = ph3d + (size_t)npw * ia;
+  for (int ig = blockIdx.x * blockDim.x + threadIdx.x; ig < npw; ig += gridDim.x * blockDim.x) {
+    const double a = wt * f[ig];
+    double re, im;                       // a * (-i)^l
+    switch (il) { case 0: re = a; im = 0.0; break; case 1: re = 0.0; im = -a; break;
+                  case 2: re = -a; im = 0.0; break; default: re = 0.0; im = a; break; }
+    const double2 e = ph[ig];            // times conj(ph3d)
+    P[(size_t)ip * npw + ig] = make_double2(re * e.x + im * e.y, im * e.x - re * e.y);
+  }
+}
+#endif  // !ABI_EMU
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+void Projectors::alloc(int npw_, int nprojs_, int istwf_k_) {
+  size_t need = (size_t)2 * npw_ * nprojs_ + 64;
+  if (need > cap) {
+    if (d_p) CUDA_CHECK(cudaFree(d_p));
+    CUDA_CHECK(cudaMalloc(&d_p, sizeof(double) * need));
+    cap = need;
+  }
+  npw = npw_; nprojs = nprojs_; istwf_k = istwf_k_;
+}
+void Projectors::release() { if (d_p) cudaFree(d_p); d_p = nullptr; cap = 0; npw = nprojs = 0; }
+
+template <typename T> static T* upload(const std::vector<T>& v) {
+  T* d = nullptr;
+  CUDA_CHECK(cudaMalloc(&d, sizeof(T) * std::max<size_t>(1, v.size())));
+  if (!v.empty()) CUDA_CHECK(cudaMemcpy(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return d;
+}
+
+void NonlopAtoms::build(int natom_, int ntypat_, int lmnmax_, const int* indlmn_, const int* nattyp_, const int* atindx1_) {
+  release();
+  natom = natom_; ntypat = ntypat_; lmnmax = lmnmax_;
+  indlmn.assign(indlmn_, indlmn_ + (size_t)6 * lmnmax * ntypat);
+  nattyp.assign(nattyp_, nattyp_ + ntypat);
+  atindx1.assign(atindx1_, atindx1_ + natom);
+  nlmn.resize(ntypat);
+  std::vector<int> ptyp, plmn, patom, pl, piln, afirst, atyp, aenl;
+  int ia = 0;
+  for (int t = 0; t < ntypat; t++) {
+    int c = 0;
+    for (int i = 0; i < lmnmax; i++) if (indlmn[2 + 6 * (i + (size_t)lmnmax * t)] > 0) c++;   // count(indlmn(3,:,itypat)>0)
+    nlmn[t] = c;
+    for (int a = 0; a < nattyp[t]; a++, ia++) {
+      ABI_CHECK(ia < natom, "sum(nattyp) exceeds natom");
+      afirst.push_back((int)ptyp.size()); atyp.push_back(t); aenl.push_back(atindx1[ia] - 1);
+      for (int i = 0; i < c; i++) {
+        ptyp.push_back(t); plmn.push_back(i); patom.push_back(ia);
+        pl.push_back(indlmn[0 + 6 * (i + (size_t)lmnmax * t)]);
+        piln.push_back(indlmn[4 + 6 * (i + (size_t)lmnmax * t)] - 1);
+      }
+    }
+  }
+  ABI_CHECK(ia == natom, "sum(nattyp) differs from natom");
+  afirst.push_back((int)ptyp.size());
+  nprojs = (int)ptyp.size();                                  // m_gemm_nonlop.F90:400-403
+  d_proj_typ = upload(ptyp); d_proj_lmn = upload(plmn); d_proj_atom = upload(patom); d_proj_l = upload(pl);
+  d_proj_iln = upload(piln); d_atom_first = upload(afirst); d_atom_typ = upload(atyp); d_atom_enl = upload(aenl);
+}
+void NonlopAtoms::release() {
+  int** ptrs[] = {&d_proj_typ, &d_proj_lmn, &d_proj_atom, &d_proj_l, &d_proj_iln, &d_atom_first, &d_atom_typ, &d_atom_enl};
+  for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+}
+
+void NonlopEnl::load(const double* enl, int d1, int d2, const double* sij, int ntypat, cudaStream_t st) {
+  release();
+  dimenl1 = d1; dimenl2 = d2;
+  CUDA_CHECK(cudaMalloc(&d_enl, sizeof(double) * std::max<size_t>(1, (size_t)d1 * d2)));
+  CUDA_CHECK(cudaMemcpyAsync(d_enl, enl, sizeof(double) * (size_t)d1 * d2, cudaMemcpyDefault, st));
+  if (sij) {
+    CUDA_CHECK(cudaMalloc(&d_sij, sizeof(double) * std::max<size_t>(1, (size_t)d1 * ntypat)));
+    CUDA_CHECK(cudaMemcpyAsync(d_sij, sij, sizeof(double) * (size_t)d1 * ntypat, cudaMemcpyDefault, st));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
+void NonlopEnl::release() {
+  if (d_enl) cudaFree(d_enl);
+  if (d_sij) cudaFree(d_sij);
+  d_enl = d_sij = nullptr;
+}
+
+struct NlWorkspace {
+  double* p = nullptr; size_t cap = 0;
+  double* get(size_t n) {
+    if (n > cap) { if (p) CUDA_CHECK(cudaFree(p)); CUDA_CHECK(cudaMalloc(&p, sizeof(double) * (n + n / 8 + 64))); cap = n + n / 8 + 64; }
+    return p;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+static NlWorkspace g_nlws[4];   // 0: partials, 1: gx, 2: gxfac, 3: gxs
+void nonlop_release_workspace() { for (auto& w : g_nlws) w.release(); }
+
+#ifndef ABI_EMU
+void prep_projectors_device(Projectors& P, const NonlopAtoms& at, const double* d_ffnl, int dimffnl, const double* d_ph3d,
+                            int matblk, double ucvol, cudaStream_t st) {
+  ABI_CHECK(matblk >= at.natom, "ph3d must hold one phase column per atom (matblk >= natom)");
+  const double wt = 4.0 * 3.14159265358979323846 / sqrt(ucvol);
+  if (at.nprojs == 0 || P.npw == 0) return;
+  dim3 grid(std::min(64, ceil_div(P.npw, 256)), at.nprojs);
+  k_prep_projectors<<<grid, 256, 0, st>>>(reinterpret_cast<double2*>(P.d_p), P.npw, at.nprojs, d_ffnl, dimffnl, at.lmnmax,
+                                          reinterpret_cast<const double2*>(d_ph3d), at.d_proj_typ, at.d_proj_lmn,
+                                          at.d_proj_atom, at.d_proj_l, wt);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+static size_t tn_smem(bool cplx) { return sizeof(double) * kStages * (kBM * kBK + (cplx ? kBN / 2 : kBN) * kBK); }
+static size_t nn_smem(bool cplx) { return sizeof(double) * kStages * ((cplx ? kBK / 2 : kBK) * kPitchM + kBN * kBK); }
+
+// split-K TN GEMM into partial buffers; returns nsplit
+static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long long lda, const double* B, long long ldb,
+                     double*& part, cudaStream_t st) {
+  TnParams p;
+  p.M = M; p.N = Neff; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb;
+  p.tiles_m = ceil_div(M, kBM); p.tiles_n = ceil_div(Neff, kBN);
+  const int tiles = p.tiles_m * p.tiles_n;
+  // pick the split count that minimises the makespan (waves of 148 CTAs per unit of work)
+  const int min_chunk = 64 * kBK;
+  const int max_split = std::max(1, std::min(64, ceil_div(K, min_chunk)));
+  int nsplit = 1; double best = 1e30;
+  for (int s = 1; s <= max_split; s++) {
+    const double cost = (double)ceil_div(tiles * s, kNumSM) / s + 0.002 * s;
+    if (cost < best - 1e-12) { best = cost; nsplit = s; }
+  }
+  int kchunk = ceil_div(ceil_div(K, nsplit), kBK) * kBK;
+  nsplit = ceil_div(K, kchunk);
+  p.nsplit = nsplit; p.kchunk = kchunk;
+  part = g_nlws[0].get((size_t)nsplit * Neff * M);
+  p.part = part;
+  const size_t smem = tn_smem(cplx);
+  if (cplx) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_dgemm_tn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dgemm_tn<true><<<tiles * nsplit, kThreads, smem, st>>>(p);
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(k_dgemm_tn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dgemm_tn<false><<<tiles * nsplit, kThreads, smem, st>>>(p);
+  }
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+  return nsplit;
+}
+
+static void launch_nn(bool cplx, int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
+                      long long ldc, const double* add, cudaStream_t st) {
+  NnParams p;
+  p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.add = add;
+  p.tiles_m = ceil_div(M, kBM); p.tiles_n = ceil_div(N, kBN);
+  const size_t smem = nn_smem(cplx);
+  if (cplx) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_dgemm_nn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dgemm_nn<true><<<p.tiles_m * p.tiles_n, kThreads, smem, st>>>(p);
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(k_dgemm_nn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dgemm_nn<false><<<p.tiles_m * p.tiles_n, kThreads, smem, st>>>(p);
+  }
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+__global__ void k_reduce_plain(const double* __restrict__ part, double* __restrict__ C, long long ldc, int M, int N, int nsplit, double alpha) {
+  const long long total = (long long)M * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx % M); const long long n = idx / M;
+    double s = 0.0;
+    for (int z = 0; z < nsplit; z++) s += part[((size_t)z * N + n) * M + m];
+    C[n * ldc + m] = alpha * s;
+  }
+}
+
+void dgemm_tn(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
+              double alpha, cudaStream_t st) {
+  double* part = nullptr;
+  const int nsplit = launch_tn(false, M, N, K, A, lda, B, ldb, part, st);
+  k_reduce_plain<<<std::min(kNumSM * 8, (int)ceil_div<long long>((long long)M * N, 256)), 256, 0, st>>>(part, C, ldc, M, N, nsplit, alpha);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const NonlopEnl& enl, int choice, int cpopt, int paw_opt,
+                        int me_g0, const double* d_lambda, int ndat, const double* vectin, double* vectout, double* svectout,
+                        double* projections, cudaStream_t st) {
+  ABI_CHECK(choice == 0 || choice == 1 || choice == 7, "gemm_nonlop: only choice 0, 1, 7 (signs=2) are on the getghc path");
+  ABI_CHECK(paw_opt >= 0 && paw_opt <= 4, "gemm_nonlop: bad paw_opt");
+  ABI_CHECK(P.nprojs == at.nprojs, "gemm_nonlop: projectors were prepared for a different atom table");
+  const int npw = P.npw, nprojs = P.nprojs;
+  if (nprojs == 0 || ndat == 0) {
+    if (vectout) CUDA_CHECK(cudaMemsetAsync(vectout, 0, sizeof(double) * 2 * (size_t)npw * ndat, st));
+    if (svectout && vectin) CUDA_CHECK(cudaMemcpyAsync(svectout, vectin, sizeof(double) * 2 * (size_t)npw * ndat, cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  const bool cplx = P.istwf_k == 1;
+  const int cplex = cplx ? 2 : 1;
+  const long long ldv = 2LL * npw;
+  const long long ldg = ((long long)cplex * nprojs + 1) & ~1LL;      // even: 16-byte aligned columns for cp.async
+  double* gx = g_nlws[1].get((size_t)ldg * ndat);
+  double* gxfac = g_nlws[2].get((size_t)ldg * ndat);
+  double* gxs = (paw_opt == 3 || paw_opt == 4) ? g_nlws[3].get((size_t)ldg * ndat) : nullptr;
+  if (ldg != (long long)cplex * nprojs) {   // keep the pad element finite (it multiplies zero-filled A rows)
+    CUDA_CHECK(cudaMemsetAsync(gx, 0, sizeof(double) * ldg * ndat, st));
+    CUDA_CHECK(cudaMemsetAsync(gxfac, 0, sizeof(double) * ldg * ndat, st));
+    if (gxs) CUDA_CHECK(cudaMemsetAsync(gxs, 0, sizeof(double) * ldg * ndat, st));
+  }
+  const bool nc_fused = (choice == 1 && paw_opt == 0);
+  const int blocks = std::min(kNumSM * 8, (int)ceil_div<long long>((long long)nprojs * ndat, 256));
+  if (cpopt >= 2) {
+    // <p|c> already in memory (m_gemm_nonlop.F90:719-734)
+    ABI_CHECK(projections != nullptr, "gemm_nonlop: cpopt>=2 needs the projections buffer");
+    k_load_proj<<<blocks, 256, 0, st>>>(projections, gx, ldg, nprojs, ndat, cplex);
+    CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+    if (nc_fused) {
+      k_nc_scale<<<blocks, 256, 0, st>>>(gx, gxfac, ldg, nprojs, ndat, cplex, enl.d_enl, enl.dimenl1, at.d_proj_typ, at.d_proj_iln);
+      CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    }
+  } else {
+    ABI_CHECK(vectin != nullptr, "gemm_nonlop: vectin is required");
+    double* part = nullptr;
+    const int nsplit = launch_tn(cplx, nprojs, cplex * ndat, 2 * npw, P.d_p, ldv, vectin, ldv, part, st);
+    ReduceParams r;
+    r.M = nprojs; r.ndat = ndat; r.cplex = cplex; r.nsplit = nsplit; r.neff = cplex * ndat; r.part = part;
+    r.scale = cplx ? 1.0 : 2.0;
+    r.g0fix = (P.istwf_k == 2 && me_g0 == 1) ? 1 : 0;
+    r.A = P.d_p; r.lda = ldv; r.B = vectin; r.ldb = ldv; r.gx = gx; r.ldg = ldg;
+    r.proj_out = (cpopt >= 0 || choice == 0) ? projections : nullptr;
+    r.gxfac = nc_fused ? gxfac : nullptr; r.ekb = nc_fused ? enl.d_enl : nullptr; r.dimenl1 = enl.dimenl1;
+    r.proj_typ = at.d_proj_typ; r.proj_iln = at.d_proj_iln;
+    k_reduce_proj<<<blocks, 256, 0, st>>>(r);
+    CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+  }
+  if (choice == 0) return;
+  const double* zfac = gxfac;
+  const double* zs = gxs;
+  if (choice == 7) {
+    zs = gx;                                   // s_projections = projections (m_gemm_nonlop.F90:856-861)
+  } else if (paw_opt != 0) {
+    ABI_CHECK(enl.d_enl != nullptr, "gemm_nonlop: D_ij not loaded");
+    ABI_CHECK(!(paw_opt >= 2) || enl.d_sij != nullptr, "gemm_nonlop: S_ij not loaded");
+    k_paw_opernlc<<<dim3(at.natom, ndat), 64, 0, st>>>(gx, gxfac, gxs, ldg, cplex, at.d_atom_first, at.d_atom_typ, at.d_atom_enl,
+                                                       enl.d_enl, enl.d_sij, enl.dimenl1, paw_opt, d_lambda);
+    CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+  }
+  // opernlb
+  if (choice == 7 || paw_opt == 3 || paw_opt == 4) {
+    ABI_CHECK(svectout != nullptr && vectin != nullptr, "gemm_nonlop: svectout/vectin required for the overlap");
+    launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zs, ldg, svectout, ldv, vectin, st);   // + vectin, m_opernlb_gemm.F90:654-665
+  }
+  if (choice == 1 && (paw_opt == 0 || paw_opt == 1 || paw_opt == 2 || paw_opt == 4)) {
+    ABI_CHECK(vectout != nullptr, "gemm_nonlop: vectout required");
+    launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zfac, ldg, vectout, ldv, nullptr, st);
+  }
+}
+#else
+void prep_projectors_device(Projectors&, const NonlopAtoms&, const double*, int, const double*, int, double, cudaStream_t) {}
+void gemm_nonlop_device(const Projectors&, const NonlopAtoms&, const NonlopEnl&, int, int, int, int, const double*, int,
+                        const double*, double*, double*, double*, cudaStream_t) {}
+void dgemm_tn(int, int, int, const double*, long long, const double*, long long, double*, long long, double, cudaStream_t) {}
+#endif
+
+}  // namespace abi

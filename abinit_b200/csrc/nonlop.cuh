@@ -1,0 +1,61 @@
+// gemm_nonlop on sm_100a (internal header).
+// Reference semantics: src/66_nonlocal/m_gemm_nonlop.F90:191-1242, m_gemm_nonlop_projectors.F90:792-1038,
+// m_opernla_gemm.F90:361-712, m_opernlc_ylm_allwf.F90:231-1349, m_opernlb_gemm.F90:353-837.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace abi {
+
+// Projectors of one k-point, resident on the device as the real view of P(2, npw, nprojs):
+// a column-major (2*npw) x nprojs FP64 matrix (rows = re/im interleaved plane-wave coefficients).
+struct Projectors {
+  int npw = 0, nprojs = 0, istwf_k = 1;
+  double* d_p = nullptr;          // (2*npw) * nprojs doubles (+ padding)
+  size_t cap = 0;
+  void alloc(int npw_, int nprojs_, int istwf_k_);
+  void release();
+};
+
+// Per-type / per-atom description of the non-local operator (flattened gs_hamiltonian_type fields)
+struct NonlopAtoms {
+  int natom = 0, ntypat = 0, lmnmax = 0, nprojs = 0;
+  std::vector<int> indlmn;        // 6 * lmnmax * ntypat (Fortran order)
+  std::vector<int> nattyp, atindx1, nlmn;
+  // device tables, one entry per projector
+  int* d_proj_typ = nullptr;      // type of the projector's atom
+  int* d_proj_lmn = nullptr;      // ilmn (0-based) inside the atom
+  int* d_proj_atom = nullptr;     // atom index in the type-sorted order (0-based)
+  int* d_proj_l = nullptr;        // l quantum number
+  int* d_proj_iln = nullptr;      // iln (0-based)
+  int* d_atom_first = nullptr;    // natom+1: first projector of each sorted atom
+  int* d_atom_typ = nullptr;      // natom
+  int* d_atom_enl = nullptr;      // natom: atindx1-1 (column of the D_ij array)
+  void build(int natom, int ntypat, int lmnmax, const int* indlmn, const int* nattyp, const int* atindx1);
+  void release();
+};
+
+struct NonlopEnl {
+  int dimenl1 = 0, dimenl2 = 0;
+  double* d_enl = nullptr;        // dimenl1 * dimenl2
+  double* d_sij = nullptr;        // dimenl1 * ntypat or null
+  void load(const double* enl, int dimenl1, int dimenl2, const double* sij, int ntypat, cudaStream_t st);
+  void release();
+};
+
+// Build P on the device (prep_projectors). ffnl / ph3d are DEVICE pointers in Fortran layout.
+void prep_projectors_device(Projectors& P, const NonlopAtoms& at, const double* d_ffnl, int dimffnl,
+                            const double* d_ph3d, int matblk, double ucvol, cudaStream_t st);
+
+// gemm_nonlop, choice in {0,1,7}, signs=2.  All data pointers are DEVICE pointers (may be null when unused):
+//   vectin, vectout, svectout : (2, npw, ndat) ; projections : (cplex, nprojs, ndat)
+void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const NonlopEnl& enl, int choice, int cpopt,
+                        int paw_opt, int me_g0, const double* d_lambda, int ndat, const double* vectin,
+                        double* vectout, double* svectout, double* projections, cudaStream_t st);
+
+// plain tensor-core GEMMs (also used by the Gram kernels of xg.cu); all device pointers, column-major
+//   TN: C(M,N) = alpha * A(K,M)^T B(K,N)      NN: C(M,N) = A(M,K) B(K,N)
+void dgemm_tn(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
+              long long ldc, double alpha, cudaStream_t st);
+
+}  // namespace abi

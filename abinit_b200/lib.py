@@ -1,0 +1,77 @@
+"""ctypes binding of the C-ABI declared in include/abinit_b200.h (the same symbols a Fortran
+``iso_c_binding`` interface block binds)."""
+from __future__ import annotations
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class LibraryNotBuilt(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libabinit_b200.so")
+
+
+# every symbol include/abinit_b200.h declares (checked by tests/test_abi_symbols.py)
+SYMBOLS = [
+    "abi_b200_init", "abi_b200_finalize", "abi_b200_set_stream", "abi_b200_set_async", "abi_b200_synchronize",
+    "abi_b200_kernel_launches", "abi_b200_version",
+    "abi_b200_fourwf_", "abi_b200_alloc_fourwf_", "abi_b200_free_fourwf_", "gpu_fourwf_", "alloc_gpu_fourwf_",
+    "free_gpu_fourwf_", "abi_b200_set_me_g0", "abi_b200_fourwf_set_impl", "abi_b200_fourwf_counter",
+    "abi_b200_init_gemm_nonlop_", "abi_b200_destroy_gemm_nonlop_", "abi_b200_prep_projectors_",
+    "abi_b200_set_projectors_", "abi_b200_set_gemm_nonlop_ikpt_", "abi_b200_gemm_nonlop_",
+    "abi_b200_nonlop_counter",
+    "abi_b200_ham_create", "abi_b200_ham_destroy", "abi_b200_ham_load_spin", "abi_b200_ham_load_enl",
+    "abi_b200_ham_load_k", "abi_b200_ham_set_projectors", "abi_b200_ham_nprojs", "abi_b200_getghc_",
+    "abi_b200_xg_gram_",
+]
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """Load libabinit_b200.so.  Raises LibraryNotBuilt (never falls back to a CPU path)."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or library_path()
+    if not os.path.exists(p):
+        raise LibraryNotBuilt(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). abinit_b200 has no CPU fallback.")
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    vp, ip, dp = C.c_void_p, C.c_void_p, C.c_void_p   # all array arguments are passed as raw addresses
+    lib.abi_b200_init.argtypes = [C.c_int]
+    lib.abi_b200_set_stream.argtypes = [vp]
+    lib.abi_b200_set_async.argtypes = [C.c_int]
+    lib.abi_b200_kernel_launches.restype = C.c_longlong
+    lib.abi_b200_fourwf_counter.restype = C.c_longlong
+    lib.abi_b200_version.restype = C.c_char_p
+    lib.abi_b200_set_me_g0.argtypes = [C.c_int]
+    lib.abi_b200_fourwf_set_impl.argtypes = [C.c_int]
+    for name in ("abi_b200_fourwf_", "gpu_fourwf_"):
+        getattr(lib, name).argtypes = [vp] * 24
+    lib.abi_b200_alloc_fourwf_.argtypes = [vp] * 4
+    if hasattr(lib, "abi_b200_gemm_nonlop_"):
+        lib.abi_b200_nonlop_counter.restype = C.c_longlong
+        lib.abi_b200_init_gemm_nonlop_.argtypes = [vp]
+        lib.abi_b200_prep_projectors_.argtypes = [vp] * 12
+        lib.abi_b200_set_projectors_.argtypes = [vp] * 5
+        lib.abi_b200_set_gemm_nonlop_ikpt_.argtypes = [vp]
+        lib.abi_b200_gemm_nonlop_.argtypes = [vp] * 28
+        lib.abi_b200_ham_create.restype = vp
+        lib.abi_b200_ham_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_double]
+        lib.abi_b200_ham_destroy.argtypes = [vp]
+        lib.abi_b200_ham_load_spin.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.abi_b200_ham_load_enl.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        lib.abi_b200_ham_load_k.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int]
+        lib.abi_b200_ham_set_projectors.argtypes = [vp, vp, C.c_int]
+        lib.abi_b200_ham_nprojs.argtypes = [vp]
+        lib.abi_b200_ham_nprojs.restype = C.c_int
+        lib.abi_b200_getghc_.argtypes = [vp] * 13
+        lib.abi_b200_xg_gram_.argtypes = [vp] * 11
+    if path is None:
+        _LIB = lib
+    return lib

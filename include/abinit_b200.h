@@ -1,0 +1,134 @@
+/* abinit_b200 -- B200-native (sm_100a) drop-in for ABINIT's getghc hot path: fourwf + gemm_nonlop + assembly.
+ *
+ * C-ABI boundary.  Every entry point below is what the reference's Fortran would bind through
+ * iso_c_binding for this path; the citation next to each one names the reference interface it replaces
+ * (paths relative to the ABINIT source tree).  Conventions follow the reference's own C/CUDA plug points
+ * (src/46_manage_cuda/gpu_fourwf.cu:133-156): Fortran array layouts (column-major, re/im interleaved
+ * real(dp)(2,*) complex data, kg(3,npw) integer triplets), no torch or C++ types in any signature.
+ *
+ * Pointer residency: every data pointer may be a HOST pointer or a DEVICE pointer (cudaMalloc'ed on the
+ * current device).  The library inspects it (cudaPointerGetAttributes) and only stages host arrays --
+ * the same contract as the reference's offload path, which skips transfers for arrays the caller already
+ * mapped (src/66_wfs/m_getghc.F90:378-394, src/46_ghc_omp/m_ompgpu_fourwf.F90:247-262).
+ *
+ * Error convention: none of these functions returns a status.  Invalid input or a CUDA failure prints a
+ * YAML-style "--- !ERROR" document to stderr and calls abort(), like ABI_ERROR -> abi_abort
+ * (shared/common/src/incs/abi_common.h:307-309) and abi_cabort() (gpu_fourwf.cu:196-207).
+ * There is no CPU fallback anywhere in the library.
+ *
+ * Threading: one host thread per GPU drives the library (src/66_wfs/m_getghc.F90:2442-2449).
+ * Calls are synchronous from the caller's point of view unless abi_b200_set_async(1) was called.
+ */
+#ifndef ABINIT_B200_H
+#define ABINIT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------------
+ * Library lifecycle.  Replaces alloc_hamilt_gpu / dealloc_hamilt_gpu
+ * (src/66_nonlocal/m_alloc_hamilt_gpu.F90:96,237) and the device pick of
+ * shared/common/src/17_gpu_toolbox/m_initcuda.F90:326-333 (device = mod(rank, ndevices)).
+ * ---------------------------------------------------------------------------------------------------- */
+void abi_b200_init(int rank);                 /* selects device rank % ndevices, creates the stream */
+void abi_b200_finalize(void);                 /* frees plans, tables, workspaces */
+void abi_b200_set_stream(void* cuda_stream);  /* run on a caller-owned cudaStream_t (NULL -> internal stream) */
+void abi_b200_set_async(int flag);            /* 1: do not synchronise before returning (device pointers only) */
+void abi_b200_synchronize(void);              /* gpu_device_synchronize, src/79_seqpar_mpi/m_chebfiwf.F90:377-379 */
+long long abi_b200_kernel_launches(void);     /* kernels launched by this library so far (bench accounting) */
+const char* abi_b200_version(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * fourwf.  Same symbol shape as the legacy CUDA plug point
+ *   extern "C" void gpu_fourwf_(...)            src/46_manage_cuda/gpu_fourwf.cu:133-156
+ * called from fourwf (src/53_ffts/m_fft.F90:2383-2387): all scalars by reference, weight_r/weight_i arrays
+ * of ndat, trailing underscore.  Supports option 0,1,2,3; cplex 1,2 (option 2); istwf_k 1..9; ndat>=1.
+ * Requires n4,n5,n6 == n1,n2,n3 (as every GPU path of the reference, gpu_fourwf.cu:196-201).
+ * mpi_enreg is opaque and ignored except through me_g0 (set with abi_b200_set_me_g0, default 1).
+ * ---------------------------------------------------------------------------------------------------- */
+void abi_b200_fourwf_(int* cplex, double* denpot, double* fofgin, double* fofgout, double* fofr,
+                      int* gboundin, int* gboundout, int* istwf_k, int* kg_kin, int* kg_kout, int* mgfft,
+                      void* mpi_enreg, int* ndat, int* ngfft, int* npwin, int* npwout, int* n4, int* n5, int* n6,
+                      int* option, int* paral_kgb, int* tim_fourwf, double* weight_r, double* weight_i);
+/* alloc_gpu_fourwf_ / free_gpu_fourwf_ (gpu_fourwf.cu:290,350): pre-size / release the work buffers */
+void abi_b200_alloc_fourwf_(int* ngfft, int* ndat, int* npwin, int* npwout);
+void abi_b200_free_fourwf_(void);
+/* The legacy symbol names themselves, so that an ABINIT built with the legacy CUDA plug point can link this
+ * library in place of src/46_manage_cuda/gpu_fourwf.cu without touching m_fft.F90 (identical signatures). */
+void gpu_fourwf_(int* cplex, double* denpot, double* fofgin, double* fofgout, double* fofr, int* gboundin,
+                 int* gboundout, int* istwf_k, int* kg_kin, int* kg_kout, int* mgfft, void* mpi_enreg, int* ndat,
+                 int* ngfft, int* npwin, int* npwout, int* n4, int* n5, int* n6, int* option, int* paral_kgb,
+                 int* tim_fourwf, double* weight_r, double* weight_i);
+void alloc_gpu_fourwf_(int* ngfft, int* ndat, int* npwin, int* npwout);
+void free_gpu_fourwf_(void);
+void abi_b200_set_me_g0(int me_g0);           /* mpi_enreg%me_g0_fft (src/53_ffts/m_fft.F90:2346) */
+/* force the generic (full-box) or the fused implementation of option 2: 0 auto, 1 generic, 2 fused */
+void abi_b200_fourwf_set_impl(int impl);
+/* fourwf_counter of src/53_ffts/m_fft.F90:2333-2336 */
+long long abi_b200_fourwf_counter(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * gemm_nonlop.  Projector lifecycle mirrors init_gemm_nonlop / set_gemm_nonlop_ikpt / prep_projectors /
+ * destroy_gemm_nonlop (src/66_nonlocal/m_gemm_nonlop_projectors.F90:199-253,555-575,792-1038).
+ * The apply call has the argument list of gemm_nonlop_gpu (src/66_nonlocal/m_gemm_nonlop_gpu.F90:134,
+ * called at src/66_nonlocal/m_nonlop.F90:800-808) restricted to what choice in {0,1,7}, signs=2 reads, with
+ * cprjin flattened to the `vectproj` buffer projections(cplex, nprojs, nspinor*ndat)
+ * (src/66_nonlocal/m_gemm_nonlop.F90:503-508); the Fortran shim does the pawcprj pack/unpack (:719-789).
+ * ---------------------------------------------------------------------------------------------------- */
+void abi_b200_init_gemm_nonlop_(int* nkpt);
+void abi_b200_destroy_gemm_nonlop_(void);
+/* Build and cache P for k-point slot *ikpt (1-based).  ffnl(npw,dimffnl,lmnmax,ntypat), ph3d(2,npw,matblk)
+ * with atoms sorted by type, indlmn(6,lmnmax,ntypat), nattyp(ntypat).  P stays on the device. */
+void abi_b200_prep_projectors_(int* ikpt, int* npw, int* lmnmax, int* ntypat, int* indlmn, int* nattyp,
+                               int* istwf_k, double* ucvol, double* ffnl, double* ph3d, int* dimffnl,
+                               int* matblk);
+/* Test/benchmark hook: install an explicit P(2,npw,nprojs) instead of building it from ffnl/ph3d. */
+void abi_b200_set_projectors_(int* ikpt, int* npw, int* nprojs, int* istwf_k, double* projs);
+void abi_b200_set_gemm_nonlop_ikpt_(int* ikpt);
+void abi_b200_gemm_nonlop_(int* atindx1, int* choice, int* cpopt, double* vectproj, int* dimenl1, int* dimenl2,
+                           int* dimekbq, double* enl, int* indlmn, int* istwf_k, double* lambda, int* lmnmax,
+                           int* natom, int* nattyp, int* ndat, int* nnlout, int* npwin, int* npwout,
+                           int* nspinor, int* nspinortot, int* ntypat, int* paw_opt, double* sij,
+                           double* svectout, int* useylm, double* vectin, double* vectout, int* signs);
+long long abi_b200_nonlop_counter(void);      /* nonlop_counter, src/66_nonlocal/m_nonlop.F90:389-392 */
+
+/* ------------------------------------------------------------------------------------------------------
+ * getghc (fused fast path).  gs_hamiltonian_type (src/66_nonlocal/m_hamiltonian.F90:99-467) is flattened
+ * into an opaque handle filled by the same three steps the reference performs:
+ *   init      -> abi_b200_ham_create      (gs_hamk%init,      src/79_seqpar_mpi/m_vtorho.F90:640)
+ *   load_spin -> abi_b200_ham_load_spin   (vlocal per spin,   m_vtorho.F90:804)
+ *   load_k    -> abi_b200_ham_load_k      (kg,kinpw,ffnl,ph3d m_vtorho.F90:1035-1045; P built here)
+ * abi_b200_getghc_ has the argument list of getghc (src/66_wfs/m_getghc.F90:182-202) with gs_ham -> handle,
+ * cwaveprj -> flattened projections, mpi_enreg dropped.  nspinor=1, nvloc=1, k==k' (select_k default).
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct abi_b200_ham abi_b200_ham_t;
+abi_b200_ham_t* abi_b200_ham_create(const int* ngfft, int natom, int ntypat, int lmnmax, const int* indlmn,
+                                    const int* nattyp, const int* atindx1, int usepaw, double ucvol);
+void abi_b200_ham_destroy(abi_b200_ham_t* h);
+void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_vloc, int n4, int n5, int n6);
+/* enl: NC ekb(dimenl1=lnmax, ntypat); PAW dij(dimenl1=lmn2_size, natom).  sij(dimenl1, ntypat) (PAW) or NULL */
+void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, const double* sij);
+void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw,
+                         const double* ffnl, int dimffnl, const double* ph3d, int matblk, int me_g0);
+/* benchmark/test hook: explicit projectors instead of ffnl/ph3d (pass ffnl=ph3d=NULL to load_k) */
+void abi_b200_ham_set_projectors(abi_b200_ham_t* h, const double* projs, int nprojs);
+int abi_b200_ham_nprojs(const abi_b200_ham_t* h);
+void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc, double* gsc,
+                      abi_b200_ham_t** gs_ham, double* gvnlxc, double* lambda, int* ndat, int* prtvol,
+                      int* sij_opt, int* tim_getghc, int* type_calc);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Block Rayleigh-Ritz Gram matrices (xgBlock_gemm + xgBlock_mpi_sum, src/45_xgTools/m_xg.F90:1674-1976,
+ * 3636-3663; called by xg_RayleighRitz, src/45_xgTools/m_xg_ortho_RR.F90:384,388).
+ * C(ncols_a, ncols_b) = alpha * A^H B (+ beta C) on row shards; space 1 = SPACE_C (complex),
+ * 2 = SPACE_CR (real view of istwfk>=2 data: 2 Re(A^H B) minus the doubled G=0 term when me_g0=1).
+ * The cross-rank sum is an in-stream NCCL allreduce issued by the host wrapper (abinit_b200.parallel).
+ * ---------------------------------------------------------------------------------------------------- */
+void abi_b200_xg_gram_(int* space, int* rows, int* ncols_a, int* ncols_b, double* a, int* lda, double* b,
+                       int* ldb, double* c, int* ldc, int* me_g0);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABINIT_B200_H */

@@ -1,0 +1,20 @@
+import os
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """The product library, initialised on cuda:0. GPU tests call through this C-ABI only."""
+    import abinit_b200
+    abinit_b200.init(0)
+    yield abinit_b200
+    abinit_b200.finalize()

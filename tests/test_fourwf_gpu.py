@@ -1,0 +1,108 @@
+"""GPU parity: fourwf through the C-ABI vs the oracle (FP64, tolerance 1e-11 relative per band, north-star)."""
+import numpy as np
+import pytest
+from oracle import fourwf as ofw, gsphere as g
+from problems import make_problem, rel_err_per_band
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-11   # BASELINE.json north_star: "match the reference's CPU getghc ... to 1e-11 relative in FP64"
+
+
+def _run(lib, p, option, impl, weight_r=0.7, weight_i=0.3):
+    n1, n2, n3 = p.ngfft
+    rng = np.random.default_rng(7)
+    out = np.zeros((p.ndat, p.npw), dtype=np.complex128)
+    fofr = np.zeros((p.ndat, n3, n2, n1), dtype=np.complex128)
+    den = p.vlocal.copy()
+    if option == 1:
+        den = np.ascontiguousarray(np.abs(p.vlocal.real))
+    if option == 3:
+        fofr[:] = rng.standard_normal(fofr.shape) + 1j * rng.standard_normal(fofr.shape)
+    ref_out, ref_r, ref_den = ofw.fourwf(p.cplex, den.copy(), p.cwavef, fofr.copy(), p.kg, p.kg, p.ngfft, option,
+                                         p.istwf_k, weight_r=weight_r, weight_i=weight_i)
+    lib.fourwf(p.cplex, den, p.cwavef, out, fofr, None, None, p.istwf_k, p.kgF, p.kgF, max(p.ngfft), None, p.ndat,
+               p.ngfft, p.npw, p.npw, n1, n2, n3, option, weight_r=weight_r, weight_i=weight_i, impl=impl)
+    if option in (2, 3):
+        return rel_err_per_band(out, ref_out)
+    if option == 0:
+        return rel_err_per_band(fofr, ref_r)
+    return rel_err_per_band(den[None], ref_den[None])
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("istwf_k,kpt", [(1, (.1, .2, .3)), (2, (0, 0, 0)), (3, (.5, 0, 0)), (4, (0, 0, .5)),
+                                          (5, (.5, 0, .5)), (6, (0, .5, 0)), (7, (.5, .5, 0)), (8, (0, .5, .5)),
+                                          (9, (.5, .5, .5))])
+def test_option2_all_istwfk(lib, impl, istwf_k, kpt):
+    p = make_problem(6.0, (8.0, 9.0, 7.5), kpt, istwf_k, ndat=3)
+    assert _run(lib, p, 2, impl) < TOL
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+def test_option2_complex_potential(lib, impl):
+    p = make_problem(6.0, 8.0, (.1, .2, .3), 1, ndat=2, cplex=2)
+    assert _run(lib, p, 2, impl) < TOL
+
+
+@pytest.mark.parametrize("option", [0, 1, 3])
+@pytest.mark.parametrize("istwf_k,kpt", [(1, (.1, .2, .3)), (2, (0, 0, 0))])
+def test_options_0_1_3(lib, option, istwf_k, kpt):
+    p = make_problem(6.0, 8.0, kpt, istwf_k, ndat=3)
+    assert _run(lib, p, option, 0) < TOL
+
+
+@pytest.mark.parametrize("ngfft", [(28, 35, 21), (24, 24, 24), (45, 50, 54), (56, 60, 64), (25, 27, 32), (96, 96, 96)])
+def test_option2_mixed_radix_boxes(lib, ngfft):
+    """radices 2,3,5,7 (7-smooth sizes are explicit ngfft cases) in every pass position."""
+    p = make_problem(4.0, 9.0, (.1, 0, .3), 1, ndat=2, ngfft=ngfft)
+    for impl in (1, 2):
+        assert _run(lib, p, 2, impl) < TOL
+
+
+@pytest.mark.parametrize("ndat", [1, 5, 16])
+def test_option2_ndat_and_clusters(lib, ndat, monkeypatch):
+    p = make_problem(8.0, 10.0, (0, 0, 0), 1, ndat=ndat)
+    assert _run(lib, p, 2, 2) < TOL
+
+
+def test_fftprof_known_answer(lib):
+    """The reference's own unit-test vectors (src/70_gw/m_fft_prof.F90:873,936-960): c(G)=exp(-(2pi)^2 G.gmet.G),
+    V=cos(2pi g0.r), g0=(1,-1,2) => out(G) = 1/2 [c(G-g0) + c(G+g0)] (zero outside the sphere).
+    Tolerance: the cross-library spread stored in tests/unitary/Refs/tfourwf_01.stdout:129 (3.4e-16) x 10."""
+    ecut, L, kpt = 10.0, 12.0, (.1, .2, .3)
+    _, gmet, _ = g.metric(np.eye(3) * L)
+    ng = g.getng(2.0, ecut, gmet, kpt)
+    kg = g.kpgsph(ecut, gmet, kpt, 1)
+    npw = kg.shape[1]
+    gsq = (2 * np.pi) ** 2 * np.einsum("ip,ij,jp->p", kg, gmet, kg.astype(float))
+    c = np.ascontiguousarray(np.exp(-gsq)[None, :].astype(np.complex128))
+    g0 = np.array([1, -1, 2])
+    n1, n2, n3 = ng
+    i3, i2, i1 = np.meshgrid(np.arange(n3), np.arange(n2), np.arange(n1), indexing="ij")
+    V = np.ascontiguousarray(np.cos(2 * np.pi * (g0[0] * i1 / n1 + g0[1] * i2 / n2 + g0[2] * i3 / n3)))
+    full = ofw.sphere_to_box(c, kg, ng, 1)[0]
+    exp = 0.5 * (np.roll(full, (g0[2], g0[1], g0[0]), (0, 1, 2)) + np.roll(full, (-g0[2], -g0[1], -g0[0]), (0, 1, 2)))
+    w1, w2, w3 = ofw._wrap(kg, ng)
+    ref = exp[w3, w2, w1]
+    kgF = np.ascontiguousarray(kg.T)
+    for impl in (1, 2):
+        out = np.zeros((1, npw), dtype=np.complex128)
+        lib.fourwf(1, V, c, out, None, None, None, 1, kgF, kgF, max(ng), None, 1, ng, npw, npw, n1, n2, n3, 2, impl=impl)
+        assert np.abs(out[0] - ref).max() < 3.4e-15
+
+
+def test_device_pointers_and_roundtrip(lib):
+    """Device-resident arguments are used in place (m_getghc.F90:378-394 contract); option 0 then option 3 is the
+    identity on the sphere (fftbox/fftu round-trip tests, src/53_ffts/m_fft.F90:1445-1656)."""
+    import torch
+    p = make_problem(8.0, 10.0, (.1, .2, .3), 1, ndat=4)
+    n1, n2, n3 = p.ngfft
+    d_c = torch.from_numpy(p.cwavef.view(np.float64).reshape(p.ndat, p.npw, 2)).cuda()
+    d_r = torch.zeros((p.ndat, n3, n2, n1, 2), dtype=torch.float64, device="cuda")
+    d_o = torch.zeros_like(d_c)
+    lib.fourwf(1, None, d_c, None, d_r, None, None, 1, p.kgF, p.kgF, max(p.ngfft), None, p.ndat, p.ngfft, p.npw, p.npw,
+               n1, n2, n3, 0)
+    lib.fourwf(1, None, None, d_o, d_r, None, None, 1, p.kgF, p.kgF, max(p.ngfft), None, p.ndat, p.ngfft, p.npw, p.npw,
+               n1, n2, n3, 3)
+    torch.cuda.synchronize()
+    assert rel_err_per_band(d_o.cpu().numpy(), d_c.cpu().numpy()) < TOL

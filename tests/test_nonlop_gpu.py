@@ -1,0 +1,104 @@
+"""GPU parity: gemm_nonlop (choice 0/1/7, signs=2) through the C-ABI vs the oracle, 1e-11 relative per band."""
+import numpy as np
+import pytest
+from oracle import nonlop as onl
+from problems import make_problem, rel_err_per_band
+from abinit_b200 import api
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-11
+
+
+def _setup(lib, p, ikpt=1):
+    api.prep_projectors(ikpt, p.npw, p.indlmn, p.nattyp, p.istwf_k, p.ucvol, p.ffnl, p.ph3d)
+    api.set_gemm_nonlop_ikpt(ikpt)
+    P = onl.prep_projectors(p.ffnl, p.ph3d, p.indlmn, p.nattyp, p.ucvol)
+    return P
+
+
+def _apply(p, choice, paw_opt, cpopt=-1, projections=None, lambda_=None):
+    cplex = 2 if p.istwf_k == 1 else 1
+    nprojs = onl.count_nprojs(p.indlmn, p.nattyp)
+    vout = np.zeros((p.ndat, p.npw), dtype=np.complex128)
+    sout = np.zeros((p.ndat, p.npw), dtype=np.complex128)
+    proj = np.zeros((p.ndat, nprojs, cplex)) if projections is None else projections
+    api.gemm_nonlop(p.atindx1, choice, cpopt, proj, p.enl, p.indlmn, p.istwf_k, lambda_, p.natom, p.nattyp, p.ndat,
+                    p.npw, p.npw, 1, p.ntypat, paw_opt, p.sij, sout, p.cwavef, vout)
+    return vout, sout, proj
+
+
+def _proj_as_complex(proj, cplex):
+    return proj[..., 0] + 1j * proj[..., 1] if cplex == 2 else proj[..., 0]
+
+
+@pytest.mark.parametrize("istwf_k,kpt", [(1, (.1, .2, .3)), (2, (0, 0, 0)), (3, (.5, 0, 0)), (9, (.5, .5, .5))])
+@pytest.mark.parametrize("ndat", [1, 5, 12])
+def test_nc_choice1(lib, istwf_k, kpt, ndat):
+    p = make_problem(7.0, (8.0, 9.0, 7.5), kpt, istwf_k, ndat=ndat, natom_per_type=(2, 1), lmax_per_type=(1, 2))
+    P = _setup(lib, p)
+    vout, _, proj = _apply(p, 1, 0, cpopt=0)
+    rv, _, rgx = onl.gemm_nonlop(P, p.cwavef, p.enl, p.sij, p.indlmn, p.nattyp, p.atindx1 - 1, istwf_k, 1, 0)
+    assert rel_err_per_band(vout, rv) < TOL
+    assert rel_err_per_band(_proj_as_complex(proj, 2 if istwf_k == 1 else 1), rgx) < TOL
+
+
+@pytest.mark.parametrize("istwf_k,kpt", [(1, (.1, .2, .3)), (2, (0, 0, 0))])
+@pytest.mark.parametrize("paw_opt", [1, 2, 3, 4])
+def test_paw(lib, istwf_k, kpt, paw_opt):
+    p = make_problem(7.0, 8.5, kpt, istwf_k, ndat=6, natom_per_type=(1, 3), lmax_per_type=(2, 1), usepaw=1)
+    P = _setup(lib, p)
+    lam = np.linspace(-0.3, 0.4, p.ndat)
+    vout, sout, _ = _apply(p, 1, paw_opt, lambda_=lam)
+    rv, rs, _ = onl.gemm_nonlop(P, p.cwavef, p.enl, p.sij, p.indlmn, p.nattyp, p.atindx1 - 1, istwf_k, 1, paw_opt,
+                                lambda_=lam)
+    if rv is not None:
+        assert rel_err_per_band(vout, rv) < TOL
+    if rs is not None:
+        assert rel_err_per_band(sout, rs) < TOL
+
+
+def test_choice0_choice7_and_cpopt2(lib):
+    p = make_problem(7.0, 8.5, (.1, .2, .3), 1, ndat=4, natom_per_type=(2,), lmax_per_type=(2,), usepaw=1)
+    P = _setup(lib, p)
+    _, _, proj = _apply(p, 0, 4, cpopt=0)                                   # projections only
+    rgx = onl.opernla(P, p.cwavef, 1)
+    assert rel_err_per_band(_proj_as_complex(proj, 2), rgx) < TOL
+    _, sout7, _ = _apply(p, 7, 3)
+    _, rs7, _ = onl.gemm_nonlop(P, p.cwavef, p.enl, p.sij, p.indlmn, p.nattyp, p.atindx1 - 1, 1, 7, 3)
+    assert rel_err_per_band(sout7, rs7) < TOL
+    # cpopt=2: <p|c> taken from the caller's buffer (m_gemm_nonlop.F90:719-734): feed a *modified* buffer
+    proj2 = np.ascontiguousarray(proj * 1.5)
+    vout, sout, _ = _apply(p, 1, 4, cpopt=2, projections=proj2)
+    rv, rs, _ = onl.gemm_nonlop(P, p.cwavef, p.enl, p.sij, p.indlmn, p.nattyp, p.atindx1 - 1, 1, 1, 4, cpopt=2,
+                                projections=_proj_as_complex(proj2, 2))
+    assert rel_err_per_band(vout, rv) < TOL and rel_err_per_band(sout, rs) < TOL
+
+
+def test_naive_per_atom_statement(lib):
+    """gemm_nonlop == sum_a sum_ij |p_i> D_ij <p_j|psi> evaluated atom by atom (SURVEY 8c invariant (ii))."""
+    p = make_problem(6.0, 8.0, (.25, 0, .1), 1, ndat=3, natom_per_type=(2, 2), lmax_per_type=(1, 1), usepaw=1)
+    _setup(lib, p)
+    vout, sout, _ = _apply(p, 1, 4)
+    rv, rs = onl.nonlop_naive(p.ffnl, p.ph3d, p.indlmn, p.nattyp, p.atindx1 - 1, p.ucvol, p.cwavef, p.enl, p.sij, 4)
+    assert rel_err_per_band(vout, rv) < TOL and rel_err_per_band(sout, rs) < TOL
+
+
+def test_explicit_projectors_larger(lib):
+    """Random explicit P (bench-style), sizes that exercise several M/N tiles, K tails and split-K."""
+    rng = np.random.default_rng(3)
+    for istwf_k, npw, nprojs, ndat in ((2, 4097, 300, 70), (1, 2051, 259, 33)):
+        p = make_problem(3.0, 6.0, (0, 0, 0) if istwf_k == 2 else (.1, .2, .3), istwf_k, ndat=1)
+        P = (rng.standard_normal((nprojs, npw)) + 1j * rng.standard_normal((nprojs, npw))) / np.sqrt(npw)
+        c = rng.standard_normal((ndat, npw)) + 1j * rng.standard_normal((ndat, npw))
+        if istwf_k == 2:
+            P[:, 0] = P[:, 0].real; c[:, 0] = c[:, 0].real
+        indlmn = np.zeros((1, 1, 6), dtype=np.int32); indlmn[0, 0] = (0, 0, 1, 1, 1, 1)
+        nattyp = np.array([nprojs], dtype=np.int32); atindx1 = np.arange(1, nprojs + 1, dtype=np.int32)
+        enl = rng.standard_normal((1, 1))
+        api.set_projectors(2, npw, nprojs, istwf_k, np.ascontiguousarray(P))
+        api.set_gemm_nonlop_ikpt(2)
+        vout = np.zeros((ndat, npw), dtype=np.complex128)
+        api.gemm_nonlop(atindx1, 1, -1, None, enl, indlmn, istwf_k, None, nprojs, nattyp, ndat, npw, npw, 1, 1, 0, None,
+                        None, np.ascontiguousarray(c), vout)
+        rv, _, _ = onl.gemm_nonlop(P, c, enl, None, indlmn, nattyp, atindx1 - 1, istwf_k, 1, 0)
+        assert rel_err_per_band(vout, rv) < TOL

@@ -1,0 +1,7 @@
+#!/bin/bash
+# Developer tool: builds the single-thread emulation of the fourwf kernels (see emu_shim.h). Not a product path.
+set -e
+cd "$(dirname "$0")"
+SRC=../../abinit_b200/csrc
+g++ -O2 -std=c++17 -DABI_EMU -I. -I$SRC -x c++ -shared -fPIC -o libabinit_b200_emu.so \
+   $SRC/fourwf.cu $SRC/context.cu $SRC/api_fourwf.cu nonlop_stub.cpp -Wno-unused-function 2>&1 | grep -v "warning: ignoring" | head -50
