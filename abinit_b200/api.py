@@ -89,6 +89,19 @@ def kernel_launches() -> int:
     return int(L().abi_b200_kernel_launches())
 
 
+def profile_enable(on: bool):
+    L().abi_b200_profile_enable(1 if on else 0)
+
+
+def profile_collect() -> dict:
+    """{kernel class: (total ms, launches)} since profile_enable(True)."""
+    names = C.create_string_buffer(4096)
+    ms = (C.c_double * 64)(); cnt = (C.c_longlong * 64)()
+    n = L().abi_b200_profile_collect(names, 4096, ms, cnt, 64)
+    keys = [k for k in names.value.decode().split(";") if k]
+    return {keys[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+
 def fourwf(cplex, denpot, fofgin, fofgout, fofr, gboundin, gboundout, istwf_k, kg_kin, kg_kout, mgfft, mpi_enreg,
            ndat, ngfft, npwin, npwout, n4, n5, n6, option, tim_fourwf=0, weight_r=1.0, weight_i=1.0,
            weight_array_r=None, weight_array_i=None, me_g0=1, impl=0):

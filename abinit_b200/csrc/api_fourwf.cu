@@ -58,6 +58,10 @@ void abi_b200_set_stream(void* s) {
 void abi_b200_set_async(int flag) { ctx().async = flag != 0; }
 void abi_b200_synchronize(void) { ensure_init(); CUDA_CHECK(cudaStreamSynchronize(ctx().stream)); }
 long long abi_b200_kernel_launches(void) { return g_kernel_launches; }
+void abi_b200_profile_enable(int on) { ensure_init(); prof_enable(on != 0); }
+int abi_b200_profile_collect(char* names, int names_cap, double* ms, long long* counts, int cap) {
+  ensure_init(); return prof_collect(names, names_cap, ms, counts, cap);
+}
 void abi_b200_set_me_g0(int me_g0) { ctx().me_g0 = me_g0; }
 void abi_b200_fourwf_set_impl(int impl) { ctx().fourwf_impl = impl; }
 long long abi_b200_fourwf_counter(void) { return ctx().fourwf_counter; }

@@ -1,5 +1,6 @@
 #include "context.cuh"
 #include "fourwf.cuh"
+#include <string>
 
 namespace abi {
 
@@ -54,5 +55,67 @@ DevArg::DevArg(int slot, const void* p, size_t nbytes, bool in) {
 void DevArg::copy_back() {
   if (staged && dev) CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx().stream));
 }
+
+// ---- profiler ----
+#ifndef ABI_EMU
+struct ProfRec { int id; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<std::string> g_prof_names;
+static std::vector<double> g_prof_ms;
+static std::vector<long long> g_prof_cnt;
+static std::vector<ProfRec> g_prof_open;
+static std::vector<cudaEvent_t> g_prof_pool;
+static int prof_id(const char* name) {
+  for (size_t i = 0; i < g_prof_names.size(); i++) if (g_prof_names[i] == name) return (int)i;
+  g_prof_names.push_back(name); g_prof_ms.push_back(0.0); g_prof_cnt.push_back(0);
+  return (int)g_prof_names.size() - 1;
+}
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); return e;
+}
+static void prof_drain() {
+  if (g_prof_open.empty()) return;
+  CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+  for (auto& r : g_prof_open) {
+    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+    g_prof_ms[r.id] += ms; g_prof_cnt[r.id]++;
+    g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+  }
+  g_prof_open.clear();
+}
+ProfScope::ProfScope(const char* name) : id(-1) {
+  if (!g_prof_on) return;
+  if (g_prof_open.size() >= 4096) prof_drain();
+  id = prof_id(name);
+  ProfRec r; r.id = id; r.a = prof_event(); r.b = prof_event();
+  CUDA_CHECK(cudaEventRecord(r.a, ctx().stream));
+  g_prof_open.push_back(r); slot = (int)g_prof_open.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (id < 0 || slot < 0 || slot >= (int)g_prof_open.size()) return;
+  cudaEventRecord(g_prof_open[slot].b, ctx().stream);
+}
+void prof_enable(bool on) {
+  if (!on) prof_drain();
+  g_prof_on = on;
+  if (on) { for (auto& v : g_prof_ms) v = 0.0; for (auto& v : g_prof_cnt) v = 0; }
+}
+int prof_collect(char* names, int names_cap, double* ms, long long* counts, int cap) {
+  prof_drain();
+  int n = 0; std::string all;
+  for (size_t i = 0; i < g_prof_names.size() && n < cap; i++) {
+    if (g_prof_cnt[i] == 0) continue;
+    ms[n] = g_prof_ms[i]; counts[n] = g_prof_cnt[i]; all += g_prof_names[i]; all += ";"; n++;
+  }
+  snprintf(names, names_cap, "%s", all.c_str());
+  return n;
+}
+#else
+ProfScope::ProfScope(const char*) : id(-1) {}
+ProfScope::~ProfScope() {}
+void prof_enable(bool) {}
+int prof_collect(char*, int, double*, long long*, int) { return 0; }
+#endif
 
 }  // namespace abi

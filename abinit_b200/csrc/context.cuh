@@ -38,4 +38,13 @@ struct DevArg {
   template <typename T> T* as() const { return reinterpret_cast<T*>(dev); }
 };
 
+// Optional per-kernel-class device timers (CUDA events on the library stream) for bench.py's roofline object.
+struct ProfScope {
+  int id; int slot = -1;
+  explicit ProfScope(const char* name);
+  ~ProfScope();
+};
+void prof_enable(bool on);
+int prof_collect(char* names, int names_cap, double* ms, long long* counts, int cap);   // syncs; returns #classes
+
 }  // namespace abi

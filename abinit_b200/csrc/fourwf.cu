@@ -15,6 +15,7 @@
 //        K3  x FFT^-1 on the output lines, gather to the sphere, * 1/N, fused kinetic/non-local assembly
 //      HBM traffic per band: read psi, write W1, read W1, write W1', read W1', write H psi (+V via L2).
 #include "fourwf.cuh"
+#include "context.cuh"
 #include <algorithm>
 #include <map>
 #include <unordered_map>
@@ -788,8 +789,9 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
 
   for (int b0 = 0; b0 < ndat; b0 += chunk) {
     const int nb = std::min(chunk, ndat - b0);
+    { ProfScope ps("fourwf_x_forward");
     ABI_LAUNCH(k_fw_x_forward, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st,
-               d_fofgin + (size_t)b0 * pl.npw_in, W1, t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_in);
+               d_fofgin + (size_t)b0 * pl.npw_in, W1, t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_in); }
     MidParams P;
     P.n1 = n1; P.n2 = n2; P.n3 = n3; P.nb = nb; P.nlin = pl.nlin; P.nlout = pl.nlout; P.nU = pl.nU;
     P.cplex = v.cplex; P.lb = lb; P.csize = cs; P.nclusters = nclusters;
@@ -797,6 +799,7 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
     P.inpl_start = pl.d_inpl_start; P.lin_u = pl.d_lin_u; P.lin_pos2 = pl.d_lin_pos2;
     P.outpl_start = pl.d_outpl_start; P.lout_u = pl.d_lout_u; P.lout_pos2 = pl.d_lout_pos2;
     P.u_i3 = pl.d_u_i3; P.u_flags = pl.d_u_flags; P.p2 = t2.plan; P.p3 = t3.plan;
+    { ProfScope ps("fourwf_plane_stage");
 #ifdef ABI_EMU
     ABI_LAUNCH(k_fw_mid<false>, dim3(nclusters), dim3(256), smem_mid, st, P);
 #else
@@ -812,13 +815,15 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
       CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_fw_mid<true>, P));
     }
 #endif
+    }
     FourwfEpilogue e = epi;
     if (e.cwavef) e.cwavef += (size_t)b0 * pl.npw_out;
     if (e.gvnlxc) e.gvnlxc += (size_t)b0 * pl.npw_out;
     if (e.gsc) e.gsc += (size_t)b0 * pl.npw_out;
+    { ProfScope ps("fourwf_x_backward");
     ABI_LAUNCH(k_fw_x_backward, dim3(ceil_div(pl.nlout, lx), nb), dim3(256), smem_x, st, W1o,
                d_fofgout + (size_t)b0 * pl.npw_out, t1.plan, pl.d_out_ent, pl.d_lout_estart, pl.nlout, lx, pl.npw_out,
-               xnorm, zero_im, e, kin_filter);
+               xnorm, zero_im, e, kin_filter); }
     g_kernel_launches += 3;
   }
 }

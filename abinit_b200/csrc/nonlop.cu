@@ -17,6 +17,7 @@
 //    kernel fuses the x2 / G=0 fix-up, the projections store and the NC ekb scaling (opernlc).
 #include "nonlop.cuh"
 #include "fourwf.cuh"   // g_kernel_launches
+#include "context.cuh"
 #include <algorithm>
 
 namespace abi {
@@ -481,6 +482,7 @@ static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long lo
   part = g_nlws[0].get((size_t)nsplit * Neff * M);
   p.part = part;
   const size_t smem = tn_smem(cplx);
+  ProfScope ps("dgemm_tn_opernla");
   if (cplx) {
     CUDA_CHECK(cudaFuncSetAttribute(k_dgemm_tn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_dgemm_tn<true><<<tiles * nsplit, kThreads, smem, st>>>(p);
@@ -499,6 +501,7 @@ static void launch_nn(bool cplx, int M, int N, int K, const double* A, long long
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.add = add;
   p.tiles_m = ceil_div(M, kBM); p.tiles_n = ceil_div(N, kBN);
   const size_t smem = nn_smem(cplx);
+  ProfScope ps("dgemm_nn_opernlb");
   if (cplx) {
     CUDA_CHECK(cudaFuncSetAttribute(k_dgemm_nn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_dgemm_nn<true><<<p.tiles_m * p.tiles_n, kThreads, smem, st>>>(p);
@@ -578,6 +581,7 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
     r.proj_out = (cpopt >= 0 || choice == 0) ? projections : nullptr;
     r.gxfac = nc_fused ? gxfac : nullptr; r.ekb = nc_fused ? enl.d_enl : nullptr; r.dimenl1 = enl.dimenl1;
     r.proj_typ = at.d_proj_typ; r.proj_iln = at.d_proj_iln;
+    ProfScope ps("reduce_opernlc");
     k_reduce_proj<<<blocks, 256, 0, st>>>(r);
     CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;

@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- getghc band-applications/s on synthetic wavefunctions/potentials of the Si-512 shape.
+
+One "step" = one getghc call (type_calc=0: fourwf option 2 + gemm_nonlop choice 1 + kinetic assembly) on a block of
+`ndat` bands at Gamma.  Weak scaling: every rank (one per GPU) applies H to its own band block with P, V_loc, kg and
+kinpw replicated; there is no data-path collective in getghc.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload si512] [--ndat 128] [--istwfk 2]
+  python bench.py --impl reference ...   # the reference algorithm (oracle port) on the host cores, bounded sample
+
+Prints ONE JSON line (contract in the task statement): value = device-resident throughput; e2e = the same call with
+HOST buffers (H2D/D2H inside the timed region); roofline = dominant kernel (DMMA GEMM of gemm_nonlop) against the
+measured cuBLAS DGEMM peak of this pool's B200 (profiles/fp64_peak_r01.json -- MEASURED_PEAKS.json holds no FP64
+figure), plus the fourwf HBM fraction as an extra; cpu_baseline = oracle port timed on the box's host cores.
+"""
+from __future__ import annotations
+import argparse, json, os, subprocess, sys, threading, time
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="si512")
+    ap.add_argument("--ndat", type=int, default=128)
+    ap.add_argument("--istwfk", type=int, default=2)
+    ap.add_argument("--cpu-bands", type=int, default=8, help="bands in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    hbm, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            hbm = float(json.load(open(p))["hbm_gbs"]); hbm_src = "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    fp64, fp64_src = 35.45, "profiles/fp64_peak_r01.json (cuBLAS DGEMM 8192^3 on this pool's B200, burst = 4 s sustained)"
+    q = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+    if os.path.exists(q):
+        try:
+            fp64 = float(json.load(open(q))["dgemm_8192"]["burst_tflops"])
+        except Exception:
+            pass
+    return hbm, hbm_src, fp64, fp64_src
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []; self.proc = None; self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(args):
+    from abinit_b200 import workload as wl
+    cfg = wl.CONFIGS[args.workload]
+    kg, kin = wl.gsphere_orthorhombic(cfg["ecut"], cfg["L"], (0.0, 0.0, 0.0), args.istwfk)
+    npw = kg.shape[0]
+    # outermost 0.5 % shell carries the huge*1e-10 sentinel (m_kg.F90:422-429) so the filter branch is live
+    thr = np.quantile(kin, 0.995)
+    kinpw = np.where(kin >= thr, wl.HUGE * 1e-10, kin)
+    indlmn, lnmax = wl.nc_indlmn(cfg["lmax"], cfg["nproj_per_l"])
+    nlmn = indlmn.shape[1]
+    natom = cfg["natom"]
+    w = dict(cfg=cfg, kg=kg, kinpw=np.ascontiguousarray(kinpw), kin_raw=kin, npw=npw, indlmn=indlmn, lnmax=lnmax, nlmn=nlmn,
+             natom=natom, nprojs=natom * nlmn, ngfft=cfg["ngfft"], ucvol=float(cfg["L"]) ** 3,
+             nattyp=np.array([natom], dtype=np.int32), atindx1=np.arange(1, natom + 1, dtype=np.int32),
+             vlocal=wl.smooth_potential(cfg["ngfft"], seed=1234 + 1),
+             ekb=np.ascontiguousarray(np.random.Generator(np.random.PCG64(1235)).standard_normal((1, lnmax))))
+    return w
+
+
+def algorithmic_units(w, istwfk, ndat):
+    """bytes per band-application for fourwf and flops per band-application for gemm_nonlop."""
+    n1, n2, n3 = w["ngfft"]
+    kg = w["kg"]
+    full = kg if istwfk == 1 else np.concatenate([kg, -kg])
+    lines = np.unique(np.mod(full[:, 1], n2).astype(np.int64) * n3 + np.mod(full[:, 2], n3))
+    C = int(lines.size)
+    N = n1 * n2 * n3
+    b_fw = 32.0 * w["npw"] + 64.0 * C * n1 + (8.0 * N + 20.0 * w["npw"]) / ndat
+    g = 2
+    f_nl = g * (8.0 if istwfk == 1 else 4.0) * w["npw"] * w["nprojs"]
+    return b_fw, f_nl, C
+
+
+def run_reference(args):
+    """The reference's CPU algorithm for the path (oracle port; the Fortran reference cannot be built here: no Fortran
+    compiler), all host threads (OpenBLAS + pocketfft workers), each step a bounded sample of `cpu_bands` bands."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import getghc as ogh
+    w = build_workload(args)
+    nb = args.cpu_bands
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t0 = time.time()
+    gen = torch.Generator().manual_seed(4321)
+    Pr = (torch.randn((w["nprojs"], w["npw"]), generator=gen, dtype=torch.float64) / np.sqrt(w["npw"])).numpy()
+    Pi = (torch.randn((w["nprojs"], w["npw"]), generator=gen, dtype=torch.float64) / np.sqrt(w["npw"])).numpy()
+    if args.istwfk == 2:
+        Pi[:, 0] = 0.0
+
+    class SplitP:       # P_r / P_i held separately like the reference does for istwf_k>1 (m_gemm_nonlop_projectors.F90)
+        real = Pr; imag = Pi
+    P = SplitP if args.istwfk >= 2 else (Pr + 1j * Pi)
+    rng = np.random.Generator(np.random.PCG64(99))
+    c = rng.standard_normal((nb, w["npw"])) + 1j * rng.standard_normal((nb, w["npw"]))
+    if args.istwfk == 2:
+        c[:, 0] = c[:, 0].real
+    kg3 = np.ascontiguousarray(w["kg"].T)
+    setup_s = time.time() - t0
+
+    def step():
+        ogh.getghc(c, w["vlocal"], kg3, w["ngfft"], w["kinpw"], P, w["ekb"], None, w["indlmn"], w["nattyp"],
+                   w["atindx1"] - 1, istwf_k=args.istwfk, usepaw=0, workers=cores)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    t1 = time.time()
+    for _ in range(args.steps):
+        step()
+    dt = time.time() - t1
+    val = nb * args.steps / dt
+    out = {"metric": "getghc band-applications/s", "value": val, "unit": "band-applications/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+           "config": {"workload": f"{args.workload}: box {w['ngfft']}, npw {w['npw']}, nprojs {w['nprojs']}, istwfk {args.istwfk}",
+                      "sample": f"{nb} bands per step"},
+           "cpu_baseline": {"value": val, "unit": "band-applications/s", "cores": cores, "kind": "port",
+                            "sample": f"{nb} bands x {args.steps} steps of the full-size operator (oracle NumPy/SciPy port: pocketfft + OpenBLAS); set-up {setup_s:.0f} s untimed"},
+           "e2e": {"value": val, "unit": "band-applications/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import abinit_b200 as ab
+    from abinit_b200 import api
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ab.init(local)
+    stream = torch.cuda.Stream(device=dev)
+    api.set_stream(stream.cuda_stream)
+
+    w = build_workload(args)
+    ndat, npw, nprojs = args.ndat, w["npw"], w["nprojs"]
+    ham = ab.Hamiltonian(w["ngfft"], w["natom"], 1, w["nlmn"], w["indlmn"], w["nattyp"], w["atindx1"], 0, w["ucvol"])
+    ham.load_spin(w["vlocal"], 1)
+    ham.load_enl(w["ekb"], None)
+    ham.load_k(args.istwfk, w["kg"], w["kinpw"], None, None, me_g0=1)
+    with torch.cuda.stream(stream):
+        gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+        P = torch.randn((nprojs, npw, 2), generator=gen, device=dev, dtype=torch.float64) / np.sqrt(npw)
+        if args.istwfk == 2:
+            P[:, 0, 1] = 0.0
+        cw = torch.randn((ndat, npw, 2), generator=gen, device=dev, dtype=torch.float64)
+        if args.istwfk == 2:
+            cw[:, 0, 1] = 0.0
+        ghc = torch.zeros_like(cw)
+    stream.synchronize()
+    ham.set_projectors(P, nprojs)
+    del P
+    torch.cuda.empty_cache()
+
+    def step_dev():
+        ab.getghc(-1, cw, None, ghc, None, ham, None, None, None, ndat)
+
+    def barrier():
+        stream.synchronize(); torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    api.set_async(True)
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = ab.kernel_launches()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ab.kernel_launches() - l0
+    clocks = sampler.stop()
+    tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    value = world * ndat * args.steps / (ms * 1e-3)
+
+    # per-kernel-class device times (second pass, same work) for the roofline object
+    api.profile_enable(True)
+    for _ in range(args.steps):
+        step_dev()
+    prof = api.profile_collect()
+    api.profile_enable(False)
+
+    # end-to-end: host (pinned) buffers through the same public call
+    e2e = None
+    if not args.no_e2e:
+        api.set_async(False)
+        h_c = torch.empty((ndat, npw, 2), dtype=torch.float64).pin_memory(); h_c.copy_(cw.cpu())
+        h_g = torch.empty((ndat, npw, 2), dtype=torch.float64).pin_memory()
+        hc, hg = h_c.numpy(), h_g.numpy()
+        for _ in range(2):
+            ab.getghc(-1, hc, None, hg, None, ham, None, None, None, ndat)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ab.getghc(-1, hc, None, hg, None, ham, None, None, None, ndat)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ndat * args.steps / float(dt.item()), "unit": "band-applications/s",
+               "h2d_bytes_per_step": int(ndat * npw * 16), "d2h_bytes_per_step": int(ndat * npw * 16)}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    hbm, hbm_src, fp64, fp64_src = peaks()
+    b_fw, f_nl, C = algorithmic_units(w, args.istwfk, ndat)
+    def per_launch(name):
+        t, c = prof.get(name, (0.0, 0))
+        return (t / c) if c else None
+    t_tn, t_nn = per_launch("dgemm_tn_opernla"), per_launch("dgemm_nn_opernlb")
+    t_fw = sum((per_launch(k) or 0.0) * (prof.get(k, (0, 0))[1] / max(1, args.steps)) for k in
+               ("fourwf_x_forward", "fourwf_plane_stage", "fourwf_x_backward"))
+    roof = None
+    if t_nn:
+        flops_launch = 0.5 * f_nl * ndat                    # one of the two GEMMs of a getghc step
+        ach = flops_launch / (t_nn * 1e-3) / 1e12
+        roof = {"kernel": "k_dgemm_nn (opernlb: vect = P . gxfac, DMMA m8n8k4)", "bound": "tensor", "achieved": ach, "peak": fp64,
+                "unit": "TFLOP/s", "frac": ach / fp64, "traffic": None, "peak_source": fp64_src,
+                "flops_per_launch": flops_launch, "ms_per_launch": t_nn}
+    extra = {}
+    if t_tn:
+        ach = 0.5 * f_nl * ndat / (t_tn * 1e-3) / 1e12
+        extra["roofline_opernla"] = {"kernel": "k_dgemm_tn (split-K P^T psi)", "bound": "tensor", "achieved": ach, "peak": fp64,
+                                     "unit": "TFLOP/s", "frac": ach / fp64, "ms_per_launch": t_tn}
+    if t_fw:
+        ach = b_fw * ndat / (t_fw * 1e-3) / 1e9
+        extra["roofline_fourwf"] = {"kernel": "fourwf option 2 (3 fused kernels)", "bound": "hbm", "achieved": ach, "peak": hbm,
+                                    "unit": "GB/s", "frac": ach / hbm, "peak_source": hbm_src, "bytes_per_band": b_fw,
+                                    "ms_per_step": t_fw, "lines_C": C}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                   "--workload", args.workload, "--istwfk", str(args.istwfk), "--cpu-bands", str(args.cpu_bands)]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as ex:   # the baseline is reported, never a gate
+            cpu = {"value": None, "unit": "band-applications/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    out = {"metric": "getghc band-applications/s", "value": value, "unit": "band-applications/s", "n_gpus": world,
+           "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"{args.workload} (BASELINE configs[1] shape): FFT box {w['ngfft']}, Gamma, istwfk {args.istwfk}, "
+                                  f"npw {npw}, nprojs {nprojs}, band block {ndat} per GPU, NC (paw_opt 0), type_calc 0",
+                      "l2": "inputs larger than L2 (P = %.1f GB streamed twice per step)" % (16.0 * npw * nprojs / 1e9),
+                      "parallelism": f"band blocks over {world} GPU(s), no data-path collective"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+           "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+    out.update(extra)
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,11 @@ void abi_b200_set_async(int flag);            /* 1: do not synchronise before re
 void abi_b200_synchronize(void);              /* gpu_device_synchronize, src/79_seqpar_mpi/m_chebfiwf.F90:377-379 */
 long long abi_b200_kernel_launches(void);     /* kernels launched by this library so far (bench accounting) */
 const char* abi_b200_version(void);
+/* Per-kernel-class device timers (CUDA events on the library stream), the measurement twin of the reference's
+ * timab slots 840+ (fourwf) / 220+ (nonlop) (shared/common/src/18_timing/m_time.F90:746).  collect() synchronises
+ * and returns the number of classes; names are ';'-separated, ms are summed durations, counts are launches. */
+void abi_b200_profile_enable(int on);
+int abi_b200_profile_collect(char* names, int names_cap, double* ms, long long* counts, int cap);
 
 /* ------------------------------------------------------------------------------------------------------
  * fourwf.  Same symbol shape as the legacy CUDA plug point
