@@ -41,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(log)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nvcc, "-shared", "-o", out] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     with open(stamp_file, "w") as fh:
         fh.write(stamp)

@@ -36,6 +36,7 @@ def make_problem(ecut, L, kpt=(0.0, 0.0, 0.0), istwf_k=1, ndat=4, seed=1234, ngf
         c[:, 0] = c[:, 0].real
     c /= np.linalg.norm(c, axis=1, keepdims=True)
     p.cwavef = np.ascontiguousarray(c)
+    rng = rng_op
     # smooth local potential: 8 small-G cosines, amplitude 0.5 Ha, mean -0.3 Ha
     i3, i2, i1 = np.meshgrid(np.arange(n3), np.arange(n2), np.arange(n1), indexing="ij")
     v = np.full((n3, n2, n1), -0.3)
@@ -66,7 +67,6 @@ def make_problem(ecut, L, kpt=(0.0, 0.0, 0.0), istwf_k=1, ndat=4, seed=1234, ngf
             indlmn[t, i] = ch
     p.indlmn = indlmn
     p.lnmax = max(ch[4] for lst in chans for ch in lst)
-    rng_wf, rng = rng, rng_op
     perm = rng.permutation(p.natom)
     p.atindx1 = (perm + 1).astype(np.int32)                    # sorted position -> original atom (1-based)
     p.xred = rng.uniform(0, 1, size=(3, p.natom))              # already type-sorted order
