@@ -89,6 +89,11 @@ def kernel_launches() -> int:
     return int(L().abi_b200_kernel_launches())
 
 
+def set_tuning(name: str, value: int):
+    """Tuning knobs of the fused fourwf path (include/abinit_b200.h: abi_b200_fourwf_set_tuning)."""
+    L().abi_b200_fourwf_set_tuning(name.encode(), int(value))
+
+
 def profile_enable(on: bool):
     L().abi_b200_profile_enable(1 if on else 0)
 

@@ -2,6 +2,7 @@
 #include "../../include/abinit_b200.h"
 #include "context.cuh"
 #include "fourwf.cuh"
+#include <string>
 
 using namespace abi;
 
@@ -65,6 +66,18 @@ int abi_b200_profile_collect(char* names, int names_cap, double* ms, long long* 
 void abi_b200_set_me_g0(int me_g0) { ctx().me_g0 = me_g0; }
 void abi_b200_fourwf_set_impl(int impl) { ctx().fourwf_impl = impl; }
 long long abi_b200_fourwf_counter(void) { return ctx().fourwf_counter; }
+void abi_b200_fourwf_set_tuning(const char* name, int value) {
+  FourwfTuning& t = fourwf_tuning();
+  const std::string k(name ? name : "");
+  if (k == "plane") t.plane = value;
+  else if (k == "plane_cfg") t.plane_cfg = value;
+  else if (k == "plane_ctas_per_sm") t.plane_ctas_per_sm = value;
+  else if (k == "cluster") t.cluster = value;
+  else if (k == "lines_x") t.lines_x = value;
+  else if (k == "smem_kb_mid") t.smem_kb_mid = value;
+  else if (k == "band_chunk") t.band_chunk = value;
+  else ABI_ERROR("abi_b200_fourwf_set_tuning: unknown knob");
+}
 
 void abi_b200_alloc_fourwf_(int* ngfft, int* ndat, int* npwin, int* npwout) {
   (void)ndat; (void)npwin; (void)npwout;

@@ -15,6 +15,7 @@
 //        K3  x FFT^-1 on the output lines, gather to the sphere, * 1/N, fused kinetic/non-local assembly
 //      HBM traffic per band: read psi, write W1, read W1, write W1', read W1', write H psi (+V via L2).
 #include "fourwf.cuh"
+#include "plane_stage.cuh"
 #include "context.cuh"
 #include <algorithm>
 #include <map>
@@ -38,6 +39,9 @@ FourwfTuning& fourwf_tuning() {
     if (const char* e = getenv("ABI_B200_FOURWF_LINES_X")) t.lines_x = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_SMEM_KB")) t.smem_kb_mid = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_BAND_CHUNK")) t.band_chunk = atoi(e);
+    if (const char* e = getenv("ABI_B200_FOURWF_PLANE")) t.plane = atoi(e);
+    if (const char* e = getenv("ABI_B200_FOURWF_PLANE_CFG")) t.plane_cfg = atoi(e);
+    if (const char* e = getenv("ABI_B200_FOURWF_PLANE_CTAS")) t.plane_ctas_per_sm = atoi(e);
   }
   return t;
 }
@@ -166,7 +170,7 @@ struct Workspace {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 static Workspace g_ws[4];
-void fourwf_release_workspace() { for (auto& w : g_ws) w.release(); }
+void fourwf_release_workspace() { for (auto& w : g_ws) w.release(); plane_stage_release(); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Planner
@@ -290,8 +294,27 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
     pl->d_u_i3 = to_device(u_i3, pl->owned);
     pl->d_u_flags = to_device(u_flags, pl->owned);
 
+    bool plane_ok = (n2 == n3) && plane_stage_supported(n2) && n2 < 32768;
+    // at most two contiguous runs of a sorted index list: {a, la, b, lb}; false if it needs more
+    auto two_runs = [](const std::vector<int>& r, int out[4]) {
+      out[0] = out[1] = out[2] = out[3] = 0;
+      if (r.empty()) return true;
+      size_t k = 1;
+      while (k < r.size() && r[k] == r[k - 1] + 1) k++;
+      out[0] = r[0]; out[1] = (int)k;
+      if (k == r.size()) return true;
+      out[2] = r[k]; out[3] = (int)(r.size() - k);
+      for (size_t q = k + 1; q < r.size(); q++) if (r[q] != r[q - 1] + 1) return false;
+      return true;
+    };
+    {
+      std::vector<int> zs(u_i3.begin(), u_i3.end());
+      int zr[4];
+      if (!two_runs(zs, zr)) plane_ok = false;
+      pl->za = zr[0]; pl->zla = zr[1]; pl->zb = zr[2]; pl->zlb = zr[3];
+    }
     auto build = [&](std::vector<Ent>& es, bool dit_positions, int& nlines, int2*& d_ent, int*& d_estart, int*& d_lu,
-                     unsigned short*& d_lpos2, int*& d_plstart) {
+                     unsigned short*& d_lpos2, int*& d_plstart, int*& d_pstart, short4*& d_pruns) {
       // sort by (plane u, i2, then original order) -> lines of one plane are contiguous
       std::vector<int> order(es.size());
       for (size_t i = 0; i < es.size(); i++) order[i] = (int)i;
@@ -320,6 +343,24 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
       estart.push_back((int)order.size());
       for (int u = 0; u < pl->nU; u++) plstart[u + 1] += plstart[u];
       nlines = line + 1;
+      // plane-stage row descriptors: the i2 of the lines of plane u (ascending) as at most two runs
+      {
+        std::vector<int> pstart(pl->nU, 0); std::vector<short4> pruns(pl->nU);
+        std::vector<std::vector<int>> rows(pl->nU);
+        int pv = -1;
+        for (size_t k = 0; k < order.size(); k++) {
+          const Ent& e = es[order[k]];
+          int kk = u_of_i3[e.i3] * n2 + e.i2;
+          if (kk != pv) { pv = kk; rows[u_of_i3[e.i3]].push_back(e.i2); }
+        }
+        for (int u = 0; u < pl->nU; u++) {
+          pstart[u] = plstart[u];
+          int rr[4];
+          if (!two_runs(rows[u], rr)) plane_ok = false;
+          pruns[u].x = (short)rr[0]; pruns[u].y = (short)rr[1]; pruns[u].z = (short)rr[2]; pruns[u].w = (short)rr[3];
+        }
+        d_pstart = to_device(pstart, pl->owned); d_pruns = to_device(pruns, pl->owned);
+      }
       d_ent = to_device(ent, pl->owned);
       d_estart = to_device(estart, pl->owned);
       d_lu = to_device(lu, pl->owned);
@@ -327,8 +368,11 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
       d_plstart = to_device(plstart, pl->owned);
       (void)dit_positions;
     };
-    build(ents, true, pl->nlin, pl->d_in_ent, pl->d_lin_estart, pl->d_lin_u, pl->d_lin_pos2, pl->d_inpl_start);
-    build(oents, false, pl->nlout, pl->d_out_ent, pl->d_lout_estart, pl->d_lout_u, pl->d_lout_pos2, pl->d_outpl_start);
+    build(ents, true, pl->nlin, pl->d_in_ent, pl->d_lin_estart, pl->d_lin_u, pl->d_lin_pos2, pl->d_inpl_start,
+          pl->d_pin_start, pl->d_pin_runs);
+    build(oents, false, pl->nlout, pl->d_out_ent, pl->d_lout_estart, pl->d_lout_u, pl->d_lout_pos2, pl->d_outpl_start,
+          pl->d_pout_start, pl->d_pout_runs);
+    pl->plane_ok = plane_ok;
   }
   FourwfPlan* raw = pl.get();
   cache[key] = std::move(pl);
@@ -799,7 +843,18 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
     P.inpl_start = pl.d_inpl_start; P.lin_u = pl.d_lin_u; P.lin_pos2 = pl.d_lin_pos2;
     P.outpl_start = pl.d_outpl_start; P.lout_u = pl.d_lout_u; P.lout_pos2 = pl.d_lout_pos2;
     P.u_i3 = pl.d_u_i3; P.u_flags = pl.d_u_flags; P.p2 = t2.plan; P.p3 = t3.plan;
-    { ProfScope ps("fourwf_plane_stage");
+    if (getenv("ABI_B200_DEBUG")) fprintf(stderr, "abinit_b200: fourwf fused: plane_ok=%d tune.plane=%d nU=%d z=[%d,+%d)U[%d,+%d)\n", (int)pl.plane_ok, tune.plane, pl.nU, pl.za, pl.zla, pl.zb, pl.zlb);
+    if (pl.plane_ok && tune.plane) {
+      ProfScope ps("fourwf_plane_stage");
+      PlaneParams Q;
+      Q.n1 = n1; Q.n2 = n2; Q.n3 = n3; Q.nb = nb; Q.nU = pl.nU; Q.cplex = v.cplex; Q.za = pl.za; Q.zla = pl.zla; Q.zb = pl.zb; Q.zlb = pl.zlb;
+      Q.nlin = pl.nlin; Q.nlout = pl.nlout; Q.nunits = (long long)nb * n1;
+      Q.W1 = W1; Q.W1o = W1o; Q.S = nullptr; Q.vT = v.d_vT; Q.tw = t2.plan.tw;
+      Q.in_start = pl.d_pin_start; Q.in_runs = pl.d_pin_runs;
+      Q.out_start = pl.d_pout_start; Q.out_runs = pl.d_pout_runs;
+      plane_stage_launch(n2, Q, st);
+    } else
+    { ProfScope ps("fourwf_plane_cluster");
 #ifdef ABI_EMU
     ABI_LAUNCH(k_fw_mid<false>, dim3(nclusters), dim3(256), smem_mid, st, P);
 #else

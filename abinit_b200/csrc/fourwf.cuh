@@ -51,6 +51,12 @@ struct FourwfPlan {
   int* d_outpl_start = nullptr;  // nU+1
   unsigned short* d_u_i3 = nullptr;      // nU
   unsigned char* d_u_flags = nullptr;    // bit0: has input lines, bit1: has output lines
+  // ---- plane-stage tables (plane_stage.cuh): the i2 of the rows of a plane, and the occupied i3, are each at most two
+  // contiguous runs [a,a+la) U [b,b+lb) (true for every convex G-sphere, shifted or time-reversal completed)
+  bool plane_ok = false;
+  int za = 0, zla = 0, zb = 0, zlb = 0;
+  int* d_pin_start = nullptr; short4* d_pin_runs = nullptr;      // nU each
+  int* d_pout_start = nullptr; short4* d_pout_runs = nullptr;
   std::vector<void*> owned;      // device allocations to free
   void release();
 };
@@ -79,7 +85,12 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
                        int ndat, const FourwfEpilogue& epi, cudaStream_t st);
 
 // tuning knobs (env ABI_B200_* override), reported by bench.py
-struct FourwfTuning { int cluster = 0; int lines_x = 32; int smem_kb_mid = 0; int band_chunk = 0; };
+struct FourwfTuning {
+  int cluster = 0; int lines_x = 32; int smem_kb_mid = 0; int band_chunk = 0;
+  int plane = 1;               // 1: register-resident two-pass plane stage (plane_stage.cuh) when the box allows it
+  int plane_cfg = 0;           // 0 auto, 1: (G=8, 4 warps), 2: (G=4, 8 warps)
+  int plane_ctas_per_sm = 0;   // 0: occupancy / L2-budget limited
+};
 FourwfTuning& fourwf_tuning();
 
 // launch counter for bench.py's gpu_launches

@@ -1,0 +1,47 @@
+// Launcher templates of the fourwf plane stage (included by plane_stage.cu and the plane_inst_*.cu instantiation units).
+#pragma once
+#include "plane_stage.cuh"
+#include "fourwf.cuh"
+#include "context.cuh"
+#include <algorithm>
+
+namespace abi {
+void* plane_scratch_get(size_t bytes);
+
+// L2 budget for the S planes of all resident CTAs (B200: 126 MB L2; leave room for the W1 / V_loc streams)
+constexpr size_t kScratchL2Budget = (size_t)80 << 20;
+template <int R1, int R2, int G, int WARPS>
+void launch_cfg(PlaneParams& P, cudaStream_t st) {
+  using F = PlaneFft<R1, R2, G>;
+  auto kern = k_fw_plane<R1, R2, G, WARPS>;
+  const size_t smem = sizeof(double2) * ((size_t)F::N + (size_t)WARPS * F::ESIZE);
+  int cps = 1;
+#ifndef ABI_EMU
+  static bool attr_done = false;
+  if (!attr_done) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, WARPS * 32, smem));
+  ABI_CHECK(cps >= 1, "plane stage: kernel does not fit on an SM");
+#endif
+  const size_t sbytes = sizeof(double2) * (size_t)P.nU * P.n2;
+  const FourwfTuning& tune = fourwf_tuning();
+  int by_l2 = (int)std::max<size_t>(1, kScratchL2Budget / (sbytes * kNumSM));
+  cps = std::min(cps, by_l2);
+  if (tune.plane_ctas_per_sm > 0) cps = std::min(cps, tune.plane_ctas_per_sm);
+  long long grid = std::min<long long>(P.nunits, (long long)kNumSM * cps);
+#ifdef ABI_EMU
+  grid = std::min<long long>(grid, 3);
+#endif
+  P.S = (double2*)plane_scratch_get(sbytes * (size_t)grid);
+  ABI_LAUNCH(kern, dim3((unsigned)grid), dim3(WARPS * 32), smem, st, P);
+}
+
+template <int R1, int R2>
+void plane_launch_n(PlaneParams& P, cudaStream_t st) {
+  const int cfg = fourwf_tuning().plane_cfg;
+  const bool big = (cfg == 2) || (cfg == 0 && R1 * R2 > 200);
+  if (big) launch_cfg<R1, R2, 4, 8>(P, st);
+  else launch_cfg<R1, R2, 8, 4>(P, st);
+}
+
+
+}  // namespace abi

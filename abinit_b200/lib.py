@@ -21,7 +21,7 @@ SYMBOLS = [
     "abi_b200_init", "abi_b200_finalize", "abi_b200_set_stream", "abi_b200_set_async", "abi_b200_synchronize",
     "abi_b200_kernel_launches", "abi_b200_version", "abi_b200_profile_enable", "abi_b200_profile_collect",
     "abi_b200_fourwf_", "abi_b200_alloc_fourwf_", "abi_b200_free_fourwf_", "gpu_fourwf_", "alloc_gpu_fourwf_",
-    "free_gpu_fourwf_", "abi_b200_set_me_g0", "abi_b200_fourwf_set_impl", "abi_b200_fourwf_counter",
+    "free_gpu_fourwf_", "abi_b200_set_me_g0", "abi_b200_fourwf_set_impl", "abi_b200_fourwf_set_tuning", "abi_b200_fourwf_counter",
     "abi_b200_init_gemm_nonlop_", "abi_b200_destroy_gemm_nonlop_", "abi_b200_prep_projectors_",
     "abi_b200_set_projectors_", "abi_b200_set_gemm_nonlop_ikpt_", "abi_b200_gemm_nonlop_",
     "abi_b200_nonlop_counter",
@@ -54,6 +54,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.abi_b200_version.restype = C.c_char_p
     lib.abi_b200_set_me_g0.argtypes = [C.c_int]
     lib.abi_b200_fourwf_set_impl.argtypes = [C.c_int]
+    lib.abi_b200_fourwf_set_tuning.argtypes = [C.c_char_p, C.c_int]
     for name in ("abi_b200_fourwf_", "gpu_fourwf_"):
         getattr(lib, name).argtypes = [vp] * 24
     lib.abi_b200_alloc_fourwf_.argtypes = [vp] * 4

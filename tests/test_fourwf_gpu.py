@@ -59,6 +59,48 @@ def test_option2_mixed_radix_boxes(lib, ngfft):
         assert _run(lib, p, 2, impl) < TOL
 
 
+def _plane_problem(n, kpt, istwf_k, ndat, n1=None, cplex=1):
+    """Sphere diameter ~ n/2 (boxcut 2) so that the pruned passes see realistic occupancies; n1 < n shrinks the cell
+    along x to keep the oracle's full-box FFT small at the largest n."""
+    L = 10.0
+    gmax = n / 4.0 - 0.75
+    ecut = 0.5 * (gmax * 2 * np.pi / L) ** 2
+    n1 = n1 or n
+    return make_problem(ecut, (L * n1 / n, L, L), kpt, istwf_k, ndat=ndat, ngfft=(n1, n, n), cplex=cplex)
+
+
+@pytest.mark.parametrize("n", [24, 30, 32, 36, 40, 45, 48, 50, 54, 56, 60, 64, 72, 75, 80, 81, 84, 90, 96, 100, 108, 112,
+                               120, 128, 135, 144, 150, 160, 168, 180, 192, 196, 225, 240, 256])
+def test_option2_plane_stage_every_length(lib, n):
+    """Every FFT length of the register-resident two-pass plane stage (plane_stage.cuh), both warp layouts."""
+    from abinit_b200 import api
+    big = n > 128
+    p = _plane_problem(n, (.1, .2, .3), 1, ndat=1 if big else 2, n1=(n if not big else 36))
+    for cfg in (1, 2):
+        api.set_tuning("plane_cfg", cfg)
+        try:
+            assert _run(lib, p, 2, 2) < TOL
+        finally:
+            api.set_tuning("plane_cfg", 0)
+
+
+@pytest.mark.parametrize("istwf_k,kpt", [(2, (0, 0, 0)), (3, (.5, 0, 0)), (5, (.5, 0, .5)), (8, (0, .5, .5)), (9, (.5, .5, .5))])
+def test_option2_plane_stage_time_reversal(lib, istwf_k, kpt):
+    p = _plane_problem(48, kpt, istwf_k, ndat=3, n1=45)
+    assert _run(lib, p, 2, 2) < TOL
+    from abinit_b200 import api
+    api.set_tuning("plane", 0)          # same box through the cluster/L2 plane kernel (fallback path)
+    try:
+        assert _run(lib, p, 2, 2) < TOL
+    finally:
+        api.set_tuning("plane", 1)
+
+
+def test_option2_plane_stage_complex_potential_many_bands(lib):
+    p = _plane_problem(60, (.1, .2, .3), 1, ndat=7, cplex=2)
+    assert _run(lib, p, 2, 2) < TOL
+
+
 @pytest.mark.parametrize("ndat", [1, 5, 16])
 def test_option2_ndat_and_clusters(lib, ndat, monkeypatch):
     p = make_problem(8.0, 10.0, (0, 0, 0), 1, ndat=ndat)

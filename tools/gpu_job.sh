@@ -24,7 +24,7 @@ for what in "$@"; do
         > gpurun_out/launches_${TAG}.log 2>&1
       tail -2 gpurun_out/launches_${TAG}.log ;;
     ncu)
-      for k in ${NCU_KERNELS:-k_dgemm_nn k_dgemm_tn k_fw_mid k_fw_x_forward k_fw_x_backward}; do
+      for k in ${NCU_KERNELS:-k_dgemm_nn k_dgemm_tn k_fw_plane k_fw_x_forward k_fw_x_backward}; do
         timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f \
           -o gpurun_out/ncu_${k}_${TAG} python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e ${BENCH_ARGS:-} \
           > gpurun_out/ncu_${k}_${TAG}.log 2>&1
