@@ -52,8 +52,12 @@ template <typename T> ABI_HD T ceil_div(T a, T b) { return (a + b - 1) / b; }
 #ifndef ABI_EMU
 ABI_DEV double2 ldcg2(const double2* p) { return __ldcg(p); }
 ABI_DEV void stcg2(double2* p, double2 v) { __stcg(p, v); }
+ABI_DEV double ldg1(const double* p) { return __ldg(p); }
+ABI_DEV double2 ldg2(const double2* p) { return __ldg(p); }
 #else
 inline double2 ldcg2(const double2* p) { return *p; }
 inline void stcg2(double2* p, double2 v) { *p = v; }
+inline double ldg1(const double* p) { return *p; }
+inline double2 ldg2(const double2* p) { return *p; }
 #endif
 }  // namespace abi

@@ -172,21 +172,27 @@ struct PlaneFft {
         const int line = w % G, k1 = w / G;
         if (w < G * R1 && line < nl) {
           double2* e = E + k1 * ZK + line;
+          // V_loc of this lane's R2 grid points first: the loads fly while the exchange buffer is read and transformed
+          double2 vv[R2];
+          if (P.cplex == 1) {
+            const double* vp = vplane + (size_t)k1 * n2 + c0 + line;
+#pragma unroll
+            for (int k2 = 0; k2 < R2; k2++) vv[k2] = make_double2(ldg1(vp + (size_t)(R1 * k2) * n2), 0.0);
+          } else {
+            const double2* vp = reinterpret_cast<const double2*>(vplane) + (size_t)k1 * n2 + c0 + line;
+#pragma unroll
+            for (int k2 = 0; k2 < R2; k2++) vv[k2] = ldg2(vp + (size_t)(R1 * k2) * n2);
+          }
           double2 v[R2];
 #pragma unroll
           for (int j = 0; j < R2; j++) v[j] = e[j * G];
           Dft<R2, +1>::run(v);
           if (P.cplex == 1) {
-            const double* vp = vplane + (size_t)k1 * n2 + c0 + line;
 #pragma unroll
-            for (int k2 = 0; k2 < R2; k2++) {
-              const double vv = vp[(size_t)(R1 * k2) * n2];
-              v[k2].x *= vv; v[k2].y *= vv;
-            }
+            for (int k2 = 0; k2 < R2; k2++) { v[k2].x *= vv[k2].x; v[k2].y *= vv[k2].x; }
           } else {
-            const double2* vp = reinterpret_cast<const double2*>(vplane) + (size_t)k1 * n2 + c0 + line;
 #pragma unroll
-            for (int k2 = 0; k2 < R2; k2++) v[k2] = cmul(v[k2], vp[(size_t)(R1 * k2) * n2]);
+            for (int k2 = 0; k2 < R2; k2++) v[k2] = cmul(v[k2], vv[k2]);
           }
           Dft<R2, -1>::run(v);
           e[0] = v[0];
@@ -267,7 +273,7 @@ struct PlaneFft {
 
 // one CTA = one (band, i1) plane at a time; warps take line batches round-robin inside each phase
 template <int R1, int R2, int G, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_fw_plane(PlaneParams P) {
+__global__ void __launch_bounds__(WARPS * 32, (WARPS >= 16 ? 1 : 2)) k_fw_plane(PlaneParams P) {
   using F = PlaneFft<R1, R2, G>;
   ABI_DYN_SMEM(double2, sm);
   double2* tw = sm;                                    // n entries

@@ -38,9 +38,11 @@ void launch_cfg(PlaneParams& P, cudaStream_t st) {
 template <int R1, int R2>
 void plane_launch_n(PlaneParams& P, cudaStream_t st) {
   const int cfg = fourwf_tuning().plane_cfg;
-  const bool big = (cfg == 2) || (cfg == 0 && R1 * R2 > 200);
-  if (big) launch_cfg<R1, R2, 4, 8>(P, st);
-  else launch_cfg<R1, R2, 8, 4>(P, st);
+  // measured on B200 (Si-512 box, 64 bands): (4 columns x 8 warps, 2 CTAs/SM) 4.24 ms, (4 x 16, 1 CTA/SM) 4.51 ms,
+  // (8 x 4, 2 CTAs/SM) 5.15 ms -- the stage is latency bound, so warps per SM win over lane efficiency
+  if (cfg == 3) launch_cfg<R1, R2, 4, 16>(P, st);
+  else if (cfg == 1) launch_cfg<R1, R2, 8, 4>(P, st);
+  else launch_cfg<R1, R2, 4, 8>(P, st);
 }
 
 
