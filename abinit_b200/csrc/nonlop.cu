@@ -26,11 +26,16 @@ namespace abi {
 // ---------------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kBM = 128, kBN = 128, kBK = 16, kThreads = 512, kStages = 4;
-constexpr int kPitchM = kBM + 8;       // M-contiguous tile pitch (doubles): 1088 B = 64 mod 128 -> 2 wavefronts/LDS.64
+constexpr int kBK = 16;
+// tile configurations (measured on B200 with tools/gemm_lab.cu, Si-512 shapes, cuBLAS DGEMM = 35.45 TFLOP/s):
+//   TN (opernla): 16 warps x (32x32) = 128x128 CTA tile, 4 stages, 1 CTA/SM            -> 34.97 TFLOP/s
+//   NN (opernlb):  8 warps x (32x32) =  64x128 CTA tile, 3 stages, 2 CTAs/SM (the two CTAs of an SM share the DMMA
+//                  pipe, which removes the 15.2-wave tail of the 128x128 tiling)         -> 34.18 TFLOP/s
+struct TnCfg { static constexpr int WM = 32, WN = 32, WARPS_M = 4, WARPS_N = 4, STAGES = 4, MINB = 1; };
+struct NnCfg { static constexpr int WM = 32, WN = 32, WARPS_M = 2, WARPS_N = 4, STAGES = 3, MINB = 2; };
 
+// K-major tile [rows][16]: the 16-byte chunk c of row r is stored at chunk c ^ swz(r) -> conflict-free LDS.64 fragments
 ABI_DEV int swz(int r) { return ((r & 3) << 1) | ((r >> 2) & 1); }
-ABI_DEV int addr_k(int row, int k) { return row * kBK + ((((k >> 1) ^ swz(row)) << 1) | (k & 1)); }
 
 ABI_DEV void cp_async16(double* smem_dst, const double* gsrc, bool pred) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -44,50 +49,77 @@ ABI_DEV void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+// v with its sign bit xor-ed by `mask` (0 or 0x80000000): integer pipe, keeps the FP64 pipe for the DMMAs
+ABI_DEV double flip_sign(double v, int mask) { return __hiloint2double(__double2hiint(v) ^ mask, __double2loint(v)); }
 
 // ---------------------------------------------------------------------------------------------------------
 // TN: part[z][n][m] = sum_{k in split z} A[k + m lda] * Beff[k][n]
 //   CPLX: Beff columns are (psi_j, -i psi_j) pairs read from one smem row per band
+// NN: C[m + n ldc] = sum_k Aeff[m][k] * B[k + n ldb]   (+ add[m + n ldc])
+//   A is M-contiguous (P real view). CPLX: k = 2p+c, Aeff[m][2p] = A[m][p], Aeff[m][2p+1] = (iP)[m][p]
+// Both: cp.async multi-stage pipeline into shared memory, fragments double-buffered in registers (the loads of
+// k-step kk+1 are in flight while the 16 DMMAs of k-step kk issue), one block barrier per 16-wide k tile.
 // ---------------------------------------------------------------------------------------------------------
-struct TnParams {
-  int M, N, K;                 // N = effective columns (2*ndat when CPLX)
+struct GemmParams {
+  int M, N, K;                 // TN: N = effective columns (2*ndat when CPLX); NN: K = number of A columns (nprojs)
   const double* A; long long lda;
-  const double* B; long long ldb;
-  double* part;                // [nsplit][N][M]
+  const double* B; long long ldb;   // K-contiguous columns
+  double* C; long long ldc;    // NN: output ; TN: partial buffer [nsplit][N][M]
+  const double* add;           // NN only: optional, same layout as C
   int nsplit, kchunk, tiles_m, tiles_n;
 };
 
-template <bool CPLX>
-__global__ void __launch_bounds__(kThreads, 1) k_dgemm_tn(TnParams p) {
+template <bool TN, bool CPLX, class Cfg>
+__global__ void __launch_bounds__(Cfg::WARPS_M * Cfg::WARPS_N * 32, Cfg::MINB) k_dgemm(GemmParams p) {
+  constexpr int WM = Cfg::WM, WN = Cfg::WN, WARPS_N = Cfg::WARPS_N, STAGES = Cfg::STAGES;
+  constexpr int BM = WM * Cfg::WARPS_M, BN = WN * WARPS_N, NT = Cfg::WARPS_M * WARPS_N * 32;
+  constexpr int FM = WM / 8, FN = WN / 8;
+  constexpr int PITCH = BM + 4;                            // M-major A tile: 32 bytes mod 128 -> 4 k rows = 4 bank quarters
+  constexpr int AROWS = (!TN && CPLX) ? kBK / 2 : kBK;     // NN: A columns (p) per stage
+  constexpr int BROWS = (TN && CPLX) ? BN / 2 : BN;        // TN complex: one smem row per band = two effective columns
+  constexpr int A_STAGE = TN ? BM * kBK : AROWS * PITCH;
+  constexpr int B_STAGE = BROWS * kBK;
   extern __shared__ __align__(16) double smem_d[];
-  constexpr int BROWS = CPLX ? kBN / 2 : kBN;
-  double* As = smem_d;                                  // [stages][128*16]
-  double* Bs = smem_d + kStages * kBM * kBK;            // [stages][BROWS*16]
+  double* As = smem_d;
+  double* Bs = smem_d + STAGES * A_STAGE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
+  const int wm = (warp / WARPS_N) * WM, wn = (warp % WARPS_N) * WN;
   int bid = blockIdx.x;
   const int tn = bid % p.tiles_n; bid /= p.tiles_n;
   const int tm = bid % p.tiles_m; const int z = bid / p.tiles_m;
-  const int m0 = tm * kBM, n0 = tn * kBN;
-  const int k_begin = z * p.kchunk, k_end = min(p.K, k_begin + p.kchunk);
+  const int m0 = tm * BM, n0 = tn * BN;
+  // k range in units of the smem k index (TN: rows of A^T; NN real: A columns; NN complex: 2 per A column)
+  const int k_total = (!TN && CPLX) ? 2 * p.K : p.K;
+  const int k_begin = TN ? z * p.kchunk : 0, k_end = TN ? min(k_total, k_begin + p.kchunk) : k_total;
   const int nkt = (k_end - k_begin + kBK - 1) / kBK;
-  const int brow0 = CPLX ? n0 / 2 : n0;
-  const int nrows_b = CPLX ? p.N / 2 : p.N;
+  const int brow0 = (TN && CPLX) ? n0 / 2 : n0;
+  const int nrows_b = (TN && CPLX) ? p.N / 2 : p.N;
 
   auto load_stage = [&](int s, int kt) {
     const int k0 = k_begin + kt * kBK;
-    double* as = As + s * kBM * kBK;
-    double* bs = Bs + s * BROWS * kBK;
+    double* as = As + s * A_STAGE;
+    double* bs = Bs + s * B_STAGE;
+    if (TN) {
 #pragma unroll
-    for (int c = tid; c < kBM * 8; c += kThreads) {
-      const int row = c >> 3, ch = c & 7;
-      const int gm = m0 + row, gk = k0 + ch * 2;
-      const bool ok = gm < p.M && gk < k_end;
-      cp_async16(as + row * kBK + ((ch ^ swz(row)) << 1), ok ? p.A + (long long)gm * p.lda + gk : p.A, ok);
+      for (int c = tid; c < BM * 8; c += NT) {
+        const int row = c >> 3, ch = c & 7;
+        const int gm = m0 + row, gk = k0 + ch * 2;
+        const bool ok = gm < p.M && gk < k_end;
+        cp_async16(as + row * kBK + ((ch ^ swz(row)) << 1), ok ? p.A + (long long)gm * p.lda + gk : p.A, ok);
+      }
+    } else {
+      const int p0 = CPLX ? k0 / 2 : k0;
+#pragma unroll
+      for (int c = tid; c < AROWS * (BM / 2); c += NT) {
+        const int krow = c / (BM / 2), ch = c % (BM / 2);
+        const int gk = p0 + krow, gm = m0 + ch * 2;
+        const bool ok = gk < p.K && gm < p.M;
+        cp_async16(as + krow * PITCH + ch * 2, ok ? p.A + (long long)gk * p.lda + gm : p.A, ok);
+      }
     }
 #pragma unroll
-    for (int c = tid; c < BROWS * 8; c += kThreads) {
+    for (int c = tid; c < BROWS * 8; c += NT) {
       const int row = c >> 3, ch = c & 7;
       const int gn = brow0 + row, gk = k0 + ch * 2;
       const bool ok = gn < nrows_b && gk < k_end;
@@ -95,160 +127,115 @@ __global__ void __launch_bounds__(kThreads, 1) k_dgemm_tn(TnParams p) {
     }
   };
 
-  double acc[4][4][2];
+  double acc[FM][FN][2];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < FM; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int s = 0; s < kStages - 1; s++) { if (s < nkt) load_stage(s, s); cp_async_commit(); }
+  // Per-lane fragment addresses for k-step 0 (doubles inside a stage).  K-major tiles: the k-step only changes the
+  // 16-byte chunk index by kk*2, which commutes with the swizzle xor -> address(kk) = address(0) ^ (kk*4).
+  int a_off[FM], b_off[FN];
+  int a_flip = 0, b_flip = 0;
+#pragma unroll
+  for (int i = 0; i < FM; i++) {
+    const int row = wm + 8 * i + g;
+    if (TN) a_off[i] = row * kBK + ((((t >> 1) ^ swz(row)) << 1) | (t & 1));
+    else if (!CPLX) a_off[i] = t * PITCH + row;
+    else a_off[i] = (t >> 1) * PITCH + ((t & 1) ? (row ^ 1) : row);      // odd k: (iP)[m] = -+P[m^1]
+  }
+  if (!TN && CPLX) a_flip = ((t & 1) && !(g & 1)) ? (int)0x80000000 : 0;  // (iP) even rows (real parts) = -Im P
+#pragma unroll
+  for (int j = 0; j < FN; j++) {
+    const int col = wn + 8 * j + g;
+    if (TN && CPLX) {
+      const int row = col >> 1, kq = (col & 1) ? (t ^ 1) : t;            // odd effective column: -i psi
+      b_off[j] = row * kBK + ((((kq >> 1) ^ swz(row)) << 1) | (kq & 1));
+    } else {
+      b_off[j] = col * kBK + ((((t >> 1) ^ swz(col)) << 1) | (t & 1));
+    }
+  }
+  if (TN && CPLX) b_flip = ((g & 1) && (t & 1)) ? (int)0x80000000 : 0;    // Re(-i psi) = Im psi, Im(-i psi) = -Re psi
+  auto ld_frags = [&](const double* as, const double* bs, int kk, double (&a)[FM], double (&b)[FN]) {
+#pragma unroll
+    for (int i = 0; i < FM; i++) {
+      if (TN) a[i] = as[a_off[i] ^ (kk * 4)];
+      else if (!CPLX) a[i] = as[a_off[i] + kk * 4 * PITCH];
+      else a[i] = flip_sign(as[a_off[i] + kk * 2 * PITCH], a_flip);
+    }
+#pragma unroll
+    for (int j = 0; j < FN; j++) {
+      const double v = bs[b_off[j] ^ (kk * 4)];
+      b[j] = (TN && CPLX) ? flip_sign(v, b_flip) : v;
+    }
+  };
+
+  for (int s = 0; s < STAGES - 1; s++) { if (s < nkt) load_stage(s, s); cp_async_commit(); }
+  cp_async_wait<STAGES - 2>();
+  __syncthreads();
+  double a[2][FM], b[2][FN];
+  ld_frags(As, Bs, 0, a[0], b[0]);
   for (int kt = 0; kt < nkt; kt++) {
-    cp_async_wait<kStages - 2>();
-    __syncthreads();
-    { const int nx = kt + kStages - 1; if (nx < nkt) load_stage(nx % kStages, nx); cp_async_commit(); }
-    const double* as = As + (kt % kStages) * kBM * kBK;
-    const double* bs = Bs + (kt % kStages) * BROWS * kBK;
+    const double* as = As + (kt % STAGES) * A_STAGE;
+    const double* bs = Bs + (kt % STAGES) * B_STAGE;
+    { const int nx = kt + STAGES - 1; if (nx < nkt) load_stage(nx % STAGES, nx); cp_async_commit(); }
 #pragma unroll
     for (int kk = 0; kk < kBK / 4; kk++) {
-      const int k = kk * 4 + t;
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = as[addr_k(wm + 8 * i + g, k)];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        if (CPLX) {
-          const int n = wn + 8 * j + g;          // effective column inside the tile
-          const int row = n >> 1;
-          if (n & 1) { const double v = bs[addr_k(row, k ^ 1)]; b[j] = (k & 1) ? -v : v; }
-          else b[j] = bs[addr_k(row, k)];
-        } else {
-          b[j] = bs[addr_k(wn + 8 * j + g, k)];
-        }
+      if (kk < kBK / 4 - 1) {
+        ld_frags(as, bs, kk + 1, a[(kk + 1) & 1], b[(kk + 1) & 1]);
+      } else {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nk = (kt + 1) % STAGES;
+        ld_frags(As + nk * A_STAGE, Bs + nk * B_STAGE, 0, a[(kk + 1) & 1], b[(kk + 1) & 1]);
       }
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < FM; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[kk & 1][i], b[kk & 1][j]);
     }
   }
   cp_async_wait<0>();
-  double* out = p.part + (size_t)z * p.N * p.M;
+  if (TN) {
+    double* out = p.C + (size_t)z * p.N * p.M;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int m = m0 + wm + 8 * i + g;
-    if (m >= p.M) continue;
+    for (int i = 0; i < FM; i++) {
+      const int m = m0 + wm + 8 * i + g;
+      if (m >= p.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int n = n0 + wn + 8 * j + 2 * t;
-      if (n < p.N) out[(size_t)n * p.M + m] = acc[i][j][0];
-      if (n + 1 < p.N) out[(size_t)(n + 1) * p.M + m] = acc[i][j][1];
+      for (int j = 0; j < FN; j++) {
+        const int n = n0 + wn + 8 * j + 2 * t;
+        if (n < p.N) out[(size_t)n * p.M + m] = acc[i][j][0];
+        if (n + 1 < p.N) out[(size_t)(n + 1) * p.M + m] = acc[i][j][1];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < FM; i++) {
+      const int m = m0 + wm + 8 * i + g;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < FN; j++) {
+        const int n = n0 + wn + 8 * j + 2 * t;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          if (n + h < p.N) {
+            const size_t o = (size_t)(n + h) * p.ldc + m;
+            double v = acc[i][j][h];
+            if (p.add) v += p.add[o];
+            p.C[o] = v;
+          }
+        }
+      }
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// NN: C[m + n ldc] = sum_k Aeff[m][k] * B[k + n ldb]   (+ add[m + n ldc])
-//   A is M-contiguous (P real view). CPLX: k = 2p+c, Aeff[m][2p] = A[m][p], Aeff[m][2p+1] = (iP)[m][p]
-// ---------------------------------------------------------------------------------------------------------
-struct NnParams {
-  int M, N, K;                 // K = number of A columns (nprojs)
-  const double* A; long long lda;
-  const double* B; long long ldb;   // K-contiguous columns: real: K doubles, CPLX: 2K doubles
-  double* C; long long ldc;
-  const double* add;           // optional, same layout as C
-  int tiles_m, tiles_n;
-};
-
-template <bool CPLX>
-__global__ void __launch_bounds__(kThreads, 1) k_dgemm_nn(NnParams p) {
-  extern __shared__ __align__(16) double smem_d[];
-  constexpr int AROWS = CPLX ? kBK / 2 : kBK;           // A columns (p) per stage
-  double* As = smem_d;                                  // [stages][AROWS*kPitchM]
-  double* Bs = smem_d + kStages * AROWS * kPitchM;      // [stages][128*16]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
-  const int tn = blockIdx.x % p.tiles_n, tm = blockIdx.x / p.tiles_n;
-  const int m0 = tm * kBM, n0 = tn * kBN;
-  const int nkt = (p.K + AROWS - 1) / AROWS;
-  const int kb_len = CPLX ? 2 * p.K : p.K;              // length of a B column in doubles
-
-  auto load_stage = [&](int s, int kt) {
-    const int p0 = kt * AROWS;
-    double* as = As + s * AROWS * kPitchM;
-    double* bs = Bs + s * kBN * kBK;
-#pragma unroll
-    for (int c = tid; c < AROWS * (kBM / 2); c += kThreads) {
-      const int krow = c / (kBM / 2), ch = c % (kBM / 2);
-      const int gk = p0 + krow, gm = m0 + ch * 2;
-      const bool ok = gk < p.K && gm < p.M;
-      cp_async16(as + krow * kPitchM + ch * 2, ok ? p.A + (long long)gk * p.lda + gm : p.A, ok);
-    }
-    const int q0 = kt * kBK;
-#pragma unroll
-    for (int c = tid; c < kBN * 8; c += kThreads) {
-      const int row = c >> 3, ch = c & 7;
-      const int gn = n0 + row, gq = q0 + ch * 2;
-      const bool ok = gn < p.N && gq < kb_len;
-      cp_async16(bs + row * kBK + ((ch ^ swz(row)) << 1), ok ? p.B + (long long)gn * p.ldb + gq : p.B, ok);
-    }
-  };
-
-  double acc[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  for (int s = 0; s < kStages - 1; s++) { if (s < nkt) load_stage(s, s); cp_async_commit(); }
-  for (int kt = 0; kt < nkt; kt++) {
-    cp_async_wait<kStages - 2>();
-    __syncthreads();
-    { const int nx = kt + kStages - 1; if (nx < nkt) load_stage(nx % kStages, nx); cp_async_commit(); }
-    const double* as = As + (kt % kStages) * AROWS * kPitchM;
-    const double* bs = Bs + (kt % kStages) * kBN * kBK;
-#pragma unroll
-    for (int kk = 0; kk < kBK / 4; kk++) {
-      const int k = kk * 4 + t;
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int m = wm + 8 * i + g;
-        if (CPLX) {
-          const int pr = k >> 1;
-          if (k & 1) { const double v = as[pr * kPitchM + (m ^ 1)]; a[i] = (m & 1) ? v : -v; }
-          else a[i] = as[pr * kPitchM + m];
-        } else {
-          a[i] = as[k * kPitchM + m];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; j++) b[j] = bs[addr_k(wn + 8 * j + g, k)];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    }
-  }
-  cp_async_wait<0>();
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int m = m0 + wm + 8 * i + g;
-    if (m >= p.M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int n = n0 + wn + 8 * j + 2 * t;
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        if (n + h < p.N) {
-          const size_t o = (size_t)(n + h) * p.ldc + m;
-          double v = acc[i][j][h];
-          if (p.add) v += p.add[o];
-          p.C[o] = v;
-        }
-      }
-    }
-  }
+template <bool TN, bool CPLX, class Cfg> constexpr size_t gemm_smem() {
+  constexpr int BM = Cfg::WM * Cfg::WARPS_M, BN = Cfg::WN * Cfg::WARPS_N;
+  constexpr int a_stage = TN ? BM * kBK : ((CPLX ? kBK / 2 : kBK) * (BM + 4));
+  constexpr int b_stage = ((TN && CPLX) ? BN / 2 : BN) * kBK;
+  return sizeof(double) * Cfg::STAGES * (a_stage + b_stage);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -458,15 +445,24 @@ void prep_projectors_device(Projectors& P, const NonlopAtoms& at, const double* 
   g_kernel_launches++;
 }
 
-static size_t tn_smem(bool cplx) { return sizeof(double) * kStages * (kBM * kBK + (cplx ? kBN / 2 : kBN) * kBK); }
-static size_t nn_smem(bool cplx) { return sizeof(double) * kStages * ((cplx ? kBK / 2 : kBK) * kPitchM + kBN * kBK); }
+template <bool TN, bool CPLX, class Cfg>
+static void launch_gemm(const GemmParams& p, int nblocks, cudaStream_t st) {
+  auto kern = k_dgemm<TN, CPLX, Cfg>;
+  constexpr size_t smem = gemm_smem<TN, CPLX, Cfg>();
+  static bool attr_done = false;
+  if (!attr_done) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+  kern<<<nblocks, Cfg::WARPS_M * Cfg::WARPS_N * 32, smem, st>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
 
 // split-K TN GEMM into partial buffers; returns nsplit
 static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long long lda, const double* B, long long ldb,
                      double*& part, cudaStream_t st) {
-  TnParams p;
-  p.M = M; p.N = Neff; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb;
-  p.tiles_m = ceil_div(M, kBM); p.tiles_n = ceil_div(Neff, kBN);
+  constexpr int BM = TnCfg::WM * TnCfg::WARPS_M, BN = TnCfg::WN * TnCfg::WARPS_N;
+  GemmParams p{};
+  p.M = M; p.N = Neff; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.add = nullptr; p.ldc = 0;
+  p.tiles_m = ceil_div(M, BM); p.tiles_n = ceil_div(Neff, BN);
   const int tiles = p.tiles_m * p.tiles_n;
   // pick the split count that minimises the makespan (waves of 148 CTAs per unit of work)
   const int min_chunk = 64 * kBK;
@@ -480,37 +476,23 @@ static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long lo
   nsplit = ceil_div(K, kchunk);
   p.nsplit = nsplit; p.kchunk = kchunk;
   part = g_nlws[0].get((size_t)nsplit * Neff * M);
-  p.part = part;
-  const size_t smem = tn_smem(cplx);
+  p.C = part;
   ProfScope ps("dgemm_tn_opernla");
-  if (cplx) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_dgemm_tn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_dgemm_tn<true><<<tiles * nsplit, kThreads, smem, st>>>(p);
-  } else {
-    CUDA_CHECK(cudaFuncSetAttribute(k_dgemm_tn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_dgemm_tn<false><<<tiles * nsplit, kThreads, smem, st>>>(p);
-  }
-  CUDA_CHECK(cudaGetLastError());
-  g_kernel_launches++;
+  if (cplx) launch_gemm<true, true, TnCfg>(p, tiles * nsplit, st);
+  else launch_gemm<true, false, TnCfg>(p, tiles * nsplit, st);
   return nsplit;
 }
 
 static void launch_nn(bool cplx, int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
                       long long ldc, const double* add, cudaStream_t st) {
-  NnParams p;
+  constexpr int BM = NnCfg::WM * NnCfg::WARPS_M, BN = NnCfg::WN * NnCfg::WARPS_N;
+  GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.add = add;
-  p.tiles_m = ceil_div(M, kBM); p.tiles_n = ceil_div(N, kBN);
-  const size_t smem = nn_smem(cplx);
+  p.tiles_m = ceil_div(M, BM); p.tiles_n = ceil_div(N, BN);
+  p.nsplit = 1; p.kchunk = 0;
   ProfScope ps("dgemm_nn_opernlb");
-  if (cplx) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_dgemm_nn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_dgemm_nn<true><<<p.tiles_m * p.tiles_n, kThreads, smem, st>>>(p);
-  } else {
-    CUDA_CHECK(cudaFuncSetAttribute(k_dgemm_nn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_dgemm_nn<false><<<p.tiles_m * p.tiles_n, kThreads, smem, st>>>(p);
-  }
-  CUDA_CHECK(cudaGetLastError());
-  g_kernel_launches++;
+  if (cplx) launch_gemm<false, true, NnCfg>(p, p.tiles_m * p.tiles_n, st);
+  else launch_gemm<false, false, NnCfg>(p, p.tiles_m * p.tiles_n, st);
 }
 
 __global__ void k_reduce_plain(const double* __restrict__ part, double* __restrict__ C, long long ldc, int M, int N, int nsplit, double alpha) {
