@@ -31,8 +31,16 @@ constexpr int kBK = 16;
 //   TN (opernla): 16 warps x (32x32) = 128x128 CTA tile, 4 stages, 1 CTA/SM            -> 34.97 TFLOP/s
 //   NN (opernlb):  8 warps x (32x32) =  64x128 CTA tile, 3 stages, 2 CTAs/SM (the two CTAs of an SM share the DMMA
 //                  pipe, which removes the 15.2-wave tail of the 128x128 tiling)         -> 34.18 TFLOP/s
-struct TnCfg { static constexpr int WM = 32, WN = 32, WARPS_M = 4, WARPS_N = 4, STAGES = 4, MINB = 1; };
-struct NnCfg { static constexpr int WM = 32, WN = 32, WARPS_M = 2, WARPS_N = 4, STAGES = 3, MINB = 2; };
+// Narrow band blocks (effective N <= 64 / <= 32) use 64- and 32-column CTA tiles of the same warp tile.
+template <int WARPS_M_, int WARPS_N_, int STAGES_, int MINB_> struct GemmCfg {
+  static constexpr int WM = 32, WN = 32, WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, STAGES = STAGES_, MINB = MINB_;
+};
+using TnCfg = GemmCfg<4, 4, 4, 1>;      // 128 x 128
+using TnCfg64 = GemmCfg<8, 2, 4, 1>;    // 256 x 64
+using TnCfg32 = GemmCfg<16, 1, 3, 1>;   // 512 x 32
+using NnCfg = GemmCfg<2, 4, 3, 2>;      //  64 x 128
+using NnCfg64 = GemmCfg<4, 2, 3, 2>;    // 128 x 64
+using NnCfg32 = GemmCfg<8, 1, 3, 2>;    // 256 x 32
 
 // K-major tile [rows][16]: the 16-byte chunk c of row r is stored at chunk c ^ swz(r) -> conflict-free LDS.64 fragments
 ABI_DEV int swz(int r) { return ((r & 3) << 1) | ((r >> 2) & 1); }
@@ -96,34 +104,69 @@ __global__ void __launch_bounds__(Cfg::WARPS_M * Cfg::WARPS_N * 32, Cfg::MINB) k
   const int brow0 = (TN && CPLX) ? n0 / 2 : n0;
   const int nrows_b = (TN && CPLX) ? p.N / 2 : p.N;
 
+  // ---- global -> shared copy plan: every thread owns fixed (row, 16-byte chunk) slots of a stage; per k tile it only
+  // advances its global pointers and re-evaluates the k-range predicate (no 64-bit index arithmetic in the main loop)
+  constexpr int KROWS_PER_PASS = NT / 8;                    // K-major tiles: rows covered by one pass of the CTA
+  static_assert(KROWS_PER_PASS % 8 == 0, "swizzle term must be identical for every pass");
+  constexpr int A_IT = TN ? (BM * 8) / NT : (AROWS * (BM / 2)) / NT;
+  constexpr int B_IT = (BROWS * 8 + NT - 1) / NT;           // narrow B tiles: only the first BROWS*8 threads copy
+  static_assert(A_IT >= 1 && (TN ? (BM * 8) % NT == 0 : (AROWS * (BM / 2)) % NT == 0), "tile/threads mismatch");
+  static_assert(B_IT == 1 || (BROWS * 8) % NT == 0, "tile/threads mismatch");
+  constexpr int MROWS_PER_PASS = NT / (BM / 2);             // M-major A tile: k rows covered by one pass
+  const int kch = (tid & 7) * 2;                            // k offset of this thread's chunk in K-major tiles
+  const double* a_ptr[A_IT]; bool a_ok[A_IT]; int a_dst;
+  const double* b_ptr[B_IT]; bool b_ok[B_IT]; int b_dst;
+  if (TN) {
+    const int row = tid >> 3;
+    a_dst = row * kBK + (((tid & 7) ^ swz(row)) << 1);
+#pragma unroll
+    for (int i = 0; i < A_IT; i++) {
+      const int gm = m0 + row + i * KROWS_PER_PASS;
+      a_ok[i] = gm < p.M;
+      a_ptr[i] = p.A + (long long)(a_ok[i] ? gm : 0) * p.lda + k_begin + kch;
+    }
+  } else {
+    const int krow = tid / (BM / 2), ch = tid % (BM / 2);
+    a_dst = krow * PITCH + ch * 2;
+    const int gm = m0 + ch * 2;
+#pragma unroll
+    for (int i = 0; i < A_IT; i++) {
+      a_ok[i] = gm < p.M;
+      a_ptr[i] = p.A + (long long)(krow + i * MROWS_PER_PASS) * p.lda + (a_ok[i] ? gm : 0);
+    }
+  }
+  {
+    const int row = tid >> 3;
+    b_dst = row * kBK + (((tid & 7) ^ swz(row)) << 1);
+#pragma unroll
+    for (int i = 0; i < B_IT; i++) {
+      const int gn = brow0 + row + i * KROWS_PER_PASS;
+      b_ok[i] = gn < nrows_b;
+      b_ptr[i] = p.B + (long long)(b_ok[i] ? gn : 0) * p.ldb + k_begin + kch;
+    }
+  }
+  const long long a_step = TN ? kBK : (long long)AROWS * p.lda;
   auto load_stage = [&](int s, int kt) {
     const int k0 = k_begin + kt * kBK;
-    double* as = As + s * A_STAGE;
-    double* bs = Bs + s * B_STAGE;
+    double* as = As + s * A_STAGE + a_dst;
+    double* bs = Bs + s * B_STAGE + b_dst;
+    const bool kok = k0 + kch < k_end;                      // K-major chunks: same k offset for all of this thread's slots
     if (TN) {
 #pragma unroll
-      for (int c = tid; c < BM * 8; c += NT) {
-        const int row = c >> 3, ch = c & 7;
-        const int gm = m0 + row, gk = k0 + ch * 2;
-        const bool ok = gm < p.M && gk < k_end;
-        cp_async16(as + row * kBK + ((ch ^ swz(row)) << 1), ok ? p.A + (long long)gm * p.lda + gk : p.A, ok);
-      }
+      for (int i = 0; i < A_IT; i++) { cp_async16(as + i * KROWS_PER_PASS * kBK, a_ptr[i], a_ok[i] && kok); a_ptr[i] += a_step; }
     } else {
-      const int p0 = CPLX ? k0 / 2 : k0;
+      const int p0 = (CPLX ? k0 / 2 : k0) + tid / (BM / 2);
 #pragma unroll
-      for (int c = tid; c < AROWS * (BM / 2); c += NT) {
-        const int krow = c / (BM / 2), ch = c % (BM / 2);
-        const int gk = p0 + krow, gm = m0 + ch * 2;
-        const bool ok = gk < p.K && gm < p.M;
-        cp_async16(as + krow * PITCH + ch * 2, ok ? p.A + (long long)gk * p.lda + gm : p.A, ok);
+      for (int i = 0; i < A_IT; i++) {
+        cp_async16(as + i * MROWS_PER_PASS * PITCH, a_ptr[i], a_ok[i] && (p0 + i * MROWS_PER_PASS < p.K));
+        a_ptr[i] += a_step;
       }
     }
 #pragma unroll
-    for (int c = tid; c < BROWS * 8; c += NT) {
-      const int row = c >> 3, ch = c & 7;
-      const int gn = brow0 + row, gk = k0 + ch * 2;
-      const bool ok = gn < nrows_b && gk < k_end;
-      cp_async16(bs + row * kBK + ((ch ^ swz(row)) << 1), ok ? p.B + (long long)gn * p.ldb + gk : p.B, ok);
+    for (int i = 0; i < B_IT; i++) {
+      // narrow B tiles (BROWS*8 < threads): the surplus threads own no slot (a zero-fill copy would land outside the tile)
+      if ((BROWS * 8) % NT == 0 || (tid >> 3) < BROWS) cp_async16(bs + i * KROWS_PER_PASS * kBK, b_ptr[i], b_ok[i] && kok);
+      b_ptr[i] += kBK;
     }
   };
 
@@ -133,39 +176,45 @@ __global__ void __launch_bounds__(Cfg::WARPS_M * Cfg::WARPS_N * 32, Cfg::MINB) k
 #pragma unroll
     for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  // Per-lane fragment addresses for k-step 0 (doubles inside a stage).  K-major tiles: the k-step only changes the
-  // 16-byte chunk index by kk*2, which commutes with the swizzle xor -> address(kk) = address(0) ^ (kk*4).
-  int a_off[FM], b_off[FN];
+  // Per-lane fragment addresses (doubles inside a stage).  K-major tiles: the k-step only changes the 16-byte chunk
+  // index by kk*2, which commutes with the swizzle xor -> address(kk) = address(0) ^ (kk*4); the swizzle term depends on
+  // (row & 7) = g only, so one address per k-step serves every fragment row block through an immediate offset.
+  int a_k[kBK / 4], b_k[kBK / 4][2];
   int a_flip = 0, b_flip = 0;
+  {
+    const int row = wm + g;
+    int a0;
+    if (TN) a0 = row * kBK + ((((t >> 1) ^ swz(row)) << 1) | (t & 1));
+    else if (!CPLX) a0 = t * PITCH + row;
+    else a0 = (t >> 1) * PITCH + ((t & 1) ? (row ^ 1) : row);             // odd k: (iP)[m] = -+P[m^1]
 #pragma unroll
-  for (int i = 0; i < FM; i++) {
-    const int row = wm + 8 * i + g;
-    if (TN) a_off[i] = row * kBK + ((((t >> 1) ^ swz(row)) << 1) | (t & 1));
-    else if (!CPLX) a_off[i] = t * PITCH + row;
-    else a_off[i] = (t >> 1) * PITCH + ((t & 1) ? (row ^ 1) : row);      // odd k: (iP)[m] = -+P[m^1]
+    for (int kk = 0; kk < kBK / 4; kk++) a_k[kk] = TN ? (a0 ^ (kk * 4)) : (a0 + kk * (CPLX ? 2 : 4) * PITCH);
   }
   if (!TN && CPLX) a_flip = ((t & 1) && !(g & 1)) ? (int)0x80000000 : 0;  // (iP) even rows (real parts) = -Im P
 #pragma unroll
-  for (int j = 0; j < FN; j++) {
-    const int col = wn + 8 * j + g;
+  for (int jp = 0; jp < 2; jp++) {
+    const int col = wn + 8 * jp + g;
+    int b0;
     if (TN && CPLX) {
       const int row = col >> 1, kq = (col & 1) ? (t ^ 1) : t;            // odd effective column: -i psi
-      b_off[j] = row * kBK + ((((kq >> 1) ^ swz(row)) << 1) | (kq & 1));
+      b0 = row * kBK + ((((kq >> 1) ^ swz(row)) << 1) | (kq & 1));
     } else {
-      b_off[j] = col * kBK + ((((t >> 1) ^ swz(col)) << 1) | (t & 1));
+      b0 = col * kBK + ((((t >> 1) ^ swz(col)) << 1) | (t & 1));
     }
+#pragma unroll
+    for (int kk = 0; kk < kBK / 4; kk++) b_k[kk][jp] = b0 ^ (kk * 4);
   }
   if (TN && CPLX) b_flip = ((g & 1) && (t & 1)) ? (int)0x80000000 : 0;    // Re(-i psi) = Im psi, Im(-i psi) = -Re psi
   auto ld_frags = [&](const double* as, const double* bs, int kk, double (&a)[FM], double (&b)[FN]) {
 #pragma unroll
     for (int i = 0; i < FM; i++) {
-      if (TN) a[i] = as[a_off[i] ^ (kk * 4)];
-      else if (!CPLX) a[i] = as[a_off[i] + kk * 4 * PITCH];
-      else a[i] = flip_sign(as[a_off[i] + kk * 2 * PITCH], a_flip);
+      const double v = as[a_k[kk] + i * 8 * (TN ? kBK : 1)];
+      a[i] = (!TN && CPLX) ? flip_sign(v, a_flip) : v;
     }
 #pragma unroll
     for (int j = 0; j < FN; j++) {
-      const double v = bs[b_off[j] ^ (kk * 4)];
+      // complex TN: effective columns 8j+g live in smem row 4j+(g>>1): j and j+2 share the swizzle term
+      const double v = (TN && CPLX) ? bs[b_k[kk][j & 1] + (j >> 1) * 8 * kBK] : bs[b_k[kk][0] + j * 8 * kBK];
       b[j] = (TN && CPLX) ? flip_sign(v, b_flip) : v;
     }
   };
@@ -459,7 +508,7 @@ static void launch_gemm(const GemmParams& p, int nblocks, cudaStream_t st) {
 // split-K TN GEMM into partial buffers; returns nsplit
 static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long long lda, const double* B, long long ldb,
                      double*& part, cudaStream_t st) {
-  constexpr int BM = TnCfg::WM * TnCfg::WARPS_M, BN = TnCfg::WN * TnCfg::WARPS_N;
+  const int BN = Neff <= 32 ? 32 : (Neff <= 64 ? 64 : 128), BM = 128 * 128 / BN;
   GemmParams p{};
   p.M = M; p.N = Neff; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.add = nullptr; p.ldc = 0;
   p.tiles_m = ceil_div(M, BM); p.tiles_n = ceil_div(Neff, BN);
@@ -478,21 +527,25 @@ static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long lo
   part = g_nlws[0].get((size_t)nsplit * Neff * M);
   p.C = part;
   ProfScope ps("dgemm_tn_opernla");
-  if (cplx) launch_gemm<true, true, TnCfg>(p, tiles * nsplit, st);
-  else launch_gemm<true, false, TnCfg>(p, tiles * nsplit, st);
+  const int nb = tiles * nsplit;
+  if (BN == 128) { if (cplx) launch_gemm<true, true, TnCfg>(p, nb, st); else launch_gemm<true, false, TnCfg>(p, nb, st); }
+  else if (BN == 64) { if (cplx) launch_gemm<true, true, TnCfg64>(p, nb, st); else launch_gemm<true, false, TnCfg64>(p, nb, st); }
+  else { if (cplx) launch_gemm<true, true, TnCfg32>(p, nb, st); else launch_gemm<true, false, TnCfg32>(p, nb, st); }
   return nsplit;
 }
 
 static void launch_nn(bool cplx, int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
                       long long ldc, const double* add, cudaStream_t st) {
-  constexpr int BM = NnCfg::WM * NnCfg::WARPS_M, BN = NnCfg::WN * NnCfg::WARPS_N;
+  const int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128), BM = 64 * 128 / BN;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.add = add;
   p.tiles_m = ceil_div(M, BM); p.tiles_n = ceil_div(N, BN);
   p.nsplit = 1; p.kchunk = 0;
   ProfScope ps("dgemm_nn_opernlb");
-  if (cplx) launch_gemm<false, true, NnCfg>(p, p.tiles_m * p.tiles_n, st);
-  else launch_gemm<false, false, NnCfg>(p, p.tiles_m * p.tiles_n, st);
+  const int nb = p.tiles_m * p.tiles_n;
+  if (BN == 128) { if (cplx) launch_gemm<false, true, NnCfg>(p, nb, st); else launch_gemm<false, false, NnCfg>(p, nb, st); }
+  else if (BN == 64) { if (cplx) launch_gemm<false, true, NnCfg64>(p, nb, st); else launch_gemm<false, false, NnCfg64>(p, nb, st); }
+  else { if (cplx) launch_gemm<false, true, NnCfg32>(p, nb, st); else launch_gemm<false, false, NnCfg32>(p, nb, st); }
 }
 
 __global__ void k_reduce_plain(const double* __restrict__ part, double* __restrict__ C, long long ldc, int M, int N, int nsplit, double alpha) {

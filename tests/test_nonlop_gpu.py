@@ -84,9 +84,11 @@ def test_naive_per_atom_statement(lib):
 
 
 def test_explicit_projectors_larger(lib):
-    """Random explicit P (bench-style), sizes that exercise several M/N tiles, K tails and split-K."""
+    """Random explicit P (bench-style), sizes that exercise several M/N tiles, K tails, split-K and every CTA tile
+    width (128/64/32 effective columns) of the real and complex TN/NN kernels."""
     rng = np.random.default_rng(3)
-    for istwf_k, npw, nprojs, ndat in ((2, 4097, 300, 70), (1, 2051, 259, 33)):
+    for istwf_k, npw, nprojs, ndat in ((2, 4097, 300, 70), (1, 2051, 259, 33), (2, 3001, 200, 40), (1, 1500, 130, 20),
+                                       (1, 1501, 131, 10), (2, 1777, 515, 9), (1, 900, 1030, 130)):
         p = make_problem(3.0, 6.0, (0, 0, 0) if istwf_k == 2 else (.1, .2, .3), istwf_k, ndat=1)
         P = (rng.standard_normal((nprojs, npw)) + 1j * rng.standard_normal((nprojs, npw))) / np.sqrt(npw)
         c = rng.standard_normal((ndat, npw)) + 1j * rng.standard_normal((ndat, npw))

@@ -12,10 +12,13 @@
 #include <cuda_runtime.h>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
+#ifndef FULLMANT
+#define FULLMANT 0
+#endif
 __host__ __device__ inline double hashval(uint64_t i, uint64_t seed) {
   uint64_t x = i * 0x9E3779B97F4A7C15ULL + seed;
   x ^= x >> 31; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 29; x *= 0x94D049BB133111EBULL; x ^= x >> 32;
-  return (double)(int64_t)(x & 0xFFFFF) / 524288.0 - 1.0;      // [-1, 1)
+  return FULLMANT ? (double)(int64_t)(x >> 11) / 4503599627370496.0 - 1.0 : (double)(int64_t)(x & 0xFFFFF) / 524288.0 - 1.0;      // [-1, 1)
 }
 __global__ void k_fill(double* p, size_t n, uint64_t seed) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = hashval(i, seed);
