@@ -71,6 +71,7 @@ void abi_b200_fourwf_set_tuning(const char* name, int value) {
   const std::string k(name ? name : "");
   if (k == "plane") t.plane = value;
   else if (k == "plane_cfg") t.plane_cfg = value;
+  else if (k == "pack2") t.pack2 = value;
   else if (k == "plane_ctas_per_sm") t.plane_ctas_per_sm = value;
   else if (k == "cluster") t.cluster = value;
   else if (k == "lines_x") t.lines_x = value;

@@ -18,6 +18,7 @@
 #include "plane_stage.cuh"
 #include "context.cuh"
 #include <algorithm>
+#include <cstring>
 #include <map>
 #include <unordered_map>
 #include <memory>
@@ -42,6 +43,7 @@ FourwfTuning& fourwf_tuning() {
     if (const char* e = getenv("ABI_B200_FOURWF_PLANE")) t.plane = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_PLANE_CFG")) t.plane_cfg = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_PLANE_CTAS")) t.plane_ctas_per_sm = atoi(e);
+    if (const char* e = getenv("ABI_B200_FOURWF_PACK2")) t.pack2 = atoi(e);
   }
   return t;
 }
@@ -221,6 +223,7 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
   auto pl = std::make_unique<FourwfPlan>();
   pl->n1 = n1; pl->n2 = n2; pl->n3 = n3; pl->istwf_k = istwf_k; pl->me_g0 = me_g0;
   pl->npw_in = npw_in; pl->npw_out = npw_out; pl->key = key;
+  pl->same_sphere = (kg_out == kg_in) || (npw_in == npw_out && memcmp(kg_in, kg_out, sizeof(int) * 3 * (size_t)npw_in) == 0);
 
   // ---- input entries: direct plane waves then time-reversed images (m_fftcore.F90:1598-1650) ----
   struct Ent { int src; int i1, i2, i3; };
@@ -580,7 +583,7 @@ void fourwf_generic(const FourwfPlan& pl, int option, int cplex, double* d_denpo
 // K1: sphere lines -> zero-padded x FFT (e^{+i}) -> W1[b][i1][line]
 __global__ void __launch_bounds__(256)
 k_fw_x_forward(const double2* __restrict__ cg, double2* __restrict__ W1, Fft1d pl, const int2* __restrict__ ent,
-               const int* __restrict__ estart, int nlines, int lines_per_cta, int npw) {
+               const int* __restrict__ estart, int nlines, int lines_per_cta, int npw, int pack_ndat) {
   ABI_DYN_SMEM(double2, sm);
   const int n = pl.n, ls = n | 1;
   double2* tw = sm;
@@ -593,13 +596,30 @@ k_fw_x_forward(const double2* __restrict__ cg, double2* __restrict__ W1, Fft1d p
   for (int w = tid; w < nl * ls; w += nthr) buf[w] = make_double2(0.0, 0.0);
   __syncthreads();
   const int e0 = estart[l0], e1 = estart[l0 + nl];
-  const double2* cgb = cg + (size_t)b * npw;
-  for (int e = e0 + tid; e < e1; e += nthr) {
-    const int2 en = ent[e];
-    double2 v = cgb[en.x & 0x3fffffff];
-    if (en.x < 0) v.y = -v.y;
-    if (en.x & (1 << 30)) v.y = 0.0;
-    buf[((en.y >> 10) - l0) * ls + (en.y & 1023)] = v;
+  if (pack_ndat == 0) {
+    const double2* cgb = cg + (size_t)b * npw;
+    for (int e = e0 + tid; e < e1; e += nthr) {
+      const int2 en = ent[e];
+      double2 v = cgb[en.x & 0x3fffffff];
+      if (en.x < 0) v.y = -v.y;
+      if (en.x & (1 << 30)) v.y = 0.0;
+      buf[((en.y >> 10) - l0) * ls + (en.y & 1023)] = v;
+    }
+  } else {
+    // Gamma point, two real-in-r bands per complex transform (the reference's double_rfft_trick,
+    // src/66_wfs/m_getghc.F90:1999-2066): E(G) = C(G) + i D(G), E(-G) = conj(C(G)) + i conj(D(G))
+    const double2* c0 = cg + (size_t)(2 * b) * npw;
+    const bool has_d = 2 * b + 1 < pack_ndat;
+    const double2* c1 = c0 + npw;
+    for (int e = e0 + tid; e < e1; e += nthr) {
+      const int2 en = ent[e];
+      const int ipw = en.x & 0x3fffffff;
+      double2 c = c0[ipw];
+      double2 d = has_d ? c1[ipw] : make_double2(0.0, 0.0);
+      if (en.x < 0) { c.y = -c.y; d.y = -d.y; }
+      if (en.x & (1 << 30)) { c.y = 0.0; d.y = 0.0; }
+      buf[((en.y >> 10) - l0) * ls + (en.y & 1023)] = make_double2(c.x - d.y, c.y + d.x);
+    }
   }
   __syncthreads();
   fft_lines_dit<+1>(buf, ls, nl, pl, tw, tid, nthr);
@@ -608,6 +628,24 @@ k_fw_x_forward(const double2* __restrict__ cg, double2* __restrict__ W1, Fft1d p
     const int i1 = w / nl, l = w - i1 * nl;
     out[(size_t)i1 * nlines + l] = buf[l * ls + i1];
   }
+}
+
+// fused getghc assembly of one output coefficient (m_getghc.F90:1266-1280, type_calc=1 filter :1003-1031)
+ABI_DEV bool fw_epilogue(const FourwfEpilogue& epi, double kin_filter, int ipw, size_t o, double2& v) {
+  if (epi.mode == 1) {
+    const double k = epi.kinpw[ipw];
+    if (k < kin_filter) {
+      const double2 c = epi.cwavef[o];
+      v.x = v.x + k * c.x; v.y = v.y + k * c.y;
+      if (epi.gvnlxc) { const double2 g = epi.gvnlxc[o]; v.x += g.x; v.y += g.y; }
+    } else {
+      if (epi.gsc) epi.gsc[o] = make_double2(0.0, 0.0);
+      return false;
+    }
+  } else if (epi.mode == 2) {
+    if (epi.kinpw[ipw] > kin_filter) return false;
+  }
+  return true;
 }
 
 // K3: W1out[b][i1][line] -> x FFT (e^{-i}) -> gather to the sphere * xnorm (+ fused getghc assembly)
@@ -639,20 +677,66 @@ k_fw_x_backward(const double2* __restrict__ W1o, double2* __restrict__ outg, Fft
     v.x *= xnorm; v.y *= xnorm;
     if (zero_im_g0 && ipw == 0) v.y = 0.0;
     const size_t o = (size_t)b * npw + ipw;
-    if (epi.mode == 1) {
-      const double k = epi.kinpw[ipw];
-      if (k < kin_filter) {
-        const double2 c = epi.cwavef[o];
-        v.x = v.x + k * c.x; v.y = v.y + k * c.y;
-        if (epi.gvnlxc) { const double2 g = epi.gvnlxc[o]; v.x += g.x; v.y += g.y; }
-      } else {
-        v = make_double2(0.0, 0.0);
-        if (epi.gsc) epi.gsc[o] = make_double2(0.0, 0.0);
-      }
-    } else if (epi.mode == 2) {
-      if (epi.kinpw[ipw] > kin_filter) v = make_double2(0.0, 0.0);
-    }
+    if (!fw_epilogue(epi, kin_filter, ipw, o, v)) v = make_double2(0.0, 0.0);
     outg[o] = v;
+  }
+}
+
+// K3 for the packed Gamma-point transform: F = H C + i H D on the full sphere;
+//   H C(G) = [F(G) + conj(F(-G))]/2,  H D(G) = [F(G) - conj(F(-G))]/(2i)   (cwavef_double_rfft_trick_unpack,
+// src/66_wfs/m_getghc.F90:2097-2171).  G and -G sit on different lines (different CTAs), so each of the two
+// contributions is added with one red.global per component onto a zero-initialised output: two addends commute
+// exactly, the result is deterministic.  The getghc assembly rides on the direct (G) contribution.
+__global__ void __launch_bounds__(256)
+k_fw_x_backward_packed(const double2* __restrict__ W1o, double2* __restrict__ outg, Fft1d pl, const int2* __restrict__ ent,
+                       const int* __restrict__ estart, int nlines, int lines_per_cta, int npw, int ndat, double xnorm,
+                       FourwfEpilogue epi, double kin_filter) {
+  ABI_DYN_SMEM(double2, sm);
+  const int n = pl.n, ls = n | 1;
+  double2* tw = sm;
+  double2* buf = sm + n;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int b = blockIdx.y;
+  const int l0 = blockIdx.x * lines_per_cta;
+  const int nl = min(lines_per_cta, nlines - l0);
+  for (int j = tid; j < n; j += nthr) tw[j] = pl.tw[j];
+  const double2* in = W1o + (size_t)b * n * nlines + l0;
+  for (int w = tid; w < nl * n; w += nthr) {
+    const int i1 = w / nl, l = w - i1 * nl;
+    buf[l * ls + i1] = in[(size_t)i1 * nlines + l];
+  }
+  __syncthreads();
+  fft_lines_dif<-1>(buf, ls, nl, pl, tw, tid, nthr);
+  const int e0 = estart[l0], e1 = estart[l0 + nl];
+  const bool has_d = 2 * b + 1 < ndat;
+  const double h = 0.5 * xnorm;
+  for (int e = e0 + tid; e < e1; e += nthr) {
+    const int2 en = ent[e];
+    const int ipw = en.x & 0x3fffffff;
+    const double2 f = buf[((en.y >> 10) - l0) * ls + (en.y & 1023)];
+    const size_t oc = (size_t)(2 * b) * npw + ipw, od = oc + npw;
+    double2 vc, vd;
+    if (en.x & (1 << 30)) {               // G = 0: H C(0) = Re F(0), H D(0) = Im F(0), both real; no image entry
+      vc = make_double2(f.x * xnorm, 0.0); vd = make_double2(f.y * xnorm, 0.0);
+    } else if (en.x >= 0) {               // direct entry: + F/2 and -i F/2
+      vc = make_double2(f.x * h, f.y * h); vd = make_double2(f.y * h, -f.x * h);
+    } else {                              // image entry holds F(-G): + conj(F)/2 and + i conj(F)/2
+      vc = make_double2(f.x * h, -f.y * h); vd = make_double2(f.y * h, f.x * h);
+    }
+    if (en.x >= 0) {                      // assembly terms once per coefficient
+      if (!fw_epilogue(epi, kin_filter, ipw, oc, vc)) vc = make_double2(0.0, 0.0);
+      if (has_d && !fw_epilogue(epi, kin_filter, ipw, od, vd)) vd = make_double2(0.0, 0.0);
+    } else if (epi.mode != 0) {
+      const double k = epi.kinpw[ipw];
+      if ((epi.mode == 1 && !(k < kin_filter)) || (epi.mode == 2 && k > kin_filter)) { vc = make_double2(0.0, 0.0); vd = vc; }
+    }
+#ifndef ABI_EMU
+    atomicAdd(&outg[oc].x, vc.x); atomicAdd(&outg[oc].y, vc.y);
+    if (has_d) { atomicAdd(&outg[od].x, vd.x); atomicAdd(&outg[od].y, vd.y); }
+#else
+    outg[oc].x += vc.x; outg[oc].y += vc.y;
+    if (has_d) { outg[od].x += vd.x; outg[od].y += vd.y; }
+#endif
   }
 }
 
@@ -810,13 +894,19 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
   const int ctas_per_sm = std::max<int>(1, std::min<int>(2, (int)(kMaxSmemPerCta / smem_mid)));
   int nclusters = std::max(1, (kNumSM * ctas_per_sm) / cs);
 
+  // Gamma point: two bands per complex transform (needs a real potential and identical in/out spheres)
+  const bool pack2 = tune.pack2 && pl.istwf_k == 2 && v.cplex == 1 && pl.same_sphere && ndat >= 2 && pl.plane_ok && tune.plane;
+  const int nlout_eff = pack2 ? pl.nlin : pl.nlout;       // packed: the output lines are the (completed) input lines
+  const int ntrans = pack2 ? (ndat + 1) / 2 : ndat;       // transforms to run
+
   // ---- band chunking bounds the workspace (W1, W1', scratch) ----
-  const size_t per_band = sizeof(double2) * (size_t)n1 * ((size_t)pl.nlin + pl.nlout);
+  const size_t per_band = sizeof(double2) * (size_t)n1 * ((size_t)pl.nlin + nlout_eff);
   int chunk = tune.band_chunk > 0 ? tune.band_chunk : (int)std::max<size_t>(1, ((size_t)3 << 30) / per_band);
-  chunk = std::min(chunk, ndat);
+  chunk = std::min(chunk, ntrans);
   double2* W1 = (double2*)g_ws[1].get(sizeof(double2) * (size_t)n1 * pl.nlin * chunk);
-  double2* W1o = (double2*)g_ws[2].get(sizeof(double2) * (size_t)n1 * pl.nlout * chunk);
-  double2* scratch = (double2*)g_ws[3].get(sizeof(double2) * (size_t)nclusters * 2 * pl.nU * n2);
+  double2* W1o = (double2*)g_ws[2].get(sizeof(double2) * (size_t)n1 * nlout_eff * chunk);
+  double2* scratch = (pl.plane_ok && tune.plane) ? nullptr
+                                                 : (double2*)g_ws[3].get(sizeof(double2) * (size_t)nclusters * 2 * pl.nU * n2);
 
   int lx = std::max(1, tune.lines_x);
   while (lx > 1 && sizeof(double2) * ((size_t)n1 + (size_t)lx * (n1 | 1)) > 110 * 1024) lx--;
@@ -824,6 +914,7 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
 #ifndef ABI_EMU
   CUDA_CHECK(cudaFuncSetAttribute(k_fw_x_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
   CUDA_CHECK(cudaFuncSetAttribute(k_fw_x_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+  CUDA_CHECK(cudaFuncSetAttribute(k_fw_x_backward_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
   CUDA_CHECK(cudaFuncSetAttribute(k_fw_mid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
   CUDA_CHECK(cudaFuncSetAttribute(k_fw_mid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
 #endif
@@ -831,11 +922,15 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
   const int zero_im = (pl.istwf_k == 2 && pl.me_g0 == 1) ? 1 : 0;
   const double kin_filter = 1.7976931348623157e308 * 1.0e-11;   // huge(0d0)*1d-11, m_getghc.F90:1272
 
-  for (int b0 = 0; b0 < ndat; b0 += chunk) {
-    const int nb = std::min(chunk, ndat - b0);
+  if (pack2) CUDA_CHECK(cudaMemsetAsync(d_fofgout, 0, sizeof(double2) * (size_t)pl.npw_out * ndat, st));
+  for (int t0 = 0; t0 < ntrans; t0 += chunk) {
+    const int nb = std::min(chunk, ntrans - t0);            // transforms in this chunk
+    const int b0 = pack2 ? 2 * t0 : t0;                     // first band of the chunk
+    const int nbands = std::min(ndat - b0, pack2 ? 2 * nb : nb);
     { ProfScope ps("fourwf_x_forward");
     ABI_LAUNCH(k_fw_x_forward, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st,
-               d_fofgin + (size_t)b0 * pl.npw_in, W1, t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_in); }
+               d_fofgin + (size_t)b0 * pl.npw_in, W1, t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_in,
+               pack2 ? nbands : 0); }
     MidParams P;
     P.n1 = n1; P.n2 = n2; P.n3 = n3; P.nb = nb; P.nlin = pl.nlin; P.nlout = pl.nlout; P.nU = pl.nU;
     P.cplex = v.cplex; P.lb = lb; P.csize = cs; P.nclusters = nclusters;
@@ -848,10 +943,10 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
       ProfScope ps("fourwf_plane_stage");
       PlaneParams Q;
       Q.n1 = n1; Q.n2 = n2; Q.n3 = n3; Q.nb = nb; Q.nU = pl.nU; Q.cplex = v.cplex; Q.za = pl.za; Q.zla = pl.zla; Q.zb = pl.zb; Q.zlb = pl.zlb;
-      Q.nlin = pl.nlin; Q.nlout = pl.nlout; Q.nunits = (long long)nb * n1;
+      Q.nlin = pl.nlin; Q.nlout = nlout_eff; Q.nunits = (long long)nb * n1;
       Q.W1 = W1; Q.W1o = W1o; Q.S = nullptr; Q.vT = v.d_vT; Q.tw = t2.plan.tw;
       Q.in_start = pl.d_pin_start; Q.in_runs = pl.d_pin_runs;
-      Q.out_start = pl.d_pout_start; Q.out_runs = pl.d_pout_runs;
+      Q.out_start = pack2 ? pl.d_pin_start : pl.d_pout_start; Q.out_runs = pack2 ? pl.d_pin_runs : pl.d_pout_runs;
       plane_stage_launch(n2, Q, st);
     } else
     { ProfScope ps("fourwf_plane_cluster");
@@ -876,9 +971,15 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
     if (e.gvnlxc) e.gvnlxc += (size_t)b0 * pl.npw_out;
     if (e.gsc) e.gsc += (size_t)b0 * pl.npw_out;
     { ProfScope ps("fourwf_x_backward");
-    ABI_LAUNCH(k_fw_x_backward, dim3(ceil_div(pl.nlout, lx), nb), dim3(256), smem_x, st, W1o,
-               d_fofgout + (size_t)b0 * pl.npw_out, t1.plan, pl.d_out_ent, pl.d_lout_estart, pl.nlout, lx, pl.npw_out,
-               xnorm, zero_im, e, kin_filter); }
+    if (pack2) {
+      ABI_LAUNCH(k_fw_x_backward_packed, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st, W1o,
+                 d_fofgout + (size_t)b0 * pl.npw_out, t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_out, nbands,
+                 xnorm, e, kin_filter);
+    } else {
+      ABI_LAUNCH(k_fw_x_backward, dim3(ceil_div(pl.nlout, lx), nb), dim3(256), smem_x, st, W1o,
+                 d_fofgout + (size_t)b0 * pl.npw_out, t1.plan, pl.d_out_ent, pl.d_lout_estart, pl.nlout, lx, pl.npw_out,
+                 xnorm, zero_im, e, kin_filter);
+    } }
     g_kernel_launches += 3;
   }
 }

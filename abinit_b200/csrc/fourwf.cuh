@@ -30,6 +30,7 @@ struct FourwfEpilogue {
 struct FourwfPlan {
   int n1 = 0, n2 = 0, n3 = 0, istwf_k = 1, me_g0 = 1;
   int npw_in = 0, npw_out = 0;
+  bool same_sphere = false;      // kg_kin == kg_kout (lets the Gamma-point path pack two bands per transform)
   uint64_t key = 0;
   // ---- generic path (options 0,1,3 and fallback shapes) ----
   int nent_in = 0;
@@ -90,6 +91,7 @@ struct FourwfTuning {
   int plane = 1;               // 1: register-resident two-pass plane stage (plane_stage.cuh) when the box allows it
   int plane_cfg = 0;           // 0 auto, 1: (G=8, 4 warps), 2: (G=4, 8 warps)
   int plane_ctas_per_sm = 0;   // 0: occupancy / L2-budget limited
+  int pack2 = 1;               // istwf_k=2: two bands per complex transform (double_rfft_trick, m_getghc.F90:1999-2171)
 };
 FourwfTuning& fourwf_tuning();
 

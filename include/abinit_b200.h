@@ -71,7 +71,8 @@ void abi_b200_set_me_g0(int me_g0);           /* mpi_enreg%me_g0_fft (src/53_fft
 /* force the generic (full-box) or the fused implementation of option 2: 0 auto, 1 generic, 2 fused */
 void abi_b200_fourwf_set_impl(int impl);
 /* tuning knobs of the fused path (no reference counterpart; also read from ABI_B200_FOURWF_* at first use):
- * "plane" 0/1, "plane_cfg" 0 auto / 1 (8 columns x 4 warps) / 2 (4 columns x 8 warps), "plane_ctas_per_sm",
+ * "plane" 0/1, "plane_cfg" 0 auto / 1 (8 columns x 4 warps) / 2 (4 columns x 8 warps) / 3 (4 x 16), "plane_ctas_per_sm",
+ * "pack2" 0/1 (istwf_k=2: two bands per complex transform),
  * "cluster", "lines_x", "smem_kb_mid", "band_chunk".  Unknown names abort. */
 void abi_b200_fourwf_set_tuning(const char* name, int value);
 /* fourwf_counter of src/53_ffts/m_fft.F90:2333-2336 */

@@ -63,6 +63,35 @@ def test_paw_sij_opt(lib, sij_opt, istwf_k, kpt):
     h.destroy()
 
 
+@pytest.mark.parametrize("ndat", [2, 5])
+@pytest.mark.parametrize("usepaw", [0, 1])
+def test_gamma_two_bands_per_transform(lib, ndat, usepaw):
+    """istwf_k=2 on a plane-stage box: two bands ride one complex transform (double_rfft_trick,
+    m_getghc.F90:1999-2171); even and odd band counts, every type_calc, PAW gsc zeroing, and the unpacked path."""
+    from abinit_b200 import api
+    p = make_problem(7.0, 9.0, (0, 0, 0), 2, ndat=ndat, ngfft=(36, 40, 40), natom_per_type=(2, 1), lmax_per_type=(1, 2),
+                     usepaw=usepaw)
+    h = _ham(p)
+    for pack in (1, 0):
+        api.set_tuning("pack2", pack)
+        try:
+            for type_calc in (0, 1, 3):
+                ghc = np.zeros((p.ndat, p.npw), dtype=np.complex128); gsc = np.zeros_like(ghc)
+                sij_opt = 1 if (usepaw and type_calc == 0) else 0
+                ab.getghc(-1, p.cwavef, None, ghc, gsc if sij_opt else None, h, None, None, None, p.ndat, sij_opt=sij_opt,
+                          type_calc=type_calc)
+                r_ghc, r_gsc, _, _ = _oracle(p, type_calc=type_calc, sij_opt=sij_opt)
+                assert rel_err_per_band(ghc, r_ghc) < TOL
+                assert np.all(ghc[:, 0].imag == 0.0)                       # Im c(G=0) = 0 (m_ompgpu_fourwf.F90:536-543)
+                if type_calc != 1:
+                    assert np.all(ghc[:, p.kinpw >= g.KIN_FILTER] == 0.0)
+                if sij_opt:
+                    assert rel_err_per_band(gsc, r_gsc) < TOL
+        finally:
+            api.set_tuning("pack2", 1)
+    h.destroy()
+
+
 def test_gvnlxc_absent_and_generic_fourwf(lib):
     """gvnlxc of size<=1 -> internal temporary (m_getghc.F90:320-331); forcing the generic fourwf gives the same."""
     p = make_problem(7.0, 8.5, (.1, .2, .3), 1, ndat=3)

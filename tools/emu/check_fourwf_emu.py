@@ -42,7 +42,9 @@ if __name__ == "__main__":
         run(4.0, 9., (0, .5, .5), 8, 1, 1, 2, impl, ng=(28, 35, 21))
     # plane-stage cases (n2 == n3 in the two-pass list), incl. non-cubic n1, Gamma, k=1/2 cases, complex V
     run(5.0, 8., (.1, .2, .3), 1, 2, 1, 2, 2, ng=(24, 24, 24))
-    run(5.0, 8., (0, 0, 0), 2, 3, 1, 2, 2, ng=(27, 30, 30))
+    run(5.0, 8., (0, 0, 0), 2, 3, 1, 2, 2, ng=(27, 30, 30))      # packed Gamma path, odd ndat
+    run(5.0, 8., (0, 0, 0), 2, 4, 1, 2, 2, ng=(24, 24, 24))
+    run(5.0, 8., (0, 0, 0), 2, 1, 1, 2, 2, ng=(24, 24, 24))
     run(5.0, 8., (.5, .5, .5), 9, 2, 1, 2, 2, ng=(32, 36, 36))
     run(5.0, 8., (.1, 0, .3), 1, 2, 2, 2, 2, ng=(25, 40, 40))
     run(7.0, 9., (0, .5, 0), 6, 1, 1, 2, 2, ng=(45, 45, 45))
