@@ -42,6 +42,7 @@ void abi_b200_finalize(void) {
   if (g_vloc_call.d_v) { cudaFree(g_vloc_call.d_v); cudaFree(g_vloc_call.d_vT); g_vloc_call = VlocDev(); }
 #ifndef ABI_EMU
   if (c.own_stream) { cudaStreamDestroy(c.stream); c.stream = 0; c.own_stream = false; }
+  if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); c.copy_stream = 0; }
 #endif
   c.initialized = false;
 }
@@ -72,6 +73,7 @@ void abi_b200_fourwf_set_tuning(const char* name, int value) {
   if (k == "plane") t.plane = value;
   else if (k == "plane_cfg") t.plane_cfg = value;
   else if (k == "pack2") t.pack2 = value;
+  else if (k == "pipeline") ctx().pipeline = value != 0;
   else if (k == "plane_ctas_per_sm") t.plane_ctas_per_sm = value;
   else if (k == "cluster") t.cluster = value;
   else if (k == "lines_x") t.lines_x = value;

@@ -67,10 +67,14 @@ __global__ void k_assemble(double2* __restrict__ ghc, double2* __restrict__ gsc,
     ghc[i] = v;
   }
 }
-__global__ void k_filter_only(double2* __restrict__ ghc, const double* __restrict__ kinpw, int npw, int ndat, double kin_filter) {
+// strict: type_calc=1 filter "kinpw > huge*1e-11" (m_getghc.F90:1003-1031); otherwise "not (kinpw < huge*1e-11)" (:1272-1277)
+__global__ void k_filter_only(double2* __restrict__ ghc, const double* __restrict__ kinpw, int npw, int ndat, double kin_filter,
+                              bool strict) {
   const long long total = (long long)npw * ndat;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-    if (kinpw[i % npw] > kin_filter) ghc[i] = make_double2(0.0, 0.0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const double k = kinpw[i % npw];
+    if (strict ? (k > kin_filter) : !(k < kin_filter)) ghc[i] = make_double2(0.0, 0.0);
+  }
 }
 #endif
 }  // namespace abi
@@ -242,6 +246,31 @@ void abi_b200_ham_set_projectors(abi_b200_ham_t* h, const double* projs, int npr
 
 int abi_b200_ham_nprojs(const abi_b200_ham_t* h) { return h->atoms.nprojs; }
 
+namespace {
+// host <-> device pipeline of one getghc call with HOST wavefunction arrays: band chunks of cwavef arrive on the copy
+// stream while fourwf runs on earlier chunks; finished row slabs of ghc leave while the last GEMM computes the next.
+struct GhcPipe {
+  Context* c; cudaEvent_t ev[2]; int flip = 0;
+  double* h_ghc; double* d_ghc; int npw, nd;
+};
+cudaEvent_t pipe_event(int i) {
+  static cudaEvent_t ev[8]; static bool init = false;
+  if (!init) { for (auto& e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); init = true; }
+  return ev[i & 7];
+}
+int g_pipe_ev = 0;
+void ship_slab(void* user, int ipw_begin, int ipw_end) {
+  GhcPipe* gp = static_cast<GhcPipe*>(user);
+  cudaEvent_t e = pipe_event(g_pipe_ev++);
+  CUDA_CHECK(cudaEventRecord(e, gp->c->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(gp->c->copy_stream, e, 0));
+  const size_t pitch = sizeof(double) * 2 * (size_t)gp->npw;
+  CUDA_CHECK(cudaMemcpy2DAsync(gp->h_ghc + 2 * (size_t)ipw_begin, pitch, gp->d_ghc + 2 * (size_t)ipw_begin, pitch,
+                               sizeof(double) * 2 * (size_t)(ipw_end - ipw_begin), gp->nd, cudaMemcpyDeviceToHost,
+                               gp->c->copy_stream));
+}
+}  // namespace
+
 void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc, double* gsc, abi_b200_ham_t** gs_ham,
                       double* gvnlxc, double* lambda, int* ndat, int* prtvol, int* sij_opt, int* tim_getghc, int* type_calc) {
   (void)prtvol; (void)tim_getghc;
@@ -256,65 +285,105 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
   if (local) ABI_CHECK(h->vloc.d_v != nullptr, "We need vlocal in gs_ham!");             // m_getghc.F90:404
   const size_t nv = sizeof(double) * 2 * (size_t)npw * nd;
   const int cplex = (h->istwf_k == 1) ? 2 : 1;
-  DevArg a_c(0, cwavef, nv, true);
+  const bool fused_fw = local && h->plan->fused_ok && c.fourwf_impl != 1;
+  // pipelined staging needs the fused fourwf (band-chunked) and host input + output arrays
+  const bool pipe = fused_fw && nd >= 8 && cwavef && ghc && !is_device_ptr(cwavef) && !is_device_ptr(ghc) && c.pipeline;
+  DevArg a_c(0, cwavef, nv, !pipe);
   DevArg a_ghc(1, ghc, nv, tc == 2);
   DevArg a_gsc(2, (*sij_opt == 1) ? gsc : nullptr, nv, false);
   DevArg a_gv(3, gvnlxc, nv, false);
   const int cpopt_here = (h->usepaw == 1) ? *cpopt : -1;                                 // m_getghc.F90:1046
   DevArg a_prj(4, (cpopt_here >= 0) ? cwaveprj : nullptr, sizeof(double) * (size_t)cplex * h->atoms.nprojs * nd, cpopt_here >= 2);
   DevArg a_lam(5, lambda, sizeof(double) * nd, true);
-  double* d_gv = a_gv.as<double>();
-  if (nonlocal && d_gv == nullptr) {
-    if (h->gvnlxc_cap < nv) { if (h->d_gvnlxc) cudaFree(h->d_gvnlxc); CUDA_CHECK(cudaMalloc(&h->d_gvnlxc, nv)); h->gvnlxc_cap = nv; }
-    d_gv = h->d_gvnlxc;
-  }
   const double kin_filter = 1.7976931348623157e308 * 1.0e-11;
-#ifndef ABI_EMU
-  if (nonlocal) {
+  int paw_opt = h->usepaw; if (*sij_opt != 0) paw_opt = *sij_opt + 3;                    // m_getghc.F90:1067
+  if (nonlocal)
     ABI_CHECK(h->P.d_p != nullptr || h->atoms.nprojs == 0, "getghc: projectors not loaded (load_k with ffnl/ph3d or set_projectors)");
-    int paw_opt = h->usepaw; if (*sij_opt != 0) paw_opt = *sij_opt + 3;                  // m_getghc.F90:1067
-    c.nonlop_counter += nd;
-    gemm_nonlop_device(h->P, h->atoms, h->enl, 1, cpopt_here, paw_opt, h->me_g0, a_lam.as<double>(), nd, a_c.as<double>(), d_gv,
-                       a_gsc.as<double>(), a_prj.as<double>(), c.stream);
-  } else if (tc == 3 && a_gv.dev) {
-    CUDA_CHECK(cudaMemsetAsync(a_gv.dev, 0, nv, c.stream));                              // m_getghc.F90:1148-1154
-  }
-#endif
+  bool ghc_shipped = false;
+
   if (local) {
+    // ---- local part first: ghc = V_loc psi + T psi (filtered); the non-local term is added by the last GEMM's epilogue
     c.fourwf_counter += 2 * nd;
     FourwfEpilogue epi;
     if (tc == 1) { epi.mode = 2; epi.kinpw = h->d_kinpw; }
-    else { epi.mode = 1; epi.kinpw = h->d_kinpw; epi.cwavef = a_c.as<double2>(); epi.gvnlxc = nonlocal ? (const double2*)d_gv : nullptr;
-           epi.gsc = a_gsc.as<double2>(); }
-    if (h->plan->fused_ok && c.fourwf_impl != 1) {
-      fourwf_fused_opt2(*h->plan, h->vloc, a_c.as<double2>(), a_ghc.as<double2>(), nd, epi, c.stream);
+    else { epi.mode = 1; epi.kinpw = h->d_kinpw; epi.cwavef = a_c.as<double2>(); epi.gvnlxc = nullptr; epi.gsc = nullptr; }
+    if (fused_fw) {
+      if (!pipe) {
+        fourwf_fused_opt2(*h->plan, h->vloc, a_c.as<double2>(), a_ghc.as<double2>(), nd, epi, c.stream);
+      } else {
+        // band chunks (even sizes keep the Gamma-point pairs together): H2D on the copy stream, fourwf behind an event
+        const int nchunk = std::min(4, nd / 4);
+        const int chunk = ceil_div(ceil_div(nd, nchunk), 2) * 2;
+        for (int b0 = 0; b0 < nd; b0 += chunk) {
+          const int nb = std::min(chunk, nd - b0);
+          const size_t off = 2 * (size_t)npw * b0;
+          CUDA_CHECK(cudaMemcpyAsync(a_c.as<double>() + off, cwavef + off, sizeof(double) * 2 * (size_t)npw * nb,
+                                     cudaMemcpyHostToDevice, c.copy_stream));
+          cudaEvent_t e = pipe_event(g_pipe_ev++);
+          CUDA_CHECK(cudaEventRecord(e, c.copy_stream));
+          CUDA_CHECK(cudaStreamWaitEvent(c.stream, e, 0));
+          FourwfEpilogue ec = epi;
+          if (ec.cwavef) ec.cwavef += (size_t)npw * b0;
+          fourwf_fused_opt2(*h->plan, h->vloc, a_c.as<double2>() + (size_t)npw * b0, a_ghc.as<double2>() + (size_t)npw * b0, nb,
+                            ec, c.stream);
+        }
+      }
     } else {
 #ifndef ABI_EMU
       fourwf_generic(*h->plan, 2, h->vloc.cplex, h->vloc.d_v, a_c.as<double2>(), a_ghc.as<double2>(), nullptr, nd, nullptr, nullptr, c.stream);
       const int blocks = std::min(kNumSM * 8, (int)ceil_div<long long>((long long)npw * nd, 256));
-      if (tc == 1) k_filter_only<<<blocks, 256, 0, c.stream>>>(a_ghc.as<double2>(), h->d_kinpw, npw, nd, kin_filter);
-      else k_assemble<<<blocks, 256, 0, c.stream>>>(a_ghc.as<double2>(), a_gsc.as<double2>(), h->d_kinpw, a_c.as<double2>(),
-                                                    nonlocal ? (const double2*)d_gv : nullptr, npw, nd, kin_filter);
+      if (tc == 1) k_filter_only<<<blocks, 256, 0, c.stream>>>(a_ghc.as<double2>(), h->d_kinpw, npw, nd, kin_filter, true);
+      else k_assemble<<<blocks, 256, 0, c.stream>>>(a_ghc.as<double2>(), nullptr, h->d_kinpw, a_c.as<double2>(), nullptr, npw, nd,
+                                                    kin_filter);
       CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
 #endif
     }
-  } else {
-#ifndef ABI_EMU
-    // type_calc == 2: non-local + kinetic added to the existing ghc (m_getghc.F90:152)
-    const int blocks = std::min(kNumSM * 8, (int)ceil_div<long long>((long long)npw * nd, 256));
-    k_assemble<<<blocks, 256, 0, c.stream>>>(a_ghc.as<double2>(), a_gsc.as<double2>(), h->d_kinpw, a_c.as<double2>(),
-                                             (const double2*)d_gv, npw, nd, kin_filter);
-    CUDA_CHECK(cudaGetLastError());
-    g_kernel_launches++;
-#endif
   }
-  a_ghc.copy_back();
+#ifndef ABI_EMU
+  if (nonlocal) {
+    c.nonlop_counter += nd;
+    if (tc == 0) {
+      NonlopFusion fuse;
+      fuse.ghc = a_ghc.as<double>(); fuse.kinpw = h->d_kinpw; fuse.kin_filter = kin_filter;
+      GhcPipe gp{&c, {}, 0, ghc, a_ghc.as<double>(), npw, nd};
+      if (pipe) { fuse.nslabs = 4; fuse.after_slab = ship_slab; fuse.user = &gp; ghc_shipped = true; }
+      gemm_nonlop_device(h->P, h->atoms, h->enl, 1, cpopt_here, paw_opt, h->me_g0, a_lam.as<double>(), nd, a_c.as<double>(),
+                         a_gv.as<double>(), a_gsc.as<double>(), a_prj.as<double>(), c.stream, &fuse);
+      if (h->atoms.nprojs == 0 || nd == 0) ghc_shipped = false;          // nothing was launched: plain copy below
+    } else {
+      // type_calc == 2: non-local + kinetic added to the caller's ghc (m_getghc.F90:152)
+      double* d_gv = a_gv.as<double>();
+      if (d_gv == nullptr) {
+        if (h->gvnlxc_cap < nv) { if (h->d_gvnlxc) cudaFree(h->d_gvnlxc); CUDA_CHECK(cudaMalloc(&h->d_gvnlxc, nv)); h->gvnlxc_cap = nv; }
+        d_gv = h->d_gvnlxc;
+      }
+      gemm_nonlop_device(h->P, h->atoms, h->enl, 1, cpopt_here, paw_opt, h->me_g0, a_lam.as<double>(), nd, a_c.as<double>(), d_gv,
+                         a_gsc.as<double>(), a_prj.as<double>(), c.stream);
+      const int blocks = std::min(kNumSM * 8, (int)ceil_div<long long>((long long)npw * nd, 256));
+      k_assemble<<<blocks, 256, 0, c.stream>>>(a_ghc.as<double2>(), nullptr, h->d_kinpw, a_c.as<double2>(), (const double2*)d_gv,
+                                               npw, nd, kin_filter);
+      CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    }
+    if (*sij_opt == 1 && a_gsc.dev) {                                    // gsc = 0 where the kinetic filter strikes
+      const int blocks = std::min(kNumSM * 8, (int)ceil_div<long long>((long long)npw * nd, 256));
+      k_filter_only<<<blocks, 256, 0, c.stream>>>(a_gsc.as<double2>(), h->d_kinpw, npw, nd, kin_filter, false);
+      CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    }
+  } else if (tc == 3 && a_gv.dev) {
+    CUDA_CHECK(cudaMemsetAsync(a_gv.dev, 0, nv, c.stream));                              // m_getghc.F90:1148-1154
+  }
+#endif
+  if (!ghc_shipped) a_ghc.copy_back();
   if (*sij_opt == 1) a_gsc.copy_back();
   if (tc != 1) a_gv.copy_back();
   if (cpopt_here >= 0 && cpopt_here < 2) a_prj.copy_back();
-  if (!c.async || a_c.staged || a_ghc.staged || a_gsc.staged || a_gv.staged || a_prj.staged)
+  if (!c.async || pipe || a_c.staged || a_ghc.staged || a_gsc.staged || a_gv.staged || a_prj.staged) {
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    if (pipe) CUDA_CHECK(cudaStreamSynchronize(c.copy_stream));
+  }
 }
 
 void abi_b200_xg_gram_(int* space, int* rows, int* ncols_a, int* ncols_b, double* a, int* lda, double* b, int* ldb, double* cmat,

@@ -27,6 +27,8 @@ void ensure_init() {
     ABI_ERROR("no CUDA device visible: abinit_b200 has no CPU fallback (north-star: sm_100a only)");
   CUDA_CHECK(cudaGetDevice(&c.device));
   if (!c.stream) { CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)); c.own_stream = true; }
+  if (!c.copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  if (const char* e = getenv("ABI_B200_PIPELINE")) c.pipeline = atoi(e) != 0;
 #endif
   c.initialized = true;
 }

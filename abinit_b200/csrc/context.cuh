@@ -15,6 +15,8 @@ struct Context {
   bool initialized = false;
   int device = 0;
   cudaStream_t stream = 0;
+  cudaStream_t copy_stream = 0;   // host<->device staging pipeline of getghc (H2D / D2H overlapped with compute)
+  bool pipeline = true;
   bool own_stream = false;
   bool async = false;
   int me_g0 = 1;

@@ -74,6 +74,8 @@ struct GemmParams {
   const double* B; long long ldb;   // K-contiguous columns
   double* C; long long ldc;    // NN: output ; TN: partial buffer [nsplit][N][M]
   const double* add;           // NN only: optional, same layout as C
+  double* C2;                  // NN only: optional copy of the bare product (gvnlxc when the sum goes to ghc)
+  const double* kin; double kin_filter;   // NN only: optional getghc filter, C = 0 where kin[m/2] >= kin_filter
   int nsplit, kchunk, tiles_m, tiles_n;
 };
 
@@ -271,7 +273,9 @@ __global__ void __launch_bounds__(Cfg::WARPS_M * Cfg::WARPS_N * 32, Cfg::MINB) k
           if (n + h < p.N) {
             const size_t o = (size_t)(n + h) * p.ldc + m;
             double v = acc[i][j][h];
+            if (p.C2) p.C2[o] = v;
             if (p.add) v += p.add[o];
+            if (p.kin && !(p.kin[m >> 1] < p.kin_filter)) v = 0.0;     // m_getghc.F90:1272-1277
             p.C[o] = v;
           }
         }
@@ -535,10 +539,12 @@ static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long lo
 }
 
 static void launch_nn(bool cplx, int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
-                      long long ldc, const double* add, cudaStream_t st) {
+                      long long ldc, const double* add, cudaStream_t st, double* C2 = nullptr, const double* kin = nullptr,
+                      double kin_filter = 0.0) {
   const int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128), BM = 64 * 128 / BN;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.add = add;
+  p.C2 = C2; p.kin = kin; p.kin_filter = kin_filter;
   p.tiles_m = ceil_div(M, BM); p.tiles_n = ceil_div(N, BN);
   p.nsplit = 1; p.kchunk = 0;
   ProfScope ps("dgemm_nn_opernlb");
@@ -569,7 +575,7 @@ void dgemm_tn(int M, int N, int K, const double* A, long long lda, const double*
 
 void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const NonlopEnl& enl, int choice, int cpopt, int paw_opt,
                         int me_g0, const double* d_lambda, int ndat, const double* vectin, double* vectout, double* svectout,
-                        double* projections, cudaStream_t st) {
+                        double* projections, cudaStream_t st, const NonlopFusion* fuse) {
   ABI_CHECK(choice == 0 || choice == 1 || choice == 7, "gemm_nonlop: only choice 0, 1, 7 (signs=2) are on the getghc path");
   ABI_CHECK(paw_opt >= 0 && paw_opt <= 4, "gemm_nonlop: bad paw_opt");
   ABI_CHECK(P.nprojs == at.nprojs, "gemm_nonlop: projectors were prepared for a different atom table");
@@ -640,14 +646,33 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
     launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zs, ldg, svectout, ldv, vectin, st);   // + vectin, m_opernlb_gemm.F90:654-665
   }
   if (choice == 1 && (paw_opt == 0 || paw_opt == 1 || paw_opt == 2 || paw_opt == 4)) {
-    ABI_CHECK(vectout != nullptr, "gemm_nonlop: vectout required");
-    launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zfac, ldg, vectout, ldv, nullptr, st);
+    if (fuse == nullptr) {
+      ABI_CHECK(vectout != nullptr, "gemm_nonlop: vectout required");
+      launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zfac, ldg, vectout, ldv, nullptr, st);
+    } else {
+      // getghc fusion: ghc += P.gxfac with the kinetic filter in the GEMM epilogue, in row slabs (each complete for
+      // every band, so the caller can ship it to the host while the next slab is computed)
+      ABI_CHECK(fuse->ghc != nullptr && fuse->kinpw != nullptr, "gemm_nonlop: fusion needs ghc and kinpw");
+      const int M = 2 * npw;
+      // slabs are whole waves of CTA tiles (2 CTAs/SM x 148 SMs x BM rows) so that cutting the GEMM adds no tail
+      const int BN = ndat <= 32 ? 32 : (ndat <= 64 ? 64 : 128), BM = 64 * 128 / BN;
+      const long long wave_rows = 2LL * kNumSM * BM;
+      const int waves = (int)ceil_div<long long>(M, wave_rows);
+      const int nslabs = std::max(1, std::min(fuse->nslabs, waves));
+      const int slab = (int)std::min<long long>(M, (long long)ceil_div(waves, nslabs) * wave_rows);
+      for (int mb = 0; mb < M; mb += slab) {
+        const int mlen = std::min(slab, M - mb);
+        launch_nn(cplx, mlen, ndat, nprojs, P.d_p + mb, ldv, zfac, ldg, fuse->ghc + mb, ldv, fuse->ghc + mb, st,
+                  vectout ? vectout + mb : nullptr, fuse->kinpw + mb / 2, fuse->kin_filter);
+        if (fuse->after_slab) fuse->after_slab(fuse->user, mb / 2, (mb + mlen) / 2);
+      }
+    }
   }
 }
 #else
 void prep_projectors_device(Projectors&, const NonlopAtoms&, const double*, int, const double*, int, double, cudaStream_t) {}
 void gemm_nonlop_device(const Projectors&, const NonlopAtoms&, const NonlopEnl&, int, int, int, int, const double*, int,
-                        const double*, double*, double*, double*, cudaStream_t) {}
+                        const double*, double*, double*, double*, cudaStream_t, const NonlopFusion*) {}
 void dgemm_tn(int, int, int, const double*, long long, const double*, long long, double*, long long, double, cudaStream_t) {}
 #endif
 

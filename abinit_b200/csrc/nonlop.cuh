@@ -47,11 +47,25 @@ struct NonlopEnl {
 void prep_projectors_device(Projectors& P, const NonlopAtoms& at, const double* d_ffnl, int dimffnl,
                             const double* d_ph3d, int matblk, double ucvol, cudaStream_t st);
 
+// getghc fusion of the last GEMM (opernlb): ghc <- (kinpw < filter) ? ghc + P.gxfac : 0 (m_getghc.F90:1266-1280 done in
+// the GEMM epilogue; `vectout`, when given, still receives the bare non-local term).  The rows are cut in `nslabs`
+// slabs; after each one `after_slab(user, ipw_begin, ipw_end)` runs on the host (used to queue the device->host copy
+// of the finished rows behind an event while the next slab is computed).
+struct NonlopFusion {
+  double* ghc = nullptr;            // (2, npw, ndat): holds V_loc psi + T psi on entry
+  const double* kinpw = nullptr;    // npw, device
+  double kin_filter = 0.0;
+  int nslabs = 1;
+  void (*after_slab)(void* user, int ipw_begin, int ipw_end) = nullptr;
+  void* user = nullptr;
+};
+
 // gemm_nonlop, choice in {0,1,7}, signs=2.  All data pointers are DEVICE pointers (may be null when unused):
 //   vectin, vectout, svectout : (2, npw, ndat) ; projections : (cplex, nprojs, ndat)
 void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const NonlopEnl& enl, int choice, int cpopt,
                         int paw_opt, int me_g0, const double* d_lambda, int ndat, const double* vectin,
-                        double* vectout, double* svectout, double* projections, cudaStream_t st);
+                        double* vectout, double* svectout, double* projections, cudaStream_t st,
+                        const NonlopFusion* fuse = nullptr);
 
 // plain tensor-core GEMMs (also used by the Gram kernels of xg.cu); all device pointers, column-major
 //   TN: C(M,N) = alpha * A(K,M)^T B(K,N)      NN: C(M,N) = A(M,K) B(K,N)
