@@ -14,8 +14,14 @@ Pinning status (see DESIGN.md "Oracle"):
     (src/70_gw/m_fft_prof.F90:873,936-976: c(G)=exp(-(2pi)^2 G.gmet.G), V=cos(2pi g0.r), g0=(1,-1,2),
      closed form out(G)=1/2[c(G-g0)+c(G+g0)]), tolerance = the cross-library spread the reference stores
      (tests/unitary/Refs/tfourwf_01.stdout:129, 3.4e-16 abs).
-  * ``nonlop.gemm_nonlop`` and ``getghc.getghc`` -- PARITY UNPINNED at vector level: the reference holds no
-    stand-alone golden vectors for them (only SCF-level observables that need a full Fortran build, which this
-    environment cannot produce: no Fortran compiler).  They are checked by mathematical invariants only
-    (naive per-atom sum, Hermiticity, istwfk=2 == istwfk=1 on the completed sphere).
+  * ``nonlop.gemm_nonlop`` (NC path: prep_projectors normalisation / phases / (-i)^l, opernla/c/b) and
+    ``getghc.getghc`` (local + kinetic + non-local assembly) -- PINNED on the reference's SCF golden numbers:
+    oracle/scf.py runs a complete LDA ground state of the tutorial test tbase3_1 AROUND getghc (psp8 tables
+    restated in oracle/psp8.py, epsatm 6.67004110 and the Ewald energy reproduced to every printed digit) and
+    reproduces tests/tutorial/Refs/tbase3_1.abo: etotal -8.51873906424 Ha to 1.4e-10 Ha, kinetic / local_psp /
+    non_local_psp / hartree / xc to < 3e-5 Ha (first order in the reference's own SCF residual) and the five printed
+    eigenvalues at k=(-1/4,1/2,0) to print precision (tests/test_scf_pins.py).  No stored per-vector dumps exist in
+    the reference, so the PAW branches (D_ij / S_ij apply, paw_opt 1-4, cprj) and istwf_k >= 2 remain pinned by
+    invariants only (naive per-atom sum, Hermiticity, istwfk=2 == istwfk=1 on the completed sphere): "parity
+    unpinned" for those branches.
 """

@@ -5,7 +5,7 @@ Restates src/66_wfs/m_getghc.F90:182-1447 for nspinor=1, nvloc=1, k == k', no Fo
   non-local part :1042-1074 nonlop(choice=1, signs=2, paw_opt = usepaw ; sij_opt/=0 -> sij_opt+3)
   assembly       :1266-1280 ghc = ghc + kinpw*cwavef + gvnlxc  (0 where kinpw >= huge*1e-11; gsc zeroed too)
   type_calc=1 filter :1003-1031
-PARITY UNPINNED at vector level for the non-local/assembled result (see oracle/__init__.py)."""
+PINNED (NC, istwf_k=1) on the reference's tbase3_1 SCF numbers through oracle/scf.py (see oracle/__init__.py)."""
 from __future__ import annotations
 import numpy as np
 from .fourwf import fourwf

@@ -6,7 +6,8 @@ Restates  prep_projectors     src/66_nonlocal/m_gemm_nonlop_projectors.F90:792-1
                               :1253-1295 (Sij)
           opernlb_gemm        src/66_nonlocal/m_opernlb_gemm.F90:353-837
           gemm_nonlop         src/66_nonlocal/m_gemm_nonlop.F90:191-1242
-PARITY UNPINNED at vector level (no stand-alone golden vectors in the reference); checked by invariants in tests/.
+NC branch PINNED through the tbase3_1 SCF numbers (oracle/scf.py, tests/test_scf_pins.py); PAW branches are parity
+unpinned by stored data and checked by invariants in tests/.
 Index conventions: indlmn is the Fortran indlmn(6, lmnmax, ntypat) stored here as numpy (ntypat, lmnmax, 6)
 (same memory, C order); l = indlmn[t, ilmn, 0], iln = indlmn[t, ilmn, 4] (1-based), validity indlmn[t, ilmn, 2] > 0.
 """

@@ -1,0 +1,387 @@
+"""Minimal norm-conserving LDA ground state around the oracle's getghc (test infrastructure only).
+
+Purpose: PIN the oracle (G-sphere, fourwf, prep_projectors / gemm_nonlop conventions, kinetic assembly) on numbers the
+reference itself stores for a full SCF run -- tests/tutorial/Refs/tbase3_1.abo (Si-2, ecut 12 Ha, etotal, the energy
+components kinetic / local_psp / non_local_psp / hartree / xc / Ewald / psp_core, eigenvalues at k=(-1/4,1/2,0)).
+Everything outside getghc is the textbook statement of what the reference does around it:
+  Ewald sum            src/67_common/m_ewald.F90 (value pinned: -8.46648022654903 Ha)
+  V_loc^psp(G)         src/67_common/m_mklocl.F90 mklocl_recipspace option 1 (structure factor * spline(q^2 V(q))/q^2,
+                       G=0 dropped, G^2 <= gsqcut*(1+1e-7) only), 1/ucvol normalisation
+  gsqcut               src/56_recipspace/m_kg.F90:96-199 getcut (double sphere, min(2, boxcut))
+  Hartree              src/56_xc/m_spacepar.F90 hartre: v_H(G) = rho(G) / (pi |G|^2) inside gsqcut
+  model core charge    src/56_xc/m_mkcore.F90:100-539 option 1 (real-space cubic-spline of xccc1d on the FFT grid)
+  xc                   ixc -1012 = libxc LDA_X + LDA_C_PW (Perdew-Wang 92, original parameters), unpolarised
+  real Ylm, ffnl       src/56_recipspace/m_initylmg.F90, src/66_nonlocal/m_mkffnl.F90:520-524 (ffnl = Ylm * f_ln(|k+G|))
+  total energy         src/67_common/m_energy.F90 / etotfor "direct" formula: sum of the seven terms above
+The Hamiltonian is applied ONLY through the callback `apply_h(k_index, cwavef) -> ghc` so that the same driver runs with
+the oracle's getghc (CPU pin test) or with the CUDA getghc through the C-ABI (GPU parity test).
+k-points: the full 2x2x2 x 4-shift grid reduced by time reversal only (no spatial symmetrisation of the density needed).
+"""
+from __future__ import annotations
+import numpy as np
+from scipy.special import erfc
+from . import gsphere as g
+
+TOLFIX = 1.0000001
+
+
+# ------------------------------------------------------------------ geometry helpers
+def gsq_grid(ngfft, gmet):
+    n1, n2, n3 = ngfft
+    f = [np.fft.fftfreq(n, 1.0 / n) for n in (n1, n2, n3)]
+    G3, G2, G1 = np.meshgrid(f[2], f[1], f[0], indexing="ij")          # arrays [i3][i2][i1]
+    G = np.stack([G1, G2, G3])
+    gsq = np.einsum("i...,ij,j...->...", G, gmet, G)
+    return G, gsq
+
+
+def getcut(ecut, gmet, ngfft):
+    """gsqcut of getcut for k=0 (m_kg.F90:121-145): boxsq = smallest |G|^2 on the box boundary planes."""
+    boxsq, _ = g.bound(gmet, (0.0, 0.0, 0.0), ngfft)
+    sphsq = 2.0 * ecut / (2 * np.pi) ** 2
+    boxcut = np.sqrt(boxsq / sphsq)
+    cutrad = min(2.0, boxcut)
+    return cutrad ** 2 * 2.0 * ecut / (2 * np.pi) ** 2, boxcut
+
+
+def ewald(rprimd, xred, zion):
+    """Ewald energy of point charges zion at xred (3,natom) in a neutralising background (Ha)."""
+    rprimd = np.asarray(rprimd); natom = xred.shape[1]
+    ucvol = abs(np.linalg.det(rprimd))
+    gprimd = np.linalg.inv(rprimd).T * 2 * np.pi
+    eta = np.sqrt(np.pi) / ucvol ** (1.0 / 3.0) * 1.2
+    xc = rprimd @ xred
+    nmax = 8
+    rng = np.arange(-nmax, nmax + 1)
+    T = np.array(np.meshgrid(rng, rng, rng, indexing="ij")).reshape(3, -1)
+    R = rprimd @ T
+    Gv = gprimd @ T
+    g2 = np.sum(Gv * Gv, axis=0)
+    nz = g2 > 1e-12
+    e = 0.0
+    for i in range(natom):
+        for j in range(natom):
+            d = (xc[:, i] - xc[:, j])[:, None] + R
+            r = np.sqrt(np.sum(d * d, axis=0))
+            m = r > 1e-10
+            e += 0.5 * zion[i] * zion[j] * np.sum(erfc(eta * r[m]) / r[m])
+            ph = np.cos(Gv[:, nz].T @ (xc[:, i] - xc[:, j]))
+            e += 0.5 * zion[i] * zion[j] * 4 * np.pi / ucvol * np.sum(np.exp(-g2[nz] / (4 * eta ** 2)) / g2[nz] * ph)
+    e -= eta / np.sqrt(np.pi) * np.sum(np.asarray(zion) ** 2)
+    e -= np.pi * np.sum(zion) ** 2 / (2 * ucvol * eta ** 2)
+    return float(e)
+
+
+# ------------------------------------------------------------------ xc: LDA_X + LDA_C_PW (libxc ids 1 and 12)
+def lda_pw92(rho):
+    """exc per particle and vxc for the unpolarised density rho (>0)."""
+    rho = np.maximum(rho, 1e-14)
+    cx = -0.75 * (3.0 / np.pi) ** (1.0 / 3.0)
+    ex = cx * rho ** (1.0 / 3.0)
+    vx = 4.0 / 3.0 * ex
+    a, a1, b1, b2, b3, b4 = 0.031091, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294
+    rs = (3.0 / (4.0 * np.pi * rho)) ** (1.0 / 3.0)
+    srs = np.sqrt(rs)
+    q0 = -2.0 * a * (1.0 + a1 * rs)
+    q1 = 2.0 * a * (b1 * srs + b2 * rs + b3 * rs * srs + b4 * rs * rs)
+    lg = np.log1p(1.0 / q1)
+    ec = q0 * lg
+    dq0 = -2.0 * a * a1
+    dq1 = a * (b1 / srs + 2.0 * b2 + 3.0 * b3 * srs + 4.0 * b4 * rs)
+    dec = dq0 * lg - q0 * dq1 / (q1 * q1 + q1)
+    vc = ec - rs / 3.0 * dec
+    return ex + ec, vx + vc
+
+
+# ------------------------------------------------------------------ potentials on the FFT grid
+def vpsp_r(ngfft, gmet, ucvol, xred_by_type, vlspl_by_type, gsqcut):
+    """mklocl_recipspace option 1."""
+    G, gsq = gsq_grid(ngfft, gmet)
+    work = np.zeros(gsq.shape, dtype=np.complex128)
+    mask = (gsq <= gsqcut * TOLFIX) & (gsq > 0)
+    gmag = np.sqrt(gsq[mask])
+    for xred, spl in zip(xred_by_type, vlspl_by_type):
+        sf = np.zeros(gmag.shape, dtype=np.complex128)
+        for ia in range(xred.shape[1]):
+            sf += np.exp(-2j * np.pi * np.einsum("i...,i->...", G[:, mask], xred[:, ia]))
+        work[mask] += sf * spl(gmag) / gsq[mask]
+    n = np.prod(ngfft)
+    return (np.fft.ifftn(work) * n).real / ucvol
+
+
+def hartree(rho_r, gsq, gsqcut):
+    rho_g = np.fft.fftn(rho_r) / rho_r.size
+    vg = np.zeros_like(rho_g)
+    mask = (gsq <= gsqcut * TOLFIX) & (gsq > 0)
+    vg[mask] = rho_g[mask] / (np.pi * gsq[mask])
+    return (np.fft.ifftn(vg) * rho_r.size).real
+
+
+def mkcore(ngfft, rprimd, xred, xccc1d, xcccrc):
+    """xccc3d[i3][i2][i1]: m_mkcore.F90:251-373 (option 1), one atom type."""
+    n = np.array(ngfft[:3]); n1xccc = xccc1d.shape[0]
+    rmet = rprimd.T @ rprimd
+    ucvol = abs(np.linalg.det(rprimd))
+    lencp = [np.linalg.norm(np.cross(rprimd[:, (i + 1) % 3], rprimd[:, (i + 2) % 3])) for i in range(3)]
+    scale = ucvol / np.array(lencp)
+    out = np.zeros((n[2], n[1], n[0]))
+    delta = 1.0 / (n1xccc - 1); d2 = delta ** 2 / 6.0
+    for ia in range(xred.shape[1]):
+        tau = np.mod(xred[:, ia] + 1.0 - np.trunc(xred[:, ia]), 1.0)
+        igrid = np.rint(tau * n).astype(int)
+        irange = 1 + np.rint(xcccrc / scale * n).astype(int)
+        ax = []
+        for mu in range(3):
+            ixp = np.arange(igrid[mu] - irange[mu], igrid[mu] + irange[mu] + 1)
+            ax.append((np.mod(ixp, n[mu]), ixp / n[mu] - tau[mu]))
+        (j3, r3), (j2, r2), (j1, r1) = ax[2], ax[1], ax[0]
+        R3, R2, R1 = np.meshgrid(r3, r2, r1, indexing="ij")
+        J3, J2, J1 = np.meshgrid(j3, j2, j1, indexing="ij")
+        rd = np.stack([R1, R2, R3])
+        dif2 = np.einsum("i...,ij,j...->...", rd, rmet, rd)
+        m = dif2 < xcccrc ** 2 - 1e-12
+        yy = np.sqrt(dif2[m]) / xcccrc
+        jj = (yy * (n1xccc - 1)).astype(int)
+        diff = yy - jj * delta
+        bb = diff * (n1xccc - 1); aa = 1.0 - bb
+        cc = aa * (aa * aa - 1.0) * d2; dd = bb * (bb * bb - 1.0) * d2
+        func = aa * xccc1d[jj, 0] + bb * xccc1d[jj + 1, 0] + cc * xccc1d[jj, 2] + dd * xccc1d[jj + 1, 2]
+        np.add.at(out, (J3[m], J2[m], J1[m]), func)
+    return out
+
+
+# ------------------------------------------------------------------ non-local form factors
+def real_ylm(kpg_cart, lmax):
+    """Orthonormal real spherical harmonics Y_lm(k+G), lm = l^2 + l + m; columns (npw, (lmax+1)^2).  Any orthonormal
+    real basis inside an l shell gives the same operator because ekb depends on (l, n) only."""
+    x, y, z = kpg_cart
+    r = np.sqrt(x * x + y * y + z * z)
+    rr = np.where(r > 1e-12, r, 1.0)
+    x, y, z = x / rr, y / rr, z / rr
+    out = np.zeros((kpg_cart.shape[1], (lmax + 1) ** 2))
+    out[:, 0] = 1.0 / np.sqrt(4 * np.pi)
+    if lmax >= 1:
+        c = np.sqrt(3.0 / (4 * np.pi))
+        out[:, 1], out[:, 2], out[:, 3] = c * y, c * z, c * x
+    if lmax >= 2:
+        c = np.sqrt(15.0 / (4 * np.pi))
+        out[:, 4] = c * x * y
+        out[:, 5] = c * y * z
+        out[:, 6] = np.sqrt(5.0 / (16 * np.pi)) * (3 * z * z - 1.0)
+        out[:, 7] = c * x * z
+        out[:, 8] = 0.5 * c * (x * x - y * y)
+    zero = r <= 1e-12
+    out[zero, 1:] = 0.0
+    return out
+
+
+def mkffnl(kg, kpt, gprimd, gmet, indlmn, ffspl):
+    """ffnl[ilmn, 0, ipw] = Ylm(k+G) * f_ln(|k+G|)   (m_mkffnl.F90:520-524; |k+G| without the 2 pi)."""
+    kpg = kg.astype(float) + np.asarray(kpt)[:, None]
+    norm = np.sqrt(np.einsum("ip,ij,jp->p", kpg, gmet, kpg))
+    cart = gprimd @ kpg
+    lmax = int(indlmn[:, 0].max())
+    ylm = real_ylm(cart, lmax)
+    out = np.zeros((indlmn.shape[0], 1, kg.shape[1]))
+    for i, row in enumerate(indlmn):
+        l, m, iln = int(row[0]), int(row[1]), int(row[4])
+        out[i, 0] = ylm[:, l * l + l + m] * ffspl[iln - 1](norm)
+    return out
+
+
+# ------------------------------------------------------------------ SCF driver
+class Setup:
+    pass
+
+
+def kgrid_tr(ngkpt=(2, 2, 2), shifts=((.5, .5, .5), (.5, 0, 0), (0, .5, 0), (0, 0, .5))):
+    """Full MP grid folded to (-1/2, 1/2], reduced by time reversal only; weights sum to 1."""
+    pts = []
+    for s in shifts:
+        for i in range(ngkpt[0]):
+            for j in range(ngkpt[1]):
+                for k in range(ngkpt[2]):
+                    v = np.array([(i + s[0]) / ngkpt[0], (j + s[1]) / ngkpt[1], (k + s[2]) / ngkpt[2]])
+                    v = v - np.rint(v); v[np.isclose(v, -0.5)] = 0.5
+                    pts.append(v)
+    out = []; w = []
+    for v in pts:
+        for q, u in enumerate(out):
+            mv = -v - np.rint(-v); mv[np.isclose(mv, -0.5)] = 0.5
+            if np.allclose(u, v) or np.allclose(u, mv):
+                w[q] += 1; break
+        else:
+            out.append(v); w.append(1)
+    w = np.array(w, dtype=float)
+    return np.array(out), w / w.sum()
+
+
+def find_symmetries(rprimd, xred):
+    """Space group of the crystal in reduced coordinates: integer matrices S (entries -1..1) preserving the real-space
+    metric, each with the fractional translation t (tried among differences of atomic positions) that maps the atom
+    set (one type) onto itself; r -> S r + t.  Si-2: 48 operations, as in tbase3_1.abo (nsym = 48)."""
+    rmet = rprimd.T @ rprimd
+    ops = []
+    rng = (-1, 0, 1)
+    natom = xred.shape[1]
+    for e in np.ndindex(*(3,) * 9):
+        S = np.array([rng[i] for i in e]).reshape(3, 3)
+        if abs(abs(np.linalg.det(S)) - 1.0) > 1e-9 or not np.allclose(S.T @ rmet @ S, rmet, atol=1e-9):
+            continue
+        for ib in range(natom):
+            t = xred[:, ib] - S @ xred[:, 0]
+            img = S @ xred + t[:, None]
+            ok = all(any(np.allclose((img[:, a] - xred[:, b]) - np.rint(img[:, a] - xred[:, b]), 0.0, atol=1e-8)
+                         for b in range(natom)) for a in range(natom))
+            if ok:
+                ops.append((S, t - np.floor(t + 1e-9))); break
+    return ops
+
+
+def symmetrize_rho(rho, ops, ngfft):
+    """rho_sym(r) = (1/nsym) sum_S rho(S r + t) on the FFT grid (the real-space statement of symrhg,
+    src/67_common/m_mkrho.F90; requires grid-compatible translations)."""
+    n1, n2, n3 = ngfft
+    n = np.array([n1, n2, n3])
+    I3, I2, I1 = np.meshgrid(np.arange(n3), np.arange(n2), np.arange(n1), indexing="ij")
+    idx = np.stack([I1, I2, I3])
+    out = np.zeros_like(rho)
+    for S, t in ops:
+        tt = t * n
+        assert np.allclose(tt, np.rint(tt), atol=1e-8)
+        j = np.einsum("ij,j...->i...", S, idx) + np.rint(tt).astype(int)[:, None, None, None]
+        j = np.mod(j, n[:, None, None, None])
+        out += rho[j[2], j[1], j[0]]
+    return out / len(ops)
+
+
+def total_energy_scf(s, apply_h, nband=5, nocc=4, tol=1e-11, maxit=60, mix=0.6, verbose=False):
+    """s: Setup with ngfft, gmet, ucvol, gsqcut, vpsp (grid), xccc3d (grid), kpts, wtk, kg[k] (3,npw), kinpw[k], ewald,
+    ecore, enl_of(k, c) -> per-band <c|Vnl|c>.  apply_h(ik, vlocal, c(nband_or_npw, npw)) -> H c.
+    Dense diagonalisation per k (H built column by column through apply_h on the identity), Anderson mixing on rho."""
+    n1, n2, n3 = s.ngfft
+    nfft = n1 * n2 * n3
+    _, gsq = gsq_grid(s.ngfft, s.gmet)
+    nelect = 2.0 * nocc
+    rho = np.full((n3, n2, n1), nelect / s.ucvol)
+    hist = []
+    res = {}
+    for it in range(maxit):
+        vh = hartree(rho, gsq, s.gsqcut)
+        exc, vxc = lda_pw92(rho + s.xccc3d)
+        vloc = s.vpsp + vh + vxc
+        rho_new = np.zeros_like(rho)
+        eig_all = []; ek = 0.0; enl = 0.0
+        for ik in range(len(s.kpts)):
+            npw = s.kg[ik].shape[1]
+            H = apply_h(ik, vloc, np.eye(npw, dtype=np.complex128))      # rows = H e_j  ->  H[j, :] = column j of H
+            H = H.T
+            herm = np.max(np.abs(H - H.conj().T))
+            H = 0.5 * (H + H.conj().T)
+            w, v = np.linalg.eigh(H)
+            eig_all.append(w[:nband].copy())
+            c = v[:, :nocc].T                                            # (nocc, npw)
+            ur = _g2r(c, s.kg[ik], s.ngfft)
+            rho_new += s.wtk[ik] * 2.0 * np.sum(np.abs(ur) ** 2, axis=0) / s.ucvol
+            kin = np.where(s.kinpw[ik] < g.KIN_FILTER, s.kinpw[ik], 0.0)
+            ek += s.wtk[ik] * 2.0 * float(np.sum(kin[None, :] * np.abs(c) ** 2))
+            enl += s.wtk[ik] * 2.0 * float(np.sum(s.enl_of(ik, c)))
+            res["herm"] = max(res.get("herm", 0.0), herm)
+        if getattr(s, "symops", None):
+            rho_new = symmetrize_rho(rho_new, s.symops, s.ngfft)
+        # energies with the OUTPUT density (what the reference prints after the last vtorho)
+        vh_o = hartree(rho_new, gsq, s.gsqcut)
+        exc_o, _ = lda_pw92(rho_new + s.xccc3d)
+        dv = s.ucvol / nfft
+        e = dict(kinetic=ek, hartree=0.5 * float(np.sum(vh_o * rho_new)) * dv,
+                 xc=float(np.sum(exc_o * (rho_new + s.xccc3d))) * dv, ewald=s.ewald, psp_core=s.ecore / s.ucvol,
+                 local_psp=float(np.sum(s.vpsp * rho_new)) * dv, non_local_psp=enl)
+        e["total"] = sum(e.values())
+        drho = float(np.sqrt(np.sum((rho_new - rho) ** 2) * dv))
+        if verbose:
+            print(f"  scf {it:2d} etot {e['total']:.12f} |drho| {drho:.2e}")
+        res.update(energies=e, eig=eig_all, rho=rho_new, iters=it + 1, drho=drho)
+        if drho < tol:
+            break
+        # Anderson (depth 4) on the density
+        hist.append((rho.ravel().copy(), (rho_new - rho).ravel().copy()))
+        hist = hist[-5:]
+        if len(hist) == 1:
+            rho = rho + mix * (rho_new - rho)
+        else:
+            X = np.array([h[0] for h in hist]); F = np.array([h[1] for h in hist])
+            dF = F[1:] - F[:-1]; dX = X[1:] - X[:-1]
+            gam, *_ = np.linalg.lstsq(dF.T, F[-1], rcond=None)
+            rho = (X[-1] + mix * F[-1] - (dX + mix * dF).T @ gam).reshape(rho.shape)
+    return res
+
+
+def _g2r(c, kg, ngfft):
+    """psi(r) on the box, unnormalised e^{+iGr} sum (fourwf option 0 convention, m_fft.F90:2201)."""
+    n1, n2, n3 = ngfft
+    box = np.zeros((c.shape[0], n3, n2, n1), dtype=np.complex128)
+    box[:, np.mod(kg[2], n3), np.mod(kg[1], n2), np.mod(kg[0], n1)] = c
+    return np.fft.ifftn(box, axes=(1, 2, 3)) * (n1 * n2 * n3)
+
+
+# ------------------------------------------------------------------ the tbase3_1 system from the committed fixture
+REF_TBASE3_1 = dict(   # tests/tutorial/Refs/tbase3_1.abo:275-288 (EnergyTerms), :262 (eigenvalues k#1), :160 (ecore*ucvol)
+    kinetic=3.12772926558809, hartree=5.47060783406466e-01, xc=-3.11674817182442, ewald=-8.46648022654903,
+    psp_core=4.04636587753304e-01, local_psp=-2.33102934151199, non_local_psp=1.31609203889785,
+    total=-8.51873906423973, eig_k1=(-0.16182, -0.05574, 0.04798, 0.09886, 0.23329), kpt1=(-0.25, 0.5, 0.0),
+    epsatm=6.67004110, ecore_ucvol=1.06720658e+02, boxcut=2.13807, npw_k=(519, 525), ucvol=2.6374446e+02)
+
+
+def setup_from_fixture(fx, irreducible=True):
+    """fx: dict-like with rprimd, xred, ecut, ngfft, zion, epsatm, ekb, indlmn, qgrid, ffspl_tab (nln, mq), ffspl_yp (nln,2),
+    vpsp, xccc3d (written by tests/golden/make_si2_fixture.py)."""
+    from . import nonlop as onl
+    from .psp8 import ClampedSpline
+    s = Setup()
+    s.rprimd = np.array(fx["rprimd"]); s.xred = np.array(fx["xred"]); s.ecut = float(fx["ecut"])
+    s.ngfft = tuple(int(x) for x in fx["ngfft"])
+    s.gprimd, s.gmet, s.ucvol = g.metric(s.rprimd)
+    s.gsqcut, s.boxcut = getcut(s.ecut, s.gmet, s.ngfft)
+    s.vpsp = np.array(fx["vpsp"]); s.xccc3d = np.array(fx["xccc3d"])
+    natom = s.xred.shape[1]
+    zion = float(fx["zion"])
+    s.ewald = ewald(s.rprimd, s.xred, [zion] * natom)
+    s.ecore = natom * float(fx["epsatm"]) * natom * zion
+    s.indlmn = np.array(fx["indlmn"], dtype=np.int32)[None]            # (ntypat=1, lmnmax, 6)
+    s.ekb = np.array(fx["ekb"])[None]                                  # (ntypat=1, lnmax)
+    s.nattyp = np.array([natom], dtype=np.int32); s.atindx1 = np.arange(natom, dtype=np.int32)
+    qg = np.array(fx["qgrid"])
+    ffspl = [ClampedSpline(qg, t, yp[0], yp[1]) for t, yp in zip(np.array(fx["ffspl_tab"]), np.array(fx["ffspl_yp"]))]
+    if irreducible:
+        # the 2 special points and weights of the reference run (tbase3_1.abo:44-45,136) + density symmetrisation
+        s.kpts = np.array([[-0.25, 0.5, 0.0], [-0.25, 0.0, 0.0]]); s.wtk = np.array([0.75, 0.25])
+        s.symops = find_symmetries(s.rprimd, s.xred)
+    else:
+        s.kpts, s.wtk = kgrid_tr(); s.symops = None
+    s.kg = []; s.kinpw = []; s.ffnl = []; s.ph3d = []; s.P = []
+    for k in s.kpts:
+        kg = g.kpgsph(s.ecut, s.gmet, k, 1)
+        s.kg.append(kg)
+        s.kinpw.append(np.ascontiguousarray(g.mkkin(s.ecut, 0.0, 1.0, s.gmet, kg, k)))
+        ff = mkffnl(kg, k, s.gprimd, s.gmet, s.indlmn[0], ffspl)[None]   # (ntypat, lmnmax, 1, npw)
+        s.ffnl.append(np.ascontiguousarray(ff))
+        s.ph3d.append(np.ascontiguousarray(g.ph3d(kg, k, s.xred)))
+        s.P.append(onl.prep_projectors(s.ffnl[-1], s.ph3d[-1], s.indlmn, s.nattyp, s.ucvol))
+    iln = s.indlmn[0, :, 4] - 1
+    ek_lmn = np.tile(s.ekb[0][iln], natom)
+
+    def enl_of(ik, c):
+        gx = c @ np.conj(s.P[ik]).T
+        return np.sum(ek_lmn[None, :] * np.abs(gx) ** 2, axis=1)
+    s.enl_of = enl_of
+    return s
+
+
+def apply_h_oracle(s):
+    from . import getghc as ogh
+
+    def apply_h(ik, vloc, c):
+        out, _, _, _ = ogh.getghc(c, vloc, s.kg[ik], s.ngfft, s.kinpw[ik], s.P[ik], s.ekb, None, s.indlmn, s.nattyp,
+                                  s.atindx1, istwf_k=1)
+        return out
+    return apply_h

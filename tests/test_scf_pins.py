@@ -1,0 +1,61 @@
+"""Oracle pinned on the reference's own SCF golden numbers: tests/tutorial/Refs/tbase3_1.abo (Si-2, ecut 12 Ha).
+
+A full LDA ground state is run AROUND the oracle's getghc (oracle/scf.py): every converged number the reference stores
+for this run depends on the G-sphere, fourwf option 2, the projector normalisation / phases / (-i)^l of prep_projectors,
+gemm_nonlop with the psp8 KB energies and the kinetic assembly being restated exactly.  The reference stopped at
+toldfe 1e-6 (last |dE| = 8.1e-9, vres2 = 2.7e-7): its total energy is variational (second order in the density error)
+while the separate components are first order, hence the two tolerances below."""
+import os
+import numpy as np
+import pytest
+from oracle import scf, gsphere as g
+
+FIX = os.path.join(os.path.dirname(__file__), "golden", "si2_tbase3.npz")
+R = scf.REF_TBASE3_1
+
+
+@pytest.fixture(scope="module")
+def setup():
+    return scf.setup_from_fixture(np.load(FIX))
+
+
+def test_setup_numbers_match_reference_log(setup):
+    s = setup
+    assert tuple(s.ngfft) == (24, 24, 24)                                   # tbase3_1.abo: ngfft 24 24 24
+    assert abs(s.boxcut - R["boxcut"]) < 1e-5                                # getcut line
+    assert abs(s.ucvol - R["ucvol"]) < 1e-5
+    assert tuple(k.shape[1] for k in s.kg) == R["npw_k"]                     # npw 519 / 525 (mpw 525)
+    assert abs(float(np.load(FIX)["epsatm"]) - R["epsatm"]) < 1e-8           # pspatm : epsatm= 6.67004110
+    assert abs(s.ecore - R["ecore_ucvol"]) < 1e-6                            # ecore*ucvol
+    assert len(s.symops) == 48                                               # nsym 48
+    assert abs(s.ewald - R["ewald"]) < 1e-12                                 # Ewald energy, all 15 digits
+
+
+def test_scf_total_energy_components_eigenvalues(setup):
+    res = scf.total_energy_scf(setup, scf.apply_h_oracle(setup))
+    e = res["energies"]
+    assert res["herm"] < 1e-13                                               # H built through getghc is Hermitian
+    assert abs(e["total"] - R["total"]) < 1e-8, e["total"] - R["total"]       # measured: 1.4e-10 Ha
+    for k in ("kinetic", "hartree", "xc", "local_psp", "non_local_psp"):
+        assert abs(e[k] - R[k]) < 5e-5, (k, e[k] - R[k])                      # first order in the reference's residual
+    assert abs(e["psp_core"] - R["psp_core"]) < 1e-12
+    assert np.max(np.abs(res["eig"][0] - np.array(R["eig_k1"]))) < 2e-5       # printed with 5 decimals
+
+
+def test_full_grid_equals_symmetrised_irreducible_wedge(setup):
+    """One Hamiltonian build on the 16 time-reversal-reduced points vs the 2 special points + 48 operations."""
+    s2 = scf.setup_from_fixture(np.load(FIX), irreducible=False)
+    assert len(s2.kpts) == 16 and abs(s2.wtk.sum() - 1) < 1e-14
+    ah1, ah2 = scf.apply_h_oracle(setup), scf.apply_h_oracle(s2)
+    vloc = s2.vpsp
+    def rho_of(s, ah):
+        rho = np.zeros(vloc.shape)
+        for ik in range(len(s.kpts)):
+            npw = s.kg[ik].shape[1]
+            H = ah(ik, vloc, np.eye(npw, dtype=np.complex128)).T
+            w, v = np.linalg.eigh(0.5 * (H + H.conj().T))
+            ur = scf._g2r(v[:, :4].T, s.kg[ik], s.ngfft)
+            rho += s.wtk[ik] * 2.0 * np.sum(np.abs(ur) ** 2, axis=0) / s.ucvol
+        return scf.symmetrize_rho(rho, s.symops, s.ngfft) if s.symops else rho
+    a, b = rho_of(setup, ah1), rho_of(s2, ah2)
+    assert np.max(np.abs(a - b)) < 1e-12
