@@ -233,3 +233,15 @@ def gemm_nonlop(atindx1, choice, cpopt, vectproj, enl, indlmn, istwf_k, lambda_,
                               _iref(nspinor), _iref(nspinor), _iref(ntypat), _iref(paw_opt),
                               None if sij_a is None else sij_a.ctypes.data, _ptr(svectout, _F, "svectout"),
                               _iref(useylm), _ptr(vectin, _F, "vectin"), _ptr(vectout, _F, "vectout"), _iref(signs))
+
+
+def nonlop(choice, cpopt, cprjin, enlout, hamk: Hamiltonian, idir, lambda_, mpi_enreg, ndat, nnlout, paw_opt, signs,
+           svectout, tim_nonlop, vectin, vectout):
+    """nonlop (src/66_nonlocal/m_nonlop.F90:336 argument list) on the gemm_nonlop route; signs=1, choice=1 fills
+    enlout(ndat) with <psi|Vnl|psi> (the call of m_chebfiwf.F90:296)."""
+    lam = np.ascontiguousarray(np.broadcast_to(np.asarray(0.0 if lambda_ is None else lambda_, dtype=np.float64), (ndat,)))
+    hp = C.c_void_p(hamk.h)
+    L().abi_b200_nonlop_(_iref(choice), _iref(cpopt), _ptr(cprjin, _F, "cprjin"), _ptr(enlout, _F, "enlout"), C.byref(hp),
+                         _iref(idir), lam.ctypes.data, _iref(ndat), _iref(nnlout), _iref(paw_opt), _iref(signs),
+                         _ptr(svectout, _F, "svectout"), _iref(tim_nonlop), _ptr(vectin, _F, "vectin"),
+                         _ptr(vectout, _F, "vectout"))

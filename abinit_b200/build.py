@@ -4,8 +4,8 @@ import os, subprocess, sys, hashlib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["fourwf.cu", "plane_stage.cu", "plane_inst_0.cu", "plane_inst_1.cu", "plane_inst_2.cu", "plane_inst_3.cu", "nonlop.cu", "context.cu", "api_fourwf.cu", "api_nonlop.cu"]
-HEADERS = ["common.cuh", "fft_engine.cuh", "plane_stage.cuh", "plane_stage_impl.cuh", "roots.inc", "fourwf.cuh", "nonlop.cuh", "context.cuh",
+SOURCES = ["fourwf.cu", "plane_stage.cu", "plane_inst_0.cu", "plane_inst_1.cu", "plane_inst_2.cu", "plane_inst_3.cu", "nonlop.cu", "context.cu", "api_fourwf.cu", "api_nonlop.cu", "xg.cu", "api_xg.cu"]
+HEADERS = ["common.cuh", "fft_engine.cuh", "plane_stage.cuh", "plane_stage_impl.cuh", "roots.inc", "fourwf.cuh", "nonlop.cuh", "context.cuh", "ham.cuh", "xg.cuh",
            os.path.join("..", "..", "include", "abinit_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
@@ -41,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(log)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     with open(stamp_file, "w") as fh:
         fh.write(stamp)

@@ -12,6 +12,8 @@ void nonlop_release_all();
 static VlocDev g_vloc_call;     // V_loc staged by the plain fourwf entry point (one per call, reused buffer)
 }
 
+namespace abi { void xg_release_workspace(); void chebfi_release_workspace(); }
+
 extern "C" {
 
 const char* abi_b200_version(void) { return "abinit_b200 0.1 (sm_100a; getghc = fourwf + gemm_nonlop)"; }
@@ -38,6 +40,8 @@ void abi_b200_finalize(void) {
   fft_tables_clear();
   fourwf_release_workspace();
   nonlop_release_all();
+  xg_release_workspace();
+  chebfi_release_workspace();
   for (auto& s : c.stage) s.release();
   if (g_vloc_call.d_v) { cudaFree(g_vloc_call.d_v); cudaFree(g_vloc_call.d_vT); g_vloc_call = VlocDev(); }
 #ifndef ABI_EMU

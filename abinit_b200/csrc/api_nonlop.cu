@@ -4,6 +4,7 @@
 #include "context.cuh"
 #include "fourwf.cuh"
 #include "nonlop.cuh"
+#include "ham.cuh"
 #include <map>
 #include <memory>
 
@@ -79,20 +80,6 @@ __global__ void k_filter_only(double2* __restrict__ ghc, const double* __restric
 #endif
 }  // namespace abi
 
-struct abi_b200_ham {
-  int ngfft[18];
-  int natom, ntypat, lmnmax, usepaw;
-  double ucvol;
-  NonlopAtoms atoms;
-  NonlopEnl enl;
-  Projectors P;
-  VlocDev vloc;
-  int istwf_k = 1, npw = 0, me_g0 = 1;
-  std::vector<int> kg;
-  double* d_kinpw = nullptr;
-  FourwfPlan* plan = nullptr;
-  double* d_gvnlxc = nullptr; size_t gvnlxc_cap = 0;
-};
 
 extern "C" {
 
@@ -384,20 +371,6 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     if (pipe) CUDA_CHECK(cudaStreamSynchronize(c.copy_stream));
   }
-}
-
-void abi_b200_xg_gram_(int* space, int* rows, int* ncols_a, int* ncols_b, double* a, int* lda, double* b, int* ldb, double* cmat,
-                       int* ldc, int* me_g0) {
-  ensure_init();
-  Context& c = ctx();
-  ABI_CHECK(*space == 2, "xg_gram: only SPACE_CR (istwfk>=2 real view) is implemented in this round");
-  ABI_CHECK(is_device_ptr(a) && is_device_ptr(b) && is_device_ptr(cmat), "xg_gram: device pointers required");
-  (void)me_g0;
-#ifndef ABI_EMU
-  // SPACE_CR: rows counts complex coefficients; the real view has 2*rows rows (m_xg.F90:1802-1882).
-  dgemm_tn(*ncols_a, *ncols_b, 2 * (*rows), a, 2LL * (*lda), b, 2LL * (*ldb), cmat, *ldc, 2.0, c.stream);
-#endif
-  if (!c.async) CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,351 @@
+// C-ABI entry points of the eigensolver side: nonlop dispatcher, xgBlock algebra, Rayleigh-Ritz, ChebFi2.
+// Reference semantics (not code): src/66_nonlocal/m_nonlop.F90:336-976, src/45_xgTools/m_xg.F90,
+// src/45_xgTools/m_xg_ortho_RR.F90:251-571, src/48_diago/m_chebfi2.F90:466-1210, src/79_seqpar_mpi/m_chebfiwf.F90:110-385.
+#include "../../include/abinit_b200.h"
+#include "context.cuh"
+#include "ham.cuh"
+#include "xg.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+using namespace abi;
+
+namespace {
+
+// ---- Chebyshev helpers (m_chebfi2.F90:1031-1064, 1084-1106) ----
+int cheb_oracle1(double xx, double aa, double bb, double tol, int nmax) {
+  const double xred = (xx - (aa + bb) / 2) / (bb - aa) * 2;
+  double yy = xred, yim1 = 1.0;
+  int nn = nmax;
+  if (1.0 / (yy * yy) < tol) {
+    nn = 1;
+  } else {
+    for (int ii = 2; ii <= nmax - 1; ii++) {
+      const double temp = yy;
+      yy = 2 * xred * yy - yim1;
+      yim1 = temp;
+      if (1.0 / (yy * yy) < tol) { nn = ii; break; }
+    }
+  }
+  return nn;
+}
+double cheb_poly1(double xx, int nn, double aa, double bb) {
+  const double xred = (xx - (aa + bb) / 2) / (bb - aa) * 2;
+  double yy = xred, yim1 = 1.0;
+  for (int ii = 2; ii <= nn; ii++) { const double temp = yy; yy = 2 * xred * yy - yim1; yim1 = temp; }
+  return yy;
+}
+
+struct Buf {
+  double* d = nullptr; size_t cap = 0;
+  double* get(size_t n) {
+    if (n > cap) { if (d) cudaFree(d); CUDA_CHECK(cudaMalloc(&d, sizeof(double) * n)); cap = n; }
+    return d;
+  }
+  void release() { if (d) cudaFree(d); d = nullptr; cap = 0; }
+};
+Buf g_cheb[5];      // AX, BX, X_next, X_prev, X (work copy)
+Buf g_small[2];     // device scalars per band
+
+struct AsyncGuard {   // inner calls must not synchronise per block
+  bool old; AsyncGuard() : old(ctx().async) { ctx().async = true; }
+  ~AsyncGuard() { ctx().async = old; }
+};
+
+// getAX_BX bound to getghc (getghc_gsc1, m_chebfiwf.F90:341-385): AX = H X, BX = S X (PAW) in band blocks of `bandpp`,
+// followed by xgBlock_zero_im_g0 on AX and BX (m_chebfi2.F90:580-581).  BX == nullptr for norm-conserving (BX = X).
+void get_ax_bx(abi_b200_ham_t* h, int space, int me_g0, int npw, int ncols, int bandpp, double* X, double* AX, double* BX) {
+  int cpopt = -1, prtvol = 0, tim = 0, type_calc = 0, sij_opt = BX ? 1 : 0;
+  const size_t col = 2 * (size_t)npw;
+  for (int b0 = 0; b0 < ncols; b0 += bandpp) {
+    int nd = std::min(bandpp, ncols - b0);
+    abi_b200_getghc_(&cpopt, X + col * b0, nullptr, AX + col * b0, BX ? BX + col * b0 : nullptr, &h, nullptr, nullptr, &nd, &prtvol,
+                     &sij_opt, &tim, &type_calc);
+  }
+  xg_zero_im_g0(space, ncols, AX, npw, me_g0, ctx().stream);
+  if (BX) xg_zero_im_g0(space, ncols, BX, npw, me_g0, ctx().stream);
+}
+
+// chebfi_rayleighRitzQuotients (m_chebfi2.F90:761-810): eig = <X|AX> / <X|BX>, host result
+void rr_quotients(int space, int me_g0, int npw, int ncols, const double* X, const double* AX, const double* BX,
+                  std::vector<double>& div, double& maxeig, double& mineig) {
+  cudaStream_t st = ctx().stream;
+  const int w = (space == SPACE_C) ? 2 : 1;
+  double* d1 = g_small[0].get((size_t)2 * w * ncols);
+  double* d2 = d1 + (size_t)w * ncols;
+  xg_colwise_dot(space, npw, ncols, X, npw, AX, npw, d1, me_g0, st);
+  xg_colwise_dot(space, npw, ncols, X, npw, BX ? BX : X, npw, d2, me_g0, st);
+  std::vector<double> hbuf((size_t)2 * w * ncols);
+  CUDA_CHECK(cudaMemcpyAsync(hbuf.data(), d1, sizeof(double) * hbuf.size(), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  div.resize(ncols);
+  maxeig = -1.7976931348623157e308; mineig = 1.7976931348623157e308;
+  for (int j = 0; j < ncols; j++) {
+    double q;
+    if (w == 1) {
+      q = hbuf[j] / hbuf[ncols + j];
+    } else {   // complex division, real part kept (xgBlock_colwiseDivision SPACE_C, max/min on dble())
+      const double ar = hbuf[2 * j], ai = hbuf[2 * j + 1], br = hbuf[2 * ncols + 2 * j], bi = hbuf[2 * ncols + 2 * j + 1];
+      q = (ar * br + ai * bi) / (br * br + bi * bi);
+    }
+    div[j] = q; maxeig = std::max(maxeig, q); mineig = std::min(mineig, q);
+  }
+}
+
+struct ChebOpts {
+  double tolerance, ecut; int ndeg_filter, nbdbuf, oracle; double oracle_factor, oracle_min_occ; int bandpp;
+};
+
+// chebfi_set_ndeg_from_residu (m_chebfi2.F90:1131-1210), single band group (shift = 0); work = one block of scratch
+int ndeg_from_residu(const ChebOpts& o, int space, int me_g0, int npw, int ncols, double lm, double lp, const double* occ,
+                     const std::vector<double>& div, int ndeg_max, const double* AX, const double* BX, double* work) {
+  cudaStream_t st = ctx().stream;
+  double* d_eig = g_small[1].get((size_t)2 * ncols);
+  double* d_res = d_eig + ncols;
+  CUDA_CHECK(cudaMemcpyAsync(d_eig, div.data(), sizeof(double) * ncols, cudaMemcpyHostToDevice, st));
+  xg_colwise_cymax(space, npw, ncols, work, npw, d_eig, BX, npw, AX, npw, st);     // H|psi> - eig S|psi>
+  xg_colwise_norm2(space, npw, ncols, work, npw, d_res, me_g0, st);
+  std::vector<double> res(ncols);
+  CUDA_CHECK(cudaMemcpyAsync(res.data(), d_res, sizeof(double) * ncols, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  int nbdbuf = 0;
+  if (o.nbdbuf > 0) nbdbuf = o.nbdbuf;
+  int ndeg = 0;
+  for (int i = 0; i < ncols; i++) {
+    double r = res[i];
+    const double occ_i = occ ? occ[i] : 1.0;
+    if (o.nbdbuf == -101) r *= occ_i;                                              // xgBlock_apply_diag(residu, occ)
+    const bool test1 = r < o.tolerance;
+    const bool test2 = (i + 1) > ncols - nbdbuf;
+    const bool test3 = o.nbdbuf == -101 && occ_i < o.oracle_min_occ;
+    int nd = 0;
+    if (!(test1 || test2 || test3)) {
+      const int n_tol = cheb_oracle1(div[i], lm, lp, o.tolerance / r, 1000);
+      if (o.oracle == 1) nd = std::min(std::min(ndeg_max, n_tol), o.ndeg_filter);
+      else if (o.oracle == 2) nd = std::min(std::min(ndeg_max, n_tol), cheb_oracle1(div[i], lm, lp, o.oracle_factor, 15));
+      else ABI_ERROR("Wrong value for chebfi%oracle");
+    }
+    ndeg = std::max(ndeg, nd);
+  }
+  return ndeg;
+}
+
+// The filter loop + amplification factors (m_chebfi2.F90:634-677, 944-995) on `ncols` bands held by this process.
+// X/AX/BX/Xnext/Xprev are device blocks (2, npw, ncols); on return *X_io points to the buffer holding the filtered X.
+void cheb_core(abi_b200_ham_t* h, int space, int me_g0, int npw, int ncols, int bandpp, double** X_io, double* AX, double* BX,
+               double** Xnext_io, double** Xprev_io, double lm, double lp, int ndeg, const std::vector<double>& div) {
+  ABI_CHECK(BX == nullptr, "chebfi: the PAW filter needs getBm1X (apply_invovl, m_invovl.F90), not available in this build");
+  cudaStream_t st = ctx().stream;
+  double *X = *X_io, *Xn = *Xnext_io, *Xp = *Xprev_io;
+  const double center = (lp + lm) * 0.5, radius = (lp - lm) * 0.5;
+  const double one_over_r = 1 / radius, two_over_r = 2 / radius;
+  for (int ideg = 0; ideg < ndeg; ideg++) {
+    // X_next = (AX - center X) * (1/r | 2/r) [- X_prev]   (chebfi_computeNextOrderChebfiPolynom, one pass)
+    xg_cheb_next(space, npw, ncols, Xn, npw, AX, npw, X, npw, ideg == 0 ? nullptr : Xp, npw, center,
+                 ideg == 0 ? one_over_r : two_over_r, st);
+    double* t = Xp; Xp = X; X = Xn; Xn = t;                                         // chebfi_swapInnerBuffers
+    get_ax_bx(h, space, me_g0, npw, ncols, bandpp, X, AX, BX);
+  }
+  // chebfi_ampfactor
+  std::vector<double> s(ncols);
+  for (int j = 0; j < ncols; j++) {
+    double amp = cheb_poly1(div[j], ndeg, lm, lp);
+    if (std::fabs(amp) < 1e-3) amp = 1e-3;
+    s[j] = 1 / amp;
+  }
+  double* d_s = g_small[1].get((size_t)2 * ncols);
+  CUDA_CHECK(cudaMemcpyAsync(d_s, s.data(), sizeof(double) * ncols, cudaMemcpyHostToDevice, st));
+  xg_scale_cols(space, npw, ncols, X, npw, d_s, st);
+  xg_scale_cols(space, npw, ncols, AX, npw, d_s, st);
+  if (BX) xg_scale_cols(space, npw, ncols, BX, npw, d_s, st);
+  CUDA_CHECK(cudaStreamSynchronize(st));     // s[] leaves scope
+  *X_io = X; *Xnext_io = Xn; *Xprev_io = Xp;
+}
+
+int space_of(const abi_b200_ham_t* h) { return h->istwf_k > 1 ? SPACE_CR : SPACE_C; }
+int me_g0_of(const abi_b200_ham_t* h) { return h->istwf_k > 1 ? ((h->istwf_k == 2 && h->me_g0 == 1) ? 1 : 0) : -1; }   // m_chebfiwf.F90:198-206
+
+}  // namespace
+
+namespace abi {
+void chebfi_release_workspace() { for (auto& b : g_cheb) b.release(); for (auto& b : g_small) b.release(); }
+}
+
+extern "C" {
+
+void abi_b200_nonlop_(int* choice, int* cpopt, double* cprjin, double* enlout, abi_b200_ham_t** hamk, int* idir, double* lambda,
+                      int* ndat, int* nnlout, int* paw_opt, int* signs, double* svectout, int* tim_nonlop, double* vectin,
+                      double* vectout) {
+  (void)idir; (void)tim_nonlop;
+  ensure_init();
+  Context& c = ctx();
+  abi_b200_ham* h = *hamk;
+  const int nd = *ndat;
+  c.nonlop_counter += nd;                                                          // m_nonlop.F90:389-392
+  ABI_CHECK(*signs == 1 || *signs == 2, "nonlop: signs must be 1 or 2");
+  ABI_CHECK(h->P.d_p != nullptr || h->atoms.nprojs == 0, "nonlop: projectors not loaded (load_k)");
+  ABI_CHECK(*signs == 2 || *nnlout >= 1, "nonlop: nnlout must be >= 1 for signs=1, choice=1");
+#ifndef ABI_EMU
+  const int cplex = (h->istwf_k == 1) ? 2 : 1;
+  const size_t nv = sizeof(double) * 2 * (size_t)h->npw * nd;
+  DevArg a_in(0, vectin, nv, true);
+  DevArg a_out(1, (*signs == 2) ? vectout : nullptr, nv, false);
+  DevArg a_sout(2, (*signs == 2) ? svectout : nullptr, nv, false);
+  DevArg a_prj(3, (*cpopt >= 0) ? cprjin : nullptr, sizeof(double) * (size_t)cplex * h->atoms.nprojs * nd, *cpopt >= 2);
+  DevArg a_lam(4, lambda, sizeof(double) * nd, true);
+  DevArg a_enl(5, (*signs == 1) ? enlout : nullptr, sizeof(double) * nd, false);
+  gemm_nonlop_device(h->P, h->atoms, h->enl, *choice, *cpopt, *paw_opt, h->me_g0, a_lam.as<double>(), nd, a_in.as<double>(),
+                     a_out.as<double>(), a_sout.as<double>(), a_prj.as<double>(), c.stream, nullptr, *signs, a_enl.as<double>());
+  if (*signs == 2) {
+    if (*choice == 1 && *paw_opt != 3) a_out.copy_back();
+    if (*choice == 7 || (*choice == 1 && (*paw_opt == 3 || *paw_opt == 4))) a_sout.copy_back();
+  } else {
+    a_enl.copy_back();
+  }
+  if ((*cpopt >= 0 && *cpopt < 2) || *choice == 0) a_prj.copy_back();
+  if (!c.async || a_in.staged || a_out.staged || a_sout.staged || a_prj.staged || a_enl.staged) CUDA_CHECK(cudaStreamSynchronize(c.stream));
+#endif
+}
+
+#ifndef ABI_EMU
+void abi_b200_xg_gram_(int* space, int* rows, int* ncols_a, int* ncols_b, double* a, int* lda, double* b, int* ldb, double* cmat,
+                       int* ldc, int* me_g0) {
+  ensure_init();
+  Context& c = ctx();
+  ABI_CHECK(is_device_ptr(a) && is_device_ptr(b) && is_device_ptr(cmat), "xg_gram: device pointers required");
+  xg_gram(*space, *rows, *ncols_a, *ncols_b, a, *lda, b, *ldb, cmat, *ldc, *me_g0, c.stream);
+  if (!c.async) CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+void abi_b200_xg_rotate_(int* space, int* rows, int* k, int* ncols_out, double* x, int* ldx, double* cmat, int* ldc) {
+  ensure_init();
+  Context& c = ctx();
+  ABI_CHECK(is_device_ptr(x) && is_device_ptr(cmat), "xg_rotate: device pointers required");
+  xg_rotate(*space, *rows, *k, *ncols_out, x, *ldx, cmat, *ldc, c.stream);
+  if (!c.async) CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+void abi_b200_xg_hegvd_(int* space, int* n, double* a, int* lda, double* b, int* ldb, double* w, int* info) {
+  ensure_init();
+  ABI_CHECK(is_device_ptr(a) && is_device_ptr(w) && (b == nullptr || is_device_ptr(b)), "xg_hegvd: device pointers required");
+  *info = xg_hegvd(*space == SPACE_C ? SPACE_C : SPACE_R, *n, a, *lda, b, *ldb, w, ctx().stream);
+}
+
+void abi_b200_xg_colwise_(int* op, int* space, int* rows, int* ncols, double* a, int* lda, double* b, int* ldb, double* w, int* ldw,
+                          double* da, double* out, int* me_g0) {
+  ensure_init();
+  Context& c = ctx();
+  switch (*op) {
+    case 0: xg_colwise_dot(*space, *rows, *ncols, a, *lda, b, *ldb, out, *me_g0, c.stream); break;
+    case 1: xg_colwise_norm2(*space, *rows, *ncols, a, *lda, out, *me_g0, c.stream); break;
+    case 2: xg_colwise_cymax(*space, *rows, *ncols, a, *lda, da, b, *ldb, w, *ldw, c.stream); break;
+    case 3: xg_scale_cols(*space, *rows, *ncols, a, *lda, da, c.stream); break;
+    case 4: xg_zero_im_g0(*space, *ncols, a, *lda, *me_g0, c.stream); break;
+    default: ABI_ERROR("xg_colwise: op must be 0 (dot), 1 (norm2), 2 (cymax), 3 (scale), 4 (zero_im_g0)");
+  }
+  if (!c.async) CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+void abi_b200_xg_rayleigh_ritz_(int* space, int* rows, int* blockdim, double* x, int* ldx, double* ax, int* ldax, double* bx,
+                                int* ldbx, double* eigenvalues, int* info, int* solve_ax_bx, int* me_g0) {
+  ensure_init();
+  Context& c = ctx();
+  ABI_CHECK(is_device_ptr(x) && is_device_ptr(ax) && (bx == nullptr || is_device_ptr(bx)), "xg_RayleighRitz: device blocks required");
+  DevArg a_eig(8, eigenvalues, sizeof(double) * (*blockdim), false);
+  *info = xg_rayleigh_ritz(*space, *rows, *blockdim, x, *ldx, ax, *ldax, bx, bx ? *ldbx : *ldx, a_eig.as<double>(), *solve_ax_bx != 0,
+                           *me_g0, c.stream);
+  a_eig.copy_back();
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+// ---- ChebFi2, split in the phases between which a band-parallel run communicates (m_chebfi2.F90:596-611, 687-705) ----
+void abi_b200_chebfi_rq_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, double* x, double* ax, double* bx, double* div,
+                         double* maxeig, double* mineig) {
+  ensure_init();
+  AsyncGuard g;
+  abi_b200_ham* h = *gs_hamk;
+  ABI_CHECK(is_device_ptr(x) && is_device_ptr(ax), "chebfi_rq: device blocks required");
+  const int space = space_of(h), me_g0 = me_g0_of(h);
+  get_ax_bx(h, space, me_g0, h->npw, *ncols, *bandpp, x, ax, h->usepaw ? bx : nullptr);
+  std::vector<double> d;
+  rr_quotients(space, me_g0, h->npw, *ncols, x, ax, h->usepaw ? bx : nullptr, d, *maxeig, *mineig);
+  std::copy(d.begin(), d.end(), div);
+}
+
+void abi_b200_chebfi_core_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, double** x, double* ax, double* bx, double** x_next,
+                           double** x_prev, double* lambda_minus, double* lambda_plus, int* ndeg_filter, double* div) {
+  ensure_init();
+  AsyncGuard g;
+  abi_b200_ham* h = *gs_hamk;
+  std::vector<double> d(div, div + *ncols);
+  cheb_core(h, space_of(h), me_g0_of(h), h->npw, *ncols, *bandpp, x, ax, h->usepaw ? bx : nullptr, x_next, x_prev, *lambda_minus,
+            *lambda_plus, *ndeg_filter, d);
+}
+
+int abi_b200_cheb_oracle1_(double* xx, double* aa, double* bb, double* tol, int* nmax) { return cheb_oracle1(*xx, *aa, *bb, *tol, *nmax); }
+double abi_b200_cheb_poly1_(double* xx, int* nn, double* aa, double* bb) { return cheb_poly1(*xx, *nn, *aa, *bb); }
+
+void abi_b200_chebfiwf2_(double* cg, double* eig, double* occ, double* enl_out, abi_b200_ham_t** gs_hamk, int* nband, int* npw,
+                         int* nspinor, int* prtvol, double* resid, double* tolwfr_diago, double* ecut, int* nline, int* nbdbuf,
+                         int* chebfi_oracle, double* oracle_factor, double* oracle_min_occ, int* bandpp) {
+  (void)prtvol;
+  ensure_init();
+  Context& c = ctx();
+  cudaStream_t st = c.stream;
+  abi_b200_ham* h = *gs_hamk;
+  const int nb = *nband, np = *npw;
+  ABI_CHECK(*nspinor == 1, "chebfiwf2: nspinor=2 is not implemented in this build");
+  ABI_CHECK(np == h->npw, "chebfiwf2: npw differs from the k-point loaded in gs_hamk");
+  ABI_CHECK(h->plan != nullptr, "chebfiwf2: load_k has not been called");
+  ABI_CHECK(*bandpp >= 1, "chebfiwf2: bandpp must be >= 1");
+  ABI_CHECK(!is_device_ptr(eig) && !is_device_ptr(resid) && (occ == nullptr || !is_device_ptr(occ)), "chebfiwf2: eig, resid, occ are host arrays");
+  const bool paw = h->usepaw == 1;
+  const int space = space_of(h), me_g0 = me_g0_of(h);
+  ChebOpts o{*tolwfr_diago, *ecut, *nline, *nbdbuf, *chebfi_oracle, *oracle_factor, *oracle_min_occ, *bandpp};
+  AsyncGuard g;
+  const size_t blk = 2 * (size_t)np * nb;
+  // X0 = cg (m_chebfiwf.F90:252); chebfi%X is a work copy (m_chebfi2.F90:549), AX, BX, X_next, X_prev are the solver's blocks
+  DevArg a_cg(10, cg, sizeof(double) * blk, true);
+  double* X = g_cheb[4].get(blk);
+  CUDA_CHECK(cudaMemcpyAsync(X, a_cg.as<double>(), sizeof(double) * blk, cudaMemcpyDeviceToDevice, st));
+  double* AX = g_cheb[0].get(blk);
+  double* BX = paw ? g_cheb[1].get(blk) : nullptr;
+  double* Xn = g_cheb[2].get(blk);
+  double* Xp = g_cheb[3].get(blk);
+  // occupancies are used by the oracle only (m_chebfiwf.F90:256-264: halved when nbdbuf=-101, nspinor=1, nsppol=1 -- the
+  // caller passes the array it wants compared with oracle_min_occ)
+  get_ax_bx(h, space, me_g0, np, nb, o.bandpp, X, AX, BX);                          // m_chebfi2.F90:578-581
+  std::vector<double> div; double maxeig, mineig;
+  rr_quotients(space, me_g0, np, nb, X, AX, BX, div, maxeig, mineig);               // :613
+  const double lambda_minus = maxeig, lambda_plus = o.ecut;                         // :547, :619
+  const int ndeg_max = cheb_oracle1(mineig, lambda_minus, lambda_plus, 1e-16, 40);  // :625
+  int ndeg = std::min(ndeg_max, o.ndeg_filter);
+  if (o.oracle > 0) ndeg = ndeg_from_residu(o, space, me_g0, np, nb, lambda_minus, lambda_plus, occ, div, ndeg_max, AX, BX ? BX : X, Xn);
+  cheb_core(h, space, me_g0, np, nb, o.bandpp, &X, AX, BX, &Xn, &Xp, lambda_minus, lambda_plus, ndeg, div);
+  // Rayleigh-Ritz (:705) and residuals (:709-716)
+  double* d_eig = g_small[0].get((size_t)2 * nb);
+  double* d_res = d_eig + nb;
+  const int info = xg_rayleigh_ritz(space, np, nb, X, np, AX, np, BX, np, d_eig, true, me_g0, st);
+  ABI_CHECK(info == 0, "chebfi: the sub-space eigenproblem failed (hegvd info /= 0)");
+  xg_colwise_cymax(space, np, nb, AX, np, d_eig, BX ? BX : X, np, AX, np, st);
+  xg_colwise_norm2(space, np, nb, AX, np, d_res, me_g0, st);
+  CUDA_CHECK(cudaMemcpyAsync(eig, d_eig, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaMemcpyAsync(resid, d_res, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaMemcpyAsync(a_cg.as<double>(), X, sizeof(double) * blk, cudaMemcpyDeviceToDevice, st));   // xgBlock_copy(X, X0) :720
+  a_cg.copy_back();
+  if (!paw && enl_out) {
+    // m_chebfiwf.F90:289-316: <psi|Vnl|psi> per band through nonlop(choice=1, signs=1, paw_opt=0)
+    double* d_enl = g_small[1].get((size_t)2 * nb);
+    for (int b0 = 0; b0 < nb; b0 += o.bandpp) {
+      const int nd = std::min(o.bandpp, nb - b0);
+      gemm_nonlop_device(h->P, h->atoms, h->enl, 1, -1, 0, h->me_g0, nullptr, nd, X + 2 * (size_t)np * b0, nullptr, nullptr, nullptr, st,
+                         nullptr, 1, d_enl + b0);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(enl_out, d_enl, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
+#endif   // ABI_EMU
+
+}  // extern "C"

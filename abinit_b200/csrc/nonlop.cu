@@ -511,7 +511,7 @@ static void launch_gemm(const GemmParams& p, int nblocks, cudaStream_t st) {
 
 // split-K TN GEMM into partial buffers; returns nsplit
 static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long long lda, const double* B, long long ldb,
-                     double*& part, cudaStream_t st) {
+                     double*& part, cudaStream_t st, const char* prof_name = "dgemm_tn_opernla") {
   const int BN = Neff <= 32 ? 32 : (Neff <= 64 ? 64 : 128), BM = 128 * 128 / BN;
   GemmParams p{};
   p.M = M; p.N = Neff; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.add = nullptr; p.ldc = 0;
@@ -530,7 +530,7 @@ static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long lo
   p.nsplit = nsplit; p.kchunk = kchunk;
   part = g_nlws[0].get((size_t)nsplit * Neff * M);
   p.C = part;
-  ProfScope ps("dgemm_tn_opernla");
+  ProfScope ps(prof_name);
   const int nb = tiles * nsplit;
   if (BN == 128) { if (cplx) launch_gemm<true, true, TnCfg>(p, nb, st); else launch_gemm<true, false, TnCfg>(p, nb, st); }
   else if (BN == 64) { if (cplx) launch_gemm<true, true, TnCfg64>(p, nb, st); else launch_gemm<true, false, TnCfg64>(p, nb, st); }
@@ -540,14 +540,14 @@ static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long lo
 
 static void launch_nn(bool cplx, int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
                       long long ldc, const double* add, cudaStream_t st, double* C2 = nullptr, const double* kin = nullptr,
-                      double kin_filter = 0.0) {
+                      double kin_filter = 0.0, const char* prof_name = "dgemm_nn_opernlb") {
   const int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128), BM = 64 * 128 / BN;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.add = add;
   p.C2 = C2; p.kin = kin; p.kin_filter = kin_filter;
   p.tiles_m = ceil_div(M, BM); p.tiles_n = ceil_div(N, BN);
   p.nsplit = 1; p.kchunk = 0;
-  ProfScope ps("dgemm_nn_opernlb");
+  ProfScope ps(prof_name);
   const int nb = p.tiles_m * p.tiles_n;
   if (BN == 128) { if (cplx) launch_gemm<false, true, NnCfg>(p, nb, st); else launch_gemm<false, false, NnCfg>(p, nb, st); }
   else if (BN == 64) { if (cplx) launch_gemm<false, true, NnCfg64>(p, nb, st); else launch_gemm<false, false, NnCfg64>(p, nb, st); }
@@ -567,19 +567,70 @@ __global__ void k_reduce_plain(const double* __restrict__ part, double* __restri
 void dgemm_tn(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
               double alpha, cudaStream_t st) {
   double* part = nullptr;
-  const int nsplit = launch_tn(false, M, N, K, A, lda, B, ldb, part, st);
+  const int nsplit = launch_tn(false, M, N, K, A, lda, B, ldb, part, st, "dgemm_tn_gram");
   k_reduce_plain<<<std::min(kNumSM * 8, (int)ceil_div<long long>((long long)M * N, 256)), 256, 0, st>>>(part, C, ldc, M, N, nsplit, alpha);
   CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
 }
 
+// complex partials [z][2n+c][m] -> C(m,n) = alpha * sum_z (part[2n] + i part[2n+1])
+__global__ void k_reduce_cplx(const double* __restrict__ part, double2* __restrict__ C, long long ldc, int M, int N, int nsplit, double alpha) {
+  const long long total = (long long)M * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx % M); const long long n = idx / M;
+    double sr = 0.0, si = 0.0;
+    for (int z = 0; z < nsplit; z++) {
+      sr += part[((size_t)z * 2 * N + 2 * n) * M + m];
+      si += part[((size_t)z * 2 * N + 2 * n + 1) * M + m];
+    }
+    C[n * ldc + m] = make_double2(alpha * sr, alpha * si);
+  }
+}
+
+void zgemm_cn(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
+              double alpha, cudaStream_t st) {
+  double* part = nullptr;
+  const int nsplit = launch_tn(true, M, 2 * N, 2 * K, A, 2 * lda, B, 2 * ldb, part, st, "dgemm_tn_gram");
+  k_reduce_cplx<<<std::min(kNumSM * 8, (int)ceil_div<long long>((long long)M * N, 256)), 256, 0, st>>>(part, (double2*)C, ldc, M, N, nsplit, alpha);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+void dgemm_nn(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
+              cudaStream_t st) {
+  launch_nn(false, M, N, K, A, lda, B, ldb, C, ldc, nullptr, st, nullptr, nullptr, 0.0, "dgemm_nn_rotate");
+}
+
+void zgemm_nn(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
+              cudaStream_t st) {
+  launch_nn(true, 2 * M, N, K, A, 2 * lda, B, 2 * ldb, C, 2 * ldc, nullptr, st, nullptr, nullptr, 0.0, "dgemm_nn_rotate");
+}
+
+// opernld, choice 1 (m_opernld_ylm_allwf.F90:160-203): enlout(idat) = sum_{ilmn, cplex} gxfac * gx
+__global__ void k_opernld(const double* __restrict__ gx, const double* __restrict__ gxfac, long long ldg, int n, double* __restrict__ enlout) {
+  __shared__ double red[256];
+  const int idat = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += gxfac[(size_t)idat * ldg + i] * gx[(size_t)idat * ldg + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) { if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w]; __syncthreads(); }
+  if (threadIdx.x == 0) enlout[idat] = red[0];
+}
+
 void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const NonlopEnl& enl, int choice, int cpopt, int paw_opt,
                         int me_g0, const double* d_lambda, int ndat, const double* vectin, double* vectout, double* svectout,
-                        double* projections, cudaStream_t st, const NonlopFusion* fuse) {
-  ABI_CHECK(choice == 0 || choice == 1 || choice == 7, "gemm_nonlop: only choice 0, 1, 7 (signs=2) are on the getghc path");
+                        double* projections, cudaStream_t st, const NonlopFusion* fuse, int signs, double* enlout) {
+  ABI_CHECK(choice == 0 || choice == 1 || choice == 7, "gemm_nonlop: only choice 0, 1, 7 are on the getghc path");
+  ABI_CHECK(signs == 2 || (signs == 1 && choice == 1), "gemm_nonlop: signs=1 is implemented for choice=1 only (energy contribution)");
+  ABI_CHECK(signs == 2 || enlout != nullptr, "gemm_nonlop: signs=1 needs enlout");
   ABI_CHECK(paw_opt >= 0 && paw_opt <= 4, "gemm_nonlop: bad paw_opt");
   ABI_CHECK(P.nprojs == at.nprojs, "gemm_nonlop: projectors were prepared for a different atom table");
   const int npw = P.npw, nprojs = P.nprojs;
+  if (signs == 1 && (nprojs == 0 || ndat == 0)) {             // m_gemm_nonlop.F90:420-423
+    if (ndat > 0) CUDA_CHECK(cudaMemsetAsync(enlout, 0, sizeof(double) * ndat, st));
+    return;
+  }
   if (nprojs == 0 || ndat == 0) {
     if (vectout) CUDA_CHECK(cudaMemsetAsync(vectout, 0, sizeof(double) * 2 * (size_t)npw * ndat, st));
     if (svectout && vectin) CUDA_CHECK(cudaMemcpyAsync(svectout, vectin, sizeof(double) * 2 * (size_t)npw * ndat, cudaMemcpyDeviceToDevice, st));
@@ -640,6 +691,13 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
     CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
+  if (signs == 1) {                                          // opernld (m_gemm_nonlop.F90:881-890)
+    const double* fac = (paw_opt == 3) ? zs : zfac;
+    k_opernld<<<ndat, 256, 0, st>>>(gx, fac, ldg, cplex * nprojs, enlout);
+    CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+    return;
+  }
   // opernlb
   if (choice == 7 || paw_opt == 3 || paw_opt == 4) {
     ABI_CHECK(svectout != nullptr && vectin != nullptr, "gemm_nonlop: svectout/vectin required for the overlap");
@@ -671,8 +729,11 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
 }
 #else
 void prep_projectors_device(Projectors&, const NonlopAtoms&, const double*, int, const double*, int, double, cudaStream_t) {}
+void dgemm_nn(int, int, int, const double*, long long, const double*, long long, double*, long long, cudaStream_t) {}
+void zgemm_nn(int, int, int, const double*, long long, const double*, long long, double*, long long, cudaStream_t) {}
+void zgemm_cn(int, int, int, const double*, long long, const double*, long long, double*, long long, double, cudaStream_t) {}
 void gemm_nonlop_device(const Projectors&, const NonlopAtoms&, const NonlopEnl&, int, int, int, int, const double*, int,
-                        const double*, double*, double*, double*, cudaStream_t, const NonlopFusion*) {}
+                        const double*, double*, double*, double*, cudaStream_t, const NonlopFusion*, int, double*) {}
 void dgemm_tn(int, int, int, const double*, long long, const double*, long long, double*, long long, double, cudaStream_t) {}
 #endif
 

@@ -60,16 +60,26 @@ struct NonlopFusion {
   void* user = nullptr;
 };
 
-// gemm_nonlop, choice in {0,1,7}, signs=2.  All data pointers are DEVICE pointers (may be null when unused):
+// gemm_nonlop, choice in {0,1,7}, signs=2, or choice=1, signs=1 (enlout(ndat) = <psi|Vnl|psi>, opernld).
+// All data pointers are DEVICE pointers (may be null when unused):
 //   vectin, vectout, svectout : (2, npw, ndat) ; projections : (cplex, nprojs, ndat)
 void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const NonlopEnl& enl, int choice, int cpopt,
                         int paw_opt, int me_g0, const double* d_lambda, int ndat, const double* vectin,
                         double* vectout, double* svectout, double* projections, cudaStream_t st,
-                        const NonlopFusion* fuse = nullptr);
+                        const NonlopFusion* fuse = nullptr, int signs = 2, double* enlout = nullptr);
 
 // plain tensor-core GEMMs (also used by the Gram kernels of xg.cu); all device pointers, column-major
 //   TN: C(M,N) = alpha * A(K,M)^T B(K,N)      NN: C(M,N) = A(M,K) B(K,N)
 void dgemm_tn(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
               long long ldc, double alpha, cudaStream_t st);
+void dgemm_nn(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
+              long long ldc, cudaStream_t st);
+// complex flavours on interleaved (re,im) data; M, N, K, lda, ldb, ldc count COMPLEX elements:
+//   zgemm_cn: C(M,N) = alpha * A(K,M)^H B(K,N)     zgemm_nn: C(M,N) = A(M,K) B(K,N)
+// (same real DMMA kernels: the -i psi / i P operands are formed at fragment-load time, see nonlop.cu)
+void zgemm_cn(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
+              long long ldc, double alpha, cudaStream_t st);
+void zgemm_nn(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
+              long long ldc, cudaStream_t st);
 
 }  // namespace abi

@@ -1,0 +1,333 @@
+// xgBlock linear algebra for the eigensolver side of getghc: Gram matrices and rotations on the DMMA GEMMs of nonlop.cu,
+// fused column-wise streaming kernels, dense sub-space eigenproblem (cuSOLVER, bound at run time), Rayleigh-Ritz.
+//
+// Reference semantics (not code): src/45_xgTools/m_xg.F90:1674-1976 (xgBlock_gemm, SPACE_CR G=0 correction :1802-1882),
+// :3301-3413 (colwiseCymax), :4341-4846 (colwiseNorm2 / colwiseDotProduct), :5851-5898 (zero_im_g0),
+// :2239-2861 (heevd / hegvd); src/45_xgTools/m_xg_ortho_RR.F90:251-571 (xg_RayleighRitz).
+//
+// Design: every streaming primitive the ChebFi2 loop strings together (scale, saxpy, scale back, saxpy ...) is ONE pass
+// here (xg_cheb_next reads AX, X, Xprev once and writes Xnext once); the column-wise reductions use one CTA per column
+// with a fixed-order tree, so results do not depend on the launch geometry.
+#include "xg.cuh"
+#include "nonlop.cuh"
+#include "fourwf.cuh"   // g_kernel_launches
+#include "context.cuh"
+#include <algorithm>
+#ifndef ABI_EMU
+#include <dlfcn.h>
+#include <cusolverDn.h>
+#endif
+
+namespace abi {
+
+#ifndef ABI_EMU
+namespace {
+struct XgWorkspace {
+  double* d = nullptr; size_t cap = 0;
+  double* get(size_t n) {
+    if (n > cap) { if (d) cudaFree(d); CUDA_CHECK(cudaMalloc(&d, sizeof(double) * n)); cap = n; }
+    return d;
+  }
+  void release() { if (d) cudaFree(d); d = nullptr; cap = 0; }
+};
+XgWorkspace g_xgws[4];   // 0: rotation slab, 1: subA, 2: subB, 3: cusolver work
+
+constexpr int kRedThreads = 512;
+
+// fixed-order block reduction of up to 2 values
+template <int NV> ABI_DEV void block_reduce(double (&v)[NV], double* red) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < NV; i++) red[i * kRedThreads + tid] = v[i];
+  __syncthreads();
+  for (int w = kRedThreads / 2; w > 0; w >>= 1) {
+    if (tid < w) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) red[i * kRedThreads + tid] += red[i * kRedThreads + tid + w];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] = red[i * kRedThreads];
+}
+
+// One CTA per column.  mode 0: <A|B> ; mode 1: |A|^2 (B unused)
+// SPACE_CR: 2 sum(a b) over the 2*rows reals, minus a(1) b(1) (dot) or a(1)^2 + a(2)^2 (norm2) when me_g0 = 1
+// SPACE_C : (sum ar br + ai bi, sum ar bi - ai br) ; SPACE_R: plain sum over `rows` reals
+__global__ void __launch_bounds__(kRedThreads) k_colwise_dot(int space, int mode, int rows, const double* __restrict__ A, long long lda,
+                                                             const double* __restrict__ B, long long ldb, double* __restrict__ out,
+                                                             int me_g0) {
+  __shared__ double red[2 * kRedThreads];
+  const int col = blockIdx.x;
+  const int cplx = space != SPACE_R;
+  const double* a = A + (cplx ? 2 : 1) * lda * col;
+  const double* b = mode == 0 ? B + (cplx ? 2 : 1) * ldb * col : a;
+  double v[2] = {0.0, 0.0};
+  if (cplx) {
+    const double2* a2 = reinterpret_cast<const double2*>(a);
+    const double2* b2 = reinterpret_cast<const double2*>(b);
+    for (int i = threadIdx.x; i < rows; i += kRedThreads) {
+      const double2 x = a2[i], y = b2[i];
+      v[0] += x.x * y.x + x.y * y.y;
+      v[1] += x.x * y.y - x.y * y.x;
+    }
+  } else {
+    for (int i = threadIdx.x; i < rows; i += kRedThreads) v[0] += a[i] * b[i];
+  }
+  block_reduce<2>(v, red);
+  if (threadIdx.x == 0) {
+    if (space == SPACE_CR) {
+      double r = 2.0 * v[0];
+      if (me_g0 == 1 && rows > 0) r -= (mode == 0) ? a[0] * b[0] : a[0] * a[0] + a[1] * a[1];
+      out[col] = r;
+    } else if (space == SPACE_C && mode == 0) {
+      out[2 * col] = v[0]; out[2 * col + 1] = v[1];
+    } else {
+      out[col] = v[0];
+    }
+  }
+}
+
+// G=0 correction of the SPACE_CR Gram matrix (m_xg.F90:1862-1882): the K=2*rows product counted the G=0 row twice
+//   W += -2 alpha (a0r b0r + a0i b0i) + alpha a0r b0r        (alpha = 1 here)
+__global__ void k_gram_g0(int na, int nb, const double* __restrict__ A, long long lda, const double* __restrict__ B, long long ldb,
+                          double* __restrict__ W, long long ldw) {
+  const long long total = (long long)na * nb;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % na); const long long j = idx / na;
+    const double a0 = A[2 * lda * i], a1 = A[2 * lda * i + 1], b0 = B[2 * ldb * j], b1 = B[2 * ldb * j + 1];
+    W[j * ldw + i] += -2.0 * (a0 * b0 + a1 * b1) + a0 * b0;
+  }
+}
+
+__global__ void k_zero_im_g0(int ncols, double* __restrict__ X, long long ldx) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < ncols) X[2 * ldx * j + 1] = 0.0;
+}
+
+// elementwise kernels on the real view: blockIdx.y = column, nreal doubles per column (even when complex)
+__global__ void k_cymax(int nreal, double* __restrict__ A, long long lda, const double* __restrict__ da, const double* __restrict__ B,
+                        long long ldb, const double* __restrict__ W, long long ldw) {
+  const int col = blockIdx.y;
+  const double d = da[col];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreal; i += gridDim.x * blockDim.x)
+    A[lda * col + i] = -d * B[ldb * col + i] + W[ldw * col + i];
+}
+
+__global__ void k_scale_cols(int nreal, double* __restrict__ X, long long ldx, const double* __restrict__ s) {
+  const int col = blockIdx.y;
+  const double f = s[col];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreal; i += gridDim.x * blockDim.x) X[ldx * col + i] *= f;
+}
+
+__global__ void k_cheb_next(int nreal, double* __restrict__ Xn, long long ldn, const double* __restrict__ AX, long long lda,
+                            const double* __restrict__ X, long long ldx, const double* __restrict__ Xp, long long ldp, double center,
+                            double scale) {
+  const int col = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreal; i += gridDim.x * blockDim.x) {
+    double v = (AX[lda * col + i] - center * X[ldx * col + i]) * scale;
+    if (Xp) v -= Xp[ldp * col + i];
+    Xn[ldn * col + i] = v;
+  }
+}
+
+dim3 ew_grid(int nreal, int ncols) { return dim3(std::max(1, std::min(64, ceil_div(nreal, 256 * 4))), ncols); }
+int real_rows(int space, int rows) { return space == SPACE_R ? rows : 2 * rows; }
+long long real_ld(int space, long long ld) { return space == SPACE_R ? ld : 2 * ld; }
+
+// ---------------------------------------------------------------------------------------------------------
+// cuSOLVER, bound at run time (the library is not a link dependency: only the Rayleigh-Ritz needs it)
+// ---------------------------------------------------------------------------------------------------------
+struct Cusolver {
+  void* lib = nullptr; cusolverDnHandle_t h = nullptr;
+  decltype(&cusolverDnCreate) create; decltype(&cusolverDnSetStream) set_stream;
+  decltype(&cusolverDnDsygvd_bufferSize) dsygvd_bs; decltype(&cusolverDnDsygvd) dsygvd;
+  decltype(&cusolverDnZhegvd_bufferSize) zhegvd_bs; decltype(&cusolverDnZhegvd) zhegvd;
+  decltype(&cusolverDnDsyevd_bufferSize) dsyevd_bs; decltype(&cusolverDnDsyevd) dsyevd;
+  decltype(&cusolverDnZheevd_bufferSize) zheevd_bs; decltype(&cusolverDnZheevd) zheevd;
+};
+Cusolver& cusolver() {
+  static Cusolver cs;
+  if (cs.h) return cs;
+  const char* cands[] = {getenv("ABI_B200_CUSOLVER"), "libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11",
+                         "/usr/local/cuda/targets/x86_64-linux/lib/libcusolver.so.11", "libcusolver.so"};
+  for (const char* c : cands) { if (c && !cs.lib) cs.lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL); }
+  ABI_CHECK(cs.lib != nullptr, "xg_hegvd: cannot load libcusolver.so.11 (set ABI_B200_CUSOLVER to its path); there is no CPU fallback");
+#define ABI_SYM(field, name) do { cs.field = reinterpret_cast<decltype(cs.field)>(dlsym(cs.lib, #name)); \
+    ABI_CHECK(cs.field != nullptr, "xg_hegvd: symbol " #name " missing in libcusolver"); } while (0)
+  ABI_SYM(create, cusolverDnCreate); ABI_SYM(set_stream, cusolverDnSetStream);
+  ABI_SYM(dsygvd_bs, cusolverDnDsygvd_bufferSize); ABI_SYM(dsygvd, cusolverDnDsygvd);
+  ABI_SYM(zhegvd_bs, cusolverDnZhegvd_bufferSize); ABI_SYM(zhegvd, cusolverDnZhegvd);
+  ABI_SYM(dsyevd_bs, cusolverDnDsyevd_bufferSize); ABI_SYM(dsyevd, cusolverDnDsyevd);
+  ABI_SYM(zheevd_bs, cusolverDnZheevd_bufferSize); ABI_SYM(zheevd, cusolverDnZheevd);
+#undef ABI_SYM
+  ABI_CHECK(cs.create(&cs.h) == CUSOLVER_STATUS_SUCCESS, "xg_hegvd: cusolverDnCreate failed");
+  return cs;
+}
+#define CUSOLVER_CHECK(call) ABI_CHECK((call) == CUSOLVER_STATUS_SUCCESS, "cuSOLVER failure in " #call)
+}  // namespace
+
+void xg_release_workspace() { for (auto& w : g_xgws) w.release(); }
+
+void xg_gram(int space, int rows, int ncols_a, int ncols_b, const double* A, long long lda, const double* B, long long ldb,
+             double* W, long long ldw, int me_g0, cudaStream_t st) {
+  ABI_CHECK(space == SPACE_R || space == SPACE_C || space == SPACE_CR, "xgBlock_gemm: bad space");
+  if (ncols_a == 0 || ncols_b == 0) return;
+  if (space == SPACE_C) {
+    zgemm_cn(ncols_a, ncols_b, rows, A, lda, B, ldb, W, ldw, 1.0, st);
+  } else if (space == SPACE_R) {
+    ABI_CHECK(rows % 2 == 0 && lda % 2 == 0 && ldb % 2 == 0, "xgBlock_gemm(SPACE_R): rows and leading dimensions must be even");
+    dgemm_tn(ncols_a, ncols_b, rows, A, lda, B, ldb, W, ldw, 1.0, st);
+  } else {
+    ABI_CHECK(me_g0 == 0 || me_g0 == 1, "xgBlock me_g0 is not initialized");                  // m_xg.F90:4591-4596
+    dgemm_tn(ncols_a, ncols_b, 2 * rows, A, 2 * lda, B, 2 * ldb, W, ldw, 2.0, st);
+    if (me_g0 == 1 && rows > 0) {
+      const int blocks = std::min(kNumSM * 4, (int)ceil_div<long long>((long long)ncols_a * ncols_b, 256));
+      k_gram_g0<<<blocks, 256, 0, st>>>(ncols_a, ncols_b, A, lda, B, ldb, W, ldw);
+      CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    }
+  }
+}
+
+void xg_rotate(int space, int rows, int k, int ncols_out, double* X, long long ldx, const double* C, long long ldc, cudaStream_t st) {
+  if (rows == 0 || ncols_out == 0) return;
+  const int M = real_rows(space, rows);
+  const long long ldxr = real_ld(space, ldx);
+  ABI_CHECK(space == SPACE_C || ldc % 2 == 0, "xg_rotate: the sub-space matrix needs an even leading dimension");
+  ABI_CHECK(space != SPACE_R || (rows % 2 == 0 && ldx % 2 == 0), "xg_rotate(SPACE_R): rows and ld must be even");
+  // row slabs of X are independent in X.C: product into a slab buffer, copy back (the reference uses a full-size
+  // temporary block, m_xg_ortho_RR.F90:524-531); slab = whole waves of 64-row CTA tiles, <= 256 MB
+  const long long budget = (256LL << 20) / (8LL * ncols_out);
+  long long slab = std::max<long long>(2 * kNumSM * 64, budget / (2 * kNumSM * 64) * (2 * kNumSM * 64));
+  slab = std::min<long long>(slab, (M + 1) & ~1LL);
+  double* tmp = g_xgws[0].get((size_t)slab * ncols_out);
+  for (long long m0 = 0; m0 < M; m0 += slab) {
+    const int mlen = (int)std::min<long long>(slab, M - m0);
+    if (space == SPACE_C) zgemm_nn(mlen / 2, ncols_out, k, X + m0, ldx, C, ldc, tmp, slab / 2, st);
+    else dgemm_nn(mlen, ncols_out, k, X + m0, ldxr, C, ldc, tmp, slab, st);
+    CUDA_CHECK(cudaMemcpy2DAsync(X + m0, sizeof(double) * ldxr, tmp, sizeof(double) * slab, sizeof(double) * mlen, ncols_out,
+                                 cudaMemcpyDeviceToDevice, st));
+  }
+}
+
+void xg_zero_im_g0(int space, int ncols, double* X, long long ldx, int me_g0, cudaStream_t st) {
+  if (space != SPACE_CR || ncols == 0) return;
+  ABI_CHECK(me_g0 >= 0, "xgBlock me_g0 is not initialized");
+  if (me_g0 != 1) return;
+  k_zero_im_g0<<<ceil_div(ncols, 256), 256, 0, st>>>(ncols, X, ldx);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+void xg_colwise_dot(int space, int rows, int ncols, const double* A, long long lda, const double* B, long long ldb, double* dots,
+                    int me_g0, cudaStream_t st) {
+  if (ncols == 0) return;
+  ABI_CHECK(space != SPACE_CR || me_g0 >= 0, "xgBlockA me_g0 is not initialized");
+  k_colwise_dot<<<ncols, kRedThreads, 0, st>>>(space, 0, rows, A, lda, B, ldb, dots, me_g0);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+void xg_colwise_norm2(int space, int rows, int ncols, const double* A, long long lda, double* norms, int me_g0, cudaStream_t st) {
+  if (ncols == 0) return;
+  ABI_CHECK(space != SPACE_CR || me_g0 >= 0, "xgBlock me_g0 is not initialized");
+  k_colwise_dot<<<ncols, kRedThreads, 0, st>>>(space, 1, rows, A, lda, A, lda, norms, me_g0);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+void xg_colwise_cymax(int space, int rows, int ncols, double* A, long long lda, const double* da, const double* B, long long ldb,
+                      const double* W, long long ldw, cudaStream_t st) {
+  if (ncols == 0 || rows == 0) return;
+  const int nreal = real_rows(space, rows);
+  k_cymax<<<ew_grid(nreal, ncols), 256, 0, st>>>(nreal, A, real_ld(space, lda), da, B, real_ld(space, ldb), W, real_ld(space, ldw));
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+void xg_scale_cols(int space, int rows, int ncols, double* X, long long ldx, const double* s, cudaStream_t st) {
+  if (ncols == 0 || rows == 0) return;
+  const int nreal = real_rows(space, rows);
+  k_scale_cols<<<ew_grid(nreal, ncols), 256, 0, st>>>(nreal, X, real_ld(space, ldx), s);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+void xg_cheb_next(int space, int rows, int ncols, double* Xnext, long long ldn, const double* AX, long long lda, const double* X,
+                  long long ldx, const double* Xprev, long long ldp, double center, double scale, cudaStream_t st) {
+  if (ncols == 0 || rows == 0) return;
+  const int nreal = real_rows(space, rows);
+  ProfScope ps("cheb_next");
+  k_cheb_next<<<ew_grid(nreal, ncols), 256, 0, st>>>(nreal, Xnext, real_ld(space, ldn), AX, real_ld(space, lda), X, real_ld(space, ldx),
+                                                     Xprev, real_ld(space, ldp), center, scale);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+int xg_hegvd(int space, int n, double* A, long long lda, double* B, long long ldb, double* w, cudaStream_t st) {
+  if (n == 0) return 0;
+  Cusolver& cs = cusolver();
+  CUSOLVER_CHECK(cs.set_stream(cs.h, st));
+  ProfScope ps("hegvd");
+  int lwork = 0;
+  const cusolverEigType_t it = CUSOLVER_EIG_TYPE_1; const cusolverEigMode_t jz = CUSOLVER_EIG_MODE_VECTOR;
+  const cublasFillMode_t up = CUBLAS_FILL_MODE_UPPER;
+  int* d_info = reinterpret_cast<int*>(g_xgws[3].get(4));
+  if (space == SPACE_C) {
+    auto* a = reinterpret_cast<cuDoubleComplex*>(A); auto* b = reinterpret_cast<cuDoubleComplex*>(B);
+    if (B) CUSOLVER_CHECK(cs.zhegvd_bs(cs.h, it, jz, up, n, a, (int)lda, b, (int)ldb, w, &lwork));
+    else CUSOLVER_CHECK(cs.zheevd_bs(cs.h, jz, up, n, a, (int)lda, w, &lwork));
+    double* work = g_xgws[3].get(4 + 2 * (size_t)lwork) + 4;
+    d_info = reinterpret_cast<int*>(g_xgws[3].d);
+    if (B) CUSOLVER_CHECK(cs.zhegvd(cs.h, it, jz, up, n, a, (int)lda, b, (int)ldb, w, reinterpret_cast<cuDoubleComplex*>(work), lwork, d_info));
+    else CUSOLVER_CHECK(cs.zheevd(cs.h, jz, up, n, a, (int)lda, w, reinterpret_cast<cuDoubleComplex*>(work), lwork, d_info));
+  } else {
+    if (B) CUSOLVER_CHECK(cs.dsygvd_bs(cs.h, it, jz, up, n, A, (int)lda, B, (int)ldb, w, &lwork));
+    else CUSOLVER_CHECK(cs.dsyevd_bs(cs.h, jz, up, n, A, (int)lda, w, &lwork));
+    double* work = g_xgws[3].get(4 + (size_t)lwork) + 4;
+    d_info = reinterpret_cast<int*>(g_xgws[3].d);
+    if (B) CUSOLVER_CHECK(cs.dsygvd(cs.h, it, jz, up, n, A, (int)lda, B, (int)ldb, w, work, lwork, d_info));
+    else CUSOLVER_CHECK(cs.dsyevd(cs.h, jz, up, n, A, (int)lda, w, work, lwork, d_info));
+  }
+  g_kernel_launches++;
+  int info = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  return info;
+}
+
+int xg_rayleigh_ritz(int space, int rows, int n, double* X, long long ldx, double* AX, long long ldax, double* BX, long long ldbx,
+                     double* eig, bool solve_ax_bx, int me_g0, cudaStream_t st) {
+  if (n == 0) return 0;
+  const bool bx_is_x = (BX == nullptr || BX == X);
+  const int sc = sub_cplex(space);
+  const int sub_space = (space == SPACE_C) ? SPACE_C : SPACE_R;
+  const long long ldw = (n + 1) & ~1LL;                                  // even: K-padding of the rotation GEMM
+  double* subA = g_xgws[1].get((size_t)sc * ldw * n);
+  CUDA_CHECK(cudaMemsetAsync(subA, 0, sizeof(double) * sc * ldw * n, st));
+  double* subB = nullptr;
+  // m_xg_ortho_RR.F90:376-380
+  xg_zero_im_g0(space, n, X, ldx, me_g0, st);
+  xg_zero_im_g0(space, n, AX, ldax, me_g0, st);
+  if (!bx_is_x) xg_zero_im_g0(space, n, BX, ldbx, me_g0, st);
+  xg_gram(space, rows, n, n, X, ldx, AX, ldax, subA, ldw, me_g0, st);     // :384
+  if (solve_ax_bx) {
+    subB = g_xgws[2].get((size_t)sc * ldw * n);
+    CUDA_CHECK(cudaMemsetAsync(subB, 0, sizeof(double) * sc * ldw * n, st));
+    xg_gram(space, rows, n, n, X, ldx, bx_is_x ? X : BX, bx_is_x ? ldx : ldbx, subB, ldw, me_g0, st);   // :388
+  }
+  const int info = xg_hegvd(sub_space, n, subA, ldw, subB, ldw, eig, st);  // heevd :441 / hegvd :465
+  if (info != 0) return info;
+  // X, AX, BX <- . Cwp (:524-531)
+  xg_rotate(space, rows, n, n, X, ldx, subA, ldw, st);
+  xg_rotate(space, rows, n, n, AX, ldax, subA, ldw, st);
+  if (!bx_is_x) xg_rotate(space, rows, n, n, BX, ldbx, subA, ldw, st);
+  return 0;
+}
+
+#else   // ABI_EMU
+void xg_release_workspace() {}
+#endif
+
+}  // namespace abi

@@ -27,7 +27,9 @@ SYMBOLS = [
     "abi_b200_nonlop_counter",
     "abi_b200_ham_create", "abi_b200_ham_destroy", "abi_b200_ham_load_spin", "abi_b200_ham_load_enl",
     "abi_b200_ham_load_k", "abi_b200_ham_set_projectors", "abi_b200_ham_nprojs", "abi_b200_getghc_",
-    "abi_b200_xg_gram_",
+    "abi_b200_nonlop_",
+    "abi_b200_xg_gram_", "abi_b200_xg_rotate_", "abi_b200_xg_hegvd_", "abi_b200_xg_colwise_", "abi_b200_xg_rayleigh_ritz_",
+    "abi_b200_chebfiwf2_", "abi_b200_chebfi_rq_", "abi_b200_chebfi_core_", "abi_b200_cheb_oracle1_", "abi_b200_cheb_poly1_",
 ]
 
 
@@ -76,6 +78,18 @@ def load_library(path: str | None = None) -> C.CDLL:
         lib.abi_b200_ham_nprojs.restype = C.c_int
         lib.abi_b200_getghc_.argtypes = [vp] * 13
         lib.abi_b200_xg_gram_.argtypes = [vp] * 11
+        lib.abi_b200_nonlop_.argtypes = [vp] * 15
+        lib.abi_b200_xg_rotate_.argtypes = [vp] * 8
+        lib.abi_b200_xg_hegvd_.argtypes = [vp] * 8
+        lib.abi_b200_xg_colwise_.argtypes = [vp] * 13
+        lib.abi_b200_xg_rayleigh_ritz_.argtypes = [vp] * 13
+        lib.abi_b200_chebfiwf2_.argtypes = [vp] * 18
+        lib.abi_b200_chebfi_rq_.argtypes = [vp] * 9
+        lib.abi_b200_chebfi_core_.argtypes = [vp] * 12
+        lib.abi_b200_cheb_oracle1_.argtypes = [vp] * 5
+        lib.abi_b200_cheb_oracle1_.restype = C.c_int
+        lib.abi_b200_cheb_poly1_.argtypes = [vp] * 4
+        lib.abi_b200_cheb_poly1_.restype = C.c_double
     if path is None:
         _LIB = lib
     return lib

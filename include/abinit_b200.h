@@ -129,14 +129,69 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
                       int* sij_opt, int* tim_getghc, int* type_calc);
 
 /* ------------------------------------------------------------------------------------------------------
- * Block Rayleigh-Ritz Gram matrices (xgBlock_gemm + xgBlock_mpi_sum, src/45_xgTools/m_xg.F90:1674-1976,
- * 3636-3663; called by xg_RayleighRitz, src/45_xgTools/m_xg_ortho_RR.F90:384,388).
- * C(ncols_a, ncols_b) = alpha * A^H B (+ beta C) on row shards; space 1 = SPACE_C (complex),
- * 2 = SPACE_CR (real view of istwfk>=2 data: 2 Re(A^H B) minus the doubled G=0 term when me_g0=1).
- * The cross-rank sum is an in-stream NCCL allreduce issued by the host wrapper (abinit_b200.parallel).
+ * nonlop dispatcher on the Hamiltonian handle (src/66_nonlocal/m_nonlop.F90:336-976, gemm_nonlop route :782-811):
+ * argument list of nonlop(choice,cpopt,cprjin,enlout,hamk,idir,lambda,mpi_enreg,ndat,nnlout,paw_opt,signs,svectout,
+ * tim_nonlop,vectin,vectout) with mpi_enreg dropped and cprjin flattened to projections(cplex,nprojs,ndat).
+ * signs=2: choice 0/1/7 as abi_b200_gemm_nonlop_.  signs=1, choice=1: enlout(ndat) = <psi|Vnl|psi>
+ * (opernld, src/66_nonlocal/m_opernld_ylm_allwf.F90:160-203; the call of src/79_seqpar_mpi/m_chebfiwf.F90:296-297).
  * ---------------------------------------------------------------------------------------------------- */
-void abi_b200_xg_gram_(int* space, int* rows, int* ncols_a, int* ncols_b, double* a, int* lda, double* b,
-                       int* ldb, double* c, int* ldc, int* me_g0);
+void abi_b200_nonlop_(int* choice, int* cpopt, double* cprjin, double* enlout, abi_b200_ham_t** hamk, int* idir,
+                      double* lambda, int* ndat, int* nnlout, int* paw_opt, int* signs, double* svectout,
+                      int* tim_nonlop, double* vectin, double* vectout);
+
+/* ------------------------------------------------------------------------------------------------------
+ * xgBlock algebra of the eigensolvers (src/45_xgTools/m_xg.F90).  Blocks are DEVICE arrays with the memory layout
+ * of cg(2, npw*nband) (xgBlock_map, m_xg.F90:716-781): `rows` complex coefficients per column, leading dimensions
+ * in complex elements.  space: 1 SPACE_R, 2 SPACE_C, 3 SPACE_CR (m_xg.F90:63-65).  Sub-space matrices (Gram matrices,
+ * eigenvectors) are real for SPACE_R/SPACE_CR and complex for SPACE_C; their leading dimension counts their elements.
+ *
+ * xg_gram     : W(ncols_a,ncols_b) = A^H B, xgBlock_gemm('t','n') (m_xg.F90:1674-1976); SPACE_CR: 2 A^T B on the real
+ *               view minus the doubled G=0 row when me_g0=1 (:1802-1882).  Row-sharded callers sum W over ranks
+ *               (xgBlock_mpi_sum :3636-3663 -> NCCL allreduce in abinit_b200.parallel).
+ * xg_rotate   : X(:,1:ncols_out) <- X(:,1:k) C(1:k,1:ncols_out), xgBlock_gemm('n','n') + xgBlock_copy
+ *               (m_xg_ortho_RR.F90:524-531); ldc must be even for the real spaces, pad row zero when k is odd.
+ * xg_hegvd    : xgBlock_hegvd(1,'v','u') / xgBlock_heevd('v','u') when b is NULL (m_xg.F90:2239-2861); eigenvectors
+ *               overwrite a, w(n) on the device.
+ * xg_colwise  : op 0 colwiseDotProduct (out(ncols), (re,im) pairs for SPACE_C) :4550-4846; 1 colwiseNorm2 :4341-4542;
+ *               2 colwiseCymax a = w - da(col) b :3301-3413; 3 per-column scale a(:,j) *= da(j) (chebfi_ampfactor);
+ *               4 zero_im_g0 :5851-5898.
+ * xg_rayleigh_ritz : xg_RayleighRitz, VAR_X branch (m_xg_ortho_RR.F90:251-571); bx NULL -> overlap block is x
+ *               (norm-conserving); eigenvalues may be a host or device array.
+ * ---------------------------------------------------------------------------------------------------- */
+void abi_b200_xg_gram_(int* space, int* rows, int* ncols_a, int* ncols_b, double* a, int* lda, double* b, int* ldb,
+                       double* c, int* ldc, int* me_g0);
+void abi_b200_xg_rotate_(int* space, int* rows, int* k, int* ncols_out, double* x, int* ldx, double* c, int* ldc);
+void abi_b200_xg_hegvd_(int* space, int* n, double* a, int* lda, double* b, int* ldb, double* w, int* info);
+void abi_b200_xg_colwise_(int* op, int* space, int* rows, int* ncols, double* a, int* lda, double* b, int* ldb,
+                          double* w, int* ldw, double* da, double* out, int* me_g0);
+void abi_b200_xg_rayleigh_ritz_(int* space, int* rows, int* blockdim, double* x, int* ldx, double* ax, int* ldax,
+                                double* bx, int* ldbx, double* eigenvalues, int* info, int* solve_ax_bx, int* me_g0);
+
+/* ------------------------------------------------------------------------------------------------------
+ * ChebFi2 (src/48_diago/m_chebfi2.F90:466-735 chebfi_run) driven as chebfiwf2 drives it
+ * (src/79_seqpar_mpi/m_chebfiwf.F90:110-330): getAX_BX is bound to the fused getghc on band blocks of `bandpp`
+ * columns (getghc_gsc1 :341-385), lambda_plus = ecut, the dtset scalars are passed flattened
+ * (tolwfr_diago, ecut, nline, nbdbuf, chebfi_oracle, oracle_factor, oracle_min_occ).
+ * cg(2,npw*nband) host or device, in/out; eig, resid, occ (may be NULL when chebfi_oracle=0), enl_out (NC only, may
+ * be NULL): host arrays of nband.  Norm-conserving only in this build (the PAW filter needs apply_invovl).
+ * The three phase functions are what a band-parallel caller strings together around its collectives
+ * (max/min of the Rayleigh quotients, m_chebfi2.F90:606-611; transposition + Rayleigh-Ritz, :687-705):
+ *   chebfi_rq   : AX,BX = getAX_BX(X); div(ncols) = <X|AX>/<X|BX>; max / min      (:575-613)
+ *   chebfi_core : the filter loop of degree ndeg_filter + chebfi_ampfactor           (:634-677)
+ *                 x, x_next, x_prev are rotated like chebfi_swapInnerBuffers: on return *x holds the filtered block.
+ * cheb_oracle1 / cheb_poly1: m_chebfi2.F90:1031-1064, 1084-1106.
+ * ---------------------------------------------------------------------------------------------------- */
+void abi_b200_chebfiwf2_(double* cg, double* eig, double* occ, double* enl_out, abi_b200_ham_t** gs_hamk, int* nband,
+                         int* npw, int* nspinor, int* prtvol, double* resid, double* tolwfr_diago, double* ecut,
+                         int* nline, int* nbdbuf, int* chebfi_oracle, double* oracle_factor, double* oracle_min_occ,
+                         int* bandpp);
+void abi_b200_chebfi_rq_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, double* x, double* ax, double* bx,
+                         double* div, double* maxeig, double* mineig);
+void abi_b200_chebfi_core_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, double** x, double* ax, double* bx,
+                           double** x_next, double** x_prev, double* lambda_minus, double* lambda_plus,
+                           int* ndeg_filter, double* div);
+int abi_b200_cheb_oracle1_(double* xx, double* aa, double* bb, double* tol, int* nmax);
+double abi_b200_cheb_poly1_(double* xx, int* nn, double* aa, double* bb);
 
 #ifdef __cplusplus
 }

@@ -255,10 +255,12 @@ def symmetrize_rho(rho, ops, ngfft):
     return out / len(ops)
 
 
-def total_energy_scf(s, apply_h, nband=5, nocc=4, tol=1e-11, maxit=60, mix=0.6, verbose=False):
+def total_energy_scf(s, apply_h, nband=5, nocc=4, tol=1e-11, maxit=60, mix=0.6, verbose=False, eigensolver=None):
     """s: Setup with ngfft, gmet, ucvol, gsqcut, vpsp (grid), xccc3d (grid), kpts, wtk, kg[k] (3,npw), kinpw[k], ewald,
     ecore, enl_of(k, c) -> per-band <c|Vnl|c>.  apply_h(ik, vlocal, c(nband_or_npw, npw)) -> H c.
-    Dense diagonalisation per k (H built column by column through apply_h on the identity), Anderson mixing on rho."""
+    Dense diagonalisation per k (H built column by column through apply_h on the identity), Anderson mixing on rho.
+    eigensolver(ik, vloc) -> (eig, c(nb, npw), enl_per_band | None), when given, replaces the dense diagonalisation (an
+    iterative solver that keeps its own wavefunctions between SCF steps, e.g. ChebFi2 through the C-ABI)."""
     n1, n2, n3 = s.ngfft
     nfft = n1 * n2 * n3
     _, gsq = gsq_grid(s.ngfft, s.gmet)
@@ -274,18 +276,25 @@ def total_energy_scf(s, apply_h, nband=5, nocc=4, tol=1e-11, maxit=60, mix=0.6, 
         eig_all = []; ek = 0.0; enl = 0.0
         for ik in range(len(s.kpts)):
             npw = s.kg[ik].shape[1]
-            H = apply_h(ik, vloc, np.eye(npw, dtype=np.complex128))      # rows = H e_j  ->  H[j, :] = column j of H
-            H = H.T
-            herm = np.max(np.abs(H - H.conj().T))
-            H = 0.5 * (H + H.conj().T)
-            w, v = np.linalg.eigh(H)
-            eig_all.append(w[:nband].copy())
-            c = v[:, :nocc].T                                            # (nocc, npw)
+            enl_bands = None
+            if eigensolver is not None:
+                w, cb, enl_bands = eigensolver(ik, vloc)
+                herm = 0.0
+                eig_all.append(np.array(w[:nband], copy=True))
+                c = np.array(cb[:nocc], copy=True)
+            else:
+                H = apply_h(ik, vloc, np.eye(npw, dtype=np.complex128))  # rows = H e_j  ->  H[j, :] = column j of H
+                H = H.T
+                herm = np.max(np.abs(H - H.conj().T))
+                H = 0.5 * (H + H.conj().T)
+                w, v = np.linalg.eigh(H)
+                eig_all.append(w[:nband].copy())
+                c = v[:, :nocc].T                                        # (nocc, npw)
             ur = _g2r(c, s.kg[ik], s.ngfft)
             rho_new += s.wtk[ik] * 2.0 * np.sum(np.abs(ur) ** 2, axis=0) / s.ucvol
             kin = np.where(s.kinpw[ik] < g.KIN_FILTER, s.kinpw[ik], 0.0)
             ek += s.wtk[ik] * 2.0 * float(np.sum(kin[None, :] * np.abs(c) ** 2))
-            enl += s.wtk[ik] * 2.0 * float(np.sum(s.enl_of(ik, c)))
+            enl += s.wtk[ik] * 2.0 * float(np.sum(s.enl_of(ik, c)) if enl_bands is None else np.sum(enl_bands[:nocc]))
             res["herm"] = max(res.get("herm", 0.0), herm)
         if getattr(s, "symops", None):
             rho_new = symmetrize_rho(rho_new, s.symops, s.ngfft)
