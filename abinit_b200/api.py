@@ -144,7 +144,7 @@ class Hamiltonian:
         self.h = lib.abi_b200_ham_create(self._ngfft.ctypes.data, int(natom), int(ntypat), int(lmnmax),
                                          self.indlmn.ctypes.data, self.nattyp.ctypes.data, self.atindx1.ctypes.data,
                                          int(usepaw), float(ucvol))
-        self.npw = 0
+        self.npw = 0; self.istwf_k = 1; self.me_g0 = 1
 
     def load_spin(self, vlocal, cplex=1):
         n1, n2, n3 = (int(x) for x in self._ngfft[:3])
@@ -158,7 +158,7 @@ class Hamiltonian:
 
     def load_k(self, istwf_k, kg_k, kinpw, ffnl=None, ph3d=None, me_g0=1):
         kg_k = np.ascontiguousarray(kg_k, dtype=np.int32)
-        self.npw = int(kg_k.shape[0])
+        self.npw = int(kg_k.shape[0]); self.istwf_k = int(istwf_k); self.me_g0 = int(me_g0)
         kin = np.ascontiguousarray(kinpw, dtype=np.float64)
         dimffnl = 0 if ffnl is None else int(ffnl.shape[-2])           # (ntypat, lmnmax, dimffnl, npw)
         matblk = 0 if ph3d is None else int(ph3d.shape[0])             # (matblk, npw) complex / (matblk, npw, 2)

@@ -33,6 +33,9 @@ def parse():
     ap.add_argument("--cpu-bands", type=int, default=8, help="bands in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scf-step", action="store_true")
+    ap.add_argument("--nband", type=int, default=1100, help="bands of the ChebFi2 (SCF-step-equivalent) leg, sharded over the GPUs")
+    ap.add_argument("--nline", type=int, default=4, help="Chebyshev filter degree of the ChebFi2 leg")
     return ap.parse_args()
 
 
@@ -281,6 +284,41 @@ def main():
         e2e = {"value": world * ndat * args.steps / float(dt.item()), "unit": "band-applications/s",
                "h2d_bytes_per_step": int(ndat * npw * 16), "d2h_bytes_per_step": int(ndat * npw * 16)}
 
+    # SCF-step-equivalent (BASELINE metric "s/SCF step"): ONE ChebFi2 call on nband bands at this k-point, band-sharded over
+    # the GPUs: (ndeg+1) getghc passes + Rayleigh-Ritz (all-to-all re-layout, Gram allreduce over NCCL, hegvd, rotations)
+    scf_step = None
+    if not args.no_scf_step:
+        from abinit_b200 import parallel as par
+        api.set_async(False)
+        f, l = par.band_block(args.nband, world, rank)
+        with torch.cuda.stream(stream):
+            gen = torch.Generator(device=dev).manual_seed(777 + rank)
+            damp = torch.from_numpy(1.0 / (1.0 + np.minimum(w["kinpw"], 1e6))).to(dev)
+            cg = torch.randn((l - f, npw, 2), generator=gen, device=dev, dtype=torch.float64) * damp[None, :, None]
+            if args.istwfk == 2:
+                cg[:, 0, 1] = 0.0
+            times = []
+            for it in range(2):                                   # first call warms up (plans, cuSOLVER handle, workspaces)
+                barrier()
+                t0 = time.perf_counter()
+                l1 = ab.kernel_launches()
+                eig, res = par.chebfi_band_parallel(ham, cg, args.nband, float(w["cfg"]["ecut"]), args.nline, bandpp=ndat)
+                barrier()
+                times.append(time.perf_counter() - t0)
+            dtm = torch.tensor([times[-1]], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(dtm, op=dist.ReduceOp.MAX)
+        api.profile_enable(True)
+        with torch.cuda.stream(stream):
+            par.chebfi_band_parallel(ham, cg, args.nband, float(w["cfg"]["ecut"]), args.nline, bandpp=ndat)
+        prof_scf = api.profile_collect()
+        api.profile_enable(False)
+        scf_step = {"value": float(dtm.item()), "unit": "s per ChebFi2 call (one k-point, SCF-step-equivalent)", "nband": args.nband,
+                    "nline": args.nline, "bands_per_gpu": l - f, "launches": int(ab.kernel_launches() - l1),
+                    "eig_min_max": [float(np.min(eig)), float(np.max(eig))], "resid_max": float(np.max(res)),
+                    "timing": "host clock between barrier + device synchronise on both sides, max over ranks (the call holds host syncs)",
+                    "kernel_ms": {k: v[0] for k, v in prof_scf.items()}}
+        del cg
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -327,7 +365,7 @@ def main():
                       "l2": "inputs larger than L2 (P = %.1f GB streamed twice per step)" % (16.0 * npw * nprojs / 1e9),
                       "parallelism": f"band blocks over {world} GPU(s), no data-path collective"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-           "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+           "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}, "scf_step": scf_step}
     out.update(extra)
     print(json.dumps(out))
     if dist is not None:

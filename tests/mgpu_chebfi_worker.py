@@ -1,0 +1,47 @@
+"""Worker of tests/test_chebfi_mgpu.py (one process per GPU, launched with torch.distributed.run): band-parallel ChebFi2
+(abinit_b200.parallel.chebfi_band_parallel: NCCL all-to-all re-layout + Gram allreduce) against the single-GPU chebfiwf2
+on the same start block."""
+import os
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import abinit_b200 as ab                      # noqa: E402
+from abinit_b200 import parallel as par, xg   # noqa: E402
+from problems import make_problem             # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ab.init(local)
+    ok = True
+    for istwf_k, kpt, nband in ((2, (0, 0, 0), 13), (1, (-.25, .5, 0), 10)):
+        p = make_problem(7.0, (8.0, 9.0, 7.5), kpt, istwf_k, ndat=nband, natom_per_type=(2,), lmax_per_type=(1,), filter_shell=False)
+        h = ab.Hamiltonian(p.ngfft, p.natom, p.ntypat, p.lmnmax, p.indlmn, p.nattyp, p.atindx1, 0, p.ucvol)
+        h.load_spin(p.vlocal, p.cplex); h.load_enl(p.enl, None); h.load_k(istwf_k, p.kgF, p.kinpw, p.ffnl, p.ph3d, me_g0=1)
+        # single-GPU reference on every rank (same input -> same output)
+        cg1 = p.cwavef.copy(); eig1 = np.zeros(nband); res1 = np.zeros(nband)
+        xg.chebfiwf2(cg1, eig1, None, None, h, nband, p.npw, 1, res1, 1e-16, p.ecut, 5, bandpp=4)
+        f, l = par.band_block(nband, world, rank)
+        cg = torch.from_numpy(np.ascontiguousarray(p.cwavef[f:l]).view(np.float64).reshape(l - f, p.npw, 2)).cuda()
+        eig, res = par.chebfi_band_parallel(h, cg, nband, p.ecut, 5, bandpp=4)
+        e_ok = np.max(np.abs(eig - eig1)) < 1e-10
+        r_ok = np.max(np.abs(res - res1[f:l]) / (np.abs(res1[f:l]) + 1e-12)) < 1e-5
+        c = cg.cpu().numpy(); c = c[..., 0] + 1j * c[..., 1]
+        v_ok = np.max(np.abs(np.abs(c) - np.abs(cg1[f:l]))) < 1e-8
+        print(f"rank {rank} istwf_k {istwf_k}: eig {e_ok} resid {r_ok} vec {v_ok}", flush=True)
+        ok = ok and e_ok and r_ok and v_ok
+        h.destroy()
+    t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -124,3 +124,45 @@ def test_gram_allreduce_gloo_world2(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env))
     rcs = [p.wait(timeout=180) for p in procs]
     assert rcs == [0, 0]
+
+
+_WORKER_T = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from abinit_b200 import parallel as par
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+rng = np.random.default_rng(3)
+ok = True
+for npw, nband in ((301, 7), (64, 2), (1000, 33)):
+    X = rng.standard_normal((nband, npw, 2))                       # the full block, same on every rank
+    f, l = par.band_block(nband, world, rank)
+    lo, hi = par.row_shard(npw, world, rank)
+    cols = torch.from_numpy(np.ascontiguousarray(X[f:l]))
+    rows = par.transpose_cols_to_rows(cols, nband, npw)            # xgTransposer STATE_COLSROWS -> STATE_LINALG
+    ok = ok and rows.shape == (nband, hi - lo, 2) and np.array_equal(rows.numpy(), X[:, lo:hi])
+    back = par.transpose_rows_to_cols(rows, nband, npw)            # and back
+    ok = ok and np.array_equal(back.numpy(), X[f:l])
+    # row-sharded SPACE_CR Gram partials (G=0 correction on the rank that owns row 0) sum to the full Gram
+    from oracle import xg as oxg
+    Xc = X[..., 0] + 1j * X[..., 1]
+    part = oxg.gram(oxg.SPACE_CR, np.ascontiguousarray(Xc[:, lo:hi]), np.ascontiguousarray(Xc[:, lo:hi]), 1 if rank == 0 else 0)
+    t = torch.from_numpy(part); dist.all_reduce(t)
+    ok = ok and np.allclose(t.numpy(), oxg.gram(oxg.SPACE_CR, Xc, Xc, 1), atol=1e-10)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_xg_transposer_gloo_world2(tmp_path):
+    """Band-sharded <-> row-sharded re-layout of the band-parallel ChebFi2 (abinit_b200.parallel), world size 2 on gloo."""
+    script = tmp_path / "worker_t.py"
+    script.write_text(_WORKER_T % {"root": ROOT})
+    port = 31500 + (os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env))
+    rcs = [p.wait(timeout=180) for p in procs]
+    assert rcs == [0, 0]
