@@ -30,11 +30,11 @@ def main():
         f, l = par.band_block(nband, world, rank)
         cg = torch.from_numpy(np.ascontiguousarray(p.cwavef[f:l]).view(np.float64).reshape(l - f, p.npw, 2)).cuda()
         eig, res = par.chebfi_band_parallel(h, cg, nband, p.ecut, 5, bandpp=4)
-        e_ok = np.max(np.abs(eig - eig1)) < 1e-10
+        e_err = float(np.max(np.abs(eig - eig1))); e_ok = e_err < 1e-8      # north_star: eigenvalues within 1e-8 Ha
         r_ok = np.max(np.abs(res - res1[f:l]) / (np.abs(res1[f:l]) + 1e-12)) < 1e-5
         c = cg.cpu().numpy(); c = c[..., 0] + 1j * c[..., 1]
         v_ok = np.max(np.abs(np.abs(c) - np.abs(cg1[f:l]))) < 1e-8
-        print(f"rank {rank} istwf_k {istwf_k}: eig {e_ok} resid {r_ok} vec {v_ok}", flush=True)
+        print(f"rank {rank} istwf_k {istwf_k}: eig {e_ok} ({e_err:.2e}) resid {r_ok} vec {v_ok}", flush=True)
         ok = ok and e_ok and r_ok and v_ok
         h.destroy()
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
