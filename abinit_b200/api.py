@@ -245,3 +245,16 @@ def nonlop(choice, cpopt, cprjin, enlout, hamk: Hamiltonian, idir, lambda_, mpi_
                          _iref(idir), lam.ctypes.data, _iref(ndat), _iref(nnlout), _iref(paw_opt), _iref(signs),
                          _ptr(svectout, _F, "svectout"), _iref(tim_nonlop), _ptr(vectin, _F, "vectin"),
                          _ptr(vectout, _F, "vectout"))
+
+
+def make_invovl(ham: Hamiltonian):
+    """make_invovl (src/66_wfs/m_invovl.F90:469) for the k-point loaded in ham."""
+    hp = C.c_void_p(ham.h)
+    L().abi_b200_make_invovl_(C.byref(hp))
+
+
+def apply_invovl(ham: Hamiltonian, cwavef, sm1cwavef, cwaveprj, npw, ndat, mpi_enreg=None, nspinor=1, block_sliced=0):
+    """apply_invovl (src/66_wfs/m_invovl.F90:790 argument list): sm1cwavef = S^-1 cwavef (PAW)."""
+    hp = C.c_void_p(ham.h)
+    L().abi_b200_apply_invovl_(C.byref(hp), _ptr(cwavef, _F, "cwavef"), _ptr(sm1cwavef, _F, "sm1cwavef"),
+                               _ptr(cwaveprj, _F, "cwaveprj"), _iref(npw), _iref(ndat), _iref(nspinor), _iref(block_sliced))

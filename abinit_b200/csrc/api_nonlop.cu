@@ -179,7 +179,7 @@ abi_b200_ham_t* abi_b200_ham_create(const int* ngfft, int natom, int ntypat, int
 void abi_b200_ham_destroy(abi_b200_ham_t* h) {
   if (!h) return;
   if (ctx().initialized) CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
-  h->atoms.release(); h->enl.release(); h->P.release();
+  h->atoms.release(); h->enl.release(); h->P.release(); h->invovl.release();
   if (h->vloc.d_v) cudaFree(h->vloc.d_v);
   if (h->vloc.d_vT) cudaFree(h->vloc.d_vT);
   if (h->d_kinpw) cudaFree(h->d_kinpw);
@@ -199,6 +199,7 @@ void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_v
 void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, const double* sij) {
   ensure_init();
   h->enl.load(enl, dimenl1, dimenl2, sij, h->ntypat, ctx().stream);
+  h->invovl.release();
 }
 
 void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw, const double* ffnl,
@@ -207,6 +208,7 @@ void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_
   Context& c = ctx();
   ABI_CHECK(!is_device_ptr(kg_k), "kg_k must be a host array");
   h->istwf_k = istwf_k; h->npw = npw; h->me_g0 = me_g0;
+  h->invovl.release();
   h->kg.assign(kg_k, kg_k + (size_t)3 * npw);
   h->plan = fourwf_get_plan(h->kg.data(), npw, h->kg.data(), npw, h->ngfft, istwf_k, me_g0);
   if (h->d_kinpw) cudaFree(h->d_kinpw);
@@ -227,6 +229,7 @@ void abi_b200_ham_set_projectors(abi_b200_ham_t* h, const double* projs, int npr
   ensure_init();
   ABI_CHECK(nprojs == h->atoms.nprojs, "set_projectors: nprojs differs from sum(nlmn*nattyp)");
   h->P.alloc(h->npw, nprojs, h->istwf_k);
+  h->invovl.release();
   CUDA_CHECK(cudaMemcpyAsync(h->P.d_p, projs, sizeof(double) * 2 * (size_t)h->npw * nprojs, cudaMemcpyDefault, ctx().stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
 }

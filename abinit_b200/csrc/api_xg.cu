@@ -135,14 +135,18 @@ int ndeg_from_residu(const ChebOpts& o, int space, int me_g0, int npw, int ncols
 // X/AX/BX/Xnext/Xprev are device blocks (2, npw, ncols); on return *X_io points to the buffer holding the filtered X.
 void cheb_core(abi_b200_ham_t* h, int space, int me_g0, int npw, int ncols, int bandpp, double** X_io, double* AX, double* BX,
                double** Xnext_io, double** Xprev_io, double lm, double lp, int ndeg, const std::vector<double>& div) {
-  ABI_CHECK(BX == nullptr, "chebfi: the PAW filter needs getBm1X (apply_invovl, m_invovl.F90), not available in this build");
   cudaStream_t st = ctx().stream;
   double *X = *X_io, *Xn = *Xnext_io, *Xp = *Xprev_io;
   const double center = (lp + lm) * 0.5, radius = (lp - lm) * 0.5;
   const double one_over_r = 1 / radius, two_over_r = 2 / radius;
   for (int ideg = 0; ideg < ndeg; ideg++) {
     // X_next = (AX - center X) * (1/r | 2/r) [- X_prev]   (chebfi_computeNextOrderChebfiPolynom, one pass)
-    xg_cheb_next(space, npw, ncols, Xn, npw, AX, npw, X, npw, ideg == 0 ? nullptr : Xp, npw, center,
+    const double* src = AX;
+    if (BX) {                                  // PAW: X_next = getBm1X(AX) = S^-1 AX (apply_invovl, m_chebfiwf.F90:390-440)
+      apply_invovl_device(h, AX, Xn, nullptr, ncols, st);
+      src = Xn;
+    }
+    xg_cheb_next(space, npw, ncols, Xn, npw, src, npw, X, npw, ideg == 0 ? nullptr : Xp, npw, center,
                  ideg == 0 ? one_over_r : two_over_r, st);
     double* t = Xp; Xp = X; X = Xn; Xn = t;                                         // chebfi_swapInnerBuffers
     get_ax_bx(h, space, me_g0, npw, ncols, bandpp, X, AX, BX);
@@ -169,7 +173,7 @@ int me_g0_of(const abi_b200_ham_t* h) { return h->istwf_k > 1 ? ((h->istwf_k == 
 }  // namespace
 
 namespace abi {
-void chebfi_release_workspace() { for (auto& b : g_cheb) b.release(); for (auto& b : g_small) b.release(); }
+void chebfi_release_workspace() { for (auto& b : g_cheb) b.release(); for (auto& b : g_small) b.release(); invovl_release_workspace(); }
 }
 
 extern "C" {
@@ -257,6 +261,30 @@ void abi_b200_xg_rayleigh_ritz_(int* space, int* rows, int* blockdim, double* x,
                            *me_g0, c.stream);
   a_eig.copy_back();
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+void abi_b200_make_invovl_(abi_b200_ham_t** ham) {
+  ensure_init();
+  make_invovl(*ham, ctx().stream);
+}
+
+void abi_b200_apply_invovl_(abi_b200_ham_t** ham, double* cwavef, double* sm1cwavef, double* cwaveprj, int* npw, int* ndat,
+                            int* nspinor, int* block_sliced) {
+  (void)block_sliced;
+  ensure_init();
+  Context& c = ctx();
+  abi_b200_ham* h = *ham;
+  ABI_CHECK(*nspinor == 1, "apply_invovl: nspinor=2 is not implemented in this build");
+  ABI_CHECK(*npw == h->npw, "apply_invovl: npw differs from the k-point loaded in ham");
+  ABI_CHECK(h->usepaw == 1, "apply_invovl: PAW only");
+  const size_t nv = sizeof(double) * 2 * (size_t)h->npw * (*ndat);
+  const int cplex = h->istwf_k == 1 ? 2 : 1;
+  DevArg a_c(0, cwavef, nv, true);
+  DevArg a_s(1, sm1cwavef, nv, false);
+  DevArg a_p(3, cwaveprj, sizeof(double) * (size_t)cplex * h->atoms.nprojs * (*ndat), false);
+  apply_invovl_device(h, a_c.as<double>(), a_s.as<double>(), a_p.as<double>(), *ndat, c.stream);
+  a_s.copy_back(); a_p.copy_back();
+  if (!c.async || a_c.staged || a_s.staged || a_p.staged) CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
 
 // ---- ChebFi2, split in the phases between which a band-parallel run communicates (m_chebfi2.F90:596-611, 687-705) ----

@@ -4,6 +4,18 @@
 #include "nonlop.cuh"
 #include <vector>
 
+namespace abi {
+// invovl_kpt_type (src/66_wfs/m_invovl.F90:120-150): per-k data of the PAW inverse overlap, device resident
+struct Invovl {
+  int nprojs = -1, cplx = 1, lmnmax = 0, ntypat = 0;
+  long long ldgram = 0;               // leading dimension of gram_projs in its own elements
+  double* d_inv_sij = nullptr;        // [ntypat][lmnmax][lmnmax] (cplx interleaved), row-major
+  double* d_inv_s_approx = nullptr;   // same shape
+  double* d_gram = nullptr;           // (cplx, ldgram, nprojs) column-major P^H P
+  void release();
+};
+}  // namespace abi
+
 struct abi_b200_ham {
   // (the members are abi:: types; the struct itself lives in the global namespace because the C header names it)
   int ngfft[18];
@@ -18,4 +30,11 @@ struct abi_b200_ham {
   double* d_kinpw = nullptr;
   abi::FourwfPlan* plan = nullptr;
   double* d_gvnlxc = nullptr; size_t gvnlxc_cap = 0;
+  abi::Invovl invovl;                 // built lazily by apply_invovl, dropped by load_k / load_enl / set_projectors
 };
+
+namespace abi {
+void make_invovl(abi_b200_ham* h, cudaStream_t st);
+void apply_invovl_device(abi_b200_ham* h, const double* cwavef, double* sm1cwavef, double* cprj, int ndat, cudaStream_t st);
+void invovl_release_workspace();
+}  // namespace abi

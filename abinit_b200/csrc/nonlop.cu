@@ -606,6 +606,29 @@ void zgemm_nn(int M, int N, int K, const double* A, long long lda, const double*
   launch_nn(true, 2 * M, N, K, A, 2 * lda, B, 2 * ldb, C, 2 * ldc, nullptr, st, nullptr, nullptr, 0.0, "dgemm_nn_rotate");
 }
 
+// opernla / opernlb as stand-alone steps (used by apply_invovl): gx is the padded internal layout [ndat][ldg]
+long long nonlop_ldg(const Projectors& P) { return ((long long)(P.istwf_k == 1 ? 2 : 1) * P.nprojs + 1) & ~1LL; }
+
+void nonlop_project(const Projectors& P, int me_g0, const double* vectin, int ndat, double* gx, cudaStream_t st) {
+  const bool cplx = P.istwf_k == 1; const int cplex = cplx ? 2 : 1;
+  const long long ldv = 2LL * P.npw, ldg = nonlop_ldg(P);
+  if (ldg != (long long)cplex * P.nprojs) CUDA_CHECK(cudaMemsetAsync(gx, 0, sizeof(double) * ldg * ndat, st));
+  double* part = nullptr;
+  const int nsplit = launch_tn(cplx, P.nprojs, cplex * ndat, 2 * P.npw, P.d_p, ldv, vectin, ldv, part, st);
+  ReduceParams r{};
+  r.M = P.nprojs; r.ndat = ndat; r.cplex = cplex; r.nsplit = nsplit; r.neff = cplex * ndat; r.part = part;
+  r.scale = cplx ? 1.0 : 2.0; r.g0fix = (P.istwf_k == 2 && me_g0 == 1) ? 1 : 0;
+  r.A = P.d_p; r.lda = ldv; r.B = vectin; r.ldb = ldv; r.gx = gx; r.ldg = ldg;
+  const int blocks = std::min(kNumSM * 8, (int)ceil_div<long long>((long long)P.nprojs * ndat, 256));
+  k_reduce_proj<<<blocks, 256, 0, st>>>(r);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+void nonlop_expand(const Projectors& P, const double* z, int ndat, double* vectout, const double* add, cudaStream_t st) {
+  launch_nn(P.istwf_k == 1, 2 * P.npw, ndat, P.nprojs, P.d_p, 2LL * P.npw, z, nonlop_ldg(P), vectout, 2LL * P.npw, add, st);
+}
+
 // opernld, choice 1 (m_opernld_ylm_allwf.F90:160-203): enlout(idat) = sum_{ilmn, cplex} gxfac * gx
 __global__ void k_opernld(const double* __restrict__ gx, const double* __restrict__ gxfac, long long ldg, int n, double* __restrict__ enlout) {
   __shared__ double red[256];
@@ -700,8 +723,9 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
   }
   // opernlb
   if (choice == 7 || paw_opt == 3 || paw_opt == 4) {
-    ABI_CHECK(svectout != nullptr && vectin != nullptr, "gemm_nonlop: svectout/vectin required for the overlap");
-    launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zs, ldg, svectout, ldv, vectin, st);   // + vectin, m_opernlb_gemm.F90:654-665
+    ABI_CHECK(svectout != nullptr && (vectin != nullptr || choice == 7), "gemm_nonlop: svectout/vectin required for the overlap");
+    // + vectin except for choice 7 (m_opernlb_gemm.F90:654-665)
+    launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zs, ldg, svectout, ldv, choice == 7 ? nullptr : vectin, st);
   }
   if (choice == 1 && (paw_opt == 0 || paw_opt == 1 || paw_opt == 2 || paw_opt == 4)) {
     if (fuse == nullptr) {

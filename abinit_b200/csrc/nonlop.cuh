@@ -68,6 +68,12 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
                         double* vectout, double* svectout, double* projections, cudaStream_t st,
                         const NonlopFusion* fuse = nullptr, int signs = 2, double* enlout = nullptr);
 
+// opernla / opernlb as stand-alone steps on the padded projection layout gx[ndat][nonlop_ldg(P)] (cplex interleaved):
+//   nonlop_project: gx = P^H psi (with the istwf_k>=2 factor 2 / G=0 correction);  nonlop_expand: vectout = P.z (+ add)
+long long nonlop_ldg(const Projectors& P);
+void nonlop_project(const Projectors& P, int me_g0, const double* vectin, int ndat, double* gx, cudaStream_t st);
+void nonlop_expand(const Projectors& P, const double* z, int ndat, double* vectout, const double* add, cudaStream_t st);
+
 // plain tensor-core GEMMs (also used by the Gram kernels of xg.cu); all device pointers, column-major
 //   TN: C(M,N) = alpha * A(K,M)^T B(K,N)      NN: C(M,N) = A(M,K) B(K,N)
 void dgemm_tn(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,

@@ -30,6 +30,7 @@ SYMBOLS = [
     "abi_b200_nonlop_",
     "abi_b200_xg_gram_", "abi_b200_xg_rotate_", "abi_b200_xg_hegvd_", "abi_b200_xg_colwise_", "abi_b200_xg_rayleigh_ritz_",
     "abi_b200_chebfiwf2_", "abi_b200_chebfi_rq_", "abi_b200_chebfi_core_", "abi_b200_cheb_oracle1_", "abi_b200_cheb_poly1_",
+    "abi_b200_make_invovl_", "abi_b200_apply_invovl_",
 ]
 
 
@@ -90,6 +91,8 @@ def load_library(path: str | None = None) -> C.CDLL:
         lib.abi_b200_cheb_oracle1_.restype = C.c_int
         lib.abi_b200_cheb_poly1_.argtypes = [vp] * 4
         lib.abi_b200_cheb_poly1_.restype = C.c_double
+        lib.abi_b200_make_invovl_.argtypes = [vp]
+        lib.abi_b200_apply_invovl_.argtypes = [vp] * 8
     if path is None:
         _LIB = lib
     return lib

@@ -173,7 +173,7 @@ void abi_b200_xg_rayleigh_ritz_(int* space, int* rows, int* blockdim, double* x,
  * columns (getghc_gsc1 :341-385), lambda_plus = ecut, the dtset scalars are passed flattened
  * (tolwfr_diago, ecut, nline, nbdbuf, chebfi_oracle, oracle_factor, oracle_min_occ).
  * cg(2,npw*nband) host or device, in/out; eig, resid, occ (may be NULL when chebfi_oracle=0), enl_out (NC only, may
- * be NULL): host arrays of nband.  Norm-conserving only in this build (the PAW filter needs apply_invovl).
+ * be NULL): host arrays of nband.  PAW: BX = S X from getghc(sij_opt=1), getBm1X = abi_b200_apply_invovl_.
  * The three phase functions are what a band-parallel caller strings together around its collectives
  * (max/min of the Rayleigh quotients, m_chebfi2.F90:606-611; transposition + Rayleigh-Ritz, :687-705):
  *   chebfi_rq   : AX,BX = getAX_BX(X); div(ncols) = <X|AX>/<X|BX>; max / min      (:575-613)
@@ -192,6 +192,20 @@ void abi_b200_chebfi_core_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, do
                            int* ndeg_filter, double* div);
 int abi_b200_cheb_oracle1_(double* xx, double* aa, double* bb, double* tol, int* nmax);
 double abi_b200_cheb_poly1_(double* xx, int* nn, double* aa, double* bb);
+
+/* ------------------------------------------------------------------------------------------------------
+ * PAW inverse overlap (src/66_wfs/m_invovl.F90): S^-1 = 1 - P (s^-1 + P^H P)^-1 P^H, the getBm1X of ChebFi2-PAW
+ * (src/79_seqpar_mpi/m_chebfiwf.F90:390-440).
+ *   make_invovl  (m_invovl.F90:469-776): builds inv_sij, inv_s_approx and gram_projs = P^H P for the k-point loaded in
+ *                the handle (from the resident projectors; ffnl/ph3d were consumed by load_k).  Called lazily by
+ *                apply_invovl; load_k / load_enl / set_projectors invalidate it.
+ *   apply_invovl (m_invovl.F90:790-1039): sm1cwavef = S^-1 cwavef, argument list of the reference with mpi_enreg dropped
+ *                and cwaveprj flattened to (cplex,nprojs,ndat) (may be NULL); block_sliced is accepted and ignored (both
+ *                settings give the same numbers, it only selects a BLAS call pattern, :1165-1231).
+ * ---------------------------------------------------------------------------------------------------- */
+void abi_b200_make_invovl_(abi_b200_ham_t** ham);
+void abi_b200_apply_invovl_(abi_b200_ham_t** ham, double* cwavef, double* sm1cwavef, double* cwaveprj, int* npw,
+                            int* ndat, int* nspinor, int* block_sliced);
 
 #ifdef __cplusplus
 }

@@ -63,8 +63,8 @@ def ndeg_from_residu(space, me_g0, ax, bx, div, occ, lm, lp, ndeg_max, tolerance
 
 
 def chebfi_run(apply_h, x0, space, me_g0, ecut, nline, tolerance=1e-20, occ=None, nbdbuf=0, oracle=0,
-               oracle_factor=1e-2, oracle_min_occ=1e-8, info=None):
-    """Returns (eigenvalues, residuals, X).  x0: (nband, npw) complex."""
+               oracle_factor=1e-2, oracle_min_occ=1e-8, info=None, get_bm1x=None):
+    """Returns (eigenvalues, residuals, X).  x0: (nband, npw) complex.  get_bm1x(AX) -> S^-1 AX for PAW (chebfi%paw)."""
     def get_ax_bx(x):
         ax, bx = apply_h(x)
         ax = np.array(ax, copy=True); bx = np.array(bx, copy=True)
@@ -90,7 +90,7 @@ def chebfi_run(apply_h, x0, space, me_g0, ecut, nline, tolerance=1e-20, occ=None
     x_prev = None
     for ideg in range(ndeg):
         # chebfi_computeNextOrderChebfiPolynom :837-896, same operation order as the reference (NC: X_next = copy of AX)
-        x_next = ax.copy()
+        x_next = ax.copy() if get_bm1x is None else np.array(get_bm1x(ax), copy=True)
         x *= center
         x_next += -1.0 * x
         x *= 1 / center

@@ -106,7 +106,7 @@ def opernlb(P, gxfac, istwf_k):
 def gemm_nonlop(P, vectin, enl, sij, indlmn, nattyp, atindx1, istwf_k, choice=1, paw_opt=0, cpopt=-1,
                 lambda_=None, projections=None, me_g0=1):
     """Returns (vectout, svectout, projections).  choice=1 signs=2; choice=0 only computes projections;
-    choice=7 applies S only with s_projections=projections (m_gemm_nonlop.F90:764-866).
+    choice=7: svectout = P . projections, s_projections=projections (m_gemm_nonlop.F90:855-861), without + vectin.
     cpopt>=2: projections are taken from the caller instead of being computed (m_gemm_nonlop.F90:719-734)."""
     vectin = np.atleast_2d(vectin)
     if cpopt >= 2:
@@ -117,7 +117,10 @@ def gemm_nonlop(P, vectin, enl, sij, indlmn, nattyp, atindx1, istwf_k, choice=1,
         return None, None, gx
     vectout = svectout = None
     if choice == 7:
-        svectout = opernlb(P, gx, istwf_k) + vectin
+        # s_projections = projections (m_gemm_nonlop.F90:855-861); vectin is NOT added for choice 7
+        # (m_opernlb_gemm.F90:654: "if(choice /= 7 ...) svectout = svectout + vectin"); apply_invovl adds it itself
+        # (m_invovl.F90:1031 sm1cwavef = cwavef + sm1cwavef)
+        svectout = opernlb(P, gx, istwf_k)
         return None, svectout, gx
     gxfac, gxs = opernlc(gx, enl, sij, indlmn, nattyp, atindx1, paw_opt, lambda_)
     if paw_opt in (3, 4):
