@@ -135,7 +135,10 @@ void abi_b200_fourwf_(int* cplex, double* denpot, double* fofgin, double* fofgou
     a_wr = DevArg(4, weight_r, sizeof(double) * nd, true);
     a_wi = DevArg(5, weight_i, sizeof(double) * nd, true);
   }
-  if (fused) {
+  if (opt == 1 && c.fourwf_impl != 1 && fourwf_fused_opt1_available(*pl)) {
+    // density accumulation on the fused zero-padded path (fofr is not produced, as in the reference's GPU paths)
+    fourwf_fused_opt1(*pl, a_in.as<double2>(), a_den.as<double>(), nd, a_wr.as<double>(), a_wi.as<double>(), c.stream);
+  } else if (fused) {
     vloc_upload(g_vloc_call, denpot, is_device_ptr(denpot), *cplex, n1, n2, n3, c.stream);
     FourwfEpilogue epi;
     fourwf_fused_opt2(*pl, g_vloc_call, a_in.as<double2>(), a_out.as<double2>(), nd, epi, c.stream);

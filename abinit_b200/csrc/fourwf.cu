@@ -984,4 +984,98 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// (C) fused option 1: rho(r) += weight_r Re(psi(r))^2 + weight_i Im(psi(r))^2  (m_fft.F90:2633-2653)
+//     K1 (x pass on the occupied lines) -> plane stage (y pass, z pass, density reduction into rhoT[i1][i3][i2]) ->
+//     one transpose-add into the caller's denpot.  No full box per band ever exists.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_rho_weights(double2* __restrict__ wxy, const double* __restrict__ wr, const double* __restrict__ wi, int ntrans,
+                              int b0, int ndat, int pack2) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntrans) return;
+  if (pack2) {
+    // E = C + i D: Re E(r) = C(r), Im E(r) = D(r), both real in r at Gamma (their own imaginary parts vanish)
+    const int a = b0 + 2 * t, b = a + 1;
+    wxy[t] = make_double2(wr[a], b < ndat ? wr[b] : 0.0);
+  } else {
+    wxy[t] = make_double2(wr[b0 + t], wi[b0 + t]);
+  }
+}
+
+__global__ void k_rho_untranspose_add(const double* __restrict__ rhoT, double* __restrict__ rho, int n1, int n2, int n3) {
+  // rho[i3][i2][i1] += rhoT[i1][i3][i2] through a 32x33 shared tile over (i1, i2) for fixed i3
+#ifndef ABI_EMU
+  __shared__ double tile[32][33];
+  const int i3 = blockIdx.z;
+  const int i1b = blockIdx.x * 32, i2b = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i1 = i1b + r, i2 = i2b + threadIdx.x;
+    tile[r][threadIdx.x] = (i1 < n1 && i2 < n2) ? rhoT[((size_t)i1 * n3 + i3) * n2 + i2] : 0.0;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i2 = i2b + r, i1 = i1b + threadIdx.x;
+    if (i1 < n1 && i2 < n2) rho[((size_t)i3 * n2 + i2) * n1 + i1] += tile[threadIdx.x][r];
+  }
+#else
+  for (int i1 = 0; i1 < n1; i1++) for (int i3 = 0; i3 < n3; i3++) for (int i2 = 0; i2 < n2; i2++)
+    rho[((size_t)i3 * n2 + i2) * n1 + i1] += rhoT[((size_t)i1 * n3 + i3) * n2 + i2];
+#endif
+}
+
+bool fourwf_fused_opt1_available(const FourwfPlan& pl) {
+  return pl.fused_ok && pl.plane_ok && fourwf_tuning().plane && plane_stage_supported(pl.n2) && pl.n2 == pl.n3;
+}
+
+void fourwf_fused_opt1(const FourwfPlan& pl, const double2* d_fofgin, double* d_denpot, int ndat, const double* d_wr,
+                       const double* d_wi, cudaStream_t st) {
+  ABI_CHECK(fourwf_fused_opt1_available(pl), "fused fourwf option 1 not available for this FFT box");
+  const int n1 = pl.n1, n2 = pl.n2, n3 = pl.n3;
+  const size_t N = (size_t)n1 * n2 * n3;
+  const FftTables& t1 = fft_tables(n1);
+  const FftTables& t2 = fft_tables(n2);
+  FourwfTuning& tune = fourwf_tuning();
+  const bool pack2 = tune.pack2 && pl.istwf_k == 2 && ndat >= 2;
+  const int ntrans = pack2 ? (ndat + 1) / 2 : ndat;
+  const size_t per_band = sizeof(double2) * (size_t)n1 * pl.nlin;
+  int chunk = tune.band_chunk > 0 ? tune.band_chunk : (int)std::max<size_t>(1, ((size_t)3 << 30) / per_band);
+  chunk = std::min(chunk, ntrans);
+  double2* W1 = (double2*)g_ws[1].get(sizeof(double2) * (size_t)n1 * pl.nlin * chunk);
+  // rhoT (N doubles) followed by the per-transform weights
+  double2* wxy = (double2*)g_ws[2].get(sizeof(double2) * (size_t)ntrans + sizeof(double) * N);
+  double* rhoT = reinterpret_cast<double*>(wxy + ntrans);
+  CUDA_CHECK(cudaMemsetAsync(rhoT, 0, sizeof(double) * N, st));
+  int lx = std::max(1, tune.lines_x);
+  while (lx > 1 && sizeof(double2) * ((size_t)n1 + (size_t)lx * (n1 | 1)) > 110 * 1024) lx--;
+  const size_t smem_x = sizeof(double2) * ((size_t)n1 + (size_t)lx * (n1 | 1));
+#ifndef ABI_EMU
+  CUDA_CHECK(cudaFuncSetAttribute(k_fw_x_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+#endif
+  for (int t0 = 0; t0 < ntrans; t0 += chunk) {
+    const int nb = std::min(chunk, ntrans - t0);
+    const int b0 = pack2 ? 2 * t0 : t0;
+    const int nbands = std::min(ndat - b0, pack2 ? 2 * nb : nb);
+    ABI_LAUNCH(k_rho_weights, dim3(ceil_div(nb, 128)), dim3(128), 0, st, wxy, d_wr, d_wi, nb, b0, ndat, pack2 ? 1 : 0);
+    { ProfScope ps("fourwf_x_forward");
+    ABI_LAUNCH(k_fw_x_forward, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st, d_fofgin + (size_t)b0 * pl.npw_in, W1,
+               t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_in, pack2 ? nbands : 0); }
+    { ProfScope ps("fourwf_plane_rho");
+    PlaneParams Q;
+    Q.n1 = n1; Q.n2 = n2; Q.n3 = n3; Q.nb = nb; Q.nU = pl.nU; Q.cplex = 1; Q.za = pl.za; Q.zla = pl.zla; Q.zb = pl.zb; Q.zlb = pl.zlb;
+    Q.nlin = pl.nlin; Q.nlout = pl.nlin; Q.nunits = (long long)nb * n1;
+    Q.W1 = W1; Q.W1o = nullptr; Q.S = nullptr; Q.vT = nullptr; Q.tw = t2.plan.tw;
+    Q.in_start = pl.d_pin_start; Q.in_runs = pl.d_pin_runs; Q.out_start = pl.d_pin_start; Q.out_runs = pl.d_pin_runs;
+    Q.rhoT = rhoT; Q.wxy = wxy;
+    plane_stage_launch_rho(n2, Q, st); }
+    g_kernel_launches += 3;
+  }
+#ifndef ABI_EMU
+  k_rho_untranspose_add<<<dim3(ceil_div(n1, 32), ceil_div(n2, 32), n3), dim3(32, 8), 0, st>>>(rhoT, d_denpot, n1, n2, n3);
+  CUDA_CHECK(cudaGetLastError());
+#else
+  k_rho_untranspose_add(rhoT, d_denpot, n1, n2, n3);
+#endif
+  g_kernel_launches++;
+}
+
 }  // namespace abi

@@ -85,6 +85,11 @@ void fourwf_generic(const FourwfPlan& pl, int option, int cplex, double* d_denpo
 void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_fofgin, double2* d_fofgout,
                        int ndat, const FourwfEpilogue& epi, cudaStream_t st);
 
+// fused option 1 (density accumulation) on the zero-padded plane stage; d_wr/d_wi: DEVICE arrays of ndat weights
+bool fourwf_fused_opt1_available(const FourwfPlan& pl);
+void fourwf_fused_opt1(const FourwfPlan& pl, const double2* d_fofgin, double* d_denpot, int ndat, const double* d_wr,
+                       const double* d_wi, cudaStream_t st);
+
 // tuning knobs (env ABI_B200_* override), reported by bench.py
 struct FourwfTuning {
   int cluster = 0; int lines_x = 32; int smem_kb_mid = 0; int band_chunk = 0;

@@ -2,12 +2,21 @@
 #include "plane_stage_impl.cuh"
 namespace abi {
 template void plane_launch_n<5, 6>(PlaneParams&, cudaStream_t);
+template void plane_launch_rho_n<5, 6>(PlaneParams&, cudaStream_t);
 template void plane_launch_n<5, 8>(PlaneParams&, cudaStream_t);
+template void plane_launch_rho_n<5, 8>(PlaneParams&, cudaStream_t);
 template void plane_launch_n<6, 10>(PlaneParams&, cudaStream_t);
+template void plane_launch_rho_n<6, 10>(PlaneParams&, cudaStream_t);
 template void plane_launch_n<8, 8>(PlaneParams&, cudaStream_t);
+template void plane_launch_rho_n<8, 8>(PlaneParams&, cudaStream_t);
 template void plane_launch_n<8, 12>(PlaneParams&, cudaStream_t);
+template void plane_launch_rho_n<8, 12>(PlaneParams&, cudaStream_t);
 template void plane_launch_n<10, 10>(PlaneParams&, cudaStream_t);
+template void plane_launch_rho_n<10, 10>(PlaneParams&, cudaStream_t);
 template void plane_launch_n<12, 12>(PlaneParams&, cudaStream_t);
+template void plane_launch_rho_n<12, 12>(PlaneParams&, cudaStream_t);
 template void plane_launch_n<12, 15>(PlaneParams&, cudaStream_t);
+template void plane_launch_rho_n<12, 15>(PlaneParams&, cudaStream_t);
 template void plane_launch_n<15, 15>(PlaneParams&, cudaStream_t);
+template void plane_launch_rho_n<15, 15>(PlaneParams&, cudaStream_t);
 }  // namespace abi

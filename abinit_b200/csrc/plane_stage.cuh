@@ -66,12 +66,16 @@ struct PlaneParams {
   // runs[u] = {a, la, b, lb}
   const int* in_start; const short4* in_runs;
   const int* out_start; const short4* out_runs;
+  // option 1 (density accumulation, k_fw_plane_rho): rhoT[i1][i3][i2] += wxy[b].x Re(psi)^2 + wxy[b].y Im(psi)^2
+  double* rhoT = nullptr; const double2* wxy = nullptr;
 };
 
 #ifdef ABI_EMU
 #define ABI_FOR_LANES for (int lane = 0; lane < 32; lane++)
 #define ABI_SYNCWARP()
+#define ABI_RED_ADD(p, v) (*(p) += (v))
 #else
+#define ABI_RED_ADD(p, v) atomicAdd((p), (v))
 #define ABI_FOR_LANES const int lane = threadIdx.x & 31;
 #define ABI_SYNCWARP() __syncwarp()
 #endif
@@ -224,6 +228,53 @@ struct PlaneFft {
     ABI_SYNCWARP();
   }
 
+  // ---------------- phase Z (option 1): columns of S -> z FFT -> rhoT += w |psi(r)|^2 ----------------
+  // fourwf option 1 (src/53_ffts/m_fft.F90:2633-2653, cg_addtorho src/44_abitools/m_cgtools.F90:2338-2384) on the same
+  // register-resident z transform; the plane of rhoT is i2-contiguous so a warp's reductions fill whole sectors.
+  ABI_DEV static void phase_z_rho(const PlaneParams& P, const double2* __restrict__ S, double* __restrict__ rplane, double2 wxy,
+                                  double2* E, const double2* tw, int c0) {
+    const int nl = min(G, P.n2 - c0);
+    const int n2 = P.n2;
+    for (int w0 = 0; w0 < G * R2; w0 += 32) {
+      ABI_FOR_LANES {
+        const int w = w0 + lane;
+        const int line = w % G, j = w / G;
+        if (w < G * R2 && line < nl) {
+          const double2* src = S + c0 + line;
+          double2 x[R1];
+#pragma unroll
+          for (int t = 0; t < R1; t++) {
+            const int u = u_of_i3(P, j + R2 * t);
+            x[t] = (u >= 0) ? ldcg2(src + (size_t)u * n2) : make_double2(0.0, 0.0);
+          }
+          Dft<R1, +1>::run(x);
+          double2* e = E + j * G + line;
+          e[0] = x[0];
+#pragma unroll
+          for (int k1 = 1; k1 < R1; k1++) e[k1 * ZK] = twf(tw, j * k1, x[k1]);
+        }
+      }
+    }
+    ABI_SYNCWARP();
+    for (int w0 = 0; w0 < G * R1; w0 += 32) {
+      ABI_FOR_LANES {
+        const int w = w0 + lane;
+        const int line = w % G, k1 = w / G;
+        if (w < G * R1 && line < nl) {
+          const double2* e = E + k1 * ZK + line;
+          double2 v[R2];
+#pragma unroll
+          for (int j = 0; j < R2; j++) v[j] = e[j * G];
+          Dft<R2, +1>::run(v);
+          double* rp = rplane + (size_t)k1 * n2 + c0 + line;
+#pragma unroll
+          for (int k2 = 0; k2 < R2; k2++) ABI_RED_ADD(rp + (size_t)(R1 * k2) * n2, wxy.x * v[k2].x * v[k2].x + wxy.y * v[k2].y * v[k2].y);
+        }
+      }
+    }
+    ABI_SYNCWARP();
+  }
+
   // ---------------- phase Y': S[u][i2] -> y FFT^-1 -> compact output rows of W1o ----------------
   ABI_DEV static void phase_yinv(const PlaneParams& P, const double2* __restrict__ S, double2* __restrict__ w1o, double2* E,
                                  const double2* tw, int u0) {
@@ -301,10 +352,40 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS >= 16 ? 1 : 2)) k_fw_plane(
   }
 }
 
+// option 1: one CTA = one (band or band pair, i1) plane: y FFT, z FFT, density accumulation (no way back)
+template <int R1, int R2, int G, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (WARPS >= 16 ? 1 : 2)) k_fw_plane_rho(PlaneParams P) {
+  using F = PlaneFft<R1, R2, G>;
+  ABI_DYN_SMEM(double2, sm);
+  double2* tw = sm;
+#ifdef ABI_EMU
+  const int warp = 0, nwarps = 1;
+  for (int j = 0; j < F::N; j++) tw[j] = P.tw[j];
+#else
+  const int warp = threadIdx.x >> 5, nwarps = WARPS;
+  for (int j = threadIdx.x; j < F::N; j += WARPS * 32) tw[j] = P.tw[j];
+#endif
+  double2* E = sm + F::N + (size_t)warp * F::ESIZE;
+  double2* S = P.S + (size_t)blockIdx.x * P.nU * P.n2;
+  __syncthreads();
+  for (long long unit = blockIdx.x; unit < P.nunits; unit += gridDim.x) {
+    const int i1 = (int)(unit / P.nb), b = (int)(unit - (long long)i1 * P.nb);
+    const double2* w1 = P.W1 + ((size_t)b * P.n1 + i1) * P.nlin;
+    double* rplane = P.rhoT + (size_t)i1 * P.n3 * P.n2;
+    const double2 wxy = P.wxy[b];
+    for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_y(P, w1, S, E, tw, u0);
+    __syncthreads();
+    for (int c0 = warp * G; c0 < P.n2; c0 += nwarps * G) F::phase_z_rho(P, S, rplane, wxy, E, tw, c0);
+    __syncthreads();
+  }
+}
+
 // host interface (plane_stage.cu)
 bool plane_stage_supported(int n);
 // launches the plane stage for n2 == n3 == n; P.S may be null on entry: the launcher sizes and provides the L2 scratch
 void plane_stage_launch(int n, PlaneParams& P, cudaStream_t st);
+// same for option 1 (P.rhoT / P.wxy set): launches k_fw_plane_rho
+void plane_stage_launch_rho(int n, PlaneParams& P, cudaStream_t st);
 void plane_stage_release();
 
 }  // namespace abi

@@ -35,6 +35,31 @@ void launch_cfg(PlaneParams& P, cudaStream_t st) {
   ABI_LAUNCH(kern, dim3((unsigned)grid), dim3(WARPS * 32), smem, st, P);
 }
 
+template <int R1, int R2, int G, int WARPS>
+void launch_cfg_rho(PlaneParams& P, cudaStream_t st) {
+  using F = PlaneFft<R1, R2, G>;
+  auto kern = k_fw_plane_rho<R1, R2, G, WARPS>;
+  const size_t smem = sizeof(double2) * ((size_t)F::N + (size_t)WARPS * F::ESIZE);
+  int cps = 1;
+#ifndef ABI_EMU
+  static bool attr_done = false;
+  if (!attr_done) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, WARPS * 32, smem));
+  ABI_CHECK(cps >= 1, "plane stage: kernel does not fit on an SM");
+#endif
+  const size_t sbytes = sizeof(double2) * (size_t)P.nU * P.n2;
+  cps = std::min(cps, (int)std::max<size_t>(1, kScratchL2Budget / (sbytes * kNumSM)));
+  long long grid = std::min<long long>(P.nunits, (long long)kNumSM * cps);
+#ifdef ABI_EMU
+  grid = std::min<long long>(grid, 3);
+#endif
+  P.S = (double2*)plane_scratch_get(sbytes * (size_t)grid);
+  ABI_LAUNCH(kern, dim3((unsigned)grid), dim3(WARPS * 32), smem, st, P);
+}
+
+template <int R1, int R2>
+void plane_launch_rho_n(PlaneParams& P, cudaStream_t st) { launch_cfg_rho<R1, R2, 4, 8>(P, st); }
+
 template <int R1, int R2>
 void plane_launch_n(PlaneParams& P, cudaStream_t st) {
   const int cfg = fourwf_tuning().plane_cfg;

@@ -319,6 +319,29 @@ def main():
                     "timing": "host clock between barrier + device synchronise on both sides, max over ranks (the call holds host syncs)",
                     "kernel_ms": {k: v[0] for k, v in prof_scf.items()}}
         del cg
+    # density build (the step after the solver): fourwf option 1 on the same band block, fused path
+    density = None
+    if not args.no_scf_step:
+        api.set_async(True)
+        with torch.cuda.stream(stream):
+            rho = torch.zeros(tuple(reversed(w["ngfft"])), device=dev, dtype=torch.float64)
+            wts = np.full(ndat, 2.0 / w["ucvol"])
+            n1, n2, n3 = w["ngfft"]
+            def dens():
+                api.fourwf(1, rho, cw, None, None, None, None, args.istwfk, w["kg"], w["kg"], max(w["ngfft"]), None, ndat, w["ngfft"],
+                           npw, npw, n1, n2, n3, 1, weight_array_r=wts, weight_array_i=wts)
+            for _ in range(3):
+                dens()
+            barrier()
+            d0 = torch.cuda.Event(enable_timing=True); d1 = torch.cuda.Event(enable_timing=True)
+            d0.record(stream)
+            for _ in range(5):
+                dens()
+            d1.record(stream)
+            barrier()
+            dms = d0.elapsed_time(d1) / 5
+        density = {"ms_per_block": dms, "bands": ndat, "bands_per_s": ndat / (dms * 1e-3), "kernel": "fourwf option 1, fused (x pass, plane stage with density reduction, transpose-add)"}
+        del rho
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -365,7 +388,7 @@ def main():
                       "l2": "inputs larger than L2 (P = %.1f GB streamed twice per step)" % (16.0 * npw * nprojs / 1e9),
                       "parallelism": f"band blocks over {world} GPU(s), no data-path collective"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-           "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}, "scf_step": scf_step}
+           "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}, "scf_step": scf_step, "density_step": density}
     out.update(extra)
     print(json.dumps(out))
     if dist is not None:
