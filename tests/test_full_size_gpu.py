@@ -1,0 +1,182 @@
+"""GPU: the BASELINE.json shapes at FULL size through size-independent properties (the oracle would need minutes to hours
+there): linearity, Hermiticity in the block metric, block-size independence, closed-form fourwf answers, Parseval for the
+density, S S^-1 = 1, S-orthonormality after ChebFi2.  All calls go through the C-ABI with device-resident blocks."""
+import numpy as np
+import pytest
+import abinit_b200 as ab
+from abinit_b200 import xg, workload as wl
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _c(t):
+    a = t.cpu().numpy()
+    return a[..., 0] + 1j * a[..., 1]
+
+
+def _setup(name, istwfk, ndat, usepaw=0, seed=0):
+    cfg = wl.CONFIGS[name]
+    kg, kin = wl.gsphere_orthorhombic(cfg["ecut"], cfg["L"], (0.0, 0.0, 0.0), istwfk)
+    npw = kg.shape[0]
+    kinpw = kin.copy()
+    kinpw[kin >= np.quantile(kin, 0.995)] = wl.HUGE * 1e-10                      # sentinel shell (m_kg.F90:422-429)
+    indlmn, lnmax = wl.nc_indlmn(cfg["lmax"], cfg["nproj_per_l"])
+    nlmn = indlmn.shape[1]; natom = cfg["natom"]; nprojs = natom * nlmn
+    rng = np.random.Generator(np.random.PCG64(100 + seed))
+    h = ab.Hamiltonian(cfg["ngfft"], natom, 1, nlmn, indlmn, np.array([natom], dtype=np.int32),
+                       np.arange(1, natom + 1, dtype=np.int32), usepaw, float(cfg["L"]) ** 3)
+    h.load_spin(wl.smooth_potential(cfg["ngfft"], seed=5), 1)
+    if usepaw:
+        lmn2 = nlmn * (nlmn + 1) // 2
+        dij = 0.3 * rng.standard_normal((natom, lmn2))
+        a = 0.1 * rng.standard_normal((nlmn, nlmn)); a = a @ a.T
+        sij = np.array([[a[i, j] for j in range(nlmn) for i in range(j + 1)]])
+        h.load_enl(dij, sij)
+    else:
+        h.load_enl(rng.standard_normal((1, lnmax)), None)
+    h.load_k(istwfk, kg, kinpw, None, None, me_g0=1)
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev).manual_seed(4321 + seed)
+    P = torch.randn((nprojs, npw, 2), generator=gen, device=dev, dtype=torch.float64) / np.sqrt(npw)
+    cw = torch.randn((ndat, npw, 2), generator=gen, device=dev, dtype=torch.float64)
+    damp = torch.from_numpy(1.0 / (1.0 + np.minimum(kin, 1e6))).to(dev)
+    cw *= damp[None, :, None]
+    if istwfk == 2:
+        P[:, 0, 1] = 0.0; cw[:, 0, 1] = 0.0
+    torch.cuda.synchronize()
+    h.set_projectors(P, nprojs)
+    del P
+    torch.cuda.empty_cache()
+    return cfg, h, cw, kg, kinpw, npw, nprojs
+
+
+def _gram(space, a, b, npw, me_g0):
+    na, nb = a.shape[0], b.shape[0]
+    w = torch.zeros((nb, na), dtype=torch.complex128 if space == xg.SPACE_C else torch.float64, device=a.device)
+    torch.cuda.synchronize()
+    xg.xg_gram(space, npw, na, nb, a, npw, b, npw, w, na, me_g0)
+    return w.cpu().numpy().T
+
+
+def test_si512_getghc_properties(lib):
+    """BASELINE configs[1]: box 180^3, Gamma (istwf_k 2), npw 144 057, nprojs 9216 (P = 21 GB), NC."""
+    ndat = 16
+    cfg, h, cw, kg, kinpw, npw, nprojs = _setup("si512", 2, ndat)
+    assert npw == 144057 and nprojs == 9216
+    ghc = torch.zeros_like(cw)
+    torch.cuda.synchronize()
+    ab.getghc(-1, cw, None, ghc, None, h, None, None, None, ndat)
+    # (1) Hermiticity in the SPACE_CR metric: <phi|H psi> is a symmetric matrix
+    A = _gram(xg.SPACE_CR, cw, ghc, npw, 1)
+    assert np.abs(A - A.T).max() < 1e-11 * np.abs(A).max()
+    # (2) linearity
+    mix = (0.7 * cw[0] - 1.3 * cw[1] + 0.25 * cw[5]).unsqueeze(0).contiguous()
+    out = torch.zeros_like(mix)
+    torch.cuda.synchronize()
+    ab.getghc(-1, mix, None, out, None, h, None, None, None, 1)
+    ref = 0.7 * ghc[0] - 1.3 * ghc[1] + 0.25 * ghc[5]
+    assert float(torch.linalg.norm(out[0] - ref) / torch.linalg.norm(ref)) < 1e-12
+    # (3) band-block independence: 16 bands at once == 6 + 10 (odd split: the Gamma pairing changes partners)
+    parts = torch.zeros_like(cw)
+    torch.cuda.synchronize()
+    ab.getghc(-1, cw[:6].contiguous(), None, parts[:6], None, h, None, None, None, 6)
+    p2 = torch.zeros((10, npw, 2), dtype=torch.float64, device=cw.device)
+    torch.cuda.synchronize()
+    ab.getghc(-1, cw[6:].contiguous(), None, p2, None, h, None, None, None, 10)
+    parts[6:] = p2
+    assert float(torch.linalg.norm(parts - ghc) / torch.linalg.norm(ghc)) < 1e-12
+    # (4) the sentinel shell is exactly zero (m_getghc.F90:1272-1277)
+    filt = torch.from_numpy(kinpw >= wl.HUGE * 1e-11).to(cw.device)
+    assert int(filt.sum()) > 0 and float(ghc[:, filt].abs().max()) == 0.0
+    h.destroy()
+
+
+def test_si512_fourwf_closed_forms_and_density(lib):
+    """fourwf at 180^3 / npw 144 057: V = const and V = cos(2 pi x) have closed forms on the sphere; option 1 obeys Parseval."""
+    cfg = wl.CONFIGS["si512"]
+    n1, n2, n3 = cfg["ngfft"]
+    kg, kin = wl.gsphere_orthorhombic(cfg["ecut"], cfg["L"], (0.0, 0.0, 0.0), 2)
+    npw = kg.shape[0]; ndat = 5
+    rng = np.random.Generator(np.random.PCG64(9))
+    c = (rng.standard_normal((ndat, npw)) + 1j * rng.standard_normal((ndat, npw))) / (1.0 + kin)[None, :]
+    c[:, 0] = c[:, 0].real
+    c = np.ascontiguousarray(c)
+    out = np.zeros_like(c)
+    v0 = np.full((n3, n2, n1), 0.37)
+    lib.fourwf(1, v0, c, out, None, None, None, 2, kg, kg, 180, None, ndat, cfg["ngfft"], npw, npw, n1, n2, n3, 2)
+    assert np.max(np.abs(out - 0.37 * c)) < 1e-13 * np.max(np.abs(c))
+    # V = cos(2 pi i1/n1): out(G) = 1/2 [c(G - e1) + c(G + e1)], with c(-G) = conj c(G) and c = 0 outside the sphere
+    vcos = np.ascontiguousarray(np.broadcast_to(np.cos(2 * np.pi * np.arange(n1) / n1)[None, None, :], (n3, n2, n1)))
+    lib.fourwf(1, vcos, c, out, None, None, None, 2, kg, kg, 180, None, ndat, cfg["ngfft"], npw, npw, n1, n2, n3, 2)
+    box = np.zeros((ndat, n3, n2, n1), dtype=np.complex128)
+    i1, i2, i3 = kg[:, 0] % n1, kg[:, 1] % n2, kg[:, 2] % n3
+    box[:, i3, i2, i1] = c
+    box[:, (-kg[:, 2]) % n3, (-kg[:, 1]) % n2, (-kg[:, 0]) % n1] = np.conj(c)
+    box[:, 0, 0, 0] = c[:, 0]
+    ref = 0.5 * (box[:, i3, i2, (i1 - 1) % n1] + box[:, i3, i2, (i1 + 1) % n1])
+    ref[:, 0] = ref[:, 0].real
+    assert np.max(np.abs(out - ref)) < 1e-12 * np.max(np.abs(ref))
+    # option 1: sum_r rho(r) / N = sum_b w_b <c_b|c_b> on the full sphere (2 sum |c|^2 - |c(0)|^2), rho >= 0
+    w = rng.uniform(0.5, 2.0, ndat)
+    rho = np.zeros((n3, n2, n1))
+    lib.fourwf(1, rho, c, None, None, None, None, 2, kg, kg, 180, None, ndat, cfg["ngfft"], npw, npw, n1, n2, n3, 1,
+               weight_array_r=w, weight_array_i=w)
+    norms = 2.0 * np.sum(np.abs(c) ** 2, axis=1) - np.abs(c[:, 0]) ** 2
+    assert abs(rho.sum() / rho.size - float(w @ norms)) < 1e-12 * float(w @ norms)
+    assert rho.min() >= 0.0
+
+
+def test_au108_paw_properties(lib):
+    """BASELINE configs[3] shape: box 96^3, istwf_k 1, nprojs 1944, PAW with S: Hermiticity of H and S, S S^-1 = 1,
+    ChebFi2-PAW leaves an S-orthonormal block whose residuals are consistent."""
+    ndat = 24
+    cfg, h, cw, kg, kinpw, npw, nprojs = _setup("au108", 1, ndat, usepaw=1, seed=3)
+    assert nprojs == 1944
+    ghc = torch.zeros_like(cw); gsc = torch.zeros_like(cw)
+    torch.cuda.synchronize()
+    ab.getghc(-1, cw, None, ghc, gsc, h, None, None, None, ndat, sij_opt=1)
+    A = _gram(xg.SPACE_C, cw, ghc, npw, -1); B = _gram(xg.SPACE_C, cw, gsc, npw, -1)
+    assert np.abs(A - A.conj().T).max() < 1e-11 * np.abs(A).max()
+    assert np.abs(B - B.conj().T).max() < 1e-11 * np.abs(B).max()
+    # S^-1 S psi = psi (apply_invovl on the output of getghc's gsc; the filtered shell is zero in gsc, so compare there)
+    back = torch.zeros_like(cw)
+    torch.cuda.synchronize()
+    ab.apply_invovl(h, gsc, back, None, npw, ndat)
+    sback = torch.zeros_like(cw); dummy = torch.zeros_like(cw)
+    torch.cuda.synchronize()
+    ab.getghc(-1, back, None, dummy, sback, h, None, None, None, ndat, sij_opt=1)
+    assert float(torch.linalg.norm(sback - gsc) / torch.linalg.norm(gsc)) < 1e-11
+    # one ChebFi2-PAW call: X^H S X = 1 and resid = |H x - e S x|^2
+    eig = np.zeros(ndat); resid = np.zeros(ndat)
+    x = cw.clone()
+    torch.cuda.synchronize()
+    xg.chebfiwf2(x, eig, None, None, h, ndat, npw, 1, resid, 1e-16, cfg["ecut"], 4, bandpp=8)
+    hx = torch.zeros_like(x); sx = torch.zeros_like(x)
+    torch.cuda.synchronize()
+    ab.getghc(-1, x, None, hx, sx, h, None, None, None, ndat, sij_opt=1)
+    G = _gram(xg.SPACE_C, x, sx, npw, -1)
+    assert np.abs(G - np.eye(ndat)).max() < 1e-9
+    r = hx - torch.from_numpy(eig).to(x.device)[:, None, None] * sx
+    r2 = (r ** 2).sum(dim=(1, 2)).cpu().numpy()
+    assert np.max(np.abs(r2 - resid) / (np.abs(resid) + 1e-14)) < 1e-6
+    assert np.all(np.diff(eig) >= -1e-12)
+    h.destroy()
+
+
+@pytest.mark.parametrize("name,istwfk,ndat", [("sweep96", 1, 64), ("sweep96", 2, 33), ("si2", 1, 8)])
+def test_sweep_points_hermiticity_and_split(lib, name, istwfk, ndat):
+    """BASELINE configs[4] sample points: Hermiticity and band-block independence."""
+    cfg, h, cw, kg, kinpw, npw, nprojs = _setup(name, istwfk, ndat, seed=7)
+    ghc = torch.zeros_like(cw)
+    torch.cuda.synchronize()
+    ab.getghc(-1, cw, None, ghc, None, h, None, None, None, ndat)
+    space, me_g0 = (xg.SPACE_C, -1) if istwfk == 1 else (xg.SPACE_CR, 1)
+    A = _gram(space, cw, ghc, npw, me_g0)
+    assert np.abs(A - A.conj().T).max() < 1e-11 * np.abs(A).max()
+    k = ndat // 3
+    a = torch.zeros((k, npw, 2), dtype=torch.float64, device=cw.device)
+    torch.cuda.synchronize()
+    ab.getghc(-1, cw[:k].contiguous(), None, a, None, h, None, None, None, k)
+    assert float(torch.linalg.norm(a - ghc[:k]) / torch.linalg.norm(ghc[:k])) < 1e-12
+    h.destroy()
