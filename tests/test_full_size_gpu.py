@@ -15,12 +15,13 @@ def _c(t):
     return a[..., 0] + 1j * a[..., 1]
 
 
-def _setup(name, istwfk, ndat, usepaw=0, seed=0):
+def _setup(name, istwfk, ndat, usepaw=0, seed=0, sentinel=True):
     cfg = wl.CONFIGS[name]
     kg, kin = wl.gsphere_orthorhombic(cfg["ecut"], cfg["L"], (0.0, 0.0, 0.0), istwfk)
     npw = kg.shape[0]
     kinpw = kin.copy()
-    kinpw[kin >= np.quantile(kin, 0.995)] = wl.HUGE * 1e-10                      # sentinel shell (m_kg.F90:422-429)
+    if sentinel:
+        kinpw[kin >= np.quantile(kin, 0.995)] = wl.HUGE * 1e-10                  # sentinel shell (m_kg.F90:422-429)
     indlmn, lnmax = wl.nc_indlmn(cfg["lmax"], cfg["nproj_per_l"])
     nlmn = indlmn.shape[1]; natom = cfg["natom"]; nprojs = natom * nlmn
     rng = np.random.Generator(np.random.PCG64(100 + seed))
@@ -44,6 +45,8 @@ def _setup(name, istwfk, ndat, usepaw=0, seed=0):
     cw *= damp[None, :, None]
     if istwfk == 2:
         P[:, 0, 1] = 0.0; cw[:, 0, 1] = 0.0
+    # the filter zeroes rows of H on the sentinel shell (m_getghc.F90:1272-1277): H is Hermitian on vectors that vanish there
+    cw[:, torch.from_numpy(kinpw >= wl.HUGE * 1e-11).to(dev)] = 0.0
     torch.cuda.synchronize()
     h.set_projectors(P, nprojs)
     del P
@@ -131,7 +134,8 @@ def test_au108_paw_properties(lib):
     """BASELINE configs[3] shape: box 96^3, istwf_k 1, nprojs 1944, PAW with S: Hermiticity of H and S, S S^-1 = 1,
     ChebFi2-PAW leaves an S-orthonormal block whose residuals are consistent."""
     ndat = 24
-    cfg, h, cw, kg, kinpw, npw, nprojs = _setup("au108", 1, ndat, usepaw=1, seed=3)
+    # no sentinel shell here: S^-1 does not respect the dilatmx filter, so the filtered S is not Hermitian on the iterates
+    cfg, h, cw, kg, kinpw, npw, nprojs = _setup("au108", 1, ndat, usepaw=1, seed=3, sentinel=False)
     assert nprojs == 1944
     ghc = torch.zeros_like(cw); gsc = torch.zeros_like(cw)
     torch.cuda.synchronize()
@@ -151,12 +155,13 @@ def test_au108_paw_properties(lib):
     eig = np.zeros(ndat); resid = np.zeros(ndat)
     x = cw.clone()
     torch.cuda.synchronize()
-    xg.chebfiwf2(x, eig, None, None, h, ndat, npw, 1, resid, 1e-16, cfg["ecut"], 4, bandpp=8)
+    for _ in range(2):      # the second call starts from an S-orthonormal block: well-conditioned sub-space problem
+        xg.chebfiwf2(x, eig, None, None, h, ndat, npw, 1, resid, 1e-16, cfg["ecut"], 4, bandpp=8)
     hx = torch.zeros_like(x); sx = torch.zeros_like(x)
     torch.cuda.synchronize()
     ab.getghc(-1, x, None, hx, sx, h, None, None, None, ndat, sij_opt=1)
     G = _gram(xg.SPACE_C, x, sx, npw, -1)
-    assert np.abs(G - np.eye(ndat)).max() < 1e-9
+    assert np.abs(G - np.eye(ndat)).max() < 1e-9, np.abs(G - np.eye(ndat)).max()
     r = hx - torch.from_numpy(eig).to(x.device)[:, None, None] * sx
     r2 = (r ** 2).sum(dim=(1, 2)).cpu().numpy()
     assert np.max(np.abs(r2 - resid) / (np.abs(resid) + 1e-14)) < 1e-6
