@@ -89,6 +89,7 @@ struct PlaneFft {
   // z-mode exchange buffer: E[k1][j][line], line fastest; for G=4 two k1 share a 128-byte wavefront -> stride = 4 mod 8
   static constexpr int ZK = (G >= 8) ? R2 * G : ((R2 * G) % 8 == 4 ? R2 * G : R2 * G + 4);
   static constexpr int ESIZE = (G * YL > R1 * ZK) ? G * YL : R1 * ZK;      // double2 per warp
+  static constexpr int ZOFF = (N * 4 + 15) / 16;                           // double2 slots of the i3 -> plane offset table
 
   ABI_DEV static double2 twf(const double2* tw, int idx, double2 v) { return cmulc(v, tw[idx]); }   // * e^{+2 pi i idx/n}
   ABI_DEV static double2 twb(const double2* tw, int idx, double2 v) { return cmul(v, tw[idx]); }    // * e^{-2 pi i idx/n}
@@ -146,7 +147,7 @@ struct PlaneFft {
   }
 
   ABI_DEV static void phase_z(const PlaneParams& P, double2* __restrict__ S, const double* __restrict__ vplane, double2* E,
-                              const double2* tw, int c0) {
+                              const double2* tw, const int* __restrict__ zoff, int c0) {
     const int nl = min(G, P.n2 - c0);
     const int n2 = P.n2;
     for (int w0 = 0; w0 < G * R2; w0 += 32) {
@@ -158,8 +159,8 @@ struct PlaneFft {
           double2 x[R1];
 #pragma unroll
           for (int t = 0; t < R1; t++) {
-            const int u = u_of_i3(P, j + R2 * t);
-            x[t] = (u >= 0) ? ldcg2(src + (size_t)u * n2) : make_double2(0.0, 0.0);
+            const int o = zoff[j + R2 * t];                      // u * n2 of the occupied plane, -1 for a zero-padded one
+            x[t] = (o >= 0) ? ldcg2(src + o) : make_double2(0.0, 0.0);
           }
           Dft<R1, +1>::run(x);
           double2* e = E + j * G + line;
@@ -219,8 +220,8 @@ struct PlaneFft {
           double2* dst = S + c0 + line;
 #pragma unroll
           for (int t = 0; t < R1; t++) {
-            const int u = u_of_i3(P, j + R2 * t);
-            if (u >= 0) stcg2(dst + (size_t)u * n2, y[t]);
+            const int o = zoff[j + R2 * t];
+            if (o >= 0) stcg2(dst + o, y[t]);
           }
         }
       }
@@ -232,7 +233,7 @@ struct PlaneFft {
   // fourwf option 1 (src/53_ffts/m_fft.F90:2633-2653, cg_addtorho src/44_abitools/m_cgtools.F90:2338-2384) on the same
   // register-resident z transform; the plane of rhoT is i2-contiguous so a warp's reductions fill whole sectors.
   ABI_DEV static void phase_z_rho(const PlaneParams& P, const double2* __restrict__ S, double* __restrict__ rplane, double2 wxy,
-                                  double2* E, const double2* tw, int c0) {
+                                  double2* E, const double2* tw, const int* __restrict__ zoff, int c0) {
     const int nl = min(G, P.n2 - c0);
     const int n2 = P.n2;
     for (int w0 = 0; w0 < G * R2; w0 += 32) {
@@ -244,8 +245,8 @@ struct PlaneFft {
           double2 x[R1];
 #pragma unroll
           for (int t = 0; t < R1; t++) {
-            const int u = u_of_i3(P, j + R2 * t);
-            x[t] = (u >= 0) ? ldcg2(src + (size_t)u * n2) : make_double2(0.0, 0.0);
+            const int o = zoff[j + R2 * t];                      // u * n2 of the occupied plane, -1 for a zero-padded one
+            x[t] = (o >= 0) ? ldcg2(src + o) : make_double2(0.0, 0.0);
           }
           Dft<R1, +1>::run(x);
           double2* e = E + j * G + line;
@@ -335,7 +336,13 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS >= 16 ? 1 : 2)) k_fw_plane(
   const int warp = threadIdx.x >> 5, nwarps = WARPS;
   for (int j = threadIdx.x; j < F::N; j += WARPS * 32) tw[j] = P.tw[j];
 #endif
-  double2* E = sm + F::N + (size_t)warp * F::ESIZE;
+  int* zoff = reinterpret_cast<int*>(sm + F::N);      // N ints: i3 -> u(i3) * n2, or -1 (built once per CTA)
+#ifdef ABI_EMU
+  for (int i3 = 0; i3 < F::N; i3++) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
+#else
+  for (int i3 = threadIdx.x; i3 < F::N; i3 += WARPS * 32) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
+#endif
+  double2* E = sm + F::N + F::ZOFF + (size_t)warp * F::ESIZE;
   double2* S = P.S + (size_t)blockIdx.x * P.nU * P.n2;
   __syncthreads();
   for (long long unit = blockIdx.x; unit < P.nunits; unit += gridDim.x) {
@@ -345,7 +352,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS >= 16 ? 1 : 2)) k_fw_plane(
     const double* vplane = P.vT + (size_t)P.cplex * i1 * P.n3 * P.n2;
     for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_y(P, w1, S, E, tw, u0);
     __syncthreads();
-    for (int c0 = warp * G; c0 < P.n2; c0 += nwarps * G) F::phase_z(P, S, vplane, E, tw, c0);
+    for (int c0 = warp * G; c0 < P.n2; c0 += nwarps * G) F::phase_z(P, S, vplane, E, tw, zoff, c0);
     __syncthreads();
     for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_yinv(P, S, w1o, E, tw, u0);
     __syncthreads();
@@ -365,7 +372,13 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS >= 16 ? 1 : 2)) k_fw_plane_
   const int warp = threadIdx.x >> 5, nwarps = WARPS;
   for (int j = threadIdx.x; j < F::N; j += WARPS * 32) tw[j] = P.tw[j];
 #endif
-  double2* E = sm + F::N + (size_t)warp * F::ESIZE;
+  int* zoff = reinterpret_cast<int*>(sm + F::N);      // N ints: i3 -> u(i3) * n2, or -1 (built once per CTA)
+#ifdef ABI_EMU
+  for (int i3 = 0; i3 < F::N; i3++) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
+#else
+  for (int i3 = threadIdx.x; i3 < F::N; i3 += WARPS * 32) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
+#endif
+  double2* E = sm + F::N + F::ZOFF + (size_t)warp * F::ESIZE;
   double2* S = P.S + (size_t)blockIdx.x * P.nU * P.n2;
   __syncthreads();
   for (long long unit = blockIdx.x; unit < P.nunits; unit += gridDim.x) {
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS >= 16 ? 1 : 2)) k_fw_plane_
     const double2 wxy = P.wxy[b];
     for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_y(P, w1, S, E, tw, u0);
     __syncthreads();
-    for (int c0 = warp * G; c0 < P.n2; c0 += nwarps * G) F::phase_z_rho(P, S, rplane, wxy, E, tw, c0);
+    for (int c0 = warp * G; c0 < P.n2; c0 += nwarps * G) F::phase_z_rho(P, S, rplane, wxy, E, tw, zoff, c0);
     __syncthreads();
   }
 }
