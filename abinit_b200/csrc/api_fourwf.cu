@@ -3,6 +3,7 @@
 #include "context.cuh"
 #include "fourwf.cuh"
 #include <string>
+#include <algorithm>
 
 using namespace abi;
 
@@ -78,6 +79,7 @@ void abi_b200_fourwf_set_tuning(const char* name, int value) {
   else if (k == "plane_cfg") t.plane_cfg = value;
   else if (k == "pack2") t.pack2 = value;
   else if (k == "pipeline") ctx().pipeline = value != 0;
+  else if (k == "pipe_chunks") ctx().pipe_chunks = std::max(1, value);
   else if (k == "plane_ctas_per_sm") t.plane_ctas_per_sm = value;
   else if (k == "cluster") t.cluster = value;
   else if (k == "lines_x") t.lines_x = value;

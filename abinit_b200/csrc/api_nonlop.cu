@@ -244,9 +244,9 @@ struct GhcPipe {
   double* h_ghc; double* d_ghc; int npw, nd;
 };
 cudaEvent_t pipe_event(int i) {
-  static cudaEvent_t ev[8]; static bool init = false;
+  static cudaEvent_t ev[32]; static bool init = false;
   if (!init) { for (auto& e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); init = true; }
-  return ev[i & 7];
+  return ev[i & 31];
 }
 int g_pipe_ev = 0;
 void ship_slab(void* user, int ipw_begin, int ipw_end) {
@@ -302,7 +302,8 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
         fourwf_fused_opt2(*h->plan, h->vloc, a_c.as<double2>(), a_ghc.as<double2>(), nd, epi, c.stream);
       } else {
         // band chunks (even sizes keep the Gamma-point pairs together): H2D on the copy stream, fourwf behind an event
-        const int nchunk = std::min(4, nd / 4);
+        // (8 chunks: the exposed head of the pipeline is the H2D of the first chunk only)
+        const int nchunk = std::max(1, std::min(c.pipe_chunks, nd / 8));
         const int chunk = ceil_div(ceil_div(nd, nchunk), 2) * 2;
         for (int b0 = 0; b0 < nd; b0 += chunk) {
           const int nb = std::min(chunk, nd - b0);
@@ -337,7 +338,7 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
       NonlopFusion fuse;
       fuse.ghc = a_ghc.as<double>(); fuse.kinpw = h->d_kinpw; fuse.kin_filter = kin_filter;
       GhcPipe gp{&c, {}, 0, ghc, a_ghc.as<double>(), npw, nd};
-      if (pipe) { fuse.nslabs = 4; fuse.after_slab = ship_slab; fuse.user = &gp; ghc_shipped = true; }
+      if (pipe) { fuse.nslabs = c.pipe_chunks; fuse.after_slab = ship_slab; fuse.user = &gp; ghc_shipped = true; }
       gemm_nonlop_device(h->P, h->atoms, h->enl, 1, cpopt_here, paw_opt, h->me_g0, a_lam.as<double>(), nd, a_c.as<double>(),
                          a_gv.as<double>(), a_gsc.as<double>(), a_prj.as<double>(), c.stream, &fuse);
       if (h->atoms.nprojs == 0 || nd == 0) ghc_shipped = false;          // nothing was launched: plain copy below

@@ -29,6 +29,7 @@ void ensure_init() {
   if (!c.stream) { CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)); c.own_stream = true; }
   if (!c.copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
   if (const char* e = getenv("ABI_B200_PIPELINE")) c.pipeline = atoi(e) != 0;
+  if (const char* e = getenv("ABI_B200_PIPE_CHUNKS")) c.pipe_chunks = atoi(e) > 0 ? atoi(e) : c.pipe_chunks;
 #endif
   c.initialized = true;
 }
