@@ -165,6 +165,15 @@ class Hamiltonian:
         L().abi_b200_ham_load_k(self.h, int(istwf_k), self.npw, kg_k.ctypes.data, kin.ctypes.data,
                                 _ptr(ffnl, _F, "ffnl"), dimffnl, _ptr(ph3d, _F, "ph3d"), matblk, int(me_g0))
 
+    def load_k_xred(self, istwf_k, kg_k, kinpw, ffnl, kpt, xred, me_g0=1):
+        """load_k with ph3d built on the device from kpt(3) and xred (natom, 3) == Fortran xred(3,natom), type-sorted."""
+        kg_k = np.ascontiguousarray(kg_k, dtype=np.int32)
+        self.npw = int(kg_k.shape[0]); self.istwf_k = int(istwf_k); self.me_g0 = int(me_g0)
+        kin = np.ascontiguousarray(kinpw, dtype=np.float64)
+        kp = np.ascontiguousarray(kpt, dtype=np.float64); xr = np.ascontiguousarray(xred, dtype=np.float64)
+        L().abi_b200_ham_load_k_xred(self.h, int(istwf_k), self.npw, kg_k.ctypes.data, kin.ctypes.data, _ptr(ffnl, _F, "ffnl"),
+                                     int(ffnl.shape[-2]), kp.ctypes.data, xr.ctypes.data, int(me_g0))
+
     def set_projectors(self, projs, nprojs):
         L().abi_b200_ham_set_projectors(self.h, _ptr(projs, _F, "projs"), int(nprojs))
 

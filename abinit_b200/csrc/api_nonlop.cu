@@ -225,6 +225,19 @@ void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
 
+void abi_b200_ham_load_k_xred(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw, const double* ffnl,
+                              int dimffnl, const double* kpt, const double* xred, int me_g0) {
+  ABI_CHECK(ffnl != nullptr && kpt != nullptr && xred != nullptr, "load_k_xred: ffnl, kpt and xred are required");
+  abi_b200_ham_load_k(h, istwf_k, npw, kg_k, kinpw, nullptr, 0, nullptr, 0, me_g0);
+  Context& c = ctx();
+  h->P.alloc(npw, h->atoms.nprojs, istwf_k);
+  DevArg a_ffnl(6, ffnl, sizeof(double) * (size_t)npw * dimffnl * h->lmnmax * h->ntypat, true);
+  DevArg a_kg(7, kg_k, sizeof(int) * 3 * (size_t)npw, true);
+  DevArg a_x(8, xred, sizeof(double) * 3 * (size_t)h->natom, true);
+  prep_projectors_xred_device(h->P, h->atoms, a_ffnl.as<double>(), dimffnl, a_kg.as<int>(), a_x.as<double>(), kpt, h->ucvol, c.stream);
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
 void abi_b200_ham_set_projectors(abi_b200_ham_t* h, const double* projs, int nprojs) {
   ensure_init();
   ABI_CHECK(nprojs == h->atoms.nprojs, "set_projectors: nprojs differs from sum(nlmn*nattyp)");

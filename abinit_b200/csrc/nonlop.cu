@@ -399,6 +399,29 @@ __global__ void k_prep_projectors(double2* __restrict__ P, int npw, int nprojs, 
     P[(size_t)ip * npw + ig] = make_double2(re * e.x + im * e.y, im * e.x - re * e.y);
   }
 }
+// prep_projectors with the structure-factor phases built in place (ph1d3d, src/56_recipspace/m_kg.F90:644-700:
+// ph3d(G, ia) = exp(2 pi i (k+G).xred_ia)): one sincospi per (plane wave, atom), reused by the atom's nlmn projectors;
+// the npw x natom phase array (1.2 GB at Si-512) never exists and is never uploaded.
+__global__ void k_prep_projectors_xred(double2* __restrict__ P, int npw, const double* __restrict__ ffnl, int dimffnl, int lmnmax,
+                                       const int* __restrict__ kg, const double* __restrict__ xred, double k1, double k2, double k3,
+                                       const int* __restrict__ atom_first, const int* __restrict__ atom_typ,
+                                       const int* __restrict__ proj_l, double wt) {
+  const int ia = blockIdx.y;
+  const int first = atom_first[ia], nlmn = atom_first[ia + 1] - first, typ = atom_typ[ia];
+  const double x1 = xred[3 * ia], x2 = xred[3 * ia + 1], x3 = xred[3 * ia + 2];
+  for (int ig = blockIdx.x * blockDim.x + threadIdx.x; ig < npw; ig += gridDim.x * blockDim.x) {
+    const double arg = (k1 + kg[3 * ig]) * x1 + (k2 + kg[3 * ig + 1]) * x2 + (k3 + kg[3 * ig + 2]) * x3;
+    double es, ec;
+    sincospi(2.0 * (arg - rint(arg)), &es, &ec);
+    for (int i = 0; i < nlmn; i++) {
+      const double a = wt * ffnl[(size_t)npw * ((size_t)dimffnl * (i + (size_t)lmnmax * typ)) + ig];
+      double re, im;
+      switch (proj_l[first + i] & 3) { case 0: re = a; im = 0.0; break; case 1: re = 0.0; im = -a; break;
+                                       case 2: re = -a; im = 0.0; break; default: re = 0.0; im = a; break; }
+      P[(size_t)(first + i) * npw + ig] = make_double2(re * ec + im * es, im * ec - re * es);
+    }
+  }
+}
 #endif  // !ABI_EMU
 
 // ---------------------------------------------------------------------------------------------------------
@@ -494,6 +517,17 @@ void prep_projectors_device(Projectors& P, const NonlopAtoms& at, const double* 
   k_prep_projectors<<<grid, 256, 0, st>>>(reinterpret_cast<double2*>(P.d_p), P.npw, at.nprojs, d_ffnl, dimffnl, at.lmnmax,
                                           reinterpret_cast<const double2*>(d_ph3d), at.d_proj_typ, at.d_proj_lmn,
                                           at.d_proj_atom, at.d_proj_l, wt);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+void prep_projectors_xred_device(Projectors& P, const NonlopAtoms& at, const double* d_ffnl, int dimffnl, const int* d_kg,
+                                 const double* d_xred, const double* kpt, double ucvol, cudaStream_t st) {
+  const double wt = 4.0 * 3.14159265358979323846 / sqrt(ucvol);
+  if (at.nprojs == 0 || P.npw == 0) return;
+  dim3 grid(std::min(64, ceil_div(P.npw, 256)), at.natom);
+  k_prep_projectors_xred<<<grid, 256, 0, st>>>(reinterpret_cast<double2*>(P.d_p), P.npw, d_ffnl, dimffnl, at.lmnmax, d_kg, d_xred,
+                                               kpt[0], kpt[1], kpt[2], at.d_atom_first, at.d_atom_typ, at.d_proj_l, wt);
   CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
 }
@@ -753,6 +787,7 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
 }
 #else
 void prep_projectors_device(Projectors&, const NonlopAtoms&, const double*, int, const double*, int, double, cudaStream_t) {}
+void prep_projectors_xred_device(Projectors&, const NonlopAtoms&, const double*, int, const int*, const double*, const double*, double, cudaStream_t) {}
 void dgemm_nn(int, int, int, const double*, long long, const double*, long long, double*, long long, cudaStream_t) {}
 void zgemm_nn(int, int, int, const double*, long long, const double*, long long, double*, long long, cudaStream_t) {}
 void zgemm_cn(int, int, int, const double*, long long, const double*, long long, double*, long long, double, cudaStream_t) {}

@@ -47,6 +47,11 @@ struct NonlopEnl {
 void prep_projectors_device(Projectors& P, const NonlopAtoms& at, const double* d_ffnl, int dimffnl,
                             const double* d_ph3d, int matblk, double ucvol, cudaStream_t st);
 
+// Same, with ph3d built in place from the reduced coordinates (ph1d3d): d_kg (3,npw) int, d_xred (3,natom) type-sorted,
+// kpt[3] host.
+void prep_projectors_xred_device(Projectors& P, const NonlopAtoms& at, const double* d_ffnl, int dimffnl, const int* d_kg,
+                                 const double* d_xred, const double* kpt, double ucvol, cudaStream_t st);
+
 // getghc fusion of the last GEMM (opernlb): ghc <- (kinpw < filter) ? ghc + P.gxfac : 0 (m_getghc.F90:1266-1280 done in
 // the GEMM epilogue; `vectout`, when given, still receives the bare non-local term).  The rows are cut in `nslabs`
 // slabs; after each one `after_slab(user, ipw_begin, ipw_end)` runs on the host (used to queue the device->host copy

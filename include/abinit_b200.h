@@ -121,6 +121,12 @@ void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_v
 void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, const double* sij);
 void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw,
                          const double* ffnl, int dimffnl, const double* ph3d, int matblk, int me_g0);
+/* load_k with the structure-factor phases built on the device: ph3d(G,ia) = exp(2 pi i (k+G).xred_ia) is what load_k computes
+ * with ph1d3d when compute_ph3d is set (src/66_nonlocal/m_hamiltonian.F90:1132-1140, src/56_recipspace/m_kg.F90:644-700);
+ * here it is fused into prep_projectors, so the npw x natom phase array is neither built on the host nor uploaded.
+ * kpt(3); xred(3,natom) with atoms sorted by type (the order of ph3d's columns). */
+void abi_b200_ham_load_k_xred(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw,
+                              const double* ffnl, int dimffnl, const double* kpt, const double* xred, int me_g0);
 /* benchmark/test hook: explicit projectors instead of ffnl/ph3d (pass ffnl=ph3d=NULL to load_k) */
 void abi_b200_ham_set_projectors(abi_b200_ham_t* h, const double* projs, int nprojs);
 int abi_b200_ham_nprojs(const abi_b200_ham_t* h);

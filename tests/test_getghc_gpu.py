@@ -139,3 +139,21 @@ def test_istwfk2_equals_istwfk1_on_completed_sphere(lib):
     tgt = np.array([lut[tuple(p1.kgF[i].tolist())] for i in sel])
     assert rel_err_per_band(g1[:, sel], g2[:, tgt]) < 1e-11
     h1.destroy(); h2.destroy()
+
+
+@pytest.mark.parametrize("istwf_k,kpt,usepaw", [(1, (-.25, .5, 0), 0), (2, (0, 0, 0), 1), (6, (0, .5, 0), 0)])
+def test_load_k_xred_builds_ph3d_on_device(lib, istwf_k, kpt, usepaw):
+    """load_k_xred (ph1d3d fused into prep_projectors on the device) == load_k with the host ph3d, and == the oracle."""
+    p = make_problem(7.0, (8.0, 9.0, 7.5), kpt, istwf_k, ndat=4, natom_per_type=(2, 1), lmax_per_type=(2, 1), usepaw=usepaw)
+    h = ab.Hamiltonian(p.ngfft, p.natom, p.ntypat, p.lmnmax, p.indlmn, p.nattyp, p.atindx1, p.usepaw, p.ucvol)
+    h.load_spin(p.vlocal, p.cplex); h.load_enl(p.enl, p.sij)
+    h.load_k_xred(p.istwf_k, p.kgF, p.kinpw, p.ffnl, p.kpt, np.ascontiguousarray(p.xred.T), me_g0=1)
+    a = np.zeros((p.ndat, p.npw), dtype=np.complex128)
+    ab.getghc(-1, p.cwavef, None, a, None, h, None, None, None, p.ndat)
+    h2 = _ham(p)
+    b = np.zeros_like(a)
+    ab.getghc(-1, p.cwavef, None, b, None, h2, None, None, None, p.ndat)
+    r_ghc, _, _, _ = _oracle(p)
+    assert rel_err_per_band(a, b) < 1e-12
+    assert rel_err_per_band(a, r_ghc) < TOL
+    h.destroy(); h2.destroy()
