@@ -354,12 +354,18 @@ def main():
     t_tn, t_nn = per_launch("dgemm_tn_opernla"), per_launch("dgemm_nn_opernlb")
     t_fw = sum((per_launch(k) or 0.0) * (prof.get(k, (0, 0))[1] / max(1, args.steps)) for k in
                ("fourwf_x_forward", "fourwf_plane_stage", "fourwf_x_backward"))
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+    except Exception:
+        pass
     roof = None
     if t_nn:
         flops_launch = 0.5 * f_nl * ndat                    # one of the two GEMMs of a getghc step
         ach = flops_launch / (t_nn * 1e-3) / 1e12
         roof = {"kernel": "k_dgemm_nn (opernlb: vect = P . gxfac, DMMA m8n8k4)", "bound": "tensor", "achieved": ach, "peak": fp64,
-                "unit": "TFLOP/s", "frac": ach / fp64, "traffic": None, "peak_source": fp64_src,
+                "unit": "TFLOP/s", "frac": ach / fp64, "traffic": (traffic.get("k_dgemm_nn") or {}).get("bytes"),
+                "traffic_source": (traffic.get("k_dgemm_nn") or {}).get("source"), "peak_source": fp64_src,
                 "flops_per_launch": flops_launch, "ms_per_launch": t_nn}
     extra = {}
     if t_tn:
