@@ -342,6 +342,36 @@ def main():
             dms = d0.elapsed_time(d1) / 5
         density = {"ms_per_block": dms, "bands": ndat, "bands_per_s": ndat / (dms * 1e-3), "kernel": "fourwf option 1, fused (x pass, plane stage with density reduction, transpose-add)"}
         del rho
+    # sanity anchor against the only fourwf timing the reference stores: option 2, cplex 1, istwfk 1,
+    # box 100^3 (ecut 30 Ha, 20 Bohr cube, k = (.1,.2,.3)): 3.8 ms per call with FFTW3 on one CPU core
+    # (tests/unitary/Refs/tfourwf_01.stdout:117-129)
+    anchor = None
+    if rank == 0 and not args.no_scf_step:
+        from abinit_b200 import workload as wl2
+        kg_a, _ = wl2.gsphere_orthorhombic(30.0, 20.0, (0.1, 0.2, 0.3), 1)
+        npw_a = kg_a.shape[0]
+        api.set_async(True)
+        with torch.cuda.stream(stream):
+            va = torch.from_numpy(wl2.smooth_potential((100, 100, 100), seed=3)).to(dev)
+            res_a = {}
+            for nd_a in (1, 64):
+                ca = torch.randn((nd_a, npw_a, 2), device=dev, dtype=torch.float64); oa = torch.zeros_like(ca)
+                def fw():
+                    api.fourwf(1, va, ca, oa, None, None, None, 1, kg_a, kg_a, 100, None, nd_a, (100, 100, 100), npw_a, npw_a,
+                               100, 100, 100, 2)
+                for _ in range(3):
+                    fw()
+                barrier()
+                a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                for _ in range(10):
+                    fw()
+                a1.record(stream)
+                barrier()
+                res_a[nd_a] = a0.elapsed_time(a1) / 10 / nd_a
+        anchor = {"case": "tfourwf_01: fourwf option 2, box 100^3, npw %d, istwfk 1, device-resident" % npw_a,
+                  "ms_per_band_ndat1": res_a[1], "ms_per_band_ndat64": res_a[64],
+                  "reference_ms_per_band": 3.8, "reference_source": "tests/unitary/Refs/tfourwf_01.stdout:117-129 (FFTW3, 1 CPU core)"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -394,7 +424,7 @@ def main():
                       "l2": "inputs larger than L2 (P = %.1f GB streamed twice per step)" % (16.0 * npw * nprojs / 1e9),
                       "parallelism": f"band blocks over {world} GPU(s), no data-path collective"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-           "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}, "scf_step": scf_step, "density_step": density}
+           "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}, "scf_step": scf_step, "density_step": density, "fourwf_anchor": anchor}
     out.update(extra)
     print(json.dumps(out))
     if dist is not None:
