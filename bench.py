@@ -345,7 +345,7 @@ def main():
     # sanity anchor against the only fourwf timing the reference stores: option 2, cplex 1, istwfk 1,
     # box 100^3 (ecut 30 Ha, 20 Bohr cube, k = (.1,.2,.3)): 3.8 ms per call with FFTW3 on one CPU core
     # (tests/unitary/Refs/tfourwf_01.stdout:117-129)
-    anchor = None
+    anchor = None                                     # rank 0 only: NO collective in this block (local synchronisation)
     if rank == 0 and not args.no_scf_step:
         from abinit_b200 import workload as wl2
         kg_a, _ = wl2.gsphere_orthorhombic(30.0, 20.0, (0.1, 0.2, 0.3), 1)
@@ -361,13 +361,13 @@ def main():
                                100, 100, 100, 2)
                 for _ in range(3):
                     fw()
-                barrier()
+                stream.synchronize()
                 a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
                 a0.record(stream)
                 for _ in range(10):
                     fw()
                 a1.record(stream)
-                barrier()
+                stream.synchronize()
                 res_a[nd_a] = a0.elapsed_time(a1) / 10 / nd_a
         anchor = {"case": "tfourwf_01: fourwf option 2, box 100^3, npw %d, istwfk 1, device-resident" % npw_a,
                   "ms_per_band_ndat1": res_a[1], "ms_per_band_ndat64": res_a[64],
