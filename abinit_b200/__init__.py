@@ -8,7 +8,7 @@ from .lib import load_library, library_path, LibraryNotBuilt  # noqa: F401
 from .api import (fourwf, gemm_nonlop, getghc, Hamiltonian, init, finalize, synchronize,  # noqa: F401
                   kernel_launches, set_stream, set_async, nonlop, make_invovl, apply_invovl)
 from . import xg  # noqa: F401
-from .xg import chebfiwf2, xg_RayleighRitz  # noqa: F401
+from .xg import chebfiwf2, lobpcgwf2, xg_RayleighRitz  # noqa: F401
 
 __all__ = ["fourwf", "gemm_nonlop", "getghc", "Hamiltonian", "init", "finalize", "synchronize",
-           "kernel_launches", "set_stream", "set_async", "nonlop", "make_invovl", "apply_invovl", "xg", "chebfiwf2", "xg_RayleighRitz", "load_library", "library_path", "LibraryNotBuilt"]
+           "kernel_launches", "set_stream", "set_async", "nonlop", "make_invovl", "apply_invovl", "xg", "chebfiwf2", "lobpcgwf2", "xg_RayleighRitz", "load_library", "library_path", "LibraryNotBuilt"]

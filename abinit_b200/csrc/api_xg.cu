@@ -311,6 +311,108 @@ void abi_b200_chebfi_core_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, do
             *lambda_plus, *ndeg_filter, d);
 }
 
+// lobpcgwf2 (src/79_seqpar_mpi/m_lobpcgwf.F90:100-250) -> lobpcg_run (src/48_diago/m_lobpcg2.F90:340-765), one block of all
+// bands (nblock_lobpcg = 1), paral_kgb = 0
+__global__ void k_build_pcon(int npw, const double* __restrict__ kinpw, double* __restrict__ pcon, double filter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npw) return;
+  const double k = kinpw[i];
+  if (k > filter) { pcon[i] = 0.0; return; }                                      // m_lobpcgwf.F90:326-331
+  const double num = 27 + k * (18 + k * (12 + 8 * k));
+  pcon[i] = num / (num + 16 * k * k * k * k);
+}
+
+void abi_b200_lobpcgwf2_(double* cg, double* eig, double* occ, double* enl_out, abi_b200_ham_t** gs_hamk, int* nband, int* npw,
+                         int* nspinor, int* prtvol, double* resid, double* tolwfr_diago, int* nline, int* nblock_lobpcg, int* nbdbuf,
+                         int* bandpp) {
+  (void)prtvol;
+  ensure_init();
+  Context& c = ctx();
+  cudaStream_t st = c.stream;
+  abi_b200_ham* h = *gs_hamk;
+  const int n = *nband, np = *npw;
+  ABI_CHECK(*nspinor == 1, "lobpcgwf2: nspinor=2 is not implemented in this build");
+  ABI_CHECK(np == h->npw && h->plan != nullptr, "lobpcgwf2: npw differs from the k-point loaded in gs_hamk");
+  ABI_CHECK(*nblock_lobpcg == 1, "lobpcgwf2: only nblock_lobpcg=1 (one block of all bands) is implemented in this build");
+  ABI_CHECK(*nbdbuf >= 0 || (*nbdbuf == -101 && occ != nullptr), "Bad value of nbdbuf");
+  const bool paw = h->usepaw == 1;
+  const int space = space_of(h), me_g0 = me_g0_of(h);
+  AsyncGuard g;
+  const size_t blk = 2 * (size_t)np * n;
+  DevArg a_cg(10, cg, sizeof(double) * blk, true);
+  // [X | W | P], [AX | AW | AP], [BX | BW | BP] (m_lobpcg2.F90:224-268); norm-conserving: BX = X, so B blocks alias the X ones
+  double* XWP = g_cheb[4].get(3 * blk);
+  double* AXWP = g_cheb[0].get(3 * blk);
+  double* BXWP = paw ? g_cheb[1].get(3 * blk) : nullptr;
+  CUDA_CHECK(cudaMemcpyAsync(XWP, a_cg.as<double>(), sizeof(double) * blk, cudaMemcpyDeviceToDevice, st));
+  double* d_pcon = g_cheb[2].get((size_t)np + 8);
+  k_build_pcon<<<ceil_div(np, 256), 256, 0, st>>>(np, h->d_kinpw, d_pcon, 1.7976931348623157e308 * 1.0e-11);
+  CUDA_CHECK(cudaGetLastError());
+  double* d_eig = g_small[0].get((size_t)4 * n);           // 3n eigenvalues + n residuals
+  double* d_res = d_eig + 3 * n;
+  double *X = XWP, *W = XWP + blk, *AX = AXWP, *AW = AXWP + blk;
+  // NC: B X = X.  The blocks the reference keeps separately (BX copy of X) are the SAME vectors, rotated identically.
+  double* BX = paw ? BXWP : XWP; double* BW = paw ? BXWP + blk : W;
+  double* Bblk = paw ? BXWP : XWP;
+  auto getax = [&](double* src, double* a_dst, double* b_dst) { get_ax_bx(h, space, me_g0, np, n, *bandpp, src, a_dst, paw ? b_dst : nullptr); };
+  const int nband_eff = (*nbdbuf >= 0) ? n - *nbdbuf : n;
+  std::vector<double> r(n);
+  getax(X, AX, BX);
+  int info = xg_b_orthonormalize(space, np, n, X, np, paw ? BX : X, np, AX, np, me_g0, st);   // m_lobpcg2.F90:497
+  (void)info;                                                // BX == X (NC) is rotated once: the xg routines skip aliased blocks
+  info = xg_rayleigh_ritz(space, np, n, X, np, AX, np, paw ? BX : nullptr, np, d_eig, false, me_g0, st);   // VAR_X, heevd :500
+  ABI_CHECK(info == 0, "lobpcg: the sub-space eigenproblem (X) failed");
+  bool compute_residu = true;
+  double min_res = 0.0, max_res = 0.0;
+  auto residuals = [&]() {
+    xg_colwise_cymax(space, np, n, W, np, d_eig, BX, np, AX, np, st);             // lobpcg_getResidu :842-854
+    xg_colwise_norm2(space, np, n, W, np, d_res, me_g0, st);
+    xg_apply_diag(space, np, n, W, np, d_pcon, st);                               // preconditioner :513
+    CUDA_CHECK(cudaMemcpyAsync(r.data(), d_res, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (*nbdbuf >= 0) {
+      min_res = max_res = 0.0;
+      for (int i = 0; i < std::max(0, nband_eff); i++) { if (i == 0) min_res = max_res = r[0]; min_res = std::min(min_res, r[i]); max_res = std::max(max_res, r[i]); }
+    } else {
+      min_res = r[0]; max_res = r[0] * occ[0];
+      for (int i = 0; i < n; i++) { min_res = std::min(min_res, r[i]); max_res = std::max(max_res, r[i] * occ[i]); }
+    }
+  };
+  for (int iline = 1; iline <= *nline; iline++) {
+    residuals();
+    if (max_res < *tolwfr_diago) { compute_residu = false; break; }
+    getax(W, AW, BW);
+    bool use_xw = (iline == 1 || min_res < 1e-27);
+    if (!use_xw) {
+      const int ierr = xg_b_orthonormalize(space, np, 3 * n, XWP, np, Bblk, np, AXWP, np, me_g0, st);   // :569
+      if (ierr != 0) use_xw = true;                                               // "did not work, try on XW" :583
+    }
+    if (use_xw) {
+      xg_b_orthonormalize(space, np, 2 * n, XWP, np, Bblk, np, AXWP, np, me_g0, st);                   // :556
+      CUDA_CHECK(cudaMemsetAsync(XWP + 2 * blk, 0, sizeof(double) * blk, st));    // P = AP = BP = 0 :557-559
+      CUDA_CHECK(cudaMemsetAsync(AXWP + 2 * blk, 0, sizeof(double) * blk, st));
+      if (paw) CUDA_CHECK(cudaMemsetAsync(BXWP + 2 * blk, 0, sizeof(double) * blk, st));
+    }
+    info = xg_rayleigh_ritz_xwp(space, np, n, use_xw ? 2 : 3, XWP, AXWP, Bblk, np, d_eig, me_g0, st);
+    if (info != 0) { fprintf(stderr, "\n--- !WARNING\nmessage: |\n    RayleighRitz (XW/XWP) did not work, but continue anyway.\n...\n"); break; }
+  }
+  if (compute_residu) residuals();
+  CUDA_CHECK(cudaMemcpyAsync(eig, d_eig, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  std::copy(r.begin(), r.end(), resid);
+  CUDA_CHECK(cudaMemcpyAsync(a_cg.as<double>(), X, sizeof(double) * blk, cudaMemcpyDeviceToDevice, st));   // lobpcg_setX0
+  a_cg.copy_back();
+  if (!paw && enl_out) {
+    double* d_enl = g_small[1].get((size_t)2 * n);
+    for (int b0 = 0; b0 < n; b0 += *bandpp) {
+      const int nd = std::min(*bandpp, n - b0);
+      gemm_nonlop_device(h->P, h->atoms, h->enl, 1, -1, 0, h->me_g0, nullptr, nd, X + 2 * (size_t)np * b0, nullptr, nullptr, nullptr, st,
+                         nullptr, 1, d_enl + b0);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(enl_out, d_enl, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
 int abi_b200_cheb_oracle1_(double* xx, double* aa, double* bb, double* tol, int* nmax) { return cheb_oracle1(*xx, *aa, *bb, *tol, *nmax); }
 double abi_b200_cheb_poly1_(double* xx, int* nn, double* aa, double* bb) { return cheb_poly1(*xx, *nn, *aa, *bb); }
 

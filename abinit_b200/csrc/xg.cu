@@ -13,6 +13,7 @@
 #include "fourwf.cuh"   // g_kernel_launches
 #include "context.cuh"
 #include <algorithm>
+#include <vector>
 #ifndef ABI_EMU
 #include <dlfcn.h>
 #include <cusolverDn.h>
@@ -131,6 +132,25 @@ __global__ void k_cheb_next(int nreal, double* __restrict__ Xn, long long ldn, c
   }
 }
 
+__global__ void k_add(int nreal, double* __restrict__ X, long long ldx, const double* __restrict__ P, long long ldp) {
+  const int col = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreal; i += gridDim.x * blockDim.x) X[ldx * col + i] += P[ldp * col + i];
+}
+
+__global__ void k_apply_diag(int nreal, int shift, double* __restrict__ X, long long ldx, const double* __restrict__ d) {
+  const int col = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreal; i += gridDim.x * blockDim.x) X[ldx * col + i] *= d[i >> shift];
+}
+
+// keep the upper triangle (incl. diagonal) of an n x n column-major matrix, zero the rest (cplx doubles per element)
+__global__ void k_zero_lower(int n, int cplx, double* __restrict__ A, long long lda) {
+  const long long total = (long long)n * n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % n); const long long j = idx / n;
+    if (i > j) for (int c = 0; c < cplx; c++) A[cplx * (j * lda + i) + c] = 0.0;
+  }
+}
+
 dim3 ew_grid(int nreal, int ncols) { return dim3(std::max(1, std::min(64, ceil_div(nreal, 256 * 4))), ncols); }
 int real_rows(int space, int rows) { return space == SPACE_R ? rows : 2 * rows; }
 long long real_ld(int space, long long ld) { return space == SPACE_R ? ld : 2 * ld; }
@@ -145,6 +165,9 @@ struct Cusolver {
   decltype(&cusolverDnZhegvd_bufferSize) zhegvd_bs; decltype(&cusolverDnZhegvd) zhegvd;
   decltype(&cusolverDnDsyevd_bufferSize) dsyevd_bs; decltype(&cusolverDnDsyevd) dsyevd;
   decltype(&cusolverDnZheevd_bufferSize) zheevd_bs; decltype(&cusolverDnZheevd) zheevd;
+  decltype(&cusolverDnDpotrf_bufferSize) dpotrf_bs; decltype(&cusolverDnDpotrf) dpotrf;
+  decltype(&cusolverDnZpotrf_bufferSize) zpotrf_bs; decltype(&cusolverDnZpotrf) zpotrf;
+  decltype(&cusolverDnXtrtri_bufferSize) xtrtri_bs; decltype(&cusolverDnXtrtri) xtrtri;
 };
 Cusolver& cusolver() {
   static Cusolver cs;
@@ -160,6 +183,9 @@ Cusolver& cusolver() {
   ABI_SYM(zhegvd_bs, cusolverDnZhegvd_bufferSize); ABI_SYM(zhegvd, cusolverDnZhegvd);
   ABI_SYM(dsyevd_bs, cusolverDnDsyevd_bufferSize); ABI_SYM(dsyevd, cusolverDnDsyevd);
   ABI_SYM(zheevd_bs, cusolverDnZheevd_bufferSize); ABI_SYM(zheevd, cusolverDnZheevd);
+  ABI_SYM(dpotrf_bs, cusolverDnDpotrf_bufferSize); ABI_SYM(dpotrf, cusolverDnDpotrf);
+  ABI_SYM(zpotrf_bs, cusolverDnZpotrf_bufferSize); ABI_SYM(zpotrf, cusolverDnZpotrf);
+  ABI_SYM(xtrtri_bs, cusolverDnXtrtri_bufferSize); ABI_SYM(xtrtri, cusolverDnXtrtri);
 #undef ABI_SYM
   ABI_CHECK(cs.create(&cs.h) == CUSOLVER_STATUS_SUCCESS, "xg_hegvd: cusolverDnCreate failed");
   return cs;
@@ -190,25 +216,46 @@ void xg_gram(int space, int rows, int ncols_a, int ncols_b, const double* A, lon
   }
 }
 
-void xg_rotate(int space, int rows, int k, int ncols_out, double* X, long long ldx, const double* C, long long ldc, cudaStream_t st) {
+void xg_gemm_nn(int space, int rows, int k, int ncols_out, const double* A, long long lda, const double* C, long long ldc, double* OUT,
+                long long ldo, cudaStream_t st) {
   if (rows == 0 || ncols_out == 0) return;
   const int M = real_rows(space, rows);
-  const long long ldxr = real_ld(space, ldx);
+  const long long ldar = real_ld(space, lda), ldor = real_ld(space, ldo);
   ABI_CHECK(space == SPACE_C || ldc % 2 == 0, "xg_rotate: the sub-space matrix needs an even leading dimension");
-  ABI_CHECK(space != SPACE_R || (rows % 2 == 0 && ldx % 2 == 0), "xg_rotate(SPACE_R): rows and ld must be even");
-  // row slabs of X are independent in X.C: product into a slab buffer, copy back (the reference uses a full-size
-  // temporary block, m_xg_ortho_RR.F90:524-531); slab = whole waves of 64-row CTA tiles, <= 256 MB
+  ABI_CHECK(space != SPACE_R || (rows % 2 == 0 && lda % 2 == 0), "xg_rotate(SPACE_R): rows and ld must be even");
+  // row slabs are independent in A.C: product into a slab buffer, then store (the reference uses a full-size temporary
+  // block, m_xg_ortho_RR.F90:524-531); slab = whole waves of 64-row CTA tiles, <= 256 MB
   const long long budget = (256LL << 20) / (8LL * ncols_out);
   long long slab = std::max<long long>(2 * kNumSM * 64, budget / (2 * kNumSM * 64) * (2 * kNumSM * 64));
   slab = std::min<long long>(slab, (M + 1) & ~1LL);
   double* tmp = g_xgws[0].get((size_t)slab * ncols_out);
   for (long long m0 = 0; m0 < M; m0 += slab) {
     const int mlen = (int)std::min<long long>(slab, M - m0);
-    if (space == SPACE_C) zgemm_nn(mlen / 2, ncols_out, k, X + m0, ldx, C, ldc, tmp, slab / 2, st);
-    else dgemm_nn(mlen, ncols_out, k, X + m0, ldxr, C, ldc, tmp, slab, st);
-    CUDA_CHECK(cudaMemcpy2DAsync(X + m0, sizeof(double) * ldxr, tmp, sizeof(double) * slab, sizeof(double) * mlen, ncols_out,
+    if (space == SPACE_C) zgemm_nn(mlen / 2, ncols_out, k, A + m0, lda, C, ldc, tmp, slab / 2, st);
+    else dgemm_nn(mlen, ncols_out, k, A + m0, ldar, C, ldc, tmp, slab, st);
+    CUDA_CHECK(cudaMemcpy2DAsync(OUT + m0, sizeof(double) * ldor, tmp, sizeof(double) * slab, sizeof(double) * mlen, ncols_out,
                                  cudaMemcpyDeviceToDevice, st));
   }
+}
+
+void xg_rotate(int space, int rows, int k, int ncols_out, double* X, long long ldx, const double* C, long long ldc, cudaStream_t st) {
+  xg_gemm_nn(space, rows, k, ncols_out, X, ldx, C, ldc, X, ldx, st);
+}
+
+void xg_add(int space, int rows, int ncols, double* X, long long ldx, const double* P, long long ldp, cudaStream_t st) {
+  if (ncols == 0 || rows == 0) return;
+  const int nreal = real_rows(space, rows);
+  k_add<<<ew_grid(nreal, ncols), 256, 0, st>>>(nreal, X, real_ld(space, ldx), P, real_ld(space, ldp));
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+void xg_apply_diag(int space, int rows, int ncols, double* X, long long ldx, const double* d, cudaStream_t st) {
+  if (ncols == 0 || rows == 0) return;
+  const int nreal = real_rows(space, rows);
+  k_apply_diag<<<ew_grid(nreal, ncols), 256, 0, st>>>(nreal, space == SPACE_R ? 0 : 1, X, real_ld(space, ldx), d);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
 }
 
 void xg_zero_im_g0(int space, int ncols, double* X, long long ldx, int me_g0, cudaStream_t st) {
@@ -295,6 +342,102 @@ int xg_hegvd(int space, int n, double* A, long long lda, double* B, long long ld
   CUDA_CHECK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
   return info;
+}
+
+// U^-1 of the Cholesky factor of the m x m sub-space matrix A (upper): potrf 'u' + trtri, strictly-lower part zeroed so
+// that the result can be used as a plain rotation matrix.  Returns potrf's info.
+static int chol_inverse_upper(int sub_space, int m, double* A, long long lda, cudaStream_t st) {
+  Cusolver& cs = cusolver();
+  CUSOLVER_CHECK(cs.set_stream(cs.h, st));
+  const int sc = sub_space == SPACE_C ? 2 : 1;
+  int lwork = 0;
+  const cublasFillMode_t up = CUBLAS_FILL_MODE_UPPER;
+  if (sc == 2) CUSOLVER_CHECK(cs.zpotrf_bs(cs.h, up, m, reinterpret_cast<cuDoubleComplex*>(A), (int)lda, &lwork));
+  else CUSOLVER_CHECK(cs.dpotrf_bs(cs.h, up, m, A, (int)lda, &lwork));
+  size_t wdev = 0, whost = 0;
+  const cudaDataType dt = sc == 2 ? CUDA_C_64F : CUDA_R_64F;
+  CUSOLVER_CHECK(cs.xtrtri_bs(cs.h, up, CUBLAS_DIAG_NON_UNIT, m, dt, A, lda, &wdev, &whost));
+  const size_t ndbl = 4 + std::max<size_t>((size_t)sc * lwork, (wdev + 7) / 8);
+  double* base = g_xgws[3].get(ndbl);
+  int* d_info = reinterpret_cast<int*>(base);
+  double* work = base + 4;
+  std::vector<char> hbuf(whost + 8);
+  if (sc == 2) CUSOLVER_CHECK(cs.zpotrf(cs.h, up, m, reinterpret_cast<cuDoubleComplex*>(A), (int)lda, reinterpret_cast<cuDoubleComplex*>(work), lwork, d_info));
+  else CUSOLVER_CHECK(cs.dpotrf(cs.h, up, m, A, (int)lda, work, lwork, d_info));
+  int info = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  g_kernel_launches++;
+  if (info != 0) return info;
+  CUSOLVER_CHECK(cs.xtrtri(cs.h, up, CUBLAS_DIAG_NON_UNIT, m, dt, A, lda, work, wdev, hbuf.data(), whost, d_info));
+  CUDA_CHECK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  k_zero_lower<<<std::min(kNumSM * 4, (int)ceil_div<long long>((long long)m * m, 256)), 256, 0, st>>>(m, sc, A, lda);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  g_kernel_launches += 2;
+  return info;
+}
+
+int xg_b_orthonormalize(int space, int rows, int m, double* X, long long ldx, double* BX, long long ldbx, double* AX, long long ldax,
+                        int me_g0, cudaStream_t st) {
+  if (m == 0) return 0;
+  const int sc = sub_cplex(space);
+  const int sub_space = (space == SPACE_C) ? SPACE_C : SPACE_R;
+  const long long ldw = (m + 1) & ~1LL;
+  double* buf = g_xgws[1].get((size_t)sc * ldw * m);
+  CUDA_CHECK(cudaMemsetAsync(buf, 0, sizeof(double) * sc * ldw * m, st));
+  xg_zero_im_g0(space, m, X, ldx, me_g0, st);                          // m_xg_ortho_RR.F90:115-119
+  if (BX != X) xg_zero_im_g0(space, m, BX, ldbx, me_g0, st);            // BX == X: norm-conserving caller (B = 1)
+  if (AX) xg_zero_im_g0(space, m, AX, ldax, me_g0, st);
+  xg_gram(space, rows, m, m, X, ldx, BX, ldbx, buf, ldw, me_g0, st);    // :122
+  const int info = chol_inverse_upper(sub_space, m, buf, ldw, st);      // potrf :125 (+ the inverse the trsm calls apply)
+  if (info != 0) return info;                                           // "Cholesky decomposition did not work"
+  xg_rotate(space, rows, m, m, X, ldx, buf, ldw, st);                   // trsm 'r','u','n' :135-142
+  if (BX != X) xg_rotate(space, rows, m, m, BX, ldbx, buf, ldw, st);
+  if (AX) xg_rotate(space, rows, m, m, AX, ldax, buf, ldw, st);
+  return 0;
+}
+
+int xg_rayleigh_ritz_xwp(int space, int rows, int n, int nvar, double* XWP, double* AXWP, double* BXWP, long long ld, double* eig,
+                         int me_g0, cudaStream_t st) {
+  ABI_CHECK(nvar == 2 || nvar == 3, "xg_RayleighRitz: nvar must be 2 (XW) or 3 (XWP)");
+  if (n == 0) return 0;
+  const int sc = sub_cplex(space);
+  const int sub_space = (space == SPACE_C) ? SPACE_C : SPACE_R;
+  const int sub = nvar * n;
+  const long long ldw = (sub + 1) & ~1LL;
+  const size_t blk = (size_t)2 * ld * n;                                 // doubles per n-column block
+  double* subA = g_xgws[1].get((size_t)sc * ldw * sub);
+  double* subB = g_xgws[2].get((size_t)sc * ldw * sub);
+  CUDA_CHECK(cudaMemsetAsync(subA, 0, sizeof(double) * sc * ldw * sub, st));
+  CUDA_CHECK(cudaMemsetAsync(subB, 0, sizeof(double) * sc * ldw * sub, st));
+  xg_zero_im_g0(space, sub, XWP, ld, me_g0, st);                          // :376-398
+  xg_zero_im_g0(space, sub, AXWP, ld, me_g0, st);
+  if (BXWP != XWP) xg_zero_im_g0(space, sub, BXWP, ld, me_g0, st);       // BXWP == XWP: norm-conserving caller (B = 1)
+  // upper-triangular block columns of the sub-space matrices (:384-412)
+  for (int v = 0; v < nvar; v++) {
+    const int rws = (v + 1) * n;
+    xg_gram(space, rows, rws, n, XWP, ld, AXWP + v * blk, ld, subA + (size_t)sc * ldw * v * n, ldw, me_g0, st);
+    xg_gram(space, rows, rws, n, XWP, ld, BXWP + v * blk, ld, subB + (size_t)sc * ldw * v * n, ldw, me_g0, st);
+  }
+  const int info = xg_hegvd(sub_space, sub, subA, ldw, subB, ldw, eig, st);   // EIGENVD, :465
+  if (info != 0) return info;
+  // X <- X Cwp(0:n) ; P <- WP Cwp(n:sub) ; X += P  (:524-560), same for the A and B blocks.  For VAR_XW the reference's
+  // product runs over [W P] with P zeroed beforehand: the W rows alone give the same result.
+  // rows n:sub of the first n eigenvectors, copied to a 16-byte aligned, K-padded matrix (subB is free after hegvd)
+  const long long ldc1 = (sub - n + 1) & ~1LL;
+  double* c1 = subB;
+  CUDA_CHECK(cudaMemsetAsync(c1, 0, sizeof(double) * sc * ldc1 * n, st));
+  CUDA_CHECK(cudaMemcpy2DAsync(c1, sizeof(double) * sc * ldc1, subA + (size_t)sc * n, sizeof(double) * sc * ldw,
+                               sizeof(double) * sc * (sub - n), n, cudaMemcpyDeviceToDevice, st));
+  double* blocks[3] = {XWP, AXWP, BXWP};
+  for (double* B0 : blocks) {
+    if (B0 == BXWP && BXWP == XWP) continue;
+    xg_rotate(space, rows, n, n, B0, ld, subA, ldw, st);
+    xg_gemm_nn(space, rows, sub - n, n, B0 + blk, ld, c1, ldc1, B0 + 2 * blk, ld, st);
+    xg_add(space, rows, n, B0, ld, B0 + 2 * blk, ld, st);
+  }
+  return 0;
 }
 
 int xg_rayleigh_ritz(int space, int rows, int n, double* X, long long ldx, double* AX, long long ldax, double* BX, long long ldbx,

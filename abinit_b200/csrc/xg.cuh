@@ -22,6 +22,21 @@ void xg_gram(int space, int rows, int ncols_a, int ncols_b, const double* A, lon
 // C must be K-padded: ldc even (real spaces) and the pad row zero when k is odd.
 void xg_rotate(int space, int rows, int k, int ncols_out, double* X, long long ldx, const double* C, long long ldc,
                cudaStream_t st);
+// OUT(:, 0:ncols_out) = A(:, 0:k) . C(0:k, 0:ncols_out) by row slabs; OUT may be any block, including columns of A itself
+// (each slab's product is complete before it is stored).  xg_rotate is the case OUT == A.
+void xg_gemm_nn(int space, int rows, int k, int ncols_out, const double* A, long long lda, const double* C, long long ldc,
+                double* OUT, long long ldo, cudaStream_t st);
+// X += P (xgBlock_add)
+void xg_add(int space, int rows, int ncols, double* X, long long ldx, const double* P, long long ldp, cudaStream_t st);
+// X(i, j) *= d(i), d real per (complex) row (xgBlock_apply_diag with a SPACE_R diagonal: the LOBPCG preconditioner)
+void xg_apply_diag(int space, int rows, int ncols, double* X, long long ldx, const double* d, cudaStream_t st);
+// xg_Borthonormalize (m_xg_ortho_RR.F90:86-150): X^H BX = U^H U (potrf 'u'), X, BX, AX <- . U^-1.  Returns potrf's info.
+int xg_b_orthonormalize(int space, int rows, int m, double* X, long long ldx, double* BX, long long ldbx, double* AX, long long ldax,
+                        int me_g0, cudaStream_t st);
+// xg_RayleighRitz, VAR_XW (nvar = 2) / VAR_XWP (nvar = 3) branches (m_xg_ortho_RR.F90:300-571) on contiguous blocks
+// [X | W | P] of n columns each: X, AX, BX, P, AP, BP updated; eig: DEVICE array of nvar*n eigenvalues.
+int xg_rayleigh_ritz_xwp(int space, int rows, int n, int nvar, double* XWP, double* AXWP, double* BXWP, long long ld, double* eig,
+                         int me_g0, cudaStream_t st);
 // xgBlock_zero_im_g0
 void xg_zero_im_g0(int space, int ncols, double* X, long long ldx, int me_g0, cudaStream_t st);
 // dots(ncols) = colwise <A|B> with the SPACE_CR conventions (xgBlock_colwiseDotProduct); SPACE_C stores (re, im) pairs

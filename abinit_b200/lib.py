@@ -29,7 +29,7 @@ SYMBOLS = [
     "abi_b200_ham_load_k", "abi_b200_ham_load_k_xred", "abi_b200_ham_set_projectors", "abi_b200_ham_nprojs", "abi_b200_getghc_",
     "abi_b200_nonlop_",
     "abi_b200_xg_gram_", "abi_b200_xg_rotate_", "abi_b200_xg_hegvd_", "abi_b200_xg_colwise_", "abi_b200_xg_rayleigh_ritz_",
-    "abi_b200_chebfiwf2_", "abi_b200_chebfi_rq_", "abi_b200_chebfi_core_", "abi_b200_cheb_oracle1_", "abi_b200_cheb_poly1_",
+    "abi_b200_chebfiwf2_", "abi_b200_lobpcgwf2_", "abi_b200_chebfi_rq_", "abi_b200_chebfi_core_", "abi_b200_cheb_oracle1_", "abi_b200_cheb_poly1_",
     "abi_b200_make_invovl_", "abi_b200_apply_invovl_",
 ]
 
@@ -86,6 +86,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         lib.abi_b200_xg_colwise_.argtypes = [vp] * 13
         lib.abi_b200_xg_rayleigh_ritz_.argtypes = [vp] * 13
         lib.abi_b200_chebfiwf2_.argtypes = [vp] * 18
+        lib.abi_b200_lobpcgwf2_.argtypes = [vp] * 15
         lib.abi_b200_chebfi_rq_.argtypes = [vp] * 9
         lib.abi_b200_chebfi_core_.argtypes = [vp] * 12
         lib.abi_b200_cheb_oracle1_.argtypes = [vp] * 5

@@ -196,6 +196,14 @@ void abi_b200_chebfi_rq_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, doub
 void abi_b200_chebfi_core_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, double** x, double* ax, double* bx,
                            double** x_next, double** x_prev, double* lambda_minus, double* lambda_plus,
                            int* ndeg_filter, double* div);
+/* LOBPCG (src/48_diago/m_lobpcg2.F90:340-765 lobpcg_run) driven as lobpcgwf2 drives it (src/79_seqpar_mpi/m_lobpcgwf.F90:
+ * 100-250): getAX_BX = fused getghc, preconditioner = build_pcon(kinpw) (:316-334), xg_Borthonormalize (Cholesky) and the
+ * X / XW / XWP Rayleigh-Ritz of src/45_xgTools/m_xg_ortho_RR.F90:86-150, 251-571.  One block of all bands
+ * (nblock_lobpcg must be 1) and paral_kgb = 0 in this build; dtset scalars flattened (tolwfr_diago, nline, nblock_lobpcg,
+ * nbdbuf).  cg in/out (host or device); eig, resid, occ (used when nbdbuf = -101), enl_out (NC, may be NULL): host arrays. */
+void abi_b200_lobpcgwf2_(double* cg, double* eig, double* occ, double* enl_out, abi_b200_ham_t** gs_hamk, int* nband,
+                         int* npw, int* nspinor, int* prtvol, double* resid, double* tolwfr_diago, int* nline,
+                         int* nblock_lobpcg, int* nbdbuf, int* bandpp);
 int abi_b200_cheb_oracle1_(double* xx, double* aa, double* bb, double* tol, int* nmax);
 double abi_b200_cheb_poly1_(double* xx, int* nn, double* aa, double* bb);
 
