@@ -431,8 +431,9 @@ int xg_rayleigh_ritz_xwp(int space, int rows, int n, int nvar, double* XWP, doub
   CUDA_CHECK(cudaMemcpy2DAsync(c1, sizeof(double) * sc * ldc1, subA + (size_t)sc * n, sizeof(double) * sc * ldw,
                                sizeof(double) * sc * (sub - n), n, cudaMemcpyDeviceToDevice, st));
   double* blocks[3] = {XWP, AXWP, BXWP};
-  for (double* B0 : blocks) {
-    if (B0 == BXWP && BXWP == XWP) continue;
+  for (int ib = 0; ib < 3; ib++) {
+    if (ib == 2 && BXWP == XWP) continue;                                 // B blocks alias the X blocks: already rotated
+    double* B0 = blocks[ib];
     xg_rotate(space, rows, n, n, B0, ld, subA, ldw, st);
     xg_gemm_nn(space, rows, sub - n, n, B0 + blk, ld, c1, ldc1, B0 + 2 * blk, ld, st);
     xg_add(space, rows, n, B0, ld, B0 + 2 * blk, ld, st);
