@@ -150,6 +150,14 @@ class Hamiltonian:
         n1, n2, n3 = (int(x) for x in self._ngfft[:3])
         L().abi_b200_ham_load_spin(self.h, _ptr(vlocal, _F, "vlocal"), int(cplex), n1, n2, n3)
 
+    def set_nspinor(self, nspinor):
+        L().abi_b200_ham_set_nspinor(self.h, int(nspinor))
+
+    def load_spin_nvloc(self, vlocal, nvloc):
+        """vlocal(n4,n5,n6,nvloc) == shape (nvloc, n6, n5, n4); nvloc = 4: [V11, V22, Re V12, Im V12]."""
+        n1, n2, n3 = (int(x) for x in self._ngfft[:3])
+        L().abi_b200_ham_load_spin_nvloc(self.h, _ptr(vlocal, _F, "vlocal"), int(nvloc), n1, n2, n3)
+
     def load_enl(self, enl, sij=None):
         enl = np.ascontiguousarray(enl, dtype=np.float64)              # (dimenl2, dimenl1) == Fortran (dimenl1,dimenl2)
         sij_a = None if sij is None else np.ascontiguousarray(sij, dtype=np.float64)

@@ -69,6 +69,33 @@ __global__ void k_assemble(double2* __restrict__ ghc, double2* __restrict__ gsc,
   }
 }
 // strict: type_calc=1 filter "kinpw > huge*1e-11" (m_getghc.F90:1003-1031); otherwise "not (kinpw < huge*1e-11)" (:1272-1277)
+// nspinor = 2: cwavef(2, npw, 2, ndat) -> compact up / dn blocks (m_getghc.F90:495-520)
+__global__ void k_spinor_split(const double2* __restrict__ cw, double2* __restrict__ up, double2* __restrict__ dn, int npw, int ndat) {
+  const long long total = (long long)npw * ndat;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / npw; const int g = (int)(i - b * npw);
+    up[i] = cw[(2 * b) * npw + g]; dn[i] = cw[(2 * b + 1) * npw + g];
+  }
+}
+// ghc_up = g1 + g4, ghc_dn = g3 + g2 (m_getghc.F90:806-830) [+ kinpw psi, filtered (:1266-1280) when with_kin;
+// filter only (type_calc = 1, :1003-1031) otherwise]
+__global__ void k_spinor_combine(double2* __restrict__ ghc, const double2* __restrict__ g1, const double2* __restrict__ g2,
+                                 const double2* __restrict__ g3, const double2* __restrict__ g4, const double2* __restrict__ cw,
+                                 const double* __restrict__ kinpw, int npw, int ndat, double kin_filter, int with_kin) {
+  const long long total = (long long)npw * ndat;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / npw; const int g = (int)(i - b * npw);
+    const double k = kinpw[g];
+    const long long ou = (2 * b) * npw + g, od = (2 * b + 1) * npw + g;
+    double2 u = make_double2(g1[i].x + g4[i].x, g1[i].y + g4[i].y), d = make_double2(g3[i].x + g2[i].x, g3[i].y + g2[i].y);
+    if (with_kin) {
+      if (k < kin_filter) { const double2 cu = cw[ou], cd = cw[od]; u.x += k * cu.x; u.y += k * cu.y; d.x += k * cd.x; d.y += k * cd.y; }
+      else { u = make_double2(0.0, 0.0); d = u; }
+    } else if (k > kin_filter) { u = make_double2(0.0, 0.0); d = u; }
+    ghc[ou] = u; ghc[od] = d;
+  }
+}
+
 __global__ void k_filter_only(double2* __restrict__ ghc, const double* __restrict__ kinpw, int npw, int ndat, double kin_filter,
                               bool strict) {
   const long long total = (long long)npw * ndat;
@@ -180,8 +207,8 @@ void abi_b200_ham_destroy(abi_b200_ham_t* h) {
   if (!h) return;
   if (ctx().initialized) CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
   h->atoms.release(); h->enl.release(); h->P.release(); h->invovl.release();
-  if (h->vloc.d_v) cudaFree(h->vloc.d_v);
-  if (h->vloc.d_vT) cudaFree(h->vloc.d_vT);
+  for (VlocDev* v : {&h->vloc, &h->vloc22, &h->vloc_ud, &h->vloc_du}) { if (v->d_v) cudaFree(v->d_v); if (v->d_vT) cudaFree(v->d_vT); }
+  if (h->d_spin_tmp) cudaFree(h->d_spin_tmp);
   if (h->d_kinpw) cudaFree(h->d_kinpw);
   if (h->d_gvnlxc) cudaFree(h->d_gvnlxc);
   delete h;
@@ -193,7 +220,48 @@ void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_v
             "FFT SIZE ERROR: when gpu mode is on the fft grid must not be augmented (n4,n5,n6 must equal n1,n2,n3)");
   ABI_CHECK(cplex_vloc == 1 || cplex_vloc == 2, "vlocal must be real (cplex=1) or complex (cplex=2)");
   vloc_upload(h->vloc, vlocal, is_device_ptr(vlocal), cplex_vloc, n4, n5, n6, ctx().stream);
+  h->nvloc = 1;
   CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+}
+
+void abi_b200_ham_set_nspinor(abi_b200_ham_t* h, int nspinor) {
+  ABI_CHECK(nspinor == 1 || nspinor == 2, "nspinor must be 1 or 2");
+  ABI_CHECK(!(nspinor == 2 && h->usepaw == 1), "nspinor=2 with PAW (spinor-mixing D_ij) is not implemented in this build");
+  h->nspinor = nspinor;
+}
+
+#ifndef ABI_EMU
+// (re, im) planes -> one interleaved complex potential, im scaled by `sign`
+__global__ void k_pack_vud(const double* __restrict__ v3, const double* __restrict__ v4, double* __restrict__ out, long long n, double sign) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    out[2 * i] = v3[i]; out[2 * i + 1] = sign * v4[i];
+  }
+}
+#endif
+
+void abi_b200_ham_load_spin_nvloc(abi_b200_ham_t* h, const double* vlocal, int nvloc, int n4, int n5, int n6) {
+  ensure_init();
+  ABI_CHECK(nvloc == 1 || nvloc == 4, "nvloc must be 1 or 4");
+  if (nvloc == 1) { abi_b200_ham_load_spin(h, vlocal, 1, n4, n5, n6); h->nvloc = 1; return; }
+  ABI_CHECK(h->nspinor == 2, "nvloc=4 requires nspinor=2 (abi_b200_ham_set_nspinor)");
+  ABI_CHECK(n4 == h->ngfft[0] && n5 == h->ngfft[1] && n6 == h->ngfft[2],
+            "FFT SIZE ERROR: when gpu mode is on the fft grid must not be augmented (n4,n5,n6 must equal n1,n2,n3)");
+#ifndef ABI_EMU
+  Context& c = ctx();
+  const size_t N = (size_t)n4 * n5 * n6;
+  const bool dev = is_device_ptr(vlocal);
+  vloc_upload(h->vloc, vlocal, dev, 1, n4, n5, n6, c.stream);                  // vlocal(:,:,:,1)
+  vloc_upload(h->vloc22, vlocal + N, dev, 1, n4, n5, n6, c.stream);            // vlocal(:,:,:,2)
+  DevArg a34(9, vlocal + 2 * N, sizeof(double) * 2 * N, true);                  // vlocal(:,:,:,3:4)
+  if (h->spin_tmp_cap < 2 * N) { if (h->d_spin_tmp) cudaFree(h->d_spin_tmp); CUDA_CHECK(cudaMalloc(&h->d_spin_tmp, sizeof(double) * 2 * N)); h->spin_tmp_cap = 2 * N; }
+  // m_getghc.F90:771-776: psi_dn -> ghc_up sees (V3, +V4); :737-742: psi_up -> ghc_dn sees (V3, -V4)
+  k_pack_vud<<<kNumSM * 4, 256, 0, c.stream>>>(a34.as<double>(), a34.as<double>() + N, h->d_spin_tmp, (long long)N, 1.0);
+  vloc_upload(h->vloc_ud, h->d_spin_tmp, true, 2, n4, n5, n6, c.stream);
+  k_pack_vud<<<kNumSM * 4, 256, 0, c.stream>>>(a34.as<double>(), a34.as<double>() + N, h->d_spin_tmp, (long long)N, -1.0);
+  vloc_upload(h->vloc_du, h->d_spin_tmp, true, 2, n4, n5, n6, c.stream);
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+#endif
+  h->nvloc = 4;
 }
 
 void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, const double* sij) {
@@ -280,7 +348,14 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
   ensure_init();
   Context& c = ctx();
   abi_b200_ham* h = *gs_ham;
-  const int tc = *type_calc, nd = *ndat, npw = h->npw;
+  // nspinor = 2 (NC, istwf_k = 1): the block is cwavef(2, npw*nspinor*ndat) -- every (band, spinor) pair is a column of npw
+  // coefficients on which the kinetic and non-local terms act separately (m_getghc.F90:1266-1280, opernlc NC branch with
+  // ekb(:,:,ispinor) equal for both components); only the local part couples them, and only when nvloc = 4.
+  if (h->nspinor == 2) {
+    ABI_CHECK(h->usepaw == 0, "getghc: nspinor=2 with PAW is not implemented in this build");
+    ABI_CHECK(h->istwf_k == 1, "getghc: nspinor=2 requires istwf_k=1");
+  }
+  const int tc = *type_calc, nd = *ndat * h->nspinor, npw = h->npw;
   ABI_CHECK(tc >= 0 && tc <= 3, "getghc: type_calc must be 0, 1, 2 or 3");
   ABI_CHECK(h->plan != nullptr, "getghc: load_k has not been called");
   ABI_CHECK(!(*sij_opt != 0 && h->usepaw == 0), "getghc: sij_opt/=0 requires PAW");   // m_getghc.F90:333-336
@@ -290,7 +365,8 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
   const int cplex = (h->istwf_k == 1) ? 2 : 1;
   const bool fused_fw = local && h->plan->fused_ok && c.fourwf_impl != 1;
   // pipelined staging needs the fused fourwf (band-chunked) and host input + output arrays
-  const bool pipe = fused_fw && nd >= 8 && cwavef && ghc && !is_device_ptr(cwavef) && !is_device_ptr(ghc) && c.pipeline;
+  const bool pipe = fused_fw && nd >= 8 && cwavef && ghc && !is_device_ptr(cwavef) && !is_device_ptr(ghc) && c.pipeline &&
+                    h->nvloc == 1;
   DevArg a_c(0, cwavef, nv, !pipe);
   DevArg a_ghc(1, ghc, nv, tc == 2);
   DevArg a_gsc(2, (*sij_opt == 1) ? gsc : nullptr, nv, false);
@@ -304,6 +380,30 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
     ABI_CHECK(h->P.d_p != nullptr || h->atoms.nprojs == 0, "getghc: projectors not loaded (load_k with ffnl/ph3d or set_projectors)");
   bool ghc_shipped = false;
 
+#ifndef ABI_EMU
+  if (local && h->nvloc == 4) {
+    // ---- non-collinear local part (m_getghc.F90:655-830): four applications on the compacted spinor components
+    //   ghc_up = F[V11] psi_up + F[V3 + i V4] psi_dn ;  ghc_dn = F[V3 - i V4] psi_up + F[V22] psi_dn
+    ABI_CHECK(h->vloc22.d_v && h->vloc_ud.d_v && h->vloc_du.d_v, "We need vlocal(:,:,:,1:4) in gs_ham! (load_spin_nvloc)");
+    const int nb = *ndat;
+    c.fourwf_counter += 8 * nb;
+    const size_t cb = (size_t)npw * nb;                                   // double2 per compact block
+    double2* t = reinterpret_cast<double2*>(c.stage[11].get(sizeof(double2) * 6 * cb));
+    double2 *up = t, *dn = t + cb, *g1 = t + 2 * cb, *g2 = t + 3 * cb, *g3 = t + 4 * cb, *g4 = t + 5 * cb;
+    const int blocks = std::min(kNumSM * 8, (int)ceil_div<long long>((long long)npw * nb, 256));
+    k_spinor_split<<<blocks, 256, 0, c.stream>>>(a_c.as<double2>(), up, dn, npw, nb);
+    auto apply_local = [&](const VlocDev& v, const double2* in, double2* out) {
+      if (fused_fw) { FourwfEpilogue e0; fourwf_fused_opt2(*h->plan, v, in, out, nb, e0, c.stream); }
+      else fourwf_generic(*h->plan, 2, v.cplex, v.d_v, in, out, nullptr, nb, nullptr, nullptr, c.stream);
+    };
+    apply_local(h->vloc, up, g1); apply_local(h->vloc22, dn, g2);
+    apply_local(h->vloc_du, up, g3); apply_local(h->vloc_ud, dn, g4);
+    k_spinor_combine<<<blocks, 256, 0, c.stream>>>(a_ghc.as<double2>(), g1, g2, g3, g4, a_c.as<double2>(), h->d_kinpw, npw, nb,
+                                                   kin_filter, tc == 1 ? 0 : 1);
+    CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches += 2;
+  } else
+#endif
   if (local) {
     // ---- local part first: ghc = V_loc psi + T psi (filtered); the non-local term is added by the last GEMM's epilogue
     c.fourwf_counter += 2 * nd;

@@ -25,6 +25,10 @@ struct abi_b200_ham {
   abi::NonlopEnl enl;
   abi::Projectors P;
   abi::VlocDev vloc;
+  // nspinor = 2 (m_hamiltonian.F90 nspinor / nvloc): nvloc = 4 keeps V22 and the two complex off-diagonal potentials
+  int nspinor = 1, nvloc = 1;
+  abi::VlocDev vloc22, vloc_ud, vloc_du;   // V22 (real); (V3 + i V4) applied to psi_dn -> ghc_up; (V3 - i V4) applied to psi_up -> ghc_dn
+  double* d_spin_tmp = nullptr; size_t spin_tmp_cap = 0;
   int istwf_k = 1, npw = 0, me_g0 = 1;
   std::vector<int> kg;
   double* d_kinpw = nullptr;

@@ -110,13 +110,18 @@ long long abi_b200_nonlop_counter(void);      /* nonlop_counter, src/66_nonlocal
  *   load_spin -> abi_b200_ham_load_spin   (vlocal per spin,   m_vtorho.F90:804)
  *   load_k    -> abi_b200_ham_load_k      (kg,kinpw,ffnl,ph3d m_vtorho.F90:1035-1045; P built here)
  * abi_b200_getghc_ has the argument list of getghc (src/66_wfs/m_getghc.F90:182-202) with gs_ham -> handle,
- * cwaveprj -> flattened projections, mpi_enreg dropped.  nspinor=1, nvloc=1, k==k' (select_k default).
+ * cwaveprj -> flattened projections, mpi_enreg dropped.  k==k' (select_k default); nspinor=2 / nvloc=4: NC only (below).
  * ---------------------------------------------------------------------------------------------------- */
 typedef struct abi_b200_ham abi_b200_ham_t;
 abi_b200_ham_t* abi_b200_ham_create(const int* ngfft, int natom, int ntypat, int lmnmax, const int* indlmn,
                                     const int* nattyp, const int* atindx1, int usepaw, double ucvol);
 void abi_b200_ham_destroy(abi_b200_ham_t* h);
 void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_vloc, int n4, int n5, int n6);
+/* nspinor = 2 (gs_hamk%nspinor, norm-conserving, istwf_k = 1): blocks are cwavef(2, npw*nspinor*ndat); ndat keeps counting bands.
+ * load_spin_nvloc: vlocal(n4,n5,n6,nvloc), nvloc = 4 = [V11, V22, Re V12, Im V12] (non-collinear magnetism): the four local
+ * applications of src/66_wfs/m_getghc.F90:655-830.  Spin-orbit projectors and PAW spinors are rejected. */
+void abi_b200_ham_set_nspinor(abi_b200_ham_t* h, int nspinor);
+void abi_b200_ham_load_spin_nvloc(abi_b200_ham_t* h, const double* vlocal, int nvloc, int n4, int n5, int n6);
 /* enl: NC ekb(dimenl1=lnmax, ntypat); PAW dij(dimenl1=lmn2_size, natom).  sij(dimenl1, ntypat) (PAW) or NULL */
 void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, const double* sij);
 void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw,

@@ -39,3 +39,35 @@ def getghc(cwavef, vlocal, kg, ngfft, kinpw, P, enl, sij, indlmn, nattyp, atindx
         if sij_opt == 1 and gsc is not None:
             gsc = np.where(ok[None, :], gsc, 0.0)
     return ghc, gsc, gvnlxc, proj
+
+
+def getghc_spinor(cwavef, vlocal, kg, ngfft, kinpw, P, enl, indlmn, nattyp, atindx1, type_calc=0, workers=None):
+    """nspinor = 2 (norm-conserving, istwf_k = 1, no spin-orbit): restates the spinor branches of m_getghc.F90
+      nvloc = 1  :555-653   the same real potential on both spinor components
+      nvloc = 4  :655-830   ghc_up = V11 psi_up + (V3 + i V4) psi_dn ; ghc_dn = (V3 - i V4) psi_up + V22 psi_dn
+      kinetic assembly :1266-1280 and nonlop per spinor component (opernlc NC: ekb(:,:,ispinor) identical for both).
+    cwavef: (ndat, 2, npw) == Fortran cwavef(2, npw*nspinor*ndat); vlocal: (n3,n2,n1) or (4,n3,n2,n1) [V11, V22, Re V12, Im V12]."""
+    cw = np.asarray(cwavef)
+    ndat, _, npw = cw.shape
+    up, dn = np.ascontiguousarray(cw[:, 0]), np.ascontiguousarray(cw[:, 1])
+    v = np.asarray(vlocal)
+    ghc = np.zeros_like(cw); gv = np.zeros_like(cw)
+    f = lambda vv, c: fourwf(2 if np.iscomplexobj(vv) else 1, vv, c, None, kg, kg, ngfft, 2, 1, workers=workers)[0]
+    if type_calc in (0, 1, 3):
+        if v.ndim == 3:
+            ghc[:, 0] = f(v, up); ghc[:, 1] = f(v, dn)
+        else:
+            g1 = f(v[0], up); g2 = f(v[1], dn)
+            g3 = f(v[2] - 1j * v[3], up); g4 = f(v[2] + 1j * v[3], dn)
+            ghc[:, 0] = g1 + g4; ghc[:, 1] = g3 + g2
+        if type_calc == 1:
+            ghc[:, :, kinpw > KIN_FILTER] = 0.0
+    if type_calc in (0, 2):
+        flat = cw.reshape(ndat * 2, npw)
+        gvf, _, _ = gemm_nonlop(P, flat, enl, None, indlmn, nattyp, atindx1, 1, choice=1, paw_opt=0, cpopt=-1)
+        gv = gvf.reshape(ndat, 2, npw)
+    if type_calc in (0, 2, 3):
+        ok = kinpw < KIN_FILTER
+        kin = np.where(ok, kinpw, 0.0)
+        ghc = np.where(ok[None, None, :], ghc + kin[None, None, :] * cw + gv, 0.0)
+    return ghc, gv

@@ -157,3 +157,43 @@ def test_load_k_xred_builds_ph3d_on_device(lib, istwf_k, kpt, usepaw):
     assert rel_err_per_band(a, b) < 1e-12
     assert rel_err_per_band(a, r_ghc) < TOL
     h.destroy(); h2.destroy()
+
+
+@pytest.mark.parametrize("nvloc", [1, 4])
+@pytest.mark.parametrize("type_calc", [0, 1, 2, 3])
+def test_nspinor2_nc(lib, nvloc, type_calc):
+    """nspinor = 2, norm-conserving: collinear potential on both spinor components (nvloc=1) and the non-collinear 2x2
+    potential (nvloc=4: V11, V22, Re V12, Im V12), every type_calc, host and device blocks, fused and generic fourwf."""
+    ndat = 3
+    p = make_problem(7.0, (8.0, 9.0, 7.5), (.1, .2, .3), 1, ndat=2 * ndat, natom_per_type=(2,), lmax_per_type=(1,))
+    n1, n2, n3 = p.ngfft
+    cw = np.ascontiguousarray(p.cwavef.reshape(ndat, 2, p.npw))
+    rng = np.random.default_rng(21)
+    if nvloc == 1:
+        vl = p.vlocal
+    else:
+        i3, i2, i1 = np.meshgrid(np.arange(n3), np.arange(n2), np.arange(n1), indexing="ij")
+        vl = np.stack([p.vlocal, p.vlocal + 0.2 * np.cos(2 * np.pi * i1 / n1), 0.15 * np.sin(2 * np.pi * i2 / n2),
+                       0.1 * np.cos(2 * np.pi * (i3 / n3 - i1 / n1))])
+        vl = np.ascontiguousarray(vl)
+    P = onl.prep_projectors(p.ffnl, p.ph3d, p.indlmn, p.nattyp, p.ucvol)
+    ghc0 = rng.standard_normal(cw.shape) + 1j * rng.standard_normal(cw.shape)
+    ref, ref_gv = ogh.getghc_spinor(cw, vl, p.kg, p.ngfft, p.kinpw, P, p.enl, p.indlmn, p.nattyp, p.atindx1 - 1, type_calc=type_calc)
+    if type_calc == 2:
+        # type_calc = 2 ADDS the non-local + kinetic part to the caller's ghc (m_getghc.F90:152)
+        ok = p.kinpw < g.KIN_FILTER
+        ref = np.where(ok[None, None, :], ghc0 + np.where(ok, p.kinpw, 0.0)[None, None, :] * cw + ref_gv, 0.0)
+    h = ab.Hamiltonian(p.ngfft, p.natom, p.ntypat, p.lmnmax, p.indlmn, p.nattyp, p.atindx1, 0, p.ucvol)
+    h.set_nspinor(2)
+    h.load_spin_nvloc(vl, nvloc)
+    h.load_enl(p.enl, None)
+    h.load_k(1, p.kgF, p.kinpw, p.ffnl, p.ph3d, me_g0=1)
+    for impl in (0, 1):
+        ab.api.L().abi_b200_fourwf_set_impl(impl)
+        out = ghc0.copy(); gv = np.zeros_like(out)
+        ab.getghc(-1, cw, None, out, None, h, gv, None, None, ndat, type_calc=type_calc)
+        assert rel_err_per_band(out.reshape(2 * ndat, -1), ref.reshape(2 * ndat, -1)) < TOL, (impl,)
+        if type_calc in (0, 2):
+            assert rel_err_per_band(gv.reshape(2 * ndat, -1), ref_gv.reshape(2 * ndat, -1)) < TOL
+    ab.api.L().abi_b200_fourwf_set_impl(0)
+    h.destroy()
