@@ -552,7 +552,9 @@ static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long lo
   p.tiles_m = ceil_div(M, BM); p.tiles_n = ceil_div(Neff, BN);
   const int tiles = p.tiles_m * p.tiles_n;
   // pick the split count that minimises the makespan (waves of 148 CTAs per unit of work)
-  const int min_chunk = 64 * kBK;
+  // few output tiles (small systems: Si-2, Fe-2 per k-point): the GPU is filled along K instead -- short chunks, or one or
+  // two CTAs walk the whole K loop at the latency of one k tile per step (111 us for K = 1480 before, launch-bound after)
+  const int min_chunk = (tiles >= kNumSM ? 64 : 8) * kBK;
   const int max_split = std::max(1, std::min(64, ceil_div(K, min_chunk)));
   int nsplit = 1; double best = 1e30;
   for (int s = 1; s <= max_split; s++) {
