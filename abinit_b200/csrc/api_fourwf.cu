@@ -2,6 +2,7 @@
 #include "../../include/abinit_b200.h"
 #include "context.cuh"
 #include "fourwf.cuh"
+#include "nonlop.cuh"
 #include <string>
 #include <algorithm>
 
@@ -79,6 +80,7 @@ void abi_b200_fourwf_set_tuning(const char* name, int value) {
   else if (k == "plane_cfg") t.plane_cfg = value;
   else if (k == "pack2") t.pack2 = value;
   else if (k == "pipeline") ctx().pipeline = value != 0;
+  else if (k == "nonlop_ozaki") ozaki_set_enabled(value);     // EXPERIMENTAL int8-sliced gemm_nonlop (ozaki.cu), default off
   else if (k == "pipe_chunks") ctx().pipe_chunks = std::max(1, value);
   else if (k == "plane_ctas_per_sm") t.plane_ctas_per_sm = value;
   else if (k == "cluster") t.cluster = value;

@@ -435,8 +435,9 @@ void Projectors::alloc(int npw_, int nprojs_, int istwf_k_) {
     cap = need;
   }
   npw = npw_; nprojs = nprojs_; istwf_k = istwf_k_;
+  stamp++;                                    // the caller is about to (re)write P: any int8-sliced copy is stale
 }
-void Projectors::release() { if (d_p) cudaFree(d_p); d_p = nullptr; cap = 0; npw = nprojs = 0; }
+void Projectors::release() { if (d_p) cudaFree(d_p); d_p = nullptr; cap = 0; npw = nprojs = 0; oz.release(); oz_stamp = 0; }
 
 template <typename T> static T* upload(const std::vector<T>& v) {
   T* d = nullptr;
@@ -505,7 +506,7 @@ struct NlWorkspace {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 static NlWorkspace g_nlws[4];   // 0: partials, 1: gx, 2: gxfac, 3: gxs
-void nonlop_release_workspace() { for (auto& w : g_nlws) w.release(); }
+void nonlop_release_workspace() { for (auto& w : g_nlws) w.release(); ozaki_release_workspace(); }
 
 #ifndef ABI_EMU
 void prep_projectors_device(Projectors& P, const NonlopAtoms& at, const double* d_ffnl, int dimffnl, const double* d_ph3d,
@@ -723,7 +724,16 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
   } else {
     ABI_CHECK(vectin != nullptr, "gemm_nonlop: vectin is required");
     double* part = nullptr;
-    const int nsplit = launch_tn(cplx, nprojs, cplex * ndat, 2 * npw, P.d_p, ldv, vectin, ldv, part, st);
+    int nsplit;
+    const bool oz = !cplx && ozaki_enabled();      // EXPERIMENTAL int8-sliced contractions (ozaki.cu), off by default
+    if (oz) {
+      if (P.oz_stamp != P.stamp) { ozaki_prepare(P, P.oz, st); P.oz_stamp = P.stamp; }
+      part = g_nlws[0].get((size_t)ndat * nprojs);
+      ozaki_project(P.oz, vectin, ndat, part, st);
+      nsplit = 1;
+    } else {
+      nsplit = launch_tn(cplx, nprojs, cplex * ndat, 2 * npw, P.d_p, ldv, vectin, ldv, part, st);
+    }
     ReduceParams r;
     r.M = nprojs; r.ndat = ndat; r.cplex = cplex; r.nsplit = nsplit; r.neff = cplex * ndat; r.part = part;
     r.scale = cplx ? 1.0 : 2.0;
@@ -761,12 +771,21 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
   if (choice == 7 || paw_opt == 3 || paw_opt == 4) {
     ABI_CHECK(svectout != nullptr && (vectin != nullptr || choice == 7), "gemm_nonlop: svectout/vectin required for the overlap");
     // + vectin except for choice 7 (m_opernlb_gemm.F90:654-665)
+    if (!cplx && ozaki_enabled() && P.oz_stamp == P.stamp)
+      ozaki_expand(P.oz, zs, ldg, ndat, svectout, 0, nullptr, nullptr, 0.0, choice == 7 ? nullptr : vectin, st);
+    else
     launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zs, ldg, svectout, ldv, choice == 7 ? nullptr : vectin, st);
   }
   if (choice == 1 && (paw_opt == 0 || paw_opt == 1 || paw_opt == 2 || paw_opt == 4)) {
+    const bool oz_b = !cplx && ozaki_enabled() && P.oz_stamp == P.stamp;
     if (fuse == nullptr) {
       ABI_CHECK(vectout != nullptr, "gemm_nonlop: vectout required");
-      launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zfac, ldg, vectout, ldv, nullptr, st);
+      if (oz_b) ozaki_expand(P.oz, zfac, ldg, ndat, vectout, 0, nullptr, nullptr, 0.0, nullptr, st);
+      else launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zfac, ldg, vectout, ldv, nullptr, st);
+    } else if (oz_b) {
+      ABI_CHECK(fuse->ghc != nullptr && fuse->kinpw != nullptr, "gemm_nonlop: fusion needs ghc and kinpw");
+      ozaki_expand(P.oz, zfac, ldg, ndat, fuse->ghc, 1, vectout, fuse->kinpw, fuse->kin_filter, nullptr, st);
+      if (fuse->after_slab) fuse->after_slab(fuse->user, 0, npw);
     } else {
       // getghc fusion: ghc += P.gxfac with the kinetic filter in the GEMM epilogue, in row slabs (each complete for
       // every band, so the caller can ship it to the host while the next slab is computed)

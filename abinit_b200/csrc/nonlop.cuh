@@ -7,12 +7,26 @@
 
 namespace abi {
 
+// EXPERIMENTAL int8-sliced copies of P (ozaki.cu, opt-in with ABI_B200_OZAKI=1; never used by default)
+struct OzakiP {
+  int npw = 0, nprojs = 0;
+  long long kp1 = 0, kp2 = 0, mp2 = 0;     // padded K of opernla, padded K and M of opernlb
+  int8_t* a_k = nullptr;                   // [7][nprojs][kp1]  slices of P columns (K = 2 npw contiguous)
+  int8_t* a_m = nullptr;                   // [7][mp2][kp2]     slices of P rows (K = nprojs contiguous)
+  double* ea_k = nullptr; double* ea_m = nullptr;   // binary exponents per projector / per row
+  void release();
+};
+bool ozaki_enabled();
+void ozaki_set_enabled(int flag);
+
 // Projectors of one k-point, resident on the device as the real view of P(2, npw, nprojs):
 // a column-major (2*npw) x nprojs FP64 matrix (rows = re/im interleaved plane-wave coefficients).
 struct Projectors {
   int npw = 0, nprojs = 0, istwf_k = 1;
   double* d_p = nullptr;          // (2*npw) * nprojs doubles (+ padding)
   size_t cap = 0;
+  mutable OzakiP oz;              // experimental, built lazily when ABI_B200_OZAKI=1
+  mutable unsigned long long oz_stamp = 0, stamp = 1;   // oz is valid when oz_stamp == stamp (stamp bumps on every (re)build of P)
   void alloc(int npw_, int nprojs_, int istwf_k_);
   void release();
 };
@@ -78,6 +92,12 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
 long long nonlop_ldg(const Projectors& P);
 void nonlop_project(const Projectors& P, int me_g0, const double* vectin, int ndat, double* gx, cudaStream_t st);
 void nonlop_expand(const Projectors& P, const double* z, int ndat, double* vectout, const double* add, cudaStream_t st);
+
+void ozaki_prepare(const Projectors& P, OzakiP& oz, cudaStream_t st);
+void ozaki_project(const OzakiP& oz, const double* vectin, int ndat, double* part, cudaStream_t st);
+void ozaki_expand(const OzakiP& oz, const double* z, long long ldz, int ndat, double* out, int fuse, double* vout, const double* kin,
+                  double kin_filter, const double* add, cudaStream_t st);
+void ozaki_release_workspace();
 
 // plain tensor-core GEMMs (also used by the Gram kernels of xg.cu); all device pointers, column-major
 //   TN: C(M,N) = alpha * A(K,M)^T B(K,N)      NN: C(M,N) = A(M,K) B(K,N)

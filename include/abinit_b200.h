@@ -73,7 +73,9 @@ void abi_b200_fourwf_set_impl(int impl);
 /* tuning knobs of the fused path (no reference counterpart; also read from ABI_B200_FOURWF_* at first use):
  * "plane" 0/1, "plane_cfg" 0 auto / 1 (8 columns x 4 warps) / 2 (4 columns x 8 warps) / 3 (4 x 16), "plane_ctas_per_sm",
  * "pack2" 0/1 (istwf_k=2: two bands per complex transform),
- * "cluster", "lines_x", "smem_kb_mid", "band_chunk".  Unknown names abort. */
+ * "cluster", "lines_x", "smem_kb_mid", "band_chunk", "pipe_chunks" (host-array getghc pipeline depth),
+ * "nonlop_ozaki" 0/1 (EXPERIMENTAL, default 0: gemm_nonlop's real contractions through exact int8 slice products,
+ * csrc/ozaki.cu; also ABI_B200_OZAKI=1).  Unknown names abort. */
 void abi_b200_fourwf_set_tuning(const char* name, int value);
 /* fourwf_counter of src/53_ffts/m_fft.F90:2333-2336 */
 long long abi_b200_fourwf_counter(void);
