@@ -416,6 +416,18 @@ def main():
             cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as ex:   # the baseline is reported, never a gate
             cpu = {"value": None, "unit": "band-applications/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    # EXPERIMENTAL (reported separately, never part of `value`): gemm_nonlop's two contractions through exact int8 slice
+    # products (csrc/ozaki.cu: own slicing + FP64 recombination around cuBLASLt int8 GEMMs) instead of the FP64 DMMA kernels.
+    # Runs in its own process after this one has released the device, so that nothing it does can touch the numbers above.
+    experimental = None
+    if world == 1 and not args.no_scf_step:
+        try:
+            ham.destroy(); ab.finalize(); del cw, ghc
+            torch.cuda.empty_cache()
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ozaki_bench.py"), "--json"], capture_output=True, text=True, timeout=600)
+            experimental = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as ex:                                   # noqa: BLE001
+            experimental = {"error": repr(ex)}
     out = {"metric": "getghc band-applications/s", "value": value, "unit": "band-applications/s", "n_gpus": world,
            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -424,7 +436,8 @@ def main():
                       "l2": "inputs larger than L2 (P = %.1f GB streamed twice per step)" % (16.0 * npw * nprojs / 1e9),
                       "parallelism": f"band blocks over {world} GPU(s), no data-path collective"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-           "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}, "scf_step": scf_step, "density_step": density, "fourwf_anchor": anchor}
+           "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}, "scf_step": scf_step, "density_step": density, "fourwf_anchor": anchor,
+           "experimental_int8_sliced": experimental}
     out.update(extra)
     print(json.dumps(out))
     if dist is not None:
