@@ -7,17 +7,15 @@
 //   the FP64 result is  2^(ea+eb) * sum_{s+t<S} 2^(-7(s+t+2)) (A_s^T B_t), summed smallest terms first.
 //   28 slice products reproduce the FP64 GEMM to ~3e-13 relative (tools/ozaki_study.py).
 //
-// In this round the int8 GEMMs themselves are cuBLASLt calls (IMMA/tcgen05 kind::i8 inside the library, bound at run time);
-// slicing, operand layout and the FP64 recombination with the getghc epilogue are this file.  The hand-written tcgen05 int8
-// kernel that would make this a product path is future work -- nothing here is used unless the
-// environment variable is set, and bench.py reports it under a separate key.
+// The int8 GEMMs are the hand-written tcgen05 kernel of igemm_tc.cuh (TMA + mbarrier ring + kind::i8 MMA into TMEM),
+// measured at 97 % (K = 2 npw) / 78 % (K = nprojs) of cuBLASLt's int8 GEMM on the Si-512 shapes (tools/igemm_lab.cu,
+// tools/probe_int8.py).  Nothing here is used unless the knob is set; bench.py reports it under a separate key.
 #include "nonlop.cuh"
 #include "fourwf.cuh"
 #include "context.cuh"
 #include <algorithm>
 #ifndef ABI_EMU
-#include <dlfcn.h>
-#include <cublasLt.h>
+#include "igemm_tc.cuh"
 #endif
 
 namespace abi {
@@ -26,44 +24,11 @@ namespace abi {
 namespace {
 constexpr int kS = 7, kBits = 7;
 
-struct Lt {
-  void* lib = nullptr; cublasLtHandle_t h = nullptr;
-  decltype(&cublasLtCreate) create; decltype(&cublasLtMatmul) matmul;
-  decltype(&cublasLtMatmulDescCreate) desc_create; decltype(&cublasLtMatmulDescSetAttribute) desc_set;
-  decltype(&cublasLtMatrixLayoutCreate) lay_create; decltype(&cublasLtMatrixLayoutDestroy) lay_destroy;
-  cublasLtMatmulDesc_t op = nullptr;
-  void* ws = nullptr; size_t ws_bytes = 64u << 20;
-};
-Lt& lt() {
-  static Lt l;
-  if (l.h) return l;
-  const char* cands[] = {getenv("ABI_B200_CUBLASLT"), "libcublasLt.so.12", "/usr/local/cuda/lib64/libcublasLt.so.12", "libcublasLt.so"};
-  for (const char* c : cands) if (c && !l.lib) l.lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
-  ABI_CHECK(l.lib != nullptr, "ozaki: cannot load libcublasLt.so.12 (set ABI_B200_CUBLASLT)");
-#define LT_SYM(f, n) do { l.f = reinterpret_cast<decltype(l.f)>(dlsym(l.lib, #n)); ABI_CHECK(l.f != nullptr, "ozaki: missing " #n); } while (0)
-  LT_SYM(create, cublasLtCreate); LT_SYM(matmul, cublasLtMatmul); LT_SYM(desc_create, cublasLtMatmulDescCreate);
-  LT_SYM(desc_set, cublasLtMatmulDescSetAttribute); LT_SYM(lay_create, cublasLtMatrixLayoutCreate); LT_SYM(lay_destroy, cublasLtMatrixLayoutDestroy);
-#undef LT_SYM
-  ABI_CHECK(l.create(&l.h) == CUBLAS_STATUS_SUCCESS, "ozaki: cublasLtCreate failed");
-  ABI_CHECK(l.desc_create(&l.op, CUBLAS_COMPUTE_32I, CUDA_R_32I) == CUBLAS_STATUS_SUCCESS, "ozaki: matmul desc");
-  cublasOperation_t t = CUBLAS_OP_T;
-  ABI_CHECK(l.desc_set(l.op, CUBLASLT_MATMUL_DESC_TRANSA, &t, sizeof t) == CUBLAS_STATUS_SUCCESS, "ozaki: transa");
-  CUDA_CHECK(cudaMalloc(&l.ws, l.ws_bytes));
-  return l;
-}
-
 // C(M x N, int32, ldc) = A(K x M, int8, lda)^T B(K x N, int8, ldb)
 void igemm_tn(int M, int N, int K, const int8_t* A, long long lda, const int8_t* B, long long ldb, int32_t* C, long long ldc, cudaStream_t st) {
-  Lt& l = lt();
-  cublasLtMatrixLayout_t la, lb, lc;
-  ABI_CHECK(l.lay_create(&la, CUDA_R_8I, K, M, lda) == CUBLAS_STATUS_SUCCESS, "ozaki: layout A");
-  ABI_CHECK(l.lay_create(&lb, CUDA_R_8I, K, N, ldb) == CUBLAS_STATUS_SUCCESS, "ozaki: layout B");
-  ABI_CHECK(l.lay_create(&lc, CUDA_R_32I, M, N, ldc) == CUBLAS_STATUS_SUCCESS, "ozaki: layout C");
-  const int32_t one = 1, zero = 0;
   ProfScope ps("ozaki_igemm");
-  const cublasStatus_t s = l.matmul(l.h, l.op, &one, A, la, B, lb, &zero, C, lc, C, lc, nullptr, l.ws, l.ws_bytes, st);
-  ABI_CHECK(s == CUBLAS_STATUS_SUCCESS, "ozaki: cublasLtMatmul(int8) failed");
-  l.lay_destroy(la); l.lay_destroy(lb); l.lay_destroy(lc);
+  igemm_tc(M, N, K, A, lda, B, ldb, C, ldc, st);
+  CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
 }
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""EXPERIMENTAL: Si-512 getghc with gemm_nonlop through int8 slice products (csrc/ozaki.cu) vs the FP64 DMMA product path:
+"""OPT-IN path: Si-512 getghc with gemm_nonlop through int8 slice products (csrc/ozaki.cu + igemm_tc.cuh) vs the default FP64 DMMA path:
 speed and agreement at full size.  python tools/ozaki_bench.py   (on the GPU box)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -52,5 +52,6 @@ if "--json" in sys.argv:
     print(json.dumps({"name": "int8-sliced gemm_nonlop (Ozaki scheme I: 7 slices x 7 bits = 28 exact int8 GEMMs per contraction), opt-in",
                       "value": ndat / (res[1][0] * 1e-3), "unit": "band-applications/s", "ms_per_step": res[1][0],
                       "fp64_path_ms_per_step_same_process": res[0][0], "max_rel_diff_vs_fp64_path": rel, "kernel_ms": res[1][1],
-                      "int8_gemm": "cuBLASLt (library) -- NOT the product path; the default is the hand-written FP64 DMMA kernel",
+                      "int8_gemm": "hand-written tcgen05 kind::i8 kernel (csrc/igemm_tc.cuh: TMA 128B-swizzled K-major tiles, mbarrier ring, int32 accumulators in TMEM)",
+                      "default": "off -- the default product path is the FP64 DMMA kernel; enable with ABI_B200_OZAKI=1",
                       "extra_memory_gb": 2 * 7 * nprojs * 2 * npw / 1e9}))
