@@ -14,12 +14,13 @@
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <algorithm>
 
 namespace abi {
 
 namespace igemm_detail {
 
-constexpr int BM = 128, BK = 128, STAGES = 4;
+constexpr int BM = 128, BK = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -59,9 +60,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return lo | (hi << 32);
 }
 
-template <int BN>
-__global__ void __launch_bounds__(128, 1) k_igemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                                                      int32_t* __restrict__ C, long long ldc, int M, int N, int nkb, int tiles_n) {
+// STAGES = 4, 1 CTA/SM: deepest ring for long K loops; STAGES = 2, 2 CTAs/SM: the second CTA's loads and MMAs cover the first
+// one's prologue / epilogue when the K loop is short (opernlb: K = nprojs).  nsplit > 1: split-K with exact integer atomics
+// (C zeroed by the caller) when there are too few output tiles to fill the chip.
+template <int BN, int STAGES, int CTAS>
+__global__ void __launch_bounds__(128, CTAS) k_igemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                         int32_t* __restrict__ C, long long ldc, int M, int N, int nkb_total, int tiles_n,
+                                                         int tiles, int nsplit) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte aligned operand ring
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -72,8 +77,11 @@ __global__ void __launch_bounds__(128, 1) k_igemm_tc(const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tn = blockIdx.x % tiles_n, tm = blockIdx.x / tiles_n;
+  const int tile = blockIdx.x % tiles, z = blockIdx.x / tiles;
+  const int tn = tile % tiles_n, tm = tile / tiles_n;
   const int m0 = tm * BM, n0 = tn * BN;
+  const int kb_per = (nkb_total + nsplit - 1) / nsplit;
+  const int kb0 = z * kb_per, nkb = max(0, min(nkb_total, kb0 + kb_per) - kb0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -97,8 +105,8 @@ __global__ void __launch_bounds__(128, 1) k_igemm_tc(const __grid_constant__ CUt
       mbar_wait(&empty[s], ph ^ 1);
       mbar_expect_tx(&full[s], STAGE_BYTES);
       uint8_t* st = smem + s * STAGE_BYTES;
-      tma_load_2d(st, &map_a, kb * BK, m0, &full[s]);
-      tma_load_2d(st + A_BYTES, &map_b, kb * BK, n0, &full[s]);
+      tma_load_2d(st, &map_a, (kb0 + kb) * BK, m0, &full[s]);
+      tma_load_2d(st + A_BYTES, &map_b, (kb0 + kb) * BK, n0, &full[s]);
     }
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer ----------------
@@ -118,6 +126,11 @@ __global__ void __launch_bounds__(128, 1) k_igemm_tc(const __grid_constant__ CUt
     umma_commit(tmem_full);                // accumulator complete
   }
   __syncwarp();
+  if (nkb == 0) {                            // empty K range of a split: nothing to add
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    return;
+  }
   // ---------------- epilogue: all 4 warps, warp w owns TMEM lanes 32w .. 32w+31 = rows m0 + 32w + lane ----------------
   mbar_wait(tmem_full, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -140,7 +153,10 @@ __global__ void __launch_bounds__(128, 1) k_igemm_tc(const __grid_constant__ CUt
 #pragma unroll
       for (int j = 0; j < 32; j++) {
         const int n = n0 + c0 + j;
-        if (n < N) C[(long long)n * ldc + m] = (int32_t)r[j];
+        if (n < N) {
+          if (nsplit == 1) C[(long long)n * ldc + m] = (int32_t)r[j];
+          else atomicAdd(&C[(long long)n * ldc + m], (int32_t)r[j]);
+        }
       }
     }
   }
@@ -176,27 +192,38 @@ inline CUtensorMap make_map(const int8_t* base, long long rows, long long K, lon
   return m;
 }
 
+
+template <int BN, int STAGES, int CTAS>
+inline void launch_igemm(const CUtensorMap& ma, const CUtensorMap& mb, int32_t* C, long long ldc, int M, int N, int nkb, int nsplit,
+                         cudaStream_t st) {
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN, tiles = tiles_m * tiles_n;
+  const size_t smem = (size_t)STAGES * (BM * BK + BN * BK) + 1024 + 256;
+  static bool done = false;
+  if (!done) { cudaFuncSetAttribute(k_igemm_tc<BN, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
+  if (nsplit > 1) cudaMemsetAsync(C, 0, sizeof(int32_t) * (size_t)ldc * N, st);
+  k_igemm_tc<BN, STAGES, CTAS><<<tiles * nsplit, 128, smem, st>>>(ma, mb, C, ldc, M, N, nkb, tiles_n, tiles, nsplit);
+}
+
 }  // namespace igemm_detail
 
-// C(M x N) = A^T B ; K % 128 == 0, lda % 16 == 0, ldb % 16 == 0, A / B 16-byte aligned
+// C(M x N) = A^T B ; K % 128 == 0, lda % 16 == 0, ldb % 16 == 0, A / B 16-byte aligned.
+// variant: 0 auto ; 1: 256-wide tiles, 4 stages, 1 CTA/SM ; 2: 256-wide, 2 stages, 2 CTAs/SM ; 3: 128-wide, 3 stages, 2 CTAs/SM
 inline void igemm_tc(int M, int N, int K, const int8_t* A, long long lda, const int8_t* B, long long ldb, int32_t* C, long long ldc,
-                     cudaStream_t st) {
+                     cudaStream_t st, int variant = 0) {
   using namespace igemm_detail;
   if (M == 0 || N == 0) return;
   if (K % BK != 0 || lda % 16 != 0 || ldb % 16 != 0) { fprintf(stderr, "igemm_tc: K must be a multiple of 128 and the pitches of 16\n"); abort(); }
-  const int bn = (N > 128) ? 256 : 128;
+  const int nkb = K / BK;
+  if (variant == 0) variant = (N <= 128) ? 3 : (nkb >= 512 ? 1 : 2);
+  const int bn = (variant == 3) ? 128 : 256;
   const CUtensorMap ma = make_map(A, M, K, lda, BM), mb = make_map(B, N, K, ldb, bn);
-  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + bn - 1) / bn;
-  const size_t smem = (size_t)STAGES * (BM * BK + bn * BK) + 1024 + 256;
-  if (bn == 256) {
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(k_igemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
-    k_igemm_tc<256><<<tiles_m * tiles_n, 128, smem, st>>>(ma, mb, C, ldc, M, N, K / BK, tiles_n);
-  } else {
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(k_igemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
-    k_igemm_tc<128><<<tiles_m * tiles_n, 128, smem, st>>>(ma, mb, C, ldc, M, N, K / BK, tiles_n);
-  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+  const int slots = 148 * (variant == 1 ? 1 : 2);
+  int nsplit = 1;
+  if (tiles < slots && nkb >= 64) nsplit = std::min(std::max(1, slots / tiles), std::max(1, nkb / 32));
+  if (variant == 1) launch_igemm<256, 4, 1>(ma, mb, C, ldc, M, N, nkb, nsplit, st);
+  else if (variant == 2) launch_igemm<256, 2, 2>(ma, mb, C, ldc, M, N, nkb, nsplit, st);
+  else launch_igemm<128, 3, 2>(ma, mb, C, ldc, M, N, nkb, nsplit, st);
 }
 
 }  // namespace abi

@@ -27,10 +27,11 @@ __global__ void k_fill(int8_t* p, size_t n, unsigned seed) {
 }
 
 int main(int argc, char** argv) {
-  const bool big = argc > 1;
-  struct Shape { int M, N, K; } small[] = {{128, 256, 128}, {128, 256, 512}, {256, 512, 1024}, {100, 36, 256}, {388, 900, 1280}, {9216, 128, 2048}};
-  Shape bigs[] = {{9216, 896, 288128}, {9216, 128, 288128}, {288116, 896, 9216}, {288116, 128, 9216}};
-  for (const Shape& sh : (big ? std::vector<Shape>(bigs, bigs + 4) : std::vector<Shape>(small, small + 6))) {
+  const bool big = argc > 1 && argv[1][0] == 'b';
+  const int variant = argc > 2 ? atoi(argv[2]) : 0;
+  struct Shape { int M, N, K; } small[] = {{128, 256, 128}, {128, 256, 512}, {256, 512, 1024}, {100, 36, 256}, {388, 900, 1280}, {9216, 128, 2048}, {256, 256, 16384}, {300, 100, 32768}};
+  Shape bigs[] = {{9216, 896, 288128}, {9216, 512, 288128}, {9216, 256, 288128}, {9216, 128, 288128}, {288116, 896, 9216}, {288116, 512, 9216}, {288116, 128, 9216}};
+  for (const Shape& sh : (big ? std::vector<Shape>(bigs, bigs + 7) : std::vector<Shape>(small, small + 8))) {
     const long long lda = sh.K, ldb = sh.K, ldc = sh.M;
     int8_t *A, *B; int32_t *C, *R;
     CK(cudaMalloc(&A, (size_t)sh.M * lda)); CK(cudaMalloc(&B, (size_t)sh.N * ldb));
@@ -38,7 +39,7 @@ int main(int argc, char** argv) {
     k_fill<<<1024, 256>>>(A, (size_t)sh.M * lda, 1u); k_fill<<<1024, 256>>>(B, (size_t)sh.N * ldb, 77u);
     CK(cudaMemset(C, 0xff, sizeof(int32_t) * (size_t)sh.N * ldc));
     CK(cudaDeviceSynchronize());
-    abi::igemm_tc(sh.M, sh.N, sh.K, A, lda, B, ldb, C, ldc, 0);
+    abi::igemm_tc(sh.M, sh.N, sh.K, A, lda, B, ldb, C, ldc, 0, variant);
     CK(cudaDeviceSynchronize());
     if (!big) {
       CK(cudaMalloc(&R, sizeof(int32_t) * (size_t)sh.N * ldc));
@@ -55,7 +56,7 @@ int main(int argc, char** argv) {
     } else {
       cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
       cudaEventRecord(e0);
-      for (int r = 0; r < 5; r++) abi::igemm_tc(sh.M, sh.N, sh.K, A, lda, B, ldb, C, ldc, 0);
+      for (int r = 0; r < 5; r++) abi::igemm_tc(sh.M, sh.N, sh.K, A, lda, B, ldb, C, ldc, 0, variant);
       cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
       float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
       printf("M=%d N=%d K=%d: %.3f ms  %.1f TOP/s\n", sh.M, sh.N, sh.K, ms, 2.0 * sh.M * sh.N * sh.K / ms / 1e9);
