@@ -39,3 +39,17 @@ def test_getghc_ozaki_vs_oracle(lib, ozaki_on, istwf_k, kpt, usepaw, ndat):
     api.set_tuning("nonlop_ozaki", 1)
     assert rel_err_per_band(ghc, ghc2) < 1e-11
     h.destroy()
+
+
+def test_igemm_tc_bit_exact_against_naive_kernel():
+    """The hand-written tcgen05 int8 GEMM (csrc/igemm_tc.cuh) against a naive kernel: regular, ragged and split-K shapes,
+    every tile variant (tools/igemm_lab.cu, built by __graft_entry__.build())."""
+    import os, subprocess
+    lab = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "igemm_lab")
+    if not os.path.exists(lab):
+        pytest.skip("tools/igemm_lab not built (python -c 'import __graft_entry__ as g; g.build()')")
+    for variant in ("0", "1", "2", "3"):
+        r = subprocess.run([lab, "small", variant], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        lines = [l for l in r.stdout.splitlines() if l.startswith("M=")]
+        assert len(lines) == 8 and all(": ok" in l for l in lines), r.stdout
