@@ -1,7 +1,7 @@
 // Development harness for the hand-written tcgen05 int8 GEMM (C int32 = A^T B, both operands K-contiguous int8) that the
 // int8-sliced gemm_nonlop (csrc/ozaki.cu) needs instead of cuBLASLt.  Checks bit-exactness against a naive kernel on small and
 // ragged shapes, then times the Si-512 shapes.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/igemm_lab tools/igemm_lab.cu -lcuda
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/igemm_lab tools/igemm_lab.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
