@@ -199,9 +199,11 @@ inline void launch_igemm(const CUtensorMap& ma, const CUtensorMap& mb, int32_t* 
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN, tiles = tiles_m * tiles_n;
   const size_t smem = (size_t)STAGES * (BM * BK + BN * BK) + 1024 + 256;
   static bool done = false;
-  if (!done) { cudaFuncSetAttribute(k_igemm_tc<BN, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
-  if (nsplit > 1) cudaMemsetAsync(C, 0, sizeof(int32_t) * (size_t)ldc * N, st);
+  auto chk = [](cudaError_t e, const char* what) { if (e != cudaSuccess) { fprintf(stderr, "igemm_tc: %s: %s\n", what, cudaGetErrorString(e)); abort(); } };
+  if (!done) { chk(cudaFuncSetAttribute(k_igemm_tc<BN, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "shared-memory opt-in"); done = true; }
+  if (nsplit > 1) chk(cudaMemsetAsync(C, 0, sizeof(int32_t) * (size_t)ldc * N, st), "memset");
   k_igemm_tc<BN, STAGES, CTAS><<<tiles * nsplit, 128, smem, st>>>(ma, mb, C, ldc, M, N, nkb, tiles_n, tiles, nsplit);
+  chk(cudaGetLastError(), "launch");
 }
 
 }  // namespace igemm_detail
