@@ -34,6 +34,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-scf-step", action="store_true")
+    ap.add_argument("--nonlop", default="fp64", choices=["fp64", "int8"],
+                    help="gemm_nonlop arithmetic: fp64 = FP64 DMMA kernels (default, the product path); int8 = opt-in exact int8 slice "
+                         "products on the tcgen05 kernel (DESIGN.md 3.5)")
     ap.add_argument("--nband", type=int, default=1100, help="bands of the ChebFi2 (SCF-step-equivalent) leg, sharded over the GPUs")
     ap.add_argument("--nline", type=int, default=4, help="Chebyshev filter degree of the ChebFi2 leg")
     return ap.parse_args()
@@ -177,7 +180,9 @@ def run_reference(args):
     val = nb * args.steps / dt
     out = {"metric": "getghc band-applications/s", "value": val, "unit": "band-applications/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+           "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64" if args.nonlop == "fp64" else "f64 (fourwf) + exact int8 slices with int32 accumulation recombined in f64 (gemm_nonlop)",
+           "data": "synthetic", "impl": "reference",
            "config": {"workload": f"{args.workload}: box {w['ngfft']}, npw {w['npw']}, nprojs {w['nprojs']}, istwfk {args.istwfk}",
                       "sample": f"{nb} bands per step"},
            "cpu_baseline": {"value": val, "unit": "band-applications/s", "cores": cores, "kind": "port",
@@ -235,6 +240,8 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    if args.nonlop == "int8":
+        api.set_tuning("nonlop_ozaki", 1)
     api.set_async(True)
     for _ in range(max(3, args.warmup)):
         step_dev()
@@ -398,6 +405,22 @@ def main():
                 "traffic_source": (traffic.get("k_dgemm_nn") or {}).get("source"), "peak_source": fp64_src,
                 "flops_per_launch": flops_launch, "ms_per_launch": t_nn}
     extra = {}
+    t_i8, n_i8 = prof.get("ozaki_igemm", (0.0, 0))
+    if n_i8:
+        # opt-in int8-sliced path: the dominant kernel is k_igemm_tc (tcgen05 kind::i8); algorithmic int8 ops of the 28 slice
+        # products of both contractions over the summed launch time of a step
+        bf16 = None
+        try:
+            bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:
+            pass
+        peak_i8 = 2.0 * bf16 if bf16 else 4500.0
+        ops_step = 28.0 * f_nl * ndat                     # 28 slice products, each with the op count of its FP64 GEMM (f_nl covers both contractions)
+        ach = ops_step / (t_i8 / args.steps * 1e-3) / 1e12
+        roof = {"kernel": "k_igemm_tc (tcgen05.mma kind::i8, int32 accumulators in TMEM; 14 launches per step)", "bound": "tensor",
+                "achieved": ach, "peak": peak_i8, "unit": "TOP/s (int8)", "frac": ach / peak_i8,
+                "traffic": None, "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (int8 dense = 2 x bf16 dense)" if bf16 else "nominal 4.5 Pop/s",
+                "ops_per_step": ops_step, "ms_per_step": t_i8 / args.steps}
     if t_tn:
         ach = 0.5 * f_nl * ndat / (t_tn * 1e-3) / 1e12
         extra["roofline_opernla"] = {"kernel": "k_dgemm_tn (split-K P^T psi)", "bound": "tensor", "achieved": ach, "peak": fp64,
@@ -420,7 +443,7 @@ def main():
     # products (csrc/ozaki.cu: own slicing + FP64 recombination around cuBLASLt int8 GEMMs) instead of the FP64 DMMA kernels.
     # Runs in its own process after this one has released the device, so that nothing it does can touch the numbers above.
     experimental = None
-    if world == 1 and not args.no_scf_step:
+    if world == 1 and not args.no_scf_step and args.nonlop == "fp64":
         try:
             ham.destroy(); ab.finalize(); del cw, ghc
             torch.cuda.empty_cache()
@@ -430,9 +453,11 @@ def main():
             experimental = {"error": repr(ex)}
     out = {"metric": "getghc band-applications/s", "value": value, "unit": "band-applications/s", "n_gpus": world,
            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64" if args.nonlop == "fp64" else "f64 (fourwf) + exact int8 slices with int32 accumulation recombined in f64 (gemm_nonlop)",
+           "data": "synthetic",
            "config": {"workload": f"{args.workload} (BASELINE configs[1] shape): FFT box {w['ngfft']}, Gamma, istwfk {args.istwfk}, "
-                                  f"npw {npw}, nprojs {nprojs}, band block {ndat} per GPU, NC (paw_opt 0), type_calc 0",
+                                  f"npw {npw}, nprojs {nprojs}, band block {ndat} per GPU, NC (paw_opt 0), type_calc 0, gemm_nonlop arithmetic {args.nonlop}",
                       "l2": "inputs larger than L2 (P = %.1f GB streamed twice per step)" % (16.0 * npw * nprojs / 1e9),
                       "parallelism": f"band blocks over {world} GPU(s), no data-path collective"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
