@@ -784,8 +784,8 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
       else launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zfac, ldg, vectout, ldv, nullptr, st);
     } else if (oz_b) {
       ABI_CHECK(fuse->ghc != nullptr && fuse->kinpw != nullptr, "gemm_nonlop: fusion needs ghc and kinpw");
-      ozaki_expand(P.oz, zfac, ldg, ndat, fuse->ghc, 1, vectout, fuse->kinpw, fuse->kin_filter, nullptr, st);
-      if (fuse->after_slab) fuse->after_slab(fuse->user, 0, npw);
+      ozaki_expand(P.oz, zfac, ldg, ndat, fuse->ghc, 1, vectout, fuse->kinpw, fuse->kin_filter, nullptr, st,
+                   std::max(4, fuse->nslabs), fuse->after_slab, fuse->user);
     } else {
       // getghc fusion: ghc += P.gxfac with the kinetic filter in the GEMM epilogue, in row slabs (each complete for
       // every band, so the caller can ship it to the host while the next slab is computed)

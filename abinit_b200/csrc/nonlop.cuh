@@ -96,7 +96,8 @@ void nonlop_expand(const Projectors& P, const double* z, int ndat, double* vecto
 void ozaki_prepare(const Projectors& P, OzakiP& oz, cudaStream_t st);
 void ozaki_project(const OzakiP& oz, const double* vectin, int ndat, double* part, cudaStream_t st);
 void ozaki_expand(const OzakiP& oz, const double* z, long long ldz, int ndat, double* out, int fuse, double* vout, const double* kin,
-                  double kin_filter, const double* add, cudaStream_t st);
+                  double kin_filter, const double* add, cudaStream_t st, int nslabs = 4, void (*after_slab)(void*, int, int) = nullptr,
+                  void* user = nullptr);
 void ozaki_release_workspace();
 
 // plain tensor-core GEMMs (also used by the Gram kernels of xg.cu); all device pointers, column-major

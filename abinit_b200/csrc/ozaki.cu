@@ -188,28 +188,40 @@ void ozaki_project(const OzakiP& oz, const double* vectin, int ndat, double* par
 
 // vect = P z through the slice products; mode as CombineParams (fusion with the getghc epilogue)
 void ozaki_expand(const OzakiP& oz, const double* z, long long ldz, int ndat, double* out, int fuse, double* vout, const double* kin,
-                  double kin_filter, const double* add, cudaStream_t st) {
+                  double kin_filter, const double* add, cudaStream_t st, int nslabs, void (*after_slab)(void*, int, int), void* user) {
   const int M = 2 * oz.npw, K = oz.nprojs;
   const int nd4 = (ndat + 3) & ~3;
   int8_t* bq = (int8_t*)g_oz[0].get((size_t)kS * nd4 * oz.kp2);
   double* eb = (double*)g_oz[1].get(sizeof(double) * nd4);
   if (nd4 != ndat) CUDA_CHECK(cudaMemsetAsync(bq, 0, (size_t)kS * nd4 * oz.kp2, st));
   k_slice_cols<<<ndat, 256, 0, st>>>(z, ldz, K, oz.kp2, nd4, bq, eb);
-  size_t tot = 0; for (int s = 0; s < kS; s++) tot += (size_t)oz.mp2 * nd4 * (kS - s);
+  g_kernel_launches++;
+  // row slabs (whole 128-row tiles): bounds the int32 workspace and lets the caller ship finished rows of ghc to the host
+  // while the next slab is computed (the after_slab hook of NonlopFusion)
+  nslabs = std::max(1, std::min(nslabs, (M + 127) / 128));
+  long long slab = ((((long long)M + nslabs - 1) / nslabs) + 127) / 128 * 128;
+  size_t tot = 0; for (int s = 0; s < kS; s++) tot += (size_t)slab * nd4 * (kS - s);
   int32_t* c = (int32_t*)g_oz[2].get(sizeof(int32_t) * tot);
-  CombineParams p{};
-  size_t off = 0;
-  for (int s = 0; s < kS; s++) {
-    const int ns = nd4 * (kS - s);
-    igemm_tn((int)oz.mp2, ns, (int)oz.kp2, oz.a_m + (size_t)s * oz.mp2 * oz.kp2, oz.kp2, bq, oz.kp2, c + off, oz.mp2, st);
-    p.C[s] = c + off; off += (size_t)oz.mp2 * ns;
+  for (long long m0 = 0; m0 < M; m0 += slab) {
+    const int mlen = (int)std::min<long long>(slab, M - m0);
+    const int mrows = (int)std::min<long long>(slab, oz.mp2 - m0);          // rows present in the int8 copy (multiple of 4)
+    CombineParams p{};
+    size_t off = 0;
+    for (int s = 0; s < kS; s++) {
+      const int ns = nd4 * (kS - s);
+      igemm_tn(mrows, ns, (int)oz.kp2, oz.a_m + ((size_t)s * oz.mp2 + m0) * oz.kp2, oz.kp2, bq, oz.kp2, c + off, slab, st);
+      p.C[s] = c + off; off += (size_t)slab * ns;
+    }
+    p.ldc = slab; p.M = mlen; p.N = ndat; p.Nstride = nd4; p.ea = oz.ea_m + m0; p.eb = eb; p.out = out + m0; p.ldo = M; p.mode = fuse ? 1 : 0;
+    p.vout = vout ? vout + m0 : nullptr; p.kin = kin ? kin + m0 / 2 : nullptr; p.kin_filter = kin_filter; p.add = add ? add + m0 : nullptr;
+    {
+      ProfScope ps("ozaki_combine");
+      k_combine<<<std::min(kNumSM * 16, (int)ceil_div<long long>((long long)mlen * ndat, 256)), 256, 0, st>>>(p);
+      CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    }
+    if (after_slab) after_slab(user, (int)(m0 / 2), (int)((m0 + mlen) / 2));
   }
-  p.ldc = oz.mp2; p.M = M; p.N = ndat; p.Nstride = nd4; p.ea = oz.ea_m; p.eb = eb; p.out = out; p.ldo = M; p.mode = fuse ? 1 : 0;
-  p.vout = vout; p.kin = kin; p.kin_filter = kin_filter; p.add = add;
-  ProfScope ps("ozaki_combine");
-  k_combine<<<std::min(kNumSM * 16, (int)ceil_div<long long>((long long)M * ndat, 256)), 256, 0, st>>>(p);
-  CUDA_CHECK(cudaGetLastError());
-  g_kernel_launches += 2;
 }
 
 void ozaki_release_workspace() { for (auto& b : g_oz) b.release(); }
