@@ -9,7 +9,7 @@ namespace abi {
 
 // EXPERIMENTAL int8-sliced copies of P (ozaki.cu, opt-in with ABI_B200_OZAKI=1; never used by default)
 struct OzakiP {
-  int npw = 0, nprojs = 0;
+  int npw = 0, nprojs = 0, cplx = 0;      // cplx = 1 (istwf_k = 1): (psi, -i psi) column pairs / (P, iP) K pairs
   long long kp1 = 0, kp2 = 0, mp2 = 0;     // padded K of opernla, padded K and M of opernlb
   int8_t* a_k = nullptr;                   // [7][nprojs][kp1]  slices of P columns (K = 2 npw contiguous)
   int8_t* a_m = nullptr;                   // [7][mp2][kp2]     slices of P rows (K = nprojs contiguous)

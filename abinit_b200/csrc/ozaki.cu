@@ -33,11 +33,14 @@ void igemm_tn(int M, int N, int K, const int8_t* A, long long lda, const int8_t*
 }
 
 // ---- slicing of a K-contiguous operand: X (K x C, FP64, ld) -> q[s][c][Kp] int8 and e[c] ----
+// pairs = 1 (complex opernla): effective column 2n is column n of X, effective column 2n+1 is (-i psi_n) in the real view,
+// i.e. value(i) = x[i+1] for even i, -x[i-1] for odd i -- formed while slicing, never materialised in FP64
 __global__ void __launch_bounds__(256) k_slice_cols(const double* __restrict__ X, long long ld, int K, long long Kp, int ncols,
-                                                     int8_t* __restrict__ q, double* __restrict__ e) {
+                                                     int8_t* __restrict__ q, double* __restrict__ e, int pairs) {
   __shared__ double red[256];
   const int c = blockIdx.x;
-  const double* x = X + ld * c;
+  const bool rot = pairs && (c & 1);
+  const double* x = X + ld * (pairs ? (c >> 1) : c);
   double m = 0.0;
   for (int i = threadIdx.x; i < K; i += 256) m = fmax(m, fabs(x[i]));
   red[threadIdx.x] = m;
@@ -49,7 +52,8 @@ __global__ void __launch_bounds__(256) k_slice_cols(const double* __restrict__ X
   if (threadIdx.x == 0) e[c] = (double)ex;
   const double inv = ldexp(1.0, -ex);
   for (long long i = threadIdx.x; i < Kp; i += 256) {
-    double r = (i < K) ? x[i] * inv : 0.0;
+    double r = 0.0;
+    if (i < K) r = (rot ? ((i & 1) ? -x[i - 1] : x[i + 1]) : x[i]) * inv;
 #pragma unroll
     for (int s = 0; s < kS; s++) {
       r *= 128.0;
@@ -61,24 +65,35 @@ __global__ void __launch_bounds__(256) k_slice_cols(const double* __restrict__ X
 }
 
 // ---- slicing of the M-contiguous P for opernlb: P (M x K, ld) -> q[s][m][Kp] (K-contiguous per row m) and e[m] ----
-__global__ void k_row_exponent(const double* __restrict__ P, long long ld, int M, int K, double* __restrict__ e) {
+// cplx = 1: row m of the effective operand holds P[m,:] and (iP)[m,:] = -+P[m^1,:], so its scale covers both rows
+__global__ void k_row_exponent(const double* __restrict__ P, long long ld, int M, int K, double* __restrict__ e, int cplx) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   double mx = 0.0;
-  for (int k = 0; k < K; k++) mx = fmax(mx, fabs(P[(long long)k * ld + m]));
+  for (int k = 0; k < K; k++) {
+    mx = fmax(mx, fabs(P[(long long)k * ld + m]));
+    if (cplx) mx = fmax(mx, fabs(P[(long long)k * ld + (m ^ 1)]));
+  }
   int ex = 0;
   if (mx > 0.0) { frexp(mx, &ex); ex += 1; }
   e[m] = (double)ex;
 }
+// cplx = 1: effective K index k = 2p + c: c = 0 -> P[m,p], c = 1 -> (iP)[m,p] = (m even ? -P[m+1,p] : P[m-1,p])
 __global__ void __launch_bounds__(256) k_slice_rows_t(const double* __restrict__ P, long long ld, int M, int K, long long Kp, long long Mp,
-                                                       const double* __restrict__ e, int8_t* __restrict__ q) {
+                                                       const double* __restrict__ e, int8_t* __restrict__ q, int cplx) {
   __shared__ int8_t tile[kS][32][33];
   const int m0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
   for (int kk = ty; kk < 32; kk += 8) {
     const int m = m0 + tx, k = k0 + kk;
     double r = 0.0;
-    if (m < M && k < K) r = P[(long long)k * ld + m] * ldexp(1.0, -(int)e[m]);
+    if (m < M && k < K) {
+      double v;
+      if (!cplx) v = P[(long long)k * ld + m];
+      else if (!(k & 1)) v = P[(long long)(k >> 1) * ld + m];
+      else v = (m & 1) ? P[(long long)(k >> 1) * ld + m - 1] : -P[(long long)(k >> 1) * ld + m + 1];
+      r = v * ldexp(1.0, -(int)e[m]);
+    }
 #pragma unroll
     for (int s = 0; s < kS; s++) { r *= 128.0; const double v = rint(r); r -= v; tile[s][kk][tx] = (int8_t)(int)v; }
   }
@@ -144,32 +159,34 @@ void OzakiP::release() {
 
 // slices of P for both contractions (once per k-point): 2 x 7 int8 copies of P
 void ozaki_prepare(const Projectors& P, OzakiP& oz, cudaStream_t st) {
-  ABI_CHECK(P.istwf_k >= 2, "ozaki: only the real (istwf_k >= 2) contractions are implemented");
   oz.release();
   const int K1 = 2 * P.npw, M1 = P.nprojs;
-  oz.npw = P.npw; oz.nprojs = P.nprojs;
-  oz.kp1 = ((long long)K1 + 127) / 128 * 128; oz.kp2 = ((long long)M1 + 127) / 128 * 128; oz.mp2 = ((long long)K1 + 3) / 4 * 4;
+  const int cplx = P.istwf_k == 1 ? 1 : 0;
+  const int K2 = (cplx ? 2 : 1) * M1;                              // opernlb: K = nprojs (real) or 2 nprojs ((P, iP) pairs)
+  oz.npw = P.npw; oz.nprojs = P.nprojs; oz.cplx = cplx;
+  oz.kp1 = ((long long)K1 + 127) / 128 * 128; oz.kp2 = ((long long)K2 + 127) / 128 * 128; oz.mp2 = ((long long)K1 + 3) / 4 * 4;
   CUDA_CHECK(cudaMalloc(&oz.a_k, (size_t)kS * M1 * oz.kp1));
   CUDA_CHECK(cudaMalloc(&oz.a_m, (size_t)kS * oz.mp2 * oz.kp2));
   CUDA_CHECK(cudaMalloc(&oz.ea_k, sizeof(double) * M1));
   CUDA_CHECK(cudaMalloc(&oz.ea_m, sizeof(double) * oz.mp2));
   CUDA_CHECK(cudaMemsetAsync(oz.ea_m, 0, sizeof(double) * oz.mp2, st));
-  k_slice_cols<<<M1, 256, 0, st>>>(P.d_p, (long long)K1, K1, oz.kp1, M1, oz.a_k, oz.ea_k);
-  k_row_exponent<<<ceil_div(K1, 256), 256, 0, st>>>(P.d_p, (long long)K1, K1, M1, oz.ea_m);
-  k_slice_rows_t<<<dim3(ceil_div<long long>(oz.mp2, 32), ceil_div<long long>(oz.kp2, 32)), 256, 0, st>>>(P.d_p, (long long)K1, K1, M1, oz.kp2, oz.mp2,
-                                                                                                  oz.ea_m, oz.a_m);
+  k_slice_cols<<<M1, 256, 0, st>>>(P.d_p, (long long)K1, K1, oz.kp1, M1, oz.a_k, oz.ea_k, 0);
+  k_row_exponent<<<ceil_div(K1, 256), 256, 0, st>>>(P.d_p, (long long)K1, K1, M1, oz.ea_m, cplx);
+  k_slice_rows_t<<<dim3(ceil_div<long long>(oz.mp2, 32), ceil_div<long long>(oz.kp2, 32)), 256, 0, st>>>(P.d_p, (long long)K1, K1, K2, oz.kp2, oz.mp2,
+                                                                                                  oz.ea_m, oz.a_m, cplx);
   CUDA_CHECK(cudaGetLastError());
   g_kernel_launches += 3;
 }
 
 // part[n][m] (FP64, the nsplit = 1 partial buffer of opernla) = P^T psi through the slice products
-void ozaki_project(const OzakiP& oz, const double* vectin, int ndat, double* part, cudaStream_t st) {
+void ozaki_project(const OzakiP& oz, const double* vectin, int ndat_bands, double* part, cudaStream_t st) {
   const int M = oz.nprojs, K = 2 * oz.npw;
+  const int ndat = (oz.cplx ? 2 : 1) * ndat_bands;                  // complex: (psi, -i psi) column pairs -> (Re, Im) of P^H psi
   const int nd4 = (ndat + 3) & ~3;                                // cuBLASLt int8: every extent a multiple of 4
   int8_t* bq = (int8_t*)g_oz[0].get((size_t)kS * nd4 * oz.kp1);
   double* eb = (double*)g_oz[1].get(sizeof(double) * nd4);
   if (nd4 != ndat) CUDA_CHECK(cudaMemsetAsync(bq, 0, (size_t)kS * nd4 * oz.kp1, st));
-  k_slice_cols<<<ndat, 256, 0, st>>>(vectin, (long long)K, K, oz.kp1, nd4, bq, eb);
+  k_slice_cols<<<ndat, 256, 0, st>>>(vectin, (long long)K, K, oz.kp1, nd4, bq, eb, oz.cplx);
   size_t tot = 0; for (int s = 0; s < kS; s++) tot += (size_t)M * nd4 * (kS - s);
   int32_t* c = (int32_t*)g_oz[2].get(sizeof(int32_t) * tot);
   CombineParams p{};
@@ -189,12 +206,12 @@ void ozaki_project(const OzakiP& oz, const double* vectin, int ndat, double* par
 // vect = P z through the slice products; mode as CombineParams (fusion with the getghc epilogue)
 void ozaki_expand(const OzakiP& oz, const double* z, long long ldz, int ndat, double* out, int fuse, double* vout, const double* kin,
                   double kin_filter, const double* add, cudaStream_t st, int nslabs, void (*after_slab)(void*, int, int), void* user) {
-  const int M = 2 * oz.npw, K = oz.nprojs;
+  const int M = 2 * oz.npw, K = (oz.cplx ? 2 : 1) * oz.nprojs;     // complex: z is (re, im) interleaved = the K index of (P, iP)
   const int nd4 = (ndat + 3) & ~3;
   int8_t* bq = (int8_t*)g_oz[0].get((size_t)kS * nd4 * oz.kp2);
   double* eb = (double*)g_oz[1].get(sizeof(double) * nd4);
   if (nd4 != ndat) CUDA_CHECK(cudaMemsetAsync(bq, 0, (size_t)kS * nd4 * oz.kp2, st));
-  k_slice_cols<<<ndat, 256, 0, st>>>(z, ldz, K, oz.kp2, nd4, bq, eb);
+  k_slice_cols<<<ndat, 256, 0, st>>>(z, ldz, K, oz.kp2, nd4, bq, eb, 0);
   g_kernel_launches++;
   // row slabs (whole 128-row tiles): bounds the int32 workspace and lets the caller ship finished rows of ghc to the host
   // while the next slab is computed (the after_slab hook of NonlopFusion)

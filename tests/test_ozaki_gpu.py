@@ -1,5 +1,5 @@
 """GPU: the EXPERIMENTAL int8-sliced gemm_nonlop (csrc/ozaki.cu, opt-in) reproduces the FP64 DMMA path and the oracle to
-the north-star tolerance on istwf_k >= 2 problems (NC getghc, PAW with S, plain gemm_nonlop)."""
+the north-star tolerance (real istwf_k >= 2 and complex istwf_k = 1 contractions, NC getghc, PAW with S)."""
 import numpy as np
 import pytest
 from oracle import getghc as ogh, nonlop as onl
@@ -17,7 +17,8 @@ def ozaki_on(lib):
     api.set_tuning("nonlop_ozaki", 0)
 
 
-@pytest.mark.parametrize("istwf_k,kpt,usepaw,ndat", [(2, (0, 0, 0), 0, 8), (2, (0, 0, 0), 0, 5), (3, (.5, 0, 0), 0, 4), (2, (0, 0, 0), 1, 6)])
+@pytest.mark.parametrize("istwf_k,kpt,usepaw,ndat", [(2, (0, 0, 0), 0, 8), (2, (0, 0, 0), 0, 5), (3, (.5, 0, 0), 0, 4), (2, (0, 0, 0), 1, 6),
+                                                     (1, (.1, .2, .3), 0, 8), (1, (-.25, .5, 0), 0, 3), (1, (.1, .2, .3), 1, 5)])
 def test_getghc_ozaki_vs_oracle(lib, ozaki_on, istwf_k, kpt, usepaw, ndat):
     p = make_problem(7.0, (8.0, 9.0, 7.5), kpt, istwf_k, ndat=ndat, natom_per_type=(2, 1), lmax_per_type=(2, 1), usepaw=usepaw)
     h = ab.Hamiltonian(p.ngfft, p.natom, p.ntypat, p.lmnmax, p.indlmn, p.nattyp, p.atindx1, p.usepaw, p.ucvol)
