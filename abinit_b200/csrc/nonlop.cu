@@ -725,9 +725,10 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
     ABI_CHECK(vectin != nullptr, "gemm_nonlop: vectin is required");
     double* part = nullptr;
     int nsplit;
-    const bool oz = ozaki_enabled();               // opt-in int8-sliced contractions (ozaki.cu), off by default
+    bool oz = ozaki_enabled();                     // opt-in int8-sliced contractions (ozaki.cu), off by default
+    if (oz && P.oz_stamp != P.stamp) { ozaki_prepare(P, P.oz, st); P.oz_stamp = P.stamp; }
+    if (oz && P.oz.failed) oz = false;
     if (oz) {
-      if (P.oz_stamp != P.stamp) { ozaki_prepare(P, P.oz, st); P.oz_stamp = P.stamp; }
       part = g_nlws[0].get((size_t)cplex * ndat * nprojs);
       ozaki_project(P.oz, vectin, ndat, part, st);
       nsplit = 1;
@@ -771,13 +772,13 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
   if (choice == 7 || paw_opt == 3 || paw_opt == 4) {
     ABI_CHECK(svectout != nullptr && (vectin != nullptr || choice == 7), "gemm_nonlop: svectout/vectin required for the overlap");
     // + vectin except for choice 7 (m_opernlb_gemm.F90:654-665)
-    if (ozaki_enabled() && P.oz_stamp == P.stamp)
+    if (ozaki_enabled() && P.oz_stamp == P.stamp && !P.oz.failed)
       ozaki_expand(P.oz, zs, ldg, ndat, svectout, 0, nullptr, nullptr, 0.0, choice == 7 ? nullptr : vectin, st);
     else
     launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zs, ldg, svectout, ldv, choice == 7 ? nullptr : vectin, st);
   }
   if (choice == 1 && (paw_opt == 0 || paw_opt == 1 || paw_opt == 2 || paw_opt == 4)) {
-    const bool oz_b = ozaki_enabled() && P.oz_stamp == P.stamp;
+    const bool oz_b = ozaki_enabled() && P.oz_stamp == P.stamp && !P.oz.failed;
     if (fuse == nullptr) {
       ABI_CHECK(vectout != nullptr, "gemm_nonlop: vectout required");
       if (oz_b) ozaki_expand(P.oz, zfac, ldg, ndat, vectout, 0, nullptr, nullptr, 0.0, nullptr, st);

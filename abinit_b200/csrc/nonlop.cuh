@@ -14,6 +14,7 @@ struct OzakiP {
   int8_t* a_k = nullptr;                   // [7][nprojs][kp1]  slices of P columns (K = 2 npw contiguous)
   int8_t* a_m = nullptr;                   // [7][mp2][kp2]     slices of P rows (K = nprojs contiguous)
   double* ea_k = nullptr; double* ea_m = nullptr;   // binary exponents per projector / per row
+  bool failed = false;                     // allocation failed: this P stays on the FP64 kernels
   void release();
 };
 bool ozaki_enabled();

@@ -154,7 +154,7 @@ void ozaki_set_enabled(int flag) { g_ozaki_on = flag ? 1 : 0; }
 
 void OzakiP::release() {
   for (void** p : {(void**)&a_k, (void**)&a_m, (void**)&ea_k, (void**)&ea_m}) { if (*p) cudaFree(*p); *p = nullptr; }
-  npw = nprojs = 0;
+  npw = nprojs = 0; failed = false;
 }
 
 // slices of P for both contractions (once per k-point): 2 x 7 int8 copies of P
@@ -165,8 +165,15 @@ void ozaki_prepare(const Projectors& P, OzakiP& oz, cudaStream_t st) {
   const int K2 = (cplx ? 2 : 1) * M1;                              // opernlb: K = nprojs (real) or 2 nprojs ((P, iP) pairs)
   oz.npw = P.npw; oz.nprojs = P.nprojs; oz.cplx = cplx;
   oz.kp1 = ((long long)K1 + 127) / 128 * 128; oz.kp2 = ((long long)K2 + 127) / 128 * 128; oz.mp2 = ((long long)K1 + 3) / 4 * 4;
-  CUDA_CHECK(cudaMalloc(&oz.a_k, (size_t)kS * M1 * oz.kp1));
-  CUDA_CHECK(cudaMalloc(&oz.a_m, (size_t)kS * oz.mp2 * oz.kp2));
+  // the int8 copies are an optimisation: when the device cannot hold them this k-point stays on the FP64 DMMA kernels
+  if (cudaMalloc(&oz.a_k, (size_t)kS * M1 * oz.kp1) != cudaSuccess || cudaMalloc(&oz.a_m, (size_t)kS * oz.mp2 * oz.kp2) != cudaSuccess) {
+    cudaGetLastError();
+    oz.release();
+    oz.failed = true;
+    fprintf(stderr, "\n--- !WARNING\nmessage: |\n    abinit_b200: not enough device memory for the int8-sliced projectors (%.1f GB); "
+                    "this k-point uses the FP64 path\n...\n", 1e-9 * ((double)kS * M1 * oz.kp1 + (double)kS * oz.mp2 * oz.kp2));
+    return;
+  }
   CUDA_CHECK(cudaMalloc(&oz.ea_k, sizeof(double) * M1));
   CUDA_CHECK(cudaMalloc(&oz.ea_m, sizeof(double) * oz.mp2));
   CUDA_CHECK(cudaMemsetAsync(oz.ea_m, 0, sizeof(double) * oz.mp2, st));
