@@ -326,6 +326,27 @@ def main():
                     "timing": "host clock between barrier + device synchronise on both sides, max over ranks (the call holds host syncs)",
                     "kernel_ms": {k: v[0] for k, v in prof_scf.items()}}
         del cg
+    # the same SCF-step-equivalent with LOBPCG (one block of all bands, nline LOBPCG iterations; single GPU only in this build)
+    lobpcg_step = None
+    if world == 1 and not args.no_scf_step:
+        from abinit_b200 import xg as xgm
+        api.set_async(False)
+        with torch.cuda.stream(stream):
+            gen = torch.Generator(device=dev).manual_seed(778)
+            damp = torch.from_numpy(1.0 / (1.0 + np.minimum(w["kinpw"], 1e6))).to(dev)
+            cgl = torch.randn((args.nband, npw, 2), generator=gen, device=dev, dtype=torch.float64) * damp[None, :, None]
+            if args.istwfk == 2:
+                cgl[:, 0, 1] = 0.0
+            eigl = np.zeros(args.nband); resl = np.zeros(args.nband)
+            tl = []
+            for it in range(2):
+                barrier(); t0 = time.perf_counter()
+                xgm.lobpcgwf2(cgl, eigl, None, None, ham, args.nband, npw, 1, resl, 1e-30, args.nline, bandpp=ndat)
+                barrier(); tl.append(time.perf_counter() - t0)
+        lobpcg_step = {"value": tl[-1], "unit": "s per LOBPCG call (one k-point, one block of all bands)", "nband": args.nband,
+                       "nline": args.nline, "eig_min_max": [float(eigl.min()), float(eigl.max())], "resid_max": float(resl.max())}
+        del cgl
+        torch.cuda.empty_cache()
     # density build (the step after the solver): fourwf option 1 on the same band block, fused path
     density = None
     if not args.no_scf_step:
@@ -461,7 +482,7 @@ def main():
                       "l2": "inputs larger than L2 (P = %.1f GB streamed twice per step)" % (16.0 * npw * nprojs / 1e9),
                       "parallelism": f"band blocks over {world} GPU(s), no data-path collective"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-           "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}, "scf_step": scf_step, "density_step": density, "fourwf_anchor": anchor,
+           "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}, "scf_step": scf_step, "lobpcg_step": lobpcg_step, "density_step": density, "fourwf_anchor": anchor,
            "experimental_int8_sliced": experimental}
     out.update(extra)
     print(json.dumps(out))
