@@ -216,8 +216,11 @@ void xg_gram(int space, int rows, int ncols_a, int ncols_b, const double* A, lon
   }
 }
 
-void xg_gemm_nn(int space, int rows, int k, int ncols_out, const double* A, long long lda, const double* C, long long ldc, double* OUT,
-                long long ldo, cudaStream_t st) {
+// upper = true: C is upper triangular (the inverse Cholesky factor of xg_Borthonormalize): output columns [j0, j1) only need
+// the first j1 columns of A, which halves the flops of the trsm-equivalent product; blocks run from the last to the first so
+// that the in-place case never reads a column block it has already overwritten.
+static void gemm_nn_impl(int space, int rows, int k, int ncols_out, const double* A, long long lda, const double* C, long long ldc,
+                         double* OUT, long long ldo, bool upper, cudaStream_t st) {
   if (rows == 0 || ncols_out == 0) return;
   const int M = real_rows(space, rows);
   const long long ldar = real_ld(space, lda), ldor = real_ld(space, ldo);
@@ -229,12 +232,35 @@ void xg_gemm_nn(int space, int rows, int k, int ncols_out, const double* A, long
   long long slab = std::max<long long>(2 * kNumSM * 64, budget / (2 * kNumSM * 64) * (2 * kNumSM * 64));
   slab = std::min<long long>(slab, (M + 1) & ~1LL);
   double* tmp = g_xgws[0].get((size_t)slab * ncols_out);
+  const int sc = sub_cplex(space);
+  const int cb = upper ? 256 : ncols_out;                          // column block of the triangular variant
   for (long long m0 = 0; m0 < M; m0 += slab) {
     const int mlen = (int)std::min<long long>(slab, M - m0);
-    if (space == SPACE_C) zgemm_nn(mlen / 2, ncols_out, k, A + m0, lda, C, ldc, tmp, slab / 2, st);
-    else dgemm_nn(mlen, ncols_out, k, A + m0, ldar, C, ldc, tmp, slab, st);
-    CUDA_CHECK(cudaMemcpy2DAsync(OUT + m0, sizeof(double) * ldor, tmp, sizeof(double) * slab, sizeof(double) * mlen, ncols_out,
-                                 cudaMemcpyDeviceToDevice, st));
+    for (int j0 = ((ncols_out - 1) / cb) * cb; j0 >= 0; j0 -= cb) {
+      const int jb = std::min(cb, ncols_out - j0);
+      const int kk = upper ? std::min(k, j0 + jb) : k;
+      const double* Cj = C + (size_t)sc * ldc * j0;
+      if (space == SPACE_C) zgemm_nn(mlen / 2, jb, kk, A + m0, lda, Cj, ldc, tmp, slab / 2, st);
+      else dgemm_nn(mlen, jb, kk, A + m0, ldar, Cj, ldc, tmp, slab, st);
+      CUDA_CHECK(cudaMemcpy2DAsync(OUT + m0 + (size_t)ldor * j0, sizeof(double) * ldor, tmp, sizeof(double) * slab, sizeof(double) * mlen, jb,
+                                   cudaMemcpyDeviceToDevice, st));
+    }
+  }
+}
+
+void xg_gemm_nn(int space, int rows, int k, int ncols_out, const double* A, long long lda, const double* C, long long ldc, double* OUT,
+                long long ldo, cudaStream_t st) {
+  gemm_nn_impl(space, rows, k, ncols_out, A, lda, C, ldc, OUT, ldo, false, st);
+}
+
+// W(0:j1, j0:j1) for every column block: the upper block-triangle of A^H B, all that potrf / heevd / hegvd ('u') read
+static void gram_upper(int space, int rows, int n, const double* A, long long lda, const double* B, long long ldb, double* W, long long ldw,
+                       int me_g0, cudaStream_t st) {
+  const int sc = sub_cplex(space), cb = 512;
+  const long long colB = real_ld(space, ldb);
+  for (int j0 = 0; j0 < n; j0 += cb) {
+    const int jb = std::min(cb, n - j0);
+    xg_gram(space, rows, j0 + jb, jb, A, lda, B + colB * j0, ldb, W + (size_t)sc * ldw * j0, ldw, me_g0, st);
   }
 }
 
@@ -389,12 +415,12 @@ int xg_b_orthonormalize(int space, int rows, int m, double* X, long long ldx, do
   xg_zero_im_g0(space, m, X, ldx, me_g0, st);                          // m_xg_ortho_RR.F90:115-119
   if (BX != X) xg_zero_im_g0(space, m, BX, ldbx, me_g0, st);            // BX == X: norm-conserving caller (B = 1)
   if (AX) xg_zero_im_g0(space, m, AX, ldax, me_g0, st);
-  xg_gram(space, rows, m, m, X, ldx, BX, ldbx, buf, ldw, me_g0, st);    // :122
+  gram_upper(space, rows, m, X, ldx, BX, ldbx, buf, ldw, me_g0, st);    // :122 (potrf 'u' reads the upper triangle only)
   const int info = chol_inverse_upper(sub_space, m, buf, ldw, st);      // potrf :125 (+ the inverse the trsm calls apply)
   if (info != 0) return info;                                           // "Cholesky decomposition did not work"
-  xg_rotate(space, rows, m, m, X, ldx, buf, ldw, st);                   // trsm 'r','u','n' :135-142
-  if (BX != X) xg_rotate(space, rows, m, m, BX, ldbx, buf, ldw, st);
-  if (AX) xg_rotate(space, rows, m, m, AX, ldax, buf, ldw, st);
+  gemm_nn_impl(space, rows, m, m, X, ldx, buf, ldw, X, ldx, true, st);  // trsm 'r','u','n' :135-142 (U^-1 is upper triangular)
+  if (BX != X) gemm_nn_impl(space, rows, m, m, BX, ldbx, buf, ldw, BX, ldbx, true, st);
+  if (AX) gemm_nn_impl(space, rows, m, m, AX, ldax, buf, ldw, AX, ldax, true, st);
   return 0;
 }
 
@@ -455,11 +481,11 @@ int xg_rayleigh_ritz(int space, int rows, int n, double* X, long long ldx, doubl
   xg_zero_im_g0(space, n, X, ldx, me_g0, st);
   xg_zero_im_g0(space, n, AX, ldax, me_g0, st);
   if (!bx_is_x) xg_zero_im_g0(space, n, BX, ldbx, me_g0, st);
-  xg_gram(space, rows, n, n, X, ldx, AX, ldax, subA, ldw, me_g0, st);     // :384
+  gram_upper(space, rows, n, X, ldx, AX, ldax, subA, ldw, me_g0, st);     // :384 (heevd / hegvd 'u' read the upper triangle only)
   if (solve_ax_bx) {
     subB = g_xgws[2].get((size_t)sc * ldw * n);
     CUDA_CHECK(cudaMemsetAsync(subB, 0, sizeof(double) * sc * ldw * n, st));
-    xg_gram(space, rows, n, n, X, ldx, bx_is_x ? X : BX, bx_is_x ? ldx : ldbx, subB, ldw, me_g0, st);   // :388
+    gram_upper(space, rows, n, X, ldx, bx_is_x ? X : BX, bx_is_x ? ldx : ldbx, subB, ldw, me_g0, st);   // :388
   }
   const int info = xg_hegvd(sub_space, n, subA, ldw, subB, ldw, eig, st);  // heevd :441 / hegvd :465
   if (info != 0) return info;
