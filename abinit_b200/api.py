@@ -275,3 +275,17 @@ def apply_invovl(ham: Hamiltonian, cwavef, sm1cwavef, cwaveprj, npw, ndat, mpi_e
     hp = C.c_void_p(ham.h)
     L().abi_b200_apply_invovl_(C.byref(hp), _ptr(cwavef, _F, "cwavef"), _ptr(sm1cwavef, _F, "sm1cwavef"),
                                _ptr(cwaveprj, _F, "cwaveprj"), _iref(npw), _iref(ndat), _iref(nspinor), _iref(block_sliced))
+
+
+def mkffnl(dimekb, dimffnl, ekb, ffnl, ffspl, gmet, gprimd, ider, idir, indlmn, kg, kpg, kpt, lmnmax, lnmax, mpsang, mqgrid, nkpg, npw,
+           ntypat, pspso, qgrid, rmet, usepaw, useylm, ylm, ylm_gr=None):
+    """mkffnl (src/66_nonlocal/m_mkffnl.F90:238 argument list), ider=0 / idir=0 / dimffnl=1 / useylm=1, on the device.
+    ffnl (out): (ntypat, lmnmax, 1, npw); ffspl: (ntypat, lnmax, 2, mqgrid); ylm: (mpsang**2, npw); kg: (npw, 3) int32."""
+    ind = np.ascontiguousarray(indlmn, dtype=np.int32); qg = np.ascontiguousarray(qgrid, dtype=np.float64)
+    kp = np.ascontiguousarray(kpt, dtype=np.float64); gp = np.ascontiguousarray(np.asarray(gprimd, dtype=np.float64).T)  # Fortran order
+    ek = None if ekb is None else np.ascontiguousarray(ekb, dtype=np.float64)
+    so = np.zeros(int(ntypat), dtype=np.int32) if pspso is None else np.ascontiguousarray(pspso, dtype=np.int32)
+    L().abi_b200_mkffnl_(_iref(dimekb), _iref(dimffnl), None if ek is None else ek.ctypes.data, _ptr(ffnl, _F, "ffnl"),
+                         _ptr(ffspl, _F, "ffspl"), None, gp.ctypes.data, _iref(ider), _iref(idir), ind.ctypes.data, _ptr(kg, _I, "kg"), None,
+                         kp.ctypes.data, _iref(lmnmax), _iref(lnmax), _iref(mpsang), _iref(mqgrid), _iref(nkpg), _iref(npw), _iref(ntypat),
+                         so.ctypes.data, qg.ctypes.data, None, _iref(usepaw), _iref(useylm), _ptr(ylm, _F, "ylm"), None)

@@ -5,6 +5,7 @@
 #include "fourwf.cuh"
 #include "nonlop.cuh"
 #include "ham.cuh"
+#include <cmath>
 #include <map>
 #include <memory>
 
@@ -145,6 +146,42 @@ void abi_b200_set_projectors_(int* ikpt, int* npw, int* nprojs, int* istwf_k, do
   CUDA_CHECK(cudaMemcpyAsync(s.P.d_p, projs, sizeof(double) * 2 * (size_t)(*npw) * (*nprojs), cudaMemcpyDefault, c.stream));
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
   g_cur_slot = *ikpt;
+}
+
+void abi_b200_mkffnl_(int* dimekb, int* dimffnl, double* ekb, double* ffnl, double* ffspl, double* gmet, double* gprimd, int* ider, int* idir,
+                      int* indlmn, int* kg, double* kpg, double* kpt, int* lmnmax, int* lnmax, int* mpsang, int* mqgrid, int* nkpg, int* npw,
+                      int* ntypat, int* pspso, double* qgrid, double* rmet, int* usepaw, int* useylm, double* ylm, double* ylm_gr) {
+  (void)gmet; (void)kpg; (void)rmet; (void)ylm_gr; (void)nkpg;
+  ensure_init();
+  Context& c = ctx();
+  ABI_CHECK(*ider == 0 && *idir == 0 && *dimffnl == 1, "mkffnl: only ider=0, idir=0 (dimffnl=1) is on the getghc path");
+  ABI_CHECK(*useylm == 1, "mkffnl: useylm=1 is required (gemm_nonlop path)");
+  ABI_CHECK(*mpsang <= 4, "Called with mpsang > 4: this subroutine will not accept lmax+1 > 4.");      // m_mkffnl.F90:291-296
+  ABI_CHECK(*mqgrid >= 2, "mkffnl: mqgrid must be >= 2");
+  ABI_CHECK(!is_device_ptr(indlmn) && !is_device_ptr(qgrid) && !is_device_ptr(kpt) && !is_device_ptr(gprimd), "mkffnl: small tables are host arrays");
+  const int np = *npw, lm = *lmnmax, nt = *ntypat;
+  // testnl (m_mkffnl.F90:452-456): PAW always; NC only where |ekb(iln,itypat)| > tol10; channel must have indlmn(6)=1 or pspso/=0
+  std::vector<unsigned char> active((size_t)lm * nt, 0);
+  for (int t = 0; t < nt; t++) for (int i = 0; i < lm; i++) {
+    const int* il = indlmn + 6 * (i + (size_t)lm * t);
+    if (il[2] <= 0) continue;
+    bool on = (il[5] == 1) || (pspso && pspso[t] != 0);
+    if (on && *usepaw == 0) on = std::fabs(ekb[(il[4] - 1) + (size_t)(*dimekb) * t]) > 1e-10;
+    active[i + (size_t)lm * t] = on ? 1 : 0;
+  }
+  const double q0 = qgrid[0], dq = (qgrid[*mqgrid - 1] - qgrid[0]) / (double)(*mqgrid - 1);
+  ABI_CHECK(dq >= 1e-12, "spacing should be strictly positive");
+  DevArg a_ffnl(0, ffnl, sizeof(double) * (size_t)np * lm * nt, false);
+  DevArg a_ffspl(1, ffspl, sizeof(double) * (size_t)(*mqgrid) * 2 * (*lnmax) * nt, true);
+  DevArg a_ylm(2, ylm, sizeof(double) * (size_t)np * (*mpsang) * (*mpsang), true);
+  DevArg a_kg(3, kg, sizeof(int) * 3 * (size_t)np, true);
+  DevArg a_ind(4, indlmn, sizeof(int) * 6 * (size_t)lm * nt, true);
+  DevArg a_gp(5, gprimd, sizeof(double) * 9, true);
+  DevArg a_act(6, active.data(), active.size(), true);
+  mkffnl_device(a_ffnl.as<double>(), np, lm, nt, a_ind.as<int>(), a_kg.as<int>(), kpt, a_gp.as<double>(), a_ffspl.as<double>(), *mqgrid, *lnmax,
+                q0, dq, a_ylm.as<double>(), a_act.as<unsigned char>(), c.stream);
+  a_ffnl.copy_back();
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
 
 void abi_b200_gemm_nonlop_(int* atindx1, int* choice, int* cpopt, double* vectproj, int* dimenl1, int* dimenl2, int* dimekbq,

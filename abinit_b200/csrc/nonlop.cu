@@ -422,6 +422,40 @@ __global__ void k_prep_projectors_xred(double2* __restrict__ P, int npw, const d
     }
   }
 }
+// mkffnl, ider = 0, useylm = 1 (src/66_nonlocal/m_mkffnl.F90:238-560): ffnl(ig,1,ilmn,itypat) = ylm(ig, l^2+l+1+m) * f_ln(|k+G|),
+// f_ln = splfit of ffspl(:,:,iln,itypat) on the uniform qgrid (shared/common/src/28_numeric_noabirule/m_splines.F90 splfit, ider 0),
+// |k+G| = |gprimd (k+G)| (no 2 pi); channels with indlmn(6)/=1 (and pspso=0) or |ekb| <= tol10 (NC) stay zero.
+__global__ void k_mkffnl(double* __restrict__ ffnl, int npw, int lmnmax, int ntypat, const int* __restrict__ indlmn,
+                         const int* __restrict__ kg, double k1, double k2, double k3, const double* __restrict__ gprimd,
+                         const double* __restrict__ ffspl, int mqgrid, int lnmax, double q0, double dq, const double* __restrict__ ylm,
+                         const unsigned char* __restrict__ active) {
+  const int ilmn = blockIdx.y % lmnmax, ityp = blockIdx.y / lmnmax;
+  const int* il = indlmn + 6 * (ilmn + (size_t)lmnmax * ityp);
+  double* out = ffnl + (size_t)npw * (ilmn + (size_t)lmnmax * ityp);
+  const bool on = active[ilmn + lmnmax * ityp] != 0;
+  const int l = il[0], m = il[1], iln = il[4];
+  const double* f = ffspl + (size_t)mqgrid * 2 * ((iln - 1) + (size_t)lnmax * ityp);
+  const double* y = ylm + (size_t)npw * (l * l + l + m);
+  const double qmax = q0 + dq * (mqgrid - 1), de2 = dq * dq / 6.0;
+  for (int ig = blockIdx.x * blockDim.x + threadIdx.x; ig < npw; ig += gridDim.x * blockDim.x) {
+    if (!on) { out[ig] = 0.0; continue; }
+    const double a = k1 + kg[3 * ig], b = k2 + kg[3 * ig + 1], c = k3 + kg[3 * ig + 2];
+    const double c1 = a * gprimd[0] + b * gprimd[3] + c * gprimd[6];     // gprimd(1,1:3) in Fortran order gprimd(i,j) = gprimd[i + 3 j]
+    const double c2 = a * gprimd[1] + b * gprimd[4] + c * gprimd[7];
+    const double c3 = a * gprimd[2] + b * gprimd[5] + c * gprimd[8];
+    const double q = sqrt(c1 * c1 + c2 * c2 + c3 * c3);
+    double v;
+    if (q >= qmax) v = f[mqgrid - 1];
+    else if (q <= q0) v = f[0];
+    else {
+      const int j = (int)((q - q0) / dq);                                 // jspl - 1
+      const double d = q - (q0 + dq * j), bb = d / dq, aa = 1.0 - bb;
+      const double cc = aa * (aa * aa - 1.0) * de2, dd = bb * (bb * bb - 1.0) * de2;
+      v = aa * f[j] + bb * f[j + 1] + cc * f[mqgrid + j] + dd * f[mqgrid + j + 1];
+    }
+    out[ig] = y[ig] * v;
+  }
+}
 #endif  // !ABI_EMU
 
 // ---------------------------------------------------------------------------------------------------------
@@ -531,6 +565,19 @@ void prep_projectors_xred_device(Projectors& P, const NonlopAtoms& at, const dou
                                                kpt[0], kpt[1], kpt[2], at.d_atom_first, at.d_atom_typ, at.d_proj_l, wt);
   CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
+}
+
+void mkffnl_device(double* d_ffnl, int npw, int lmnmax, int ntypat, const int* d_indlmn, const int* d_kg, const double* kpt,
+                   const double* d_gprimd, const double* d_ffspl, int mqgrid, int lnmax, double q0, double dq, const double* d_ylm,
+                   const unsigned char* d_active, cudaStream_t st) {
+#ifndef ABI_EMU
+  if (npw == 0) return;
+  k_mkffnl<<<dim3(std::min(64, ceil_div(npw, 256)), lmnmax * ntypat), 256, 0, st>>>(d_ffnl, npw, lmnmax, ntypat, d_indlmn, d_kg, kpt[0], kpt[1],
+                                                                                   kpt[2], d_gprimd, d_ffspl, mqgrid, lnmax, q0, dq, d_ylm,
+                                                                                   d_active);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+#endif
 }
 
 template <bool TN, bool CPLX, class Cfg>

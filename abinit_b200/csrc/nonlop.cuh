@@ -67,6 +67,11 @@ void prep_projectors_device(Projectors& P, const NonlopAtoms& at, const double* 
 void prep_projectors_xred_device(Projectors& P, const NonlopAtoms& at, const double* d_ffnl, int dimffnl, const int* d_kg,
                                  const double* d_xred, const double* kpt, double ucvol, cudaStream_t st);
 
+// mkffnl (ider = 0, useylm = 1) on the device; all pointers are DEVICE pointers except kpt; d_active(lmnmax*ntypat) = channel mask
+void mkffnl_device(double* d_ffnl, int npw, int lmnmax, int ntypat, const int* d_indlmn, const int* d_kg, const double* kpt,
+                   const double* d_gprimd, const double* d_ffspl, int mqgrid, int lnmax, double q0, double dq, const double* d_ylm,
+                   const unsigned char* d_active, cudaStream_t st);
+
 // getghc fusion of the last GEMM (opernlb): ghc <- (kinpw < filter) ? ghc + P.gxfac : 0 (m_getghc.F90:1266-1280 done in
 // the GEMM epilogue; `vectout`, when given, still receives the bare non-local term).  The rows are cut in `nslabs`
 // slabs; after each one `after_slab(user, ipw_begin, ipw_end)` runs on the host (used to queue the device->host copy

@@ -98,6 +98,14 @@ void abi_b200_prep_projectors_(int* ikpt, int* npw, int* lmnmax, int* ntypat, in
 /* Test/benchmark hook: install an explicit P(2,npw,nprojs) instead of building it from ffnl/ph3d. */
 void abi_b200_set_projectors_(int* ikpt, int* npw, int* nprojs, int* istwf_k, double* projs);
 void abi_b200_set_gemm_nonlop_ikpt_(int* ikpt);
+/* mkffnl (src/66_nonlocal/m_mkffnl.F90:238, same argument list, optional arguments dropped) restricted to what the getghc
+ * path needs: ider=0, idir=0, dimffnl=1, useylm=1: ffnl(npw,1,lmnmax,ntypat) = ylm * splfit(ffspl) at |k+G|, computed on the
+ * device.  ffnl / ffspl / ylm / kg may be host or device arrays (a device ffnl can be handed to abi_b200_ham_load_k or
+ * abi_b200_prep_projectors_ as is); indlmn, qgrid (uniform), kpt, gprimd, ekb, pspso are host arrays. */
+void abi_b200_mkffnl_(int* dimekb, int* dimffnl, double* ekb, double* ffnl, double* ffspl, double* gmet, double* gprimd,
+                      int* ider, int* idir, int* indlmn, int* kg, double* kpg, double* kpt, int* lmnmax, int* lnmax,
+                      int* mpsang, int* mqgrid, int* nkpg, int* npw, int* ntypat, int* pspso, double* qgrid, double* rmet,
+                      int* usepaw, int* useylm, double* ylm, double* ylm_gr);
 void abi_b200_gemm_nonlop_(int* atindx1, int* choice, int* cpopt, double* vectproj, int* dimenl1, int* dimenl2,
                            int* dimekbq, double* enl, int* indlmn, int* istwf_k, double* lambda, int* lmnmax,
                            int* natom, int* nattyp, int* ndat, int* nnlout, int* npwin, int* npwout,

@@ -104,3 +104,42 @@ def test_explicit_projectors_larger(lib):
                         None, np.ascontiguousarray(c), vout)
         rv, _, _ = onl.gemm_nonlop(P, c, enl, None, indlmn, nattyp, atindx1 - 1, istwf_k, 1, 0)
         assert rel_err_per_band(vout, rv) < TOL
+
+
+def test_mkffnl_on_device_matches_oracle(lib):
+    """mkffnl (ider=0, useylm=1) on the device vs the oracle's restatement (pinned through the tbase3_1 SCF): psp8 form-factor
+    splines of the Si-2 fixture at both k-points; the device-resident result feeds load_k directly."""
+    import os
+    torch = pytest.importorskip("torch")
+    from oracle import scf
+    from oracle.psp8 import ClampedSpline
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "si2_tbase3.npz"))
+    s = scf.setup_from_fixture(fx)
+    qg = np.array(fx["qgrid"]); tab = np.array(fx["ffspl_tab"]); yp = np.array(fx["ffspl_yp"])
+    nln, mq = tab.shape
+    ffspl = np.zeros((1, nln, 2, mq))
+    for i in range(nln):
+        cs = ClampedSpline(qg, tab[i], yp[i, 0], yp[i, 1])
+        ffspl[0, i, 0] = tab[i]; ffspl[0, i, 1] = cs.cs(qg, 2)          # value and second derivative tables = ffspl(:,1:2,iln,1)
+    indlmn = s.indlmn                                                  # (1, lmnmax, 6)
+    lmnmax = indlmn.shape[1]; lmax = int(indlmn[0, :, 0].max())
+    for ik, kpt in enumerate(s.kpts):
+        kg = s.kg[ik]; npw = kg.shape[1]
+        cart = s.gprimd @ (kg.astype(float) + np.asarray(kpt)[:, None])
+        ylm = np.ascontiguousarray(scf.real_ylm(cart, lmax).T)         # (mpsang^2, npw) == Fortran ylm(npw, mpsang^2)
+        ffnl_dev = torch.zeros((1, lmnmax, 1, npw), dtype=torch.float64, device="cuda")
+        api.mkffnl(nln, 1, s.ekb, ffnl_dev, np.ascontiguousarray(ffspl), None, s.gprimd, 0, 0, indlmn, np.ascontiguousarray(kg.T.astype(np.int32)),
+                   None, kpt, lmnmax, nln, lmax + 1, mq, 0, npw, 1, None, qg, None, 0, 1, ylm)
+        ref = s.ffnl[ik]                                               # (1, lmnmax, 1, npw) from oracle/scf.mkffnl
+        got = ffnl_dev.cpu().numpy()
+        assert np.max(np.abs(got - ref)) < 1e-12 * np.max(np.abs(ref))
+        # the device array goes straight into the Hamiltonian handle: same H psi as with the oracle's host ffnl
+        h = ab.Hamiltonian(s.ngfft, s.xred.shape[1], 1, lmnmax, indlmn, s.nattyp, s.atindx1 + 1, 0, s.ucvol)
+        h.load_spin(np.ascontiguousarray(s.vpsp), 1); h.load_enl(s.ekb, None)
+        h.load_k_xred(1, np.ascontiguousarray(kg.T), s.kinpw[ik], ffnl_dev, kpt, np.ascontiguousarray(s.xred.T))
+        c = np.ascontiguousarray(np.eye(npw, dtype=np.complex128)[:6])
+        out = np.zeros_like(c)
+        ab.getghc(-1, c, None, out, None, h, None, None, None, 6)
+        ref_h = scf.apply_h_oracle(s)(ik, s.vpsp, c)
+        assert rel_err_per_band(out, ref_h) < TOL
+        h.destroy()
