@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 from oracle import nonlop as onl
 from problems import make_problem, rel_err_per_band
+import abinit_b200 as ab
 from abinit_b200 import api
 
 pytestmark = pytest.mark.gpu
