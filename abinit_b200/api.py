@@ -289,3 +289,9 @@ def mkffnl(dimekb, dimffnl, ekb, ffnl, ffspl, gmet, gprimd, ider, idir, indlmn, 
                          _ptr(ffspl, _F, "ffspl"), None, gp.ctypes.data, _iref(ider), _iref(idir), ind.ctypes.data, _ptr(kg, _I, "kg"), None,
                          kp.ctypes.data, _iref(lmnmax), _iref(lnmax), _iref(mpsang), _iref(mqgrid), _iref(nkpg), _iref(npw), _iref(ntypat),
                          so.ctypes.data, qg.ctypes.data, None, _iref(usepaw), _iref(useylm), _ptr(ylm, _F, "ylm"), None)
+
+
+def initylmg_k(gprimd, kg, kpt, mpsang, npw, ylm):
+    """initylmg (src/56_recipspace/m_initylmg.F90:94) for one k-point, optder=0: ylm (out) of shape (mpsang**2, npw)."""
+    gp = np.ascontiguousarray(np.asarray(gprimd, dtype=np.float64).T); kp = np.ascontiguousarray(kpt, dtype=np.float64)
+    L().abi_b200_initylmg_k_(gp.ctypes.data, _ptr(kg, _I, "kg"), kp.ctypes.data, _iref(mpsang), _iref(npw), _ptr(ylm, _F, "ylm"))

@@ -148,6 +148,19 @@ void abi_b200_set_projectors_(int* ikpt, int* npw, int* nprojs, int* istwf_k, do
   g_cur_slot = *ikpt;
 }
 
+void abi_b200_initylmg_k_(double* gprimd, int* kg, double* kpt, int* mpsang, int* npw, double* ylm) {
+  ensure_init();
+  Context& c = ctx();
+  ABI_CHECK(*mpsang >= 1 && *mpsang <= 4, "initylmg: mpsang must be in 1..4");
+  ABI_CHECK(!is_device_ptr(gprimd) && !is_device_ptr(kpt), "initylmg: gprimd and kpt are host arrays");
+  DevArg a_ylm(0, ylm, sizeof(double) * (size_t)(*npw) * (*mpsang) * (*mpsang), false);
+  DevArg a_kg(3, kg, sizeof(int) * 3 * (size_t)(*npw), true);
+  DevArg a_gp(5, gprimd, sizeof(double) * 9, true);
+  initylmg_device(a_ylm.as<double>(), *npw, *mpsang, a_kg.as<int>(), kpt, a_gp.as<double>(), c.stream);
+  a_ylm.copy_back();
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
 void abi_b200_mkffnl_(int* dimekb, int* dimffnl, double* ekb, double* ffnl, double* ffspl, double* gmet, double* gprimd, int* ider, int* idir,
                       int* indlmn, int* kg, double* kpg, double* kpt, int* lmnmax, int* lnmax, int* mpsang, int* mqgrid, int* nkpg, int* npw,
                       int* ntypat, int* pspso, double* qgrid, double* rmet, int* usepaw, int* useylm, double* ylm, double* ylm_gr) {

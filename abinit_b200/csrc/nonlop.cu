@@ -422,6 +422,55 @@ __global__ void k_prep_projectors_xred(double2* __restrict__ P, int npw, const d
     }
   }
 }
+// initylmg, optder = 0, one k-point (src/56_recipspace/m_initylmg.F90:94-396; ass_leg_pol of shared/libpaw/src/m_paw_sphharm.F90):
+// ylm(ig, l^2+l+1+-m) real spherical harmonics of k+G with the reference's sign conventions
+__device__ double ass_leg_pol_dev(int l, int m, double x) {
+  if (fabs(x) > 1.0) x = 1.0;
+  double polmm = 1.0;
+  if (m > 0) {
+    const double sqrx = sqrt(fabs((1.0 - x) * (1.0 + x)));
+    for (int i = 1; i <= m; i++) polmm *= (1.0 - 2.0 * i) * sqrx;
+  }
+  if (l == m) return polmm;
+  double tmp1 = x * (2.0 * m + 1.0) * polmm;
+  if (l == m + 1) return tmp1;
+  double pll = 0.0;
+  for (int ll = m + 2; ll <= l; ll++) { pll = (x * (2.0 * ll - 1.0) * tmp1 - (ll + m - 1.0) * polmm) / (double)(ll - m); polmm = tmp1; tmp1 = pll; }
+  return pll;
+}
+__global__ void k_initylmg(double* __restrict__ ylm, int npw, int mpsang, const int* __restrict__ kg, double k1, double k2, double k3,
+                           const double* __restrict__ gprimd) {
+  const double tol = 1e-10, four_pi = 4.0 * 3.14159265358979323846;
+  for (int ig = blockIdx.x * blockDim.x + threadIdx.x; ig < npw; ig += gridDim.x * blockDim.x) {
+    const double a = k1 + kg[3 * ig], b = k2 + kg[3 * ig + 1], c = k3 + kg[3 * ig + 2];
+    const double xx = a * gprimd[0] + b * gprimd[3] + c * gprimd[6];
+    const double yy = a * gprimd[1] + b * gprimd[4] + c * gprimd[7];
+    const double zz = a * gprimd[2] + b * gprimd[5] + c * gprimd[8];
+    const double rr = sqrt(xx * xx + yy * yy + zz * zz);
+    ylm[ig] = 1.0 / sqrt(four_pi);
+    for (int i = 1; i < mpsang * mpsang; i++) ylm[(size_t)npw * i + ig] = 0.0;
+    if (!(rr > tol)) continue;
+    double cphi = 1.0, sphi = 0.0;
+    const double ctheta = zz / rr, stheta = sqrt(fabs((1.0 - ctheta) * (1.0 + ctheta)));
+    if (stheta > tol) { cphi = xx / (rr * stheta); sphi = yy / (rr * stheta); }
+    for (int ll = 1; ll < mpsang; ll++) {
+      const int l0 = ll * ll + ll;
+      double fact = 1.0 / (double)(ll * (ll + 1));
+      const double ylmcst = sqrt((double)(2 * ll + 1) / four_pi);
+      ylm[(size_t)npw * l0 + ig] = ylmcst * ass_leg_pol_dev(ll, 0, ctheta);
+      double onem = 1.0, er = 1.0, ei = 0.0;
+      for (int mm = 1; mm <= ll; mm++) {
+        onem = -onem;
+        const double t = er * cphi - ei * sphi; ei = er * sphi + ei * cphi; er = t;      // (cphi + i sphi)^mm
+        const double work1 = ylmcst * sqrt(fact) * onem * ass_leg_pol_dev(ll, mm, ctheta) * sqrt(2.0);
+        ylm[(size_t)npw * (l0 + mm) + ig] = work1 * er;
+        ylm[(size_t)npw * (l0 - mm) + ig] = work1 * ei;
+        if (mm != ll) fact /= (double)((ll + mm + 1) * (ll - mm));
+      }
+    }
+  }
+}
+
 // mkffnl, ider = 0, useylm = 1 (src/66_nonlocal/m_mkffnl.F90:238-560): ffnl(ig,1,ilmn,itypat) = ylm(ig, l^2+l+1+m) * f_ln(|k+G|),
 // f_ln = splfit of ffspl(:,:,iln,itypat) on the uniform qgrid (shared/common/src/28_numeric_noabirule/m_splines.F90 splfit, ider 0),
 // |k+G| = |gprimd (k+G)| (no 2 pi); channels with indlmn(6)/=1 (and pspso=0) or |ekb| <= tol10 (NC) stay zero.
@@ -565,6 +614,15 @@ void prep_projectors_xred_device(Projectors& P, const NonlopAtoms& at, const dou
                                                kpt[0], kpt[1], kpt[2], at.d_atom_first, at.d_atom_typ, at.d_proj_l, wt);
   CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
+}
+
+void initylmg_device(double* d_ylm, int npw, int mpsang, const int* d_kg, const double* kpt, const double* d_gprimd, cudaStream_t st) {
+#ifndef ABI_EMU
+  if (npw == 0) return;
+  k_initylmg<<<std::min(kNumSM * 4, ceil_div(npw, 256)), 256, 0, st>>>(d_ylm, npw, mpsang, d_kg, kpt[0], kpt[1], kpt[2], d_gprimd);
+  CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+#endif
 }
 
 void mkffnl_device(double* d_ffnl, int npw, int lmnmax, int ntypat, const int* d_indlmn, const int* d_kg, const double* kpt,

@@ -67,6 +67,8 @@ void prep_projectors_device(Projectors& P, const NonlopAtoms& at, const double* 
 void prep_projectors_xred_device(Projectors& P, const NonlopAtoms& at, const double* d_ffnl, int dimffnl, const int* d_kg,
                                  const double* d_xred, const double* kpt, double ucvol, cudaStream_t st);
 
+// initylmg (optder = 0) for one k-point: d_ylm(npw, mpsang^2) on the device
+void initylmg_device(double* d_ylm, int npw, int mpsang, const int* d_kg, const double* kpt, const double* d_gprimd, cudaStream_t st);
 // mkffnl (ider = 0, useylm = 1) on the device; all pointers are DEVICE pointers except kpt; d_active(lmnmax*ntypat) = channel mask
 void mkffnl_device(double* d_ffnl, int npw, int lmnmax, int ntypat, const int* d_indlmn, const int* d_kg, const double* kpt,
                    const double* d_gprimd, const double* d_ffspl, int mqgrid, int lnmax, double q0, double dq, const double* d_ylm,

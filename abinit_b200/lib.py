@@ -23,7 +23,7 @@ SYMBOLS = [
     "abi_b200_fourwf_", "abi_b200_alloc_fourwf_", "abi_b200_free_fourwf_", "gpu_fourwf_", "alloc_gpu_fourwf_",
     "free_gpu_fourwf_", "abi_b200_set_me_g0", "abi_b200_fourwf_set_impl", "abi_b200_fourwf_set_tuning", "abi_b200_fourwf_counter",
     "abi_b200_init_gemm_nonlop_", "abi_b200_destroy_gemm_nonlop_", "abi_b200_prep_projectors_",
-    "abi_b200_set_projectors_", "abi_b200_set_gemm_nonlop_ikpt_", "abi_b200_mkffnl_", "abi_b200_gemm_nonlop_",
+    "abi_b200_set_projectors_", "abi_b200_set_gemm_nonlop_ikpt_", "abi_b200_initylmg_k_", "abi_b200_mkffnl_", "abi_b200_gemm_nonlop_",
     "abi_b200_nonlop_counter",
     "abi_b200_ham_create", "abi_b200_ham_destroy", "abi_b200_ham_load_spin", "abi_b200_ham_set_nspinor", "abi_b200_ham_load_spin_nvloc", "abi_b200_ham_load_enl",
     "abi_b200_ham_load_k", "abi_b200_ham_load_k_xred", "abi_b200_ham_set_projectors", "abi_b200_ham_nprojs", "abi_b200_getghc_",
@@ -69,6 +69,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         lib.abi_b200_set_gemm_nonlop_ikpt_.argtypes = [vp]
         lib.abi_b200_gemm_nonlop_.argtypes = [vp] * 28
         lib.abi_b200_mkffnl_.argtypes = [vp] * 27
+        lib.abi_b200_initylmg_k_.argtypes = [vp] * 6
         lib.abi_b200_ham_create.restype = vp
         lib.abi_b200_ham_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_double]
         lib.abi_b200_ham_destroy.argtypes = [vp]

@@ -102,6 +102,8 @@ void abi_b200_set_gemm_nonlop_ikpt_(int* ikpt);
  * path needs: ider=0, idir=0, dimffnl=1, useylm=1: ffnl(npw,1,lmnmax,ntypat) = ylm * splfit(ffspl) at |k+G|, computed on the
  * device.  ffnl / ffspl / ylm / kg may be host or device arrays (a device ffnl can be handed to abi_b200_ham_load_k or
  * abi_b200_prep_projectors_ as is); indlmn, qgrid (uniform), kpt, gprimd, ekb, pspso are host arrays. */
+/* initylmg (src/56_recipspace/m_initylmg.F90:94) for ONE k-point, optder = 0: ylm(npw, mpsang^2), host or device. */
+void abi_b200_initylmg_k_(double* gprimd, int* kg, double* kpt, int* mpsang, int* npw, double* ylm);
 void abi_b200_mkffnl_(int* dimekb, int* dimffnl, double* ekb, double* ffnl, double* ffspl, double* gmet, double* gprimd,
                       int* ider, int* idir, int* indlmn, int* kg, double* kpg, double* kpt, int* lmnmax, int* lnmax,
                       int* mpsang, int* mqgrid, int* nkpg, int* npw, int* ntypat, int* pspso, double* qgrid, double* rmet,

@@ -175,6 +175,59 @@ def real_ylm(kpg_cart, lmax):
     return out
 
 
+def ass_leg_pol(l, m, x):
+    """shared/libpaw/src/m_paw_sphharm.F90 ass_leg_pol (Condon-Shortley phase included through the (1-2i) factors)."""
+    x = np.clip(x, -1.0, 1.0)
+    polmm = np.ones_like(x)
+    if m > 0:
+        sqrx = np.sqrt(np.abs((1.0 - x) * (1.0 + x)))
+        for i in range(1, m + 1):
+            polmm = polmm * (1.0 - 2.0 * i) * sqrx
+    if l == m:
+        return polmm
+    tmp1 = x * (2.0 * m + 1.0) * polmm
+    if l == m + 1:
+        return tmp1
+    for ll in range(m + 2, l + 1):
+        pll = (x * (2.0 * ll - 1.0) * tmp1 - (ll + m - 1.0) * polmm) / float(ll - m)
+        polmm = tmp1; tmp1 = pll
+    return pll
+
+
+def initylmg_k(kg, kpt, gprimd, mpsang):
+    """Real spherical harmonics with the reference's own conventions: src/56_recipspace/m_initylmg.F90:94-396, optder = 0, one
+    k-point.  Returns ylm (mpsang^2, npw) == Fortran ylm(npw, mpsang^2)."""
+    kpg = kg.astype(float) + np.asarray(kpt)[:, None]
+    xx, yy, zz = gprimd @ kpg
+    rr = np.sqrt(xx ** 2 + yy ** 2 + zz ** 2)
+    npw = kg.shape[1]
+    ylm = np.zeros((mpsang * mpsang, npw))
+    ylm[0] = 1.0 / np.sqrt(4 * np.pi)
+    ok = rr > 1e-10
+    rs = np.where(ok, rr, 1.0)
+    ctheta = np.where(ok, zz / rs, 1.0)
+    stheta = np.sqrt(np.abs((1.0 - ctheta) * (1.0 + ctheta)))
+    big = stheta > 1e-10
+    ss = np.where(big, rs * stheta, 1.0)
+    cphi = np.where(big, xx / ss, 1.0); sphi = np.where(big, yy / ss, 0.0)
+    ph = cphi + 1j * sphi
+    for ll in range(1, mpsang):
+        l0 = ll * ll + ll
+        fact = 1.0 / float(ll * (ll + 1))
+        ylmcst = np.sqrt((2 * ll + 1) / (4 * np.pi))
+        ylm[l0] = np.where(ok, ylmcst * ass_leg_pol(ll, 0, ctheta), 0.0)
+        onem = 1.0
+        for mm in range(1, ll + 1):
+            onem = -onem
+            work1 = ylmcst * np.sqrt(fact) * onem * ass_leg_pol(ll, mm, ctheta) * np.sqrt(2.0)
+            e = ph ** mm
+            ylm[l0 + mm] = np.where(ok, work1 * e.real, 0.0)
+            ylm[l0 - mm] = np.where(ok, work1 * e.imag, 0.0)
+            if mm != ll:
+                fact = fact / float((ll + mm + 1) * (ll - mm))
+    return ylm
+
+
 def mkffnl(kg, kpt, gprimd, gmet, indlmn, ffspl):
     """ffnl[ilmn, 0, ipw] = Ylm(k+G) * f_ln(|k+G|)   (m_mkffnl.F90:520-524; |k+G| without the 2 pi)."""
     kpg = kg.astype(float) + np.asarray(kpt)[:, None]

@@ -144,3 +144,23 @@ def test_mkffnl_on_device_matches_oracle(lib):
         ref_h = scf.apply_h_oracle(s)(ik, s.vpsp, c)
         assert rel_err_per_band(out, ref_h) < TOL
         h.destroy()
+
+
+@pytest.mark.parametrize("mpsang", [1, 3, 4])
+def test_initylmg_on_device_matches_oracle(lib, mpsang):
+    """initylmg (optder=0, one k-point) on the device vs the oracle restatement of m_initylmg.F90 / ass_leg_pol, incl. the
+    k+G = 0 point and points on the z axis; the spherical-harmonic addition theorem as an independent check."""
+    from oracle import scf
+    rng = np.random.default_rng(3)
+    npw = 3001
+    kg = rng.integers(-9, 10, size=(3, npw)); kg[:, 0] = 0; kg[:, 1] = (0, 0, 4); kg[:, 2] = (0, 0, -3)
+    gprimd = np.diag([0.11, 0.09, 0.13]) + 0.01 * rng.standard_normal((3, 3))
+    for kpt in ((0.0, 0.0, 0.0), (0.1, -0.2, 0.3)):
+        ref = scf.initylmg_k(kg, kpt, gprimd, mpsang)
+        ylm = np.zeros((mpsang * mpsang, npw))
+        api.initylmg_k(gprimd, np.ascontiguousarray(kg.T.astype(np.int32)), kpt, mpsang, npw, ylm)
+        assert np.max(np.abs(ylm - ref)) < 1e-13
+        for l in range(mpsang):
+            s = np.sum(ylm[l * l:(l + 1) ** 2] ** 2, axis=0)
+            nz = np.linalg.norm(gprimd @ (kg + np.asarray(kpt)[:, None]), axis=0) > 1e-10
+            assert np.allclose(s[nz], (2 * l + 1) / (4 * np.pi), atol=1e-13)
