@@ -230,6 +230,22 @@ void abi_b200_xg_rotate_(int* space, int* rows, int* k, int* ncols_out, double* 
   if (!c.async) CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
 
+void abi_b200_xg_gemm_nn_(int* space, int* rows, int* k, int* ncols_out, double* a, int* lda, double* cmat, int* ldc, double* out, int* ldo,
+                          int* upper) {
+  ensure_init();
+  Context& c = ctx();
+  ABI_CHECK(is_device_ptr(a) && is_device_ptr(cmat) && is_device_ptr(out), "xg_gemm_nn: device pointers required");
+  if (*upper) xg_gemm_nn_upper(*space, *rows, *k, *ncols_out, a, *lda, cmat, *ldc, out, *ldo, c.stream);
+  else xg_gemm_nn(*space, *rows, *k, *ncols_out, a, *lda, cmat, *ldc, out, *ldo, c.stream);
+  if (!c.async) CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+void abi_b200_xg_chol_inverse_(int* space, int* m, double* a, int* lda, int* info) {
+  ensure_init();
+  ABI_CHECK(is_device_ptr(a), "xg_chol_inverse: device pointer required");
+  *info = xg_chol_inverse(*space == SPACE_C ? SPACE_C : SPACE_R, *m, a, *lda, ctx().stream);
+}
+
 void abi_b200_xg_hegvd_(int* space, int* n, double* a, int* lda, double* b, int* ldb, double* w, int* info) {
   ensure_init();
   ABI_CHECK(is_device_ptr(a) && is_device_ptr(w) && (b == nullptr || is_device_ptr(b)), "xg_hegvd: device pointers required");
@@ -246,7 +262,9 @@ void abi_b200_xg_colwise_(int* op, int* space, int* rows, int* ncols, double* a,
     case 2: xg_colwise_cymax(*space, *rows, *ncols, a, *lda, da, b, *ldb, w, *ldw, c.stream); break;
     case 3: xg_scale_cols(*space, *rows, *ncols, a, *lda, da, c.stream); break;
     case 4: xg_zero_im_g0(*space, *ncols, a, *lda, *me_g0, c.stream); break;
-    default: ABI_ERROR("xg_colwise: op must be 0 (dot), 1 (norm2), 2 (cymax), 3 (scale), 4 (zero_im_g0)");
+    case 5: xg_add(*space, *rows, *ncols, a, *lda, b, *ldb, c.stream); break;
+    case 6: xg_apply_diag(*space, *rows, *ncols, a, *lda, da, c.stream); break;
+    default: ABI_ERROR("xg_colwise: op must be 0 (dot), 1 (norm2), 2 (cymax), 3 (scale), 4 (zero_im_g0), 5 (add), 6 (apply_diag)");
   }
   if (!c.async) CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }

@@ -253,6 +253,11 @@ void xg_gemm_nn(int space, int rows, int k, int ncols_out, const double* A, long
   gemm_nn_impl(space, rows, k, ncols_out, A, lda, C, ldc, OUT, ldo, false, st);
 }
 
+void xg_gemm_nn_upper(int space, int rows, int k, int ncols_out, const double* A, long long lda, const double* C, long long ldc, double* OUT,
+                      long long ldo, cudaStream_t st) {
+  gemm_nn_impl(space, rows, k, ncols_out, A, lda, C, ldc, OUT, ldo, true, st);
+}
+
 // W(0:j1, j0:j1) for every column block: the upper block-triangle of A^H B, all that potrf / heevd / hegvd ('u') read
 static void gram_upper(int space, int rows, int n, const double* A, long long lda, const double* B, long long ldb, double* W, long long ldw,
                        int me_g0, cudaStream_t st) {
@@ -403,6 +408,8 @@ static int chol_inverse_upper(int sub_space, int m, double* A, long long lda, cu
   g_kernel_launches += 2;
   return info;
 }
+
+int xg_chol_inverse(int sub_space, int m, double* A, long long lda, cudaStream_t st) { return chol_inverse_upper(sub_space, m, A, lda, st); }
 
 int xg_b_orthonormalize(int space, int rows, int m, double* X, long long ldx, double* BX, long long ldbx, double* AX, long long ldax,
                         int me_g0, cudaStream_t st) {

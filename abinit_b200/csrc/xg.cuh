@@ -26,6 +26,12 @@ void xg_rotate(int space, int rows, int k, int ncols_out, double* X, long long l
 // (each slab's product is complete before it is stored).  xg_rotate is the case OUT == A.
 void xg_gemm_nn(int space, int rows, int k, int ncols_out, const double* A, long long lda, const double* C, long long ldc,
                 double* OUT, long long ldo, cudaStream_t st);
+// same with an upper-triangular C (inverse Cholesky factor): triangular K ranges, in place allowed
+void xg_gemm_nn_upper(int space, int rows, int k, int ncols_out, const double* A, long long lda, const double* C, long long ldc,
+                      double* OUT, long long ldo, cudaStream_t st);
+// A(m x m, upper triangle of a Hermitian positive matrix) -> U^-1 with A = U^H U (potrf 'u' + trtri, strictly-lower part zeroed);
+// sub_space: SPACE_R or SPACE_C.  Returns potrf's info.
+int xg_chol_inverse(int sub_space, int m, double* A, long long lda, cudaStream_t st);
 // X += P (xgBlock_add)
 void xg_add(int space, int rows, int ncols, double* X, long long ldx, const double* P, long long ldp, cudaStream_t st);
 // X(i, j) *= d(i), d real per (complex) row (xgBlock_apply_diag with a SPACE_R diagonal: the LOBPCG preconditioner)

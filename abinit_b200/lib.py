@@ -28,7 +28,7 @@ SYMBOLS = [
     "abi_b200_ham_create", "abi_b200_ham_destroy", "abi_b200_ham_load_spin", "abi_b200_ham_set_nspinor", "abi_b200_ham_load_spin_nvloc", "abi_b200_ham_load_enl",
     "abi_b200_ham_load_k", "abi_b200_ham_load_k_xred", "abi_b200_ham_set_projectors", "abi_b200_ham_nprojs", "abi_b200_getghc_",
     "abi_b200_nonlop_",
-    "abi_b200_xg_gram_", "abi_b200_xg_rotate_", "abi_b200_xg_hegvd_", "abi_b200_xg_colwise_", "abi_b200_xg_rayleigh_ritz_",
+    "abi_b200_xg_gram_", "abi_b200_xg_rotate_", "abi_b200_xg_hegvd_", "abi_b200_xg_gemm_nn_", "abi_b200_xg_chol_inverse_", "abi_b200_xg_colwise_", "abi_b200_xg_rayleigh_ritz_",
     "abi_b200_chebfiwf2_", "abi_b200_lobpcgwf2_", "abi_b200_chebfi_rq_", "abi_b200_chebfi_core_", "abi_b200_cheb_oracle1_", "abi_b200_cheb_poly1_",
     "abi_b200_make_invovl_", "abi_b200_apply_invovl_",
 ]
@@ -87,6 +87,8 @@ def load_library(path: str | None = None) -> C.CDLL:
         lib.abi_b200_nonlop_.argtypes = [vp] * 15
         lib.abi_b200_xg_rotate_.argtypes = [vp] * 8
         lib.abi_b200_xg_hegvd_.argtypes = [vp] * 8
+        lib.abi_b200_xg_gemm_nn_.argtypes = [vp] * 11
+        lib.abi_b200_xg_chol_inverse_.argtypes = [vp] * 5
         lib.abi_b200_xg_colwise_.argtypes = [vp] * 13
         lib.abi_b200_xg_rayleigh_ritz_.argtypes = [vp] * 13
         lib.abi_b200_chebfiwf2_.argtypes = [vp] * 18

@@ -170,3 +170,141 @@ def chebfi_band_parallel(gs_hamk, cg_cols, nband: int, ecut: float, nline: int, 
     xg.xg_colwise("norm2", space, npw, ncols, ax, npw, out=res, me_g0=me_g0_cols)
     cg_cols.copy_(x)
     return w.cpu().numpy(), res.cpu().numpy()
+
+
+def lobpcg_band_parallel(gs_hamk, cg_cols, nband: int, nline: int, kinpw, tolwfr_diago: float = 1e-30, bandpp: int = 128, group=None):
+    """lobpcg_run with paral_kgb=1, npband = world size, one block of all bands (src/48_diago/m_lobpcg2.F90:340-765),
+    norm-conserving: getAX_BX on the rank's own band block (band-sharded layout), everything else -- B-orthonormalisation,
+    X / XW / XWP Rayleigh-Ritz, residuals, preconditioner -- on the rank's plane-wave rows (row-sharded layout) with the Gram
+    matrices summed over ranks by NCCL allreduce and the small dense problems solved redundantly on every rank; per LOBPCG
+    iteration one all-to-all out (W) and one back (AW), as the reference's xgTransposer does.
+    cg_cols: CUDA float64 tensor (my_ncols, npw, 2), updated in place.  Returns (eig[nband], resid[nband]) host arrays."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from . import xg, api
+    if gs_hamk.usepaw:
+        raise NotImplementedError("lobpcg_band_parallel: norm-conserving only in this build (PAW needs the BX blocks transposed too)")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    api.set_async(False)
+    dev = cg_cols.device
+    sync = torch.cuda.current_stream(dev).synchronize
+    ncols, npw = int(cg_cols.shape[0]), int(cg_cols.shape[1])
+    f, l = band_block(nband, world, rank)
+    if ncols != l - f:
+        raise ValueError("cg_cols does not hold this rank's band block")
+    n = nband
+    istwf_k = gs_hamk.istwf_k
+    space = xg.SPACE_CR if istwf_k > 1 else xg.SPACE_C
+    sub_space = xg.SPACE_C if space == xg.SPACE_C else xg.SPACE_R
+    sdt = torch.complex128 if space == xg.SPACE_C else torch.float64
+    lo, hi = row_shard(npw, world, rank)
+    nr = hi - lo
+    me_g0 = (1 if (istwf_k == 2 and rank == 0 and gs_hamk.me_g0 == 1) else 0) if space == xg.SPACE_CR else -1
+    # build_pcon (m_lobpcgwf.F90:316-334) on my rows
+    kin = np.asarray(kinpw, dtype=np.float64)[lo:hi]
+    big = kin > np.finfo(np.float64).max * 1e-11
+    kk = np.where(big, 0.0, kin)
+    num = 27 + kk * (18 + kk * (12 + 8 * kk))
+    pcon = torch.from_numpy(np.where(big, 0.0, num / (num + 16 * kk ** 4))).to(dev)
+    # [X | W | P] and [AX | AW | AP] on my rows; B blocks alias the X blocks (norm-conserving)
+    xwp = torch.zeros((3 * n, nr, 2), dtype=torch.float64, device=dev)
+    axwp = torch.zeros_like(xwp)
+    X, W, AX, AW = xwp[:n], xwp[n:2 * n], axwp[:n], axwp[n:2 * n]
+
+    def allsum(t):
+        if world > 1:
+            dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t, op=dist.ReduceOp.SUM, group=group)
+
+    def apply_h(src_rows, dst_rows):
+        cols = transpose_rows_to_cols(src_rows.contiguous(), n, npw, group).contiguous()
+        out = torch.empty_like(cols)
+        sync()
+        api.getghc(-1, cols, None, out, None, gs_hamk, None, None, None, ncols)
+        if space == xg.SPACE_CR:
+            xg.xg_colwise("zero_im_g0", space, npw, ncols, out, npw, me_g0=1 if (istwf_k == 2 and gs_hamk.me_g0 == 1) else 0)
+        dst_rows.copy_(transpose_cols_to_rows(out, n, npw, group))
+        return cols
+
+    def gram(a, b, na, nb, w):                       # w: column block view of a (.., ldw) tensor, written in place
+        sync()
+        xg.xg_gram(space, nr, na, nb, a, nr, b, nr, w, int(w.shape[1]), me_g0)
+
+    def b_orthonormalize(m):
+        ldw = (m + 1) & ~1
+        buf = torch.zeros((m, ldw), dtype=sdt, device=dev)
+        for blk in (xwp, axwp):
+            xg.xg_colwise("zero_im_g0", space, nr, m, blk, nr, me_g0=me_g0)
+        gram(xwp, xwp, m, m, buf)
+        allsum(buf)
+        sync()
+        info = xg.xg_chol_inverse(sub_space, m, buf, ldw)
+        if info != 0:
+            return info
+        for blk in (xwp, axwp):
+            xg.xg_gemm_nn(space, nr, m, m, blk, nr, buf, ldw, blk, nr, upper=True)
+        return 0
+
+    def rayleigh_ritz(nvar):
+        sub = nvar * n
+        ldw = (sub + 1) & ~1
+        ab = torch.zeros((2, sub, ldw), dtype=sdt, device=dev)
+        for blk in (xwp, axwp):
+            xg.xg_colwise("zero_im_g0", space, nr, sub, blk, nr, me_g0=me_g0)
+        for v in range(nvar):
+            gram(xwp, axwp[v * n:], (v + 1) * n, n, ab[0, v * n:])
+            if nvar > 1:
+                gram(xwp, xwp[v * n:], (v + 1) * n, n, ab[1, v * n:])
+        allsum(ab)
+        w = torch.empty(sub, dtype=torch.float64, device=dev)
+        sync()
+        info = xg.xg_hegvd(sub_space, sub, ab[0], ldw, ab[1] if nvar > 1 else None, ldw, w)
+        if info != 0:
+            raise RuntimeError(f"lobpcg: sub-space eigenproblem failed (info={info})")
+        vec = ab[0]                                   # eigenvectors: tensor row j = column j, first `sub` entries
+        if nvar > 1:
+            ldc1 = (sub - n + 1) & ~1
+            c1 = torch.zeros((n, ldc1), dtype=sdt, device=dev)
+            c1[:, :sub - n] = vec[:n, n:sub]
+        sync()
+        for blk in (xwp, axwp):
+            xg.xg_rotate(space, nr, n, n, blk, nr, vec, ldw)
+            if nvar > 1:
+                xg.xg_gemm_nn(space, nr, sub - n, n, blk[n:], nr, c1, ldc1, blk[2 * n:], nr)
+                xg.xg_colwise("add", space, nr, n, blk, nr, blk[2 * n:], nr)
+        return w
+
+    X.copy_(transpose_cols_to_rows(cg_cols, n, npw, group))
+    apply_h(X, AX)
+    b_orthonormalize(n)
+    eig = rayleigh_ritz(1)[:n].clone()
+    res = torch.zeros(n, dtype=torch.float64, device=dev)
+
+    def residuals():
+        sync()
+        xg.xg_colwise("cymax", space, nr, n, W, nr, X, nr, AX, nr, da=eig)       # W = AX - eig BX, BX = X
+        xg.xg_colwise("norm2", space, nr, n, W, nr, out=res, me_g0=me_g0)
+        allsum(res)
+        xg.xg_colwise("apply_diag", space, nr, n, W, nr, da=pcon)
+        r = res.cpu().numpy()
+        return r, float(r.min()), float(r.max())
+    compute_residu = True
+    r = None
+    for iline in range(1, nline + 1):
+        r, min_res, max_res = residuals()
+        if max_res < tolwfr_diago:
+            compute_residu = False
+            break
+        apply_h(W, AW)
+        use_xw = iline == 1 or min_res < 1e-27
+        if not use_xw and b_orthonormalize(3 * n) != 0:
+            use_xw = True
+        if use_xw:
+            b_orthonormalize(2 * n)
+            xwp[2 * n:].zero_(); axwp[2 * n:].zero_()
+        eig = rayleigh_ritz(2 if use_xw else 3)[:n].clone()
+    if compute_residu:
+        r, _, _ = residuals()
+    cg_cols.copy_(transpose_rows_to_cols(X.contiguous(), n, npw, group))
+    return eig.cpu().numpy(), r

@@ -26,6 +26,19 @@ def xg_rotate(space, rows, k, ncols_out, x, ldx, c, ldc):
     L().abi_b200_xg_rotate_(_iref(space), _iref(rows), _iref(k), _iref(ncols_out), _ptr(x), _iref(ldx), _ptr(c), _iref(ldc))
 
 
+def xg_gemm_nn(space, rows, k, ncols_out, a, lda, c, ldc, out, ldo, upper=False):
+    """out(:, :ncols_out) = a(:, :k) c(:k, :ncols_out); out may alias a; upper: c is upper triangular (U^-1 of xg_Borthonormalize)."""
+    L().abi_b200_xg_gemm_nn_(_iref(space), _iref(rows), _iref(k), _iref(ncols_out), _ptr(a), _iref(lda), _ptr(c), _iref(ldc), _ptr(out),
+                             _iref(ldo), _iref(1 if upper else 0))
+
+
+def xg_chol_inverse(space, m, a, lda) -> int:
+    """a (upper triangle of a Hermitian positive m x m sub-space matrix) -> U^-1 with a = U^H U; returns potrf's info."""
+    info = C.c_int(0)
+    L().abi_b200_xg_chol_inverse_(_iref(space), _iref(m), _ptr(a), _iref(lda), C.byref(info))
+    return info.value
+
+
 def xg_hegvd(space, n, a, lda, b, ldb, w) -> int:
     """hegvd(1,'v','u') (b=None: heevd('v','u')): eigenvectors overwrite a, eigenvalues in the device array w."""
     info = C.c_int(0)
@@ -35,7 +48,7 @@ def xg_hegvd(space, n, a, lda, b, ldb, w) -> int:
 
 def xg_colwise(op, space, rows, ncols, a, lda, b=None, ldb=0, w=None, ldw=0, da=None, out=None, me_g0=1):
     """op: 'dot' | 'norm2' | 'cymax' | 'scale' | 'zero_im_g0' (include/abinit_b200.h: abi_b200_xg_colwise_)."""
-    code = {"dot": 0, "norm2": 1, "cymax": 2, "scale": 3, "zero_im_g0": 4}[op]
+    code = {"dot": 0, "norm2": 1, "cymax": 2, "scale": 3, "zero_im_g0": 4, "add": 5, "apply_diag": 6}[op]
     L().abi_b200_xg_colwise_(_iref(code), _iref(space), _iref(rows), _iref(ncols), _ptr(a), _iref(lda), _ptr(b), _iref(ldb),
                              _ptr(w), _iref(ldw), _ptr(da), _ptr(out), _iref(me_g0))
 

@@ -177,7 +177,8 @@ void abi_b200_nonlop_(int* choice, int* cpopt, double* cprjin, double* enlout, a
  *               overwrite a, w(n) on the device.
  * xg_colwise  : op 0 colwiseDotProduct (out(ncols), (re,im) pairs for SPACE_C) :4550-4846; 1 colwiseNorm2 :4341-4542;
  *               2 colwiseCymax a = w - da(col) b :3301-3413; 3 per-column scale a(:,j) *= da(j) (chebfi_ampfactor);
- *               4 zero_im_g0 :5851-5898.
+ *               4 zero_im_g0 :5851-5898; 5 xgBlock_add a += b; 6 xgBlock_apply_diag a(i,:) *= da(i) (da per row: the LOBPCG
+ *               preconditioner).
  * xg_rayleigh_ritz : xg_RayleighRitz, VAR_X branch (m_xg_ortho_RR.F90:251-571); bx NULL -> overlap block is x
  *               (norm-conserving); eigenvalues may be a host or device array.
  * ---------------------------------------------------------------------------------------------------- */
@@ -185,6 +186,12 @@ void abi_b200_xg_gram_(int* space, int* rows, int* ncols_a, int* ncols_b, double
                        double* c, int* ldc, int* me_g0);
 void abi_b200_xg_rotate_(int* space, int* rows, int* k, int* ncols_out, double* x, int* ldx, double* c, int* ldc);
 void abi_b200_xg_hegvd_(int* space, int* n, double* a, int* lda, double* b, int* ldb, double* w, int* info);
+/* out(:,1:ncols_out) = a(:,1:k) c(1:k,1:ncols_out) (xgBlock_gemm 'n','n'), out may alias a; upper=1: c upper triangular
+ * (the trsm of xg_Borthonormalize, m_xg_ortho_RR.F90:135-142, with c = U^-1).  xg_chol_inverse: potrf 'u' + inverse of the
+ * factor on the m x m sub-space matrix a (xgBlock_potrf, m_xg_ortho_RR.F90:125), strictly-lower triangle zeroed. */
+void abi_b200_xg_gemm_nn_(int* space, int* rows, int* k, int* ncols_out, double* a, int* lda, double* c, int* ldc,
+                          double* out, int* ldo, int* upper);
+void abi_b200_xg_chol_inverse_(int* space, int* m, double* a, int* lda, int* info);
 void abi_b200_xg_colwise_(int* op, int* space, int* rows, int* ncols, double* a, int* lda, double* b, int* ldb,
                           double* w, int* ldw, double* da, double* out, int* me_g0);
 void abi_b200_xg_rayleigh_ritz_(int* space, int* rows, int* blockdim, double* x, int* ldx, double* ax, int* ldax,
