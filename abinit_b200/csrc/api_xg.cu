@@ -45,7 +45,7 @@ struct Buf {
   }
   void release() { if (d) cudaFree(d); d = nullptr; cap = 0; }
 };
-Buf g_cheb[5];      // AX, BX, X_next, X_prev, X (work copy)
+Buf g_cheb[6];      // AX, BX, X_next, X_prev, X (work copy), LOBPCG AllBX0
 Buf g_small[2];     // device scalars per band
 
 struct AsyncGuard {   // inner calls must not synchronise per block
@@ -329,8 +329,9 @@ void abi_b200_chebfi_core_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, do
             *lambda_plus, *ndeg_filter, d);
 }
 
-// lobpcgwf2 (src/79_seqpar_mpi/m_lobpcgwf.F90:100-250) -> lobpcg_run (src/48_diago/m_lobpcg2.F90:340-765), one block of all
-// bands (nblock_lobpcg = 1), paral_kgb = 0
+// lobpcgwf2 (src/79_seqpar_mpi/m_lobpcgwf.F90:100-250) -> lobpcg_run (src/48_diago/m_lobpcg2.F90:340-765), nblock_lobpcg
+// blocks of nband / nblock_lobpcg bands (lobpcg_orthoXwrtBlocks against the finished blocks, final Borthonormalize +
+// Rayleigh-Ritz over all bands), paral_kgb = 0
 __global__ void k_build_pcon(int npw, const double* __restrict__ kinpw, double* __restrict__ pcon, double filter) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npw) return;
@@ -348,85 +349,110 @@ void abi_b200_lobpcgwf2_(double* cg, double* eig, double* occ, double* enl_out, 
   Context& c = ctx();
   cudaStream_t st = c.stream;
   abi_b200_ham* h = *gs_hamk;
-  const int n = *nband, np = *npw;
+  const int nb_all = *nband, np = *npw, nblock = *nblock_lobpcg;
   ABI_CHECK(*nspinor == 1, "lobpcgwf2: nspinor=2 is not implemented in this build");
   ABI_CHECK(np == h->npw && h->plan != nullptr, "lobpcgwf2: npw differs from the k-point loaded in gs_hamk");
-  ABI_CHECK(*nblock_lobpcg == 1, "lobpcgwf2: only nblock_lobpcg=1 (one block of all bands) is implemented in this build");
+  ABI_CHECK(nblock >= 1 && nb_all % nblock == 0, "lobpcgwf2: nband must be a multiple of nblock_lobpcg");   // m_lobpcgwf.F90:133
   ABI_CHECK(*nbdbuf >= 0 || (*nbdbuf == -101 && occ != nullptr), "Bad value of nbdbuf");
   const bool paw = h->usepaw == 1;
   const int space = space_of(h), me_g0 = me_g0_of(h);
   AsyncGuard g;
-  const size_t blk = 2 * (size_t)np * n;
-  DevArg a_cg(10, cg, sizeof(double) * blk, true);
+  const int n = nb_all / nblock;                              // blockdim (m_lobpcgwf.F90:133)
+  const size_t col = 2 * (size_t)np;                          // doubles per band
+  const size_t blk = col * n;
+  DevArg a_cg(10, cg, sizeof(double) * col * nb_all, true);
+  double* AllX0 = a_cg.as<double>();                          // X0 of all blocks (m_lobpcg2.F90:768-782): updated block by block
+  // AX / BX of the finished blocks (lobpcg_transferAX_BX :877-900); norm-conserving: B X0 = X0
+  double* AllAX0 = nblock > 1 ? g_cheb[3].get(col * nb_all) : nullptr;
+  double* AllBX0 = nblock > 1 ? (paw ? g_cheb[5].get(col * nb_all) : AllX0) : nullptr;
   // [X | W | P], [AX | AW | AP], [BX | BW | BP] (m_lobpcg2.F90:224-268); norm-conserving: BX = X, so B blocks alias the X ones
   double* XWP = g_cheb[4].get(3 * blk);
   double* AXWP = g_cheb[0].get(3 * blk);
   double* BXWP = paw ? g_cheb[1].get(3 * blk) : nullptr;
-  CUDA_CHECK(cudaMemcpyAsync(XWP, a_cg.as<double>(), sizeof(double) * blk, cudaMemcpyDeviceToDevice, st));
   double* d_pcon = g_cheb[2].get((size_t)np + 8);
   k_build_pcon<<<ceil_div(np, 256), 256, 0, st>>>(np, h->d_kinpw, d_pcon, 1.7976931348623157e308 * 1.0e-11);
   CUDA_CHECK(cudaGetLastError());
-  double* d_eig = g_small[0].get((size_t)4 * n);           // 3n eigenvalues + n residuals
+  double* d_eig = g_small[0].get((size_t)4 * n + nb_all);    // 3n eigenvalues + n residuals of a block, nband final eigenvalues
   double* d_res = d_eig + 3 * n;
+  double* d_eig_all = d_eig + 4 * n;
   double *X = XWP, *W = XWP + blk, *AX = AXWP, *AW = AXWP + blk;
   // NC: B X = X.  The blocks the reference keeps separately (BX copy of X) are the SAME vectors, rotated identically.
   double* BX = paw ? BXWP : XWP; double* BW = paw ? BXWP + blk : W;
   double* Bblk = paw ? BXWP : XWP;
   auto getax = [&](double* src, double* a_dst, double* b_dst) { get_ax_bx(h, space, me_g0, np, n, *bandpp, src, a_dst, paw ? b_dst : nullptr); };
-  const int nband_eff = (*nbdbuf >= 0) ? n - *nbdbuf : n;
+  const int nband_eff = (*nbdbuf > 0) ? nb_all - *nbdbuf : nb_all;                  // m_lobpcg2.F90:394-398
   std::vector<double> r(n);
-  getax(X, AX, BX);
-  int info = xg_b_orthonormalize(space, np, n, X, np, paw ? BX : X, np, AX, np, me_g0, st);   // m_lobpcg2.F90:497
-  (void)info;                                                // BX == X (NC) is rotated once: the xg routines skip aliased blocks
-  info = xg_rayleigh_ritz(space, np, n, X, np, AX, np, paw ? BX : nullptr, np, d_eig, false, me_g0, st);   // VAR_X, heevd :500
-  ABI_CHECK(info == 0, "lobpcg: the sub-space eigenproblem (X) failed");
-  bool compute_residu = true;
-  double min_res = 0.0, max_res = 0.0;
-  auto residuals = [&]() {
-    xg_colwise_cymax(space, np, n, W, np, d_eig, BX, np, AX, np, st);             // lobpcg_getResidu :842-854
-    xg_colwise_norm2(space, np, n, W, np, d_res, me_g0, st);
-    xg_apply_diag(space, np, n, W, np, d_pcon, st);                               // preconditioner :513
-    CUDA_CHECK(cudaMemcpyAsync(r.data(), d_res, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    if (*nbdbuf >= 0) {
-      min_res = max_res = 0.0;
-      for (int i = 0; i < std::max(0, nband_eff); i++) { if (i == 0) min_res = max_res = r[0]; min_res = std::min(min_res, r[i]); max_res = std::max(max_res, r[i]); }
-    } else {
-      min_res = r[0]; max_res = r[0] * occ[0];
-      for (int i = 0; i < n; i++) { min_res = std::min(min_res, r[i]); max_res = std::max(max_res, r[i] * occ[i]); }
+  for (int iblock = 0; iblock < nblock; iblock++) {                                 // "big loop over blocks" :456-695
+    const int prev = iblock * n;                                                    // bands of the previous blocks
+    const double* occ_b = occ ? occ + prev : nullptr;
+    CUDA_CHECK(cudaMemcpyAsync(X, AllX0 + col * prev, sizeof(double) * blk, cudaMemcpyDeviceToDevice, st));   // lobpcg_getX0
+    if (iblock > 0) xg_ortho_wrt_blocks(space, np, prev, n, X, np, AllX0, np, AllBX0, np, me_g0, st);         // :464-469
+    getax(X, AX, BX);
+    int info = xg_b_orthonormalize(space, np, n, X, np, paw ? BX : X, np, AX, np, me_g0, st);   // :497
+    (void)info;                                              // BX == X (NC) is rotated once: the xg routines skip aliased blocks
+    info = xg_rayleigh_ritz(space, np, n, X, np, AX, np, paw ? BX : nullptr, np, d_eig, false, me_g0, st);   // VAR_X, heevd :500
+    ABI_CHECK(info == 0, "lobpcg: the sub-space eigenproblem (X) failed");
+    bool compute_residu = true;
+    double min_res = 0.0, max_res = 0.0;
+    auto residuals = [&]() {
+      xg_colwise_cymax(space, np, n, W, np, d_eig, BX, np, AX, np, st);             // lobpcg_getResidu :842-854
+      xg_colwise_norm2(space, np, n, W, np, d_res, me_g0, st);
+      xg_apply_diag(space, np, n, W, np, d_pcon, st);                               // preconditioner :513
+      CUDA_CHECK(cudaMemcpyAsync(r.data(), d_res, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      if (*nbdbuf >= 0) {                                                           // bands of this block below nband_eff :526-538
+        const int cnt = std::min(n, std::max(0, nband_eff - prev));
+        min_res = max_res = 0.0;
+        for (int i = 0; i < cnt; i++) { if (i == 0) min_res = max_res = r[0]; min_res = std::min(min_res, r[i]); max_res = std::max(max_res, r[i]); }
+      } else {
+        min_res = r[0]; max_res = r[0] * occ_b[0];
+        for (int i = 0; i < n; i++) { min_res = std::min(min_res, r[i]); max_res = std::max(max_res, r[i] * occ_b[i]); }
+      }
+    };
+    for (int iline = 1; iline <= *nline; iline++) {
+      residuals();
+      if (max_res < *tolwfr_diago) { compute_residu = false; break; }
+      if (iblock > 0) xg_ortho_wrt_blocks(space, np, prev, n, W, np, AllX0, np, AllBX0, np, me_g0, st);       // :553-555
+      getax(W, AW, BW);
+      bool use_xw = (iline == 1 || min_res < 1e-27);
+      if (!use_xw) {
+        const int ierr = xg_b_orthonormalize(space, np, 3 * n, XWP, np, Bblk, np, AXWP, np, me_g0, st);   // :569
+        if (ierr != 0) use_xw = true;                                               // "did not work, try on XW" :583
+      }
+      if (use_xw) {
+        xg_b_orthonormalize(space, np, 2 * n, XWP, np, Bblk, np, AXWP, np, me_g0, st);                   // :556
+        CUDA_CHECK(cudaMemsetAsync(XWP + 2 * blk, 0, sizeof(double) * blk, st));    // P = AP = BP = 0 :557-559
+        CUDA_CHECK(cudaMemsetAsync(AXWP + 2 * blk, 0, sizeof(double) * blk, st));
+        if (paw) CUDA_CHECK(cudaMemsetAsync(BXWP + 2 * blk, 0, sizeof(double) * blk, st));
+      }
+      info = xg_rayleigh_ritz_xwp(space, np, n, use_xw ? 2 : 3, XWP, AXWP, Bblk, np, d_eig, me_g0, st);
+      if (info != 0) { fprintf(stderr, "\n--- !WARNING\nmessage: |\n    RayleighRitz (XW/XWP) did not work, but continue anyway.\n...\n"); break; }
     }
-  };
-  for (int iline = 1; iline <= *nline; iline++) {
-    residuals();
-    if (max_res < *tolwfr_diago) { compute_residu = false; break; }
-    getax(W, AW, BW);
-    bool use_xw = (iline == 1 || min_res < 1e-27);
-    if (!use_xw) {
-      const int ierr = xg_b_orthonormalize(space, np, 3 * n, XWP, np, Bblk, np, AXWP, np, me_g0, st);   // :569
-      if (ierr != 0) use_xw = true;                                               // "did not work, try on XW" :583
+    if (compute_residu) residuals();
+    CUDA_CHECK(cudaMemcpyAsync(eig + prev, d_eig, sizeof(double) * n, cudaMemcpyDeviceToHost, st));           // :681-684
+    std::copy(r.begin(), r.end(), resid + prev);
+    CUDA_CHECK(cudaMemcpyAsync(AllX0 + col * prev, X, sizeof(double) * blk, cudaMemcpyDeviceToDevice, st));   // lobpcg_setX0
+    if (nblock > 1) {                                                                                         // lobpcg_transferAX_BX
+      CUDA_CHECK(cudaMemcpyAsync(AllAX0 + col * prev, AX, sizeof(double) * blk, cudaMemcpyDeviceToDevice, st));
+      if (paw) CUDA_CHECK(cudaMemcpyAsync(AllBX0 + col * prev, BX, sizeof(double) * blk, cudaMemcpyDeviceToDevice, st));
     }
-    if (use_xw) {
-      xg_b_orthonormalize(space, np, 2 * n, XWP, np, Bblk, np, AXWP, np, me_g0, st);                   // :556
-      CUDA_CHECK(cudaMemsetAsync(XWP + 2 * blk, 0, sizeof(double) * blk, st));    // P = AP = BP = 0 :557-559
-      CUDA_CHECK(cudaMemsetAsync(AXWP + 2 * blk, 0, sizeof(double) * blk, st));
-      if (paw) CUDA_CHECK(cudaMemsetAsync(BXWP + 2 * blk, 0, sizeof(double) * blk, st));
-    }
-    info = xg_rayleigh_ritz_xwp(space, np, n, use_xw ? 2 : 3, XWP, AXWP, Bblk, np, d_eig, me_g0, st);
-    if (info != 0) { fprintf(stderr, "\n--- !WARNING\nmessage: |\n    RayleighRitz (XW/XWP) did not work, but continue anyway.\n...\n"); break; }
+    CUDA_CHECK(cudaStreamSynchronize(st));                   // eig / r are read on the host before the next block reuses d_eig
   }
-  if (compute_residu) residuals();
-  CUDA_CHECK(cudaMemcpyAsync(eig, d_eig, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  std::copy(r.begin(), r.end(), resid);
-  CUDA_CHECK(cudaMemcpyAsync(a_cg.as<double>(), X, sizeof(double) * blk, cudaMemcpyDeviceToDevice, st));   // lobpcg_setX0
+  if (nblock > 1) {                                          // all bands once more (m_lobpcg2.F90:744-751)
+    xg_b_orthonormalize(space, np, nb_all, AllX0, np, paw ? AllBX0 : AllX0, np, AllAX0, np, me_g0, st);
+    const int info = xg_rayleigh_ritz(space, np, nb_all, AllX0, np, AllAX0, np, paw ? AllBX0 : nullptr, np, d_eig_all, false, me_g0, st);
+    ABI_CHECK(info == 0, "lobpcg: the final sub-space eigenproblem over all blocks failed");
+    CUDA_CHECK(cudaMemcpyAsync(eig, d_eig_all, sizeof(double) * nb_all, cudaMemcpyDeviceToHost, st));
+  }
   a_cg.copy_back();
   if (!paw && enl_out) {
-    double* d_enl = g_small[1].get((size_t)2 * n);
-    for (int b0 = 0; b0 < n; b0 += *bandpp) {
-      const int nd = std::min(*bandpp, n - b0);
-      gemm_nonlop_device(h->P, h->atoms, h->enl, 1, -1, 0, h->me_g0, nullptr, nd, X + 2 * (size_t)np * b0, nullptr, nullptr, nullptr, st,
+    double* d_enl = g_small[1].get((size_t)2 * nb_all);
+    for (int b0 = 0; b0 < nb_all; b0 += *bandpp) {
+      const int nd = std::min(*bandpp, nb_all - b0);
+      gemm_nonlop_device(h->P, h->atoms, h->enl, 1, -1, 0, h->me_g0, nullptr, nd, AllX0 + col * b0, nullptr, nullptr, nullptr, st,
                          nullptr, 1, d_enl + b0);
     }
-    CUDA_CHECK(cudaMemcpyAsync(enl_out, d_enl, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(enl_out, d_enl, sizeof(double) * nb_all, cudaMemcpyDeviceToHost, st));
   }
   CUDA_CHECK(cudaStreamSynchronize(st));
 }

@@ -137,6 +137,11 @@ __global__ void k_add(int nreal, double* __restrict__ X, long long ldx, const do
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreal; i += gridDim.x * blockDim.x) X[ldx * col + i] += P[ldp * col + i];
 }
 
+__global__ void k_sub(int nreal, double* __restrict__ X, long long ldx, const double* __restrict__ P, long long ldp) {
+  const int col = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreal; i += gridDim.x * blockDim.x) X[ldx * col + i] -= P[ldp * col + i];
+}
+
 __global__ void k_apply_diag(int nreal, int shift, double* __restrict__ X, long long ldx, const double* __restrict__ d) {
   const int col = blockIdx.y;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreal; i += gridDim.x * blockDim.x) X[ldx * col + i] *= d[i >> shift];
@@ -219,8 +224,9 @@ void xg_gram(int space, int rows, int ncols_a, int ncols_b, const double* A, lon
 // upper = true: C is upper triangular (the inverse Cholesky factor of xg_Borthonormalize): output columns [j0, j1) only need
 // the first j1 columns of A, which halves the flops of the trsm-equivalent product; blocks run from the last to the first so
 // that the in-place case never reads a column block it has already overwritten.
+// subtract = true: OUT -= A.C instead of OUT = A.C (xgBlock_gemm 'n','n' with alpha = -1, beta = 1).
 static void gemm_nn_impl(int space, int rows, int k, int ncols_out, const double* A, long long lda, const double* C, long long ldc,
-                         double* OUT, long long ldo, bool upper, cudaStream_t st) {
+                         double* OUT, long long ldo, bool upper, cudaStream_t st, bool subtract = false) {
   if (rows == 0 || ncols_out == 0) return;
   const int M = real_rows(space, rows);
   const long long ldar = real_ld(space, lda), ldor = real_ld(space, ldo);
@@ -242,8 +248,14 @@ static void gemm_nn_impl(int space, int rows, int k, int ncols_out, const double
       const double* Cj = C + (size_t)sc * ldc * j0;
       if (space == SPACE_C) zgemm_nn(mlen / 2, jb, kk, A + m0, lda, Cj, ldc, tmp, slab / 2, st);
       else dgemm_nn(mlen, jb, kk, A + m0, ldar, Cj, ldc, tmp, slab, st);
-      CUDA_CHECK(cudaMemcpy2DAsync(OUT + m0 + (size_t)ldor * j0, sizeof(double) * ldor, tmp, sizeof(double) * slab, sizeof(double) * mlen, jb,
-                                   cudaMemcpyDeviceToDevice, st));
+      if (subtract) {
+        k_sub<<<ew_grid(mlen, jb), 256, 0, st>>>(mlen, OUT + m0 + (size_t)ldor * j0, ldor, tmp, slab);
+        CUDA_CHECK(cudaGetLastError());
+        g_kernel_launches++;
+      } else {
+        CUDA_CHECK(cudaMemcpy2DAsync(OUT + m0 + (size_t)ldor * j0, sizeof(double) * ldor, tmp, sizeof(double) * slab, sizeof(double) * mlen, jb,
+                                     cudaMemcpyDeviceToDevice, st));
+      }
     }
   }
 }
@@ -271,6 +283,17 @@ static void gram_upper(int space, int rows, int n, const double* A, long long ld
 
 void xg_rotate(int space, int rows, int k, int ncols_out, double* X, long long ldx, const double* C, long long ldc, cudaStream_t st) {
   xg_gemm_nn(space, rows, k, ncols_out, X, ldx, C, ldc, X, ldx, st);
+}
+
+void xg_ortho_wrt_blocks(int space, int rows, int nprev, int n, double* V, long long ldv, const double* X0, long long ldx0,
+                         const double* BX0, long long ldbx0, int me_g0, cudaStream_t st) {
+  if (nprev == 0 || n == 0 || rows == 0) return;
+  const int sc = sub_cplex(space);
+  const long long ldw = (nprev + 1) & ~1LL;                              // even: K-padding of the product below
+  double* buf = g_xgws[1].get((size_t)sc * ldw * n);
+  CUDA_CHECK(cudaMemsetAsync(buf, 0, sizeof(double) * sc * ldw * n, st));
+  xg_gram(space, rows, nprev, n, BX0, ldbx0, V, ldv, buf, ldw, me_g0, st);           // buffer = BX0^H var   (m_lobpcg2.F90:829)
+  gemm_nn_impl(space, rows, nprev, n, X0, ldx0, buf, ldw, V, ldv, false, st, true);  // var = var - X0 buffer (:833)
 }
 
 void xg_add(int space, int rows, int ncols, double* X, long long ldx, const double* P, long long ldp, cudaStream_t st) {

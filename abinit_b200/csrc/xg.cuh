@@ -32,6 +32,9 @@ void xg_gemm_nn_upper(int space, int rows, int k, int ncols_out, const double* A
 // A(m x m, upper triangle of a Hermitian positive matrix) -> U^-1 with A = U^H U (potrf 'u' + trtri, strictly-lower part zeroed);
 // sub_space: SPACE_R or SPACE_C.  Returns potrf's info.
 int xg_chol_inverse(int sub_space, int m, double* A, long long lda, cudaStream_t st);
+// lobpcg_orthoXwrtBlocks (src/48_diago/m_lobpcg2.F90:803-840): V(:, 0:n) -= X0(:, 0:nprev) . (BX0^H V), in place
+void xg_ortho_wrt_blocks(int space, int rows, int nprev, int n, double* V, long long ldv, const double* X0, long long ldx0,
+                         const double* BX0, long long ldbx0, int me_g0, cudaStream_t st);
 // X += P (xgBlock_add)
 void xg_add(int space, int rows, int ncols, double* X, long long ldx, const double* P, long long ldp, cudaStream_t st);
 // X(i, j) *= d(i), d real per (complex) row (xgBlock_apply_diag with a SPACE_R diagonal: the LOBPCG preconditioner)

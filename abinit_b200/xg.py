@@ -109,9 +109,9 @@ def chebfi_core(gs_hamk: Hamiltonian, ncols, bandpp, x, ax, bx, x_next, x_prev, 
 def lobpcgwf2(cg, eig, occ, enl_out, gs_hamk: Hamiltonian, nband, npw, nspinor, resid, tolwfr_diago, nline, nblock_lobpcg=1,
               nbdbuf=0, bandpp=None, prtvol=0):
     """lobpcgwf2(cg, dtset, eig, occ, enl_out, gs_hamk, ..., nband, npw, nspinor, prtvol, resid, nbdbuf): one LOBPCG call on the
-    nband wavefunctions (one block); arguments as chebfiwf2."""
+    nband wavefunctions in nblock_lobpcg blocks of nband / nblock_lobpcg bands (m_lobpcgwf.F90:133); arguments as chebfiwf2."""
     hp = C.c_void_p(gs_hamk.h)
-    bp = int(nband if bandpp is None else bandpp)
+    bp = int(nband // nblock_lobpcg if bandpp is None else bandpp)
     L().abi_b200_lobpcgwf2_(_ptr(cg, _F, "cg"), _ptr(eig, _F, "eig"), _ptr(occ, _F, "occ"), _ptr(enl_out, _F, "enl_out"),
                             C.byref(hp), _iref(nband), _iref(npw), _iref(nspinor), _iref(prtvol), _ptr(resid, _F, "resid"),
                             _dref(tolwfr_diago), _iref(nline), _iref(nblock_lobpcg), _iref(nbdbuf), _iref(bp))

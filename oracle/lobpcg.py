@@ -1,5 +1,5 @@
-"""LOBPCG (oracle; test infrastructure only): restates src/48_diago/m_lobpcg2.F90:340-765 (lobpcg_run) for ONE block
-(blockdim = neigenpairs, paral_kgb = 0) as driven by src/79_seqpar_mpi/m_lobpcgwf.F90:100-250, with
+"""LOBPCG (oracle; test infrastructure only): restates src/48_diago/m_lobpcg2.F90:340-765 (lobpcg_run), one or several
+blocks (blockdim = neigenpairs / nblock, lobpcg_orthoXwrtBlocks :803-840, final RR on all bands :744-751), paral_kgb = 0, as driven by src/79_seqpar_mpi/m_lobpcgwf.F90:100-250, with
   xg_Borthonormalize            src/45_xgTools/m_xg_ortho_RR.F90:86-150   (X^H B X = U^H U, X <- X U^-1, also BX, AX)
   xg_RayleighRitz VAR_X/XW/XWP  src/45_xgTools/m_xg_ortho_RR.F90:251-571
   build_pcon                    src/79_seqpar_mpi/m_lobpcgwf.F90:316-334
@@ -55,8 +55,44 @@ def rayleigh_ritz_xwp(space, me_g0, n, xwp, axwp, bxwp, nvar):
     return w
 
 
-def lobpcg_run(apply_h, x0, pcon, space, me_g0, nline, tolerance=1e-20, nbdbuf=0, occ=None, info=None):
-    """One block of all bands.  Returns (eigenvalues, residuals, X)."""
+def ortho_x_wrt_blocks(space, var, x0_prev, bx0_prev, me_g0):
+    """lobpcg_orthoXwrtBlocks (m_lobpcg2.F90:803-840): var <- var - X0 (BX0^H var) with the previous blocks, in place
+    (band-major blocks: rows are bands)."""
+    buf = xg.gram(space, bx0_prev, var, me_g0)                  # (nprev, n) = BX0^H var  (xgBlock_gemm 't','n')
+    var -= buf.T @ x0_prev                                      # var(:, j) -= sum_i X0(:, i) buf(i, j)
+
+
+def lobpcg_run(apply_h, x0, pcon, space, me_g0, nline, tolerance=1e-20, nbdbuf=0, occ=None, info=None, nblock=1):
+    """lobpcg_run (m_lobpcg2.F90:340-765), paral_kgb = 0, blocks of blockdim = nband / nblock bands.  Returns
+    (eigenvalues, residuals, X) for all bands."""
+    nband, npw = x0.shape
+    assert nband % nblock == 0
+    n = nband // nblock
+    all_x0 = np.array(x0, dtype=np.complex128)
+    all_ax0 = np.zeros_like(all_x0); all_bx0 = np.zeros_like(all_x0)
+    eig_all = np.zeros(nband); resid_all = np.zeros(nband)
+    lines = []
+    for iblock in range(nblock):
+        sl = slice(iblock * n, (iblock + 1) * n)
+        sub = {}
+        e, r, x, ax, bx = _lobpcg_block(apply_h, all_x0[sl], pcon, space, me_g0, nline, tolerance, nbdbuf,
+                                        None if occ is None else occ[sl], sub, iblock, nband,
+                                        all_x0[:iblock * n], all_bx0[:iblock * n])
+        eig_all[sl] = e; resid_all[sl] = r
+        all_x0[sl] = x                                           # lobpcg_setX0
+        all_ax0[sl] = ax; all_bx0[sl] = bx                       # lobpcg_transferAX_BX
+        lines.append(sub["nline_done"])
+    if nblock > 1:                                               # m_lobpcg2.F90:744-751
+        b_orthonormalize(space, all_x0, all_bx0, all_ax0, me_g0)
+        w, xr, _, _, _ = xg.rayleigh_ritz(space, all_x0, all_ax0, all_bx0, me_g0, solve_ax_bx=False)
+        all_x0 = xr; eig_all = w.copy()
+    if info is not None:
+        info.update(nline_done=lines[0] if nblock == 1 else lines)
+    return eig_all, resid_all, all_x0
+
+
+def _lobpcg_block(apply_h, x0, pcon, space, me_g0, nline, tolerance, nbdbuf, occ, info, iblock, nband, x0_prev, bx0_prev):
+    """One block of the big loop over blocks (m_lobpcg2.F90:456-695).  Returns (eig, resid, X, AX, BX)."""
     n, npw = x0.shape
     xwp = np.zeros((3 * n, npw), dtype=np.complex128); axwp = np.zeros_like(xwp); bxwp = np.zeros_like(xwp)
     xwp[:n] = x0
@@ -68,7 +104,10 @@ def lobpcg_run(apply_h, x0, pcon, space, me_g0, nline, tolerance=1e-20, nbdbuf=0
         a, b = apply_h(src)
         a_dst[...] = a; b_dst[...] = b
         xg.zero_im_g0(space, a_dst, me_g0); xg.zero_im_g0(space, b_dst, me_g0)
-    nband_eff = n - nbdbuf if nbdbuf >= 0 else n
+    nband_eff = nband - nbdbuf if nbdbuf > 0 else nband         # m_lobpcg2.F90:394-398 (counted over ALL bands)
+    iband_min = n * iblock                                       # 0-based first band of this block
+    if iblock > 0:
+        ortho_x_wrt_blocks(space, X, x0_prev, bx0_prev, me_g0)   # :464-469
     get_ax_bx(X, AX, BX)
     b_orthonormalize(space, X, BX, AX, me_g0)
     w, xr, axr, bxr, _ = xg.rayleigh_ritz(space, X, AX, BX, me_g0, solve_ax_bx=False)      # VAR_X, heevd
@@ -83,7 +122,7 @@ def lobpcg_run(apply_h, x0, pcon, space, me_g0, nline, tolerance=1e-20, nbdbuf=0
         r = xg.colwise_norm2(space, W, me_g0)
         W[...] = W * pcon[None, :]                               # xgBlock_apply_diag(W, pcond)
         if nbdbuf >= 0:
-            eff = r[:max(nband_eff, 0)]
+            eff = r[:min(n, max(nband_eff - iband_min, 0))]      # bands of this block below nband_eff (:526-538)
             mn, mx = (float(eff.min()), float(eff.max())) if eff.size else (0.0, 0.0)
         elif nbdbuf == -101:
             mn = float(r.min()); mx = float((r * occ).max())
@@ -95,6 +134,8 @@ def lobpcg_run(apply_h, x0, pcon, space, me_g0, nline, tolerance=1e-20, nbdbuf=0
         if max_res < tolerance:
             compute_residu = False
             break
+        if iblock > 0:
+            ortho_x_wrt_blocks(space, W, x0_prev, bx0_prev, me_g0)   # :553-555
         get_ax_bx(W, AW, BW)
         if iline == 1 or min_res < 1e-27:
             b_orthonormalize(space, xwp[:2 * n], bxwp[:2 * n], axwp[:2 * n], me_g0)
@@ -114,4 +155,4 @@ def lobpcg_run(apply_h, x0, pcon, space, me_g0, nline, tolerance=1e-20, nbdbuf=0
         resid, _, _ = residuals()
     if info is not None:
         info.update(nline_done=nline_done)
-    return eig, resid, X.copy()
+    return eig, resid, X.copy(), AX.copy(), BX.copy()

@@ -156,3 +156,24 @@ def test_oracle_lobpcg_reaches_reference_eigenvalues(si2):
     assert np.max(resid[:5]) < 1e-14
     assert np.max(np.abs(w[:5] - np.array(R["eig_k1"]))) < 2e-5
     assert np.max(np.abs(xg.gram(xg.SPACE_C, x, x, -1) - np.eye(nband))) < 1e-12
+
+
+@pytest.mark.parametrize("nblock", [2, 4])
+def test_oracle_lobpcg_multiblock_reaches_reference_eigenvalues(si2, nblock):
+    """Several blocks (blockdim = nband / nblock, m_lobpcg2.F90:456-695 with lobpcg_orthoXwrtBlocks and the final
+    Rayleigh-Ritz over all bands :744-751): same dense eigenvalues / printed tbase3_1 eigenvalues as the one-block run."""
+    from oracle import lobpcg
+    s, vloc, res = si2
+    ah = scf.apply_h_oracle(s)
+    ik = 0
+    npw = s.kg[ik].shape[1]
+    rng = np.random.default_rng(3)
+    nband = 8
+    x = (rng.standard_normal((nband, npw)) + 1j * rng.standard_normal((nband, npw))) / (1.0 + s.kinpw[ik])[None, :]
+    apply_h = lambda c: (ah(ik, vloc, c), c.copy())
+    pcon = lobpcg.build_pcon(s.kinpw[ik])
+    for it in range(10):
+        w, resid, x = lobpcg.lobpcg_run(apply_h, x, pcon, xg.SPACE_C, -1, nline=4, nblock=nblock)
+    assert np.max(np.abs(w[:5] - res["eig"][ik][:5])) < 1e-10
+    assert np.max(np.abs(w[:5] - np.array(R["eig_k1"]))) < 2e-5
+    assert np.max(np.abs(xg.gram(xg.SPACE_C, x, x, -1) - np.eye(nband))) < 1e-12
