@@ -83,6 +83,7 @@ void abi_b200_fourwf_set_tuning(const char* name, int value) {
   else if (k == "nonlop_ozaki") ozaki_set_enabled(value);     // EXPERIMENTAL int8-sliced gemm_nonlop (ozaki.cu), default off
   else if (k == "pipe_chunks") ctx().pipe_chunks = std::max(1, value);
   else if (k == "plane_ctas_per_sm") t.plane_ctas_per_sm = value;
+  else if (k == "plane_split") t.plane_split = value;
   else if (k == "cluster") t.cluster = value;
   else if (k == "lines_x") t.lines_x = value;
   else if (k == "smem_kb_mid") t.smem_kb_mid = value;

@@ -297,7 +297,8 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
     pl->d_u_i3 = to_device(u_i3, pl->owned);
     pl->d_u_flags = to_device(u_flags, pl->owned);
 
-    bool plane_ok = (n2 == n3) && plane_stage_supported(n2) && n2 < 32768;
+    // n2 == n3: fused plane kernel; n2 != n3 (both lengths in the two-pass table): the split plane stage (plane_stage.cuh)
+    bool plane_ok = plane_stage_supported(n2) && plane_stage_supported(n3) && n2 < 32768 && n3 < 32768;
     // at most two contiguous runs of a sorted index list: {a, la, b, lb}; false if it needs more
     auto two_runs = [](const std::vector<int>& r, int out[4]) {
       out[0] = out[1] = out[2] = out[3] = 0;
@@ -900,7 +901,8 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
   const int ntrans = pack2 ? (ndat + 1) / 2 : ndat;       // transforms to run
 
   // ---- band chunking bounds the workspace (W1, W1', scratch) ----
-  const size_t per_band = sizeof(double2) * (size_t)n1 * ((size_t)pl.nlin + nlout_eff);
+  const bool split_plane = pl.plane_ok && tune.plane && (n2 != n3 || tune.plane_split);          // S planes of the chunk live in global memory
+  const size_t per_band = sizeof(double2) * (size_t)n1 * ((size_t)pl.nlin + nlout_eff + (split_plane ? (size_t)pl.nU * n2 : 0));
   int chunk = tune.band_chunk > 0 ? tune.band_chunk : (int)std::max<size_t>(1, ((size_t)3 << 30) / per_band);
   chunk = std::min(chunk, ntrans);
   double2* W1 = (double2*)g_ws[1].get(sizeof(double2) * (size_t)n1 * pl.nlin * chunk);
@@ -944,10 +946,10 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
       PlaneParams Q;
       Q.n1 = n1; Q.n2 = n2; Q.n3 = n3; Q.nb = nb; Q.nU = pl.nU; Q.cplex = v.cplex; Q.za = pl.za; Q.zla = pl.zla; Q.zb = pl.zb; Q.zlb = pl.zlb;
       Q.nlin = pl.nlin; Q.nlout = nlout_eff; Q.nunits = (long long)nb * n1;
-      Q.W1 = W1; Q.W1o = W1o; Q.S = nullptr; Q.vT = v.d_vT; Q.tw = t2.plan.tw;
+      Q.W1 = W1; Q.W1o = W1o; Q.S = nullptr; Q.vT = v.d_vT; Q.tw = t2.plan.tw; Q.tw3 = t3.plan.tw;
       Q.in_start = pl.d_pin_start; Q.in_runs = pl.d_pin_runs;
       Q.out_start = pack2 ? pl.d_pin_start : pl.d_pout_start; Q.out_runs = pack2 ? pl.d_pin_runs : pl.d_pout_runs;
-      plane_stage_launch(n2, Q, st);
+      plane_stage_launch(Q, st);
     } else
     { ProfScope ps("fourwf_plane_cluster");
 #ifdef ABI_EMU
@@ -980,7 +982,7 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
                  d_fofgout + (size_t)b0 * pl.npw_out, t1.plan, pl.d_out_ent, pl.d_lout_estart, pl.nlout, lx, pl.npw_out,
                  xnorm, zero_im, e, kin_filter);
     } }
-    g_kernel_launches += 3;
+    g_kernel_launches += split_plane ? 5 : 3;
   }
 }
 
@@ -1024,7 +1026,7 @@ __global__ void k_rho_untranspose_add(const double* __restrict__ rhoT, double* _
 }
 
 bool fourwf_fused_opt1_available(const FourwfPlan& pl) {
-  return pl.fused_ok && pl.plane_ok && fourwf_tuning().plane && plane_stage_supported(pl.n2) && pl.n2 == pl.n3;
+  return pl.fused_ok && pl.plane_ok && fourwf_tuning().plane && plane_stage_supported(pl.n2) && plane_stage_supported(pl.n3);
 }
 
 void fourwf_fused_opt1(const FourwfPlan& pl, const double2* d_fofgin, double* d_denpot, int ndat, const double* d_wr,
@@ -1034,10 +1036,11 @@ void fourwf_fused_opt1(const FourwfPlan& pl, const double2* d_fofgin, double* d_
   const size_t N = (size_t)n1 * n2 * n3;
   const FftTables& t1 = fft_tables(n1);
   const FftTables& t2 = fft_tables(n2);
+  const FftTables& t3 = fft_tables(n3);
   FourwfTuning& tune = fourwf_tuning();
   const bool pack2 = tune.pack2 && pl.istwf_k == 2 && ndat >= 2;
   const int ntrans = pack2 ? (ndat + 1) / 2 : ndat;
-  const size_t per_band = sizeof(double2) * (size_t)n1 * pl.nlin;
+  const size_t per_band = sizeof(double2) * (size_t)n1 * ((size_t)pl.nlin + (n2 != n3 ? (size_t)pl.nU * n2 : 0));
   int chunk = tune.band_chunk > 0 ? tune.band_chunk : (int)std::max<size_t>(1, ((size_t)3 << 30) / per_band);
   chunk = std::min(chunk, ntrans);
   double2* W1 = (double2*)g_ws[1].get(sizeof(double2) * (size_t)n1 * pl.nlin * chunk);
@@ -1063,11 +1066,11 @@ void fourwf_fused_opt1(const FourwfPlan& pl, const double2* d_fofgin, double* d_
     PlaneParams Q;
     Q.n1 = n1; Q.n2 = n2; Q.n3 = n3; Q.nb = nb; Q.nU = pl.nU; Q.cplex = 1; Q.za = pl.za; Q.zla = pl.zla; Q.zb = pl.zb; Q.zlb = pl.zlb;
     Q.nlin = pl.nlin; Q.nlout = pl.nlin; Q.nunits = (long long)nb * n1;
-    Q.W1 = W1; Q.W1o = nullptr; Q.S = nullptr; Q.vT = nullptr; Q.tw = t2.plan.tw;
+    Q.W1 = W1; Q.W1o = nullptr; Q.S = nullptr; Q.vT = nullptr; Q.tw = t2.plan.tw; Q.tw3 = t3.plan.tw;
     Q.in_start = pl.d_pin_start; Q.in_runs = pl.d_pin_runs; Q.out_start = pl.d_pin_start; Q.out_runs = pl.d_pin_runs;
     Q.rhoT = rhoT; Q.wxy = wxy;
-    plane_stage_launch_rho(n2, Q, st); }
-    g_kernel_launches += 3;
+    plane_stage_launch_rho(Q, st); }
+    g_kernel_launches += (n2 != n3) ? 4 : 3;
   }
 #ifndef ABI_EMU
   k_rho_untranspose_add<<<dim3(ceil_div(n1, 32), ceil_div(n2, 32), n3), dim3(32, 8), 0, st>>>(rhoT, d_denpot, n1, n2, n3);

@@ -61,7 +61,8 @@ struct PlaneParams {
   const double2* W1; double2* W1o;  // [b][i1][line]
   double2* S;                       // [gridDim.x][nU][n2] L2 scratch
   const double* vT;                 // V_loc as [i1][i3][i2] (cplex doubles per point)
-  const double2* tw;                // exp(-2 pi i j / n), n = n2 = n3
+  const double2* tw;                // exp(-2 pi i j / n2)
+  const double2* tw3 = nullptr;     // exp(-2 pi i j / n3) (split path, n2 != n3)
   // per occupied plane u: the rows of W1 / W1o hold i2 in [a, a+la) then [b, b+lb), starting at line start[u];
   // runs[u] = {a, la, b, lb}
   const int* in_start; const short4* in_runs;
@@ -393,12 +394,62 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS >= 16 ? 1 : 2)) k_fw_plane_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Split plane stage for n2 != n3 (non-cubic boxes): the same phases as three kernels, each templated on ONE length, with the
+// S planes of all (band, i1) units of the chunk in global memory (S[unit][nU][n2]) between them.  Costs two more round
+// trips of S than the fused kernel but keeps every transform in registers; kind: 0 = y, 1 = z (* V_loc), 2 = y^-1,
+// 3 = z + density accumulation (option 1).
+// ---------------------------------------------------------------------------------------------------------
+template <int R1, int R2, int G, int WARPS, int KIND>
+__global__ void __launch_bounds__(WARPS * 32, 2) k_fw_plane_split(PlaneParams P) {
+  using F = PlaneFft<R1, R2, G>;
+  ABI_DYN_SMEM(double2, sm);
+  double2* tw = sm;                                    // N entries of the length this kernel transforms
+  const double2* twg = (KIND == 1 || KIND == 3) ? P.tw3 : P.tw;
+#ifdef ABI_EMU
+  const int warp = 0, nwarps = 1;
+  for (int j = 0; j < F::N; j++) tw[j] = twg[j];
+#else
+  const int warp = threadIdx.x >> 5, nwarps = WARPS;
+  for (int j = threadIdx.x; j < F::N; j += WARPS * 32) tw[j] = twg[j];
+#endif
+  int* zoff = reinterpret_cast<int*>(sm + F::N);
+  if (KIND == 1 || KIND == 3) {
+#ifdef ABI_EMU
+    for (int i3 = 0; i3 < F::N; i3++) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
+#else
+    for (int i3 = threadIdx.x; i3 < F::N; i3 += WARPS * 32) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
+#endif
+  }
+  double2* E = sm + F::N + F::ZOFF + (size_t)warp * F::ESIZE;
+  __syncthreads();
+  for (long long unit = blockIdx.x; unit < P.nunits; unit += gridDim.x) {
+    const int i1 = (int)(unit / P.nb), b = (int)(unit - (long long)i1 * P.nb);
+    double2* S = P.S + (size_t)unit * P.nU * P.n2;
+    if (KIND == 0) {
+      const double2* w1 = P.W1 + ((size_t)b * P.n1 + i1) * P.nlin;
+      for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_y(P, w1, S, E, tw, u0);
+    } else if (KIND == 1) {
+      const double* vplane = P.vT + (size_t)P.cplex * i1 * P.n3 * P.n2;
+      for (int c0 = warp * G; c0 < P.n2; c0 += nwarps * G) F::phase_z(P, S, vplane, E, tw, zoff, c0);
+    } else if (KIND == 2) {
+      double2* w1o = P.W1o + ((size_t)b * P.n1 + i1) * P.nlout;
+      for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_yinv(P, S, w1o, E, tw, u0);
+    } else {
+      double* rplane = P.rhoT + (size_t)i1 * P.n3 * P.n2;
+      const double2 wxy = P.wxy[b];
+      for (int c0 = warp * G; c0 < P.n2; c0 += nwarps * G) F::phase_z_rho(P, S, rplane, wxy, E, tw, zoff, c0);
+    }
+  }
+}
+
 // host interface (plane_stage.cu)
 bool plane_stage_supported(int n);
-// launches the plane stage for n2 == n3 == n; P.S may be null on entry: the launcher sizes and provides the L2 scratch
-void plane_stage_launch(int n, PlaneParams& P, cudaStream_t st);
-// same for option 1 (P.rhoT / P.wxy set): launches k_fw_plane_rho
-void plane_stage_launch_rho(int n, PlaneParams& P, cudaStream_t st);
+// launches the plane stage for the (n2, n3) of P; P.S is provided by the launcher: the per-CTA L2 scratch of the fused kernel
+// when n2 == n3, the S planes of all units (global memory) and the three split kernels otherwise
+void plane_stage_launch(PlaneParams& P, cudaStream_t st);
+// same for option 1 (P.rhoT / P.wxy set): k_fw_plane_rho, or the y and z+density kernels of the split path
+void plane_stage_launch_rho(PlaneParams& P, cudaStream_t st);
 void plane_stage_release();
 
 }  // namespace abi

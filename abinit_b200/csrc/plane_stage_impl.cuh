@@ -60,6 +60,35 @@ void launch_cfg_rho(PlaneParams& P, cudaStream_t st) {
 template <int R1, int R2>
 void plane_launch_rho_n(PlaneParams& P, cudaStream_t st) { launch_cfg_rho<R1, R2, 4, 8>(P, st); }
 
+// one kernel of the split path (n2 != n3); P.S is already set by plane_stage_launch*
+template <int R1, int R2, int KIND>
+void launch_split_kind(PlaneParams& P, cudaStream_t st) {
+  constexpr int G = 4, WARPS = 8;
+  using F = PlaneFft<R1, R2, G>;
+  auto kern = k_fw_plane_split<R1, R2, G, WARPS, KIND>;
+  const size_t smem = sizeof(double2) * ((size_t)F::N + F::ZOFF + (size_t)WARPS * F::ESIZE);
+  int cps = 1;
+#ifndef ABI_EMU
+  static bool attr_done = false;
+  if (!attr_done) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, WARPS * 32, smem));
+  ABI_CHECK(cps >= 1, "plane stage: kernel does not fit on an SM");
+#endif
+  long long grid = std::min<long long>(P.nunits, (long long)kNumSM * cps);
+#ifdef ABI_EMU
+  grid = std::min<long long>(grid, 3);
+#endif
+  ABI_LAUNCH(kern, dim3((unsigned)grid), dim3(WARPS * 32), smem, st, P);
+}
+
+template <int R1, int R2>
+void plane_launch_split_n(int kind, PlaneParams& P, cudaStream_t st) {
+  if (kind == 0) launch_split_kind<R1, R2, 0>(P, st);
+  else if (kind == 1) launch_split_kind<R1, R2, 1>(P, st);
+  else if (kind == 2) launch_split_kind<R1, R2, 2>(P, st);
+  else launch_split_kind<R1, R2, 3>(P, st);
+}
+
 template <int R1, int R2>
 void plane_launch_n(PlaneParams& P, cudaStream_t st) {
   const int cfg = fourwf_tuning().plane_cfg;

@@ -101,6 +101,64 @@ def test_option2_plane_stage_complex_potential_many_bands(lib):
     assert _run(lib, p, 2, 2) < TOL
 
 
+def _split_problem(n1, n2, n3, kpt, istwf_k, ndat, cplex=1):
+    """Orthorhombic cell whose boxcut-2 box is (n1, n2, n3) with n2 != n3: the split plane stage (three kernels, S in HBM)."""
+    L = 10.0
+    gmax = n2 / 4.0 - 0.75
+    ecut = 0.5 * (gmax * 2 * np.pi / L) ** 2
+    return make_problem(ecut, (L * n1 / n2, L, L * n3 / n2), kpt, istwf_k, ndat=ndat, ngfft=(n1, n2, n3), cplex=cplex)
+
+
+@pytest.mark.parametrize("istwf_k,kpt,ndat", [(1, (.1, .2, .3), 3), (2, (0, 0, 0), 5), (2, (0, 0, 0), 4), (3, (.5, 0, 0), 2),
+                                               (6, (0, .5, 0), 2), (9, (.5, .5, .5), 3)])
+@pytest.mark.parametrize("ngfft", [(45, 48, 60), (36, 60, 40), (30, 72, 96)])
+def test_option2_split_plane_stage_non_cubic(lib, ngfft, istwf_k, kpt, ndat):
+    """n2 != n3 with both lengths in the two-pass table: y / z / y^-1 as three register-resident kernels (plane_stage.cuh,
+    k_fw_plane_split) instead of the cluster kernel; all time-reversal spheres, packed Gamma pairs (odd and even ndat)."""
+    p = _split_problem(*ngfft, kpt, istwf_k, ndat)
+    from abinit_b200 import api
+    api.profile_enable(True)
+    try:
+        assert _run(lib, p, 2, 2) < TOL
+        prof = api.profile_collect()
+    finally:
+        api.profile_enable(False)
+    assert "fourwf_plane_stage" in prof and "fourwf_plane_cluster" not in prof     # the split path really ran
+    api.set_tuning("plane", 0)                      # same box through the cluster/L2 plane kernel
+    try:
+        assert _run(lib, p, 2, 2) < TOL
+    finally:
+        api.set_tuning("plane", 1)
+
+
+def test_option2_split_plane_stage_complex_potential(lib):
+    p = _split_problem(40, 50, 64, (.1, .2, .3), 1, ndat=5, cplex=2)
+    assert _run(lib, p, 2, 2) < TOL
+
+
+@pytest.mark.parametrize("istwf_k,kpt,ndat", [(1, (.1, .2, .3), 3), (2, (0, 0, 0), 5), (2, (0, 0, 0), 1), (9, (.5, .5, .5), 2)])
+def test_option1_split_plane_stage_density(lib, istwf_k, kpt, ndat):
+    """fourwf option 1 on a non-cubic box: y kernel + z-with-density-reduction kernel of the split plane stage."""
+    p = _split_problem(45, 48, 60, kpt, istwf_k, ndat)
+    n1, n2, n3 = p.ngfft
+    rng = np.random.default_rng(12)
+    wr = rng.uniform(0.1, 2.0, ndat); wi = rng.uniform(0.1, 2.0, ndat)
+    den0 = np.ascontiguousarray(np.abs(p.vlocal.real))
+    _, _, ref = ofw.fourwf(1, den0.copy(), p.cwavef, None, p.kg, p.kg, p.ngfft, 1, p.istwf_k, weight_r=wr, weight_i=wi)
+    from abinit_b200 import api
+    for impl in (0, 1):
+        den = den0.copy()
+        api.profile_enable(True)
+        try:
+            lib.fourwf(1, den, p.cwavef, None, None, None, None, p.istwf_k, p.kgF, p.kgF, max(p.ngfft), None, ndat, p.ngfft, p.npw,
+                       p.npw, n1, n2, n3, 1, weight_array_r=wr, weight_array_i=wi, impl=impl)
+            prof = api.profile_collect()
+        finally:
+            api.profile_enable(False)
+        assert np.max(np.abs(den - ref)) < 1e-11 * np.max(np.abs(ref)), impl
+        assert ("fourwf_plane_rho" in prof) == (impl == 0)       # impl 0: fused path (y kernel + z-with-density kernel)
+
+
 @pytest.mark.parametrize("ndat", [1, 5, 16])
 def test_option2_ndat_and_clusters(lib, ndat, monkeypatch):
     p = make_problem(8.0, 10.0, (0, 0, 0), 1, ndat=ndat)

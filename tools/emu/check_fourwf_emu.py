@@ -48,6 +48,15 @@ if __name__ == "__main__":
     run(5.0, 8., (.5, .5, .5), 9, 2, 1, 2, 2, ng=(32, 36, 36))
     run(5.0, 8., (.1, 0, .3), 1, 2, 2, 2, 2, ng=(25, 40, 40))
     run(7.0, 9., (0, .5, 0), 6, 1, 1, 2, 2, ng=(45, 45, 45))
+    # split plane stage (n2 != n3, both in the two-pass table): generic k, packed Gamma, complex V, k=1/2 spheres, option 1
+    run(5.0, 8., (.1, .2, .3), 1, 2, 1, 2, 2, ng=(24, 30, 36))
+    run(5.0, 8., (0, 0, 0), 2, 3, 1, 2, 2, ng=(27, 36, 30))
+    run(5.0, (7., 8., 9.), (.1, 0, .3), 1, 2, 2, 2, 2, ng=(25, 40, 48))
+    run(5.0, 8., (.5, .5, .5), 9, 2, 1, 2, 2, ng=(32, 36, 40))
+    # option 1 (the emulation runs blockDim = 1, so k_rho_weights only fills transform 0: one transform per call here)
+    run(5.0, 8., (.1, .2, .3), 1, 1, 1, 1, 2, ng=(24, 30, 36))
+    run(5.0, 8., (0, 0, 0), 2, 2, 1, 1, 2, ng=(27, 36, 30))
+    run(5.0, 8., (.5, .5, .5), 9, 1, 1, 1, 2, ng=(32, 36, 40))
     run(3.0, 7., (.1, .2, .3), 1, 1, 1, 2, 2, ng=(20, 60, 60))
     for option in (0, 1, 3):
         run(6.0, 8.0, (.1, .2, .3), 1, 2, 1, option, 0)
