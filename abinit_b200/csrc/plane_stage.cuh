@@ -91,9 +91,20 @@ struct PlaneFft {
   static constexpr int ZK = (G >= 8) ? R2 * G : ((R2 * G) % 8 == 4 ? R2 * G : R2 * G + 4);
   static constexpr int ESIZE = (G * YL > R1 * ZK) ? G * YL : R1 * ZK;      // double2 per warp
   static constexpr int ZOFF = (N * 4 + 15) / 16;                           // double2 slots of the i3 -> plane offset table
-
-  ABI_DEV static double2 twf(const double2* tw, int idx, double2 v) { return cmulc(v, tw[idx]); }   // * e^{+2 pi i idx/n}
-  ABI_DEV static double2 twb(const double2* tw, int idx, double2 v) { return cmul(v, tw[idx]); }    // * e^{-2 pi i idx/n}
+  // Inter-pass twiddles w^(j k1), w = exp(-2 pi i / n), as TWO shared-memory tables so that a warp's lanes always read
+  // consecutive 16-byte words (no bank conflicts, offsets are compile-time immediates, no index multiply):
+  //   twA[k1 * R2 + j]  -- forward steps: lanes run over j at a fixed k1 per instruction
+  //   twB[j * R1 + k1]  -- inverse steps: lanes run over k1 at a fixed j per instruction
+  static constexpr int TWSIZE = 2 * N;                                     // double2 slots of both tables
+  ABI_DEV static void load_tw(double2* tws, const double2* __restrict__ twg, int tid, int nthr) {
+    for (int q = tid; q < N; q += nthr) {
+      const int k1 = q / R2, j = q - k1 * R2;
+      const double2 w = twg[j * k1];
+      tws[q] = w; tws[N + j * R1 + k1] = w;
+    }
+  }
+  ABI_DEV static double2 twf(const double2* tw, int k1, int j, double2 v) { return cmulc(v, tw[k1 * R2 + j]); }     // * e^{+2 pi i j k1/n}
+  ABI_DEV static double2 twb(const double2* tw, int k1, int j, double2 v) { return cmul(v, tw[N + j * R1 + k1]); }  // * e^{-2 pi i j k1/n}
 
   // ---------------- phase Y: compact disc rows of W1 -> S[u][i2] ----------------
   ABI_DEV static void phase_y(const PlaneParams& P, const double2* __restrict__ w1, double2* __restrict__ S, double2* E,
@@ -118,7 +129,7 @@ struct PlaneFft {
           double2* e = E + line * YL + j;
           e[0] = x[0];
 #pragma unroll
-          for (int k1 = 1; k1 < R1; k1++) e[k1 * YK] = twf(tw, j * k1, x[k1]);
+          for (int k1 = 1; k1 < R1; k1++) e[k1 * YK] = twf(tw, k1, j, x[k1]);
         }
       }
     }
@@ -167,7 +178,7 @@ struct PlaneFft {
           double2* e = E + j * G + line;
           e[0] = x[0];
 #pragma unroll
-          for (int k1 = 1; k1 < R1; k1++) e[k1 * ZK] = twf(tw, j * k1, x[k1]);
+          for (int k1 = 1; k1 < R1; k1++) e[k1 * ZK] = twf(tw, k1, j, x[k1]);
         }
       }
     }
@@ -203,7 +214,7 @@ struct PlaneFft {
           Dft<R2, -1>::run(v);
           e[0] = v[0];
 #pragma unroll
-          for (int j = 1; j < R2; j++) e[j * G] = twb(tw, j * k1, v[j]);
+          for (int j = 1; j < R2; j++) e[j * G] = twb(tw, k1, j, v[j]);
         }
       }
     }
@@ -253,7 +264,7 @@ struct PlaneFft {
           double2* e = E + j * G + line;
           e[0] = x[0];
 #pragma unroll
-          for (int k1 = 1; k1 < R1; k1++) e[k1 * ZK] = twf(tw, j * k1, x[k1]);
+          for (int k1 = 1; k1 < R1; k1++) e[k1 * ZK] = twf(tw, k1, j, x[k1]);
         }
       }
     }
@@ -294,7 +305,7 @@ struct PlaneFft {
           double2* e = E + line * YL + k1 * YK;
           e[0] = v[0];
 #pragma unroll
-          for (int j = 1; j < R2; j++) e[j] = twb(tw, j * k1, v[j]);
+          for (int j = 1; j < R2; j++) e[j] = twb(tw, k1, j, v[j]);
         }
       }
     }
@@ -329,21 +340,21 @@ template <int R1, int R2, int G, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS >= 16 ? 1 : 2)) k_fw_plane(PlaneParams P) {
   using F = PlaneFft<R1, R2, G>;
   ABI_DYN_SMEM(double2, sm);
-  double2* tw = sm;                                    // n entries
+  double2* tw = sm;                                    // twA | twB (PlaneFft::load_tw)
 #ifdef ABI_EMU
   const int warp = 0, nwarps = 1;
-  for (int j = 0; j < F::N; j++) tw[j] = P.tw[j];
+  F::load_tw(tw, P.tw, 0, 1);
 #else
   const int warp = threadIdx.x >> 5, nwarps = WARPS;
-  for (int j = threadIdx.x; j < F::N; j += WARPS * 32) tw[j] = P.tw[j];
+  F::load_tw(tw, P.tw, threadIdx.x, WARPS * 32);
 #endif
-  int* zoff = reinterpret_cast<int*>(sm + F::N);      // N ints: i3 -> u(i3) * n2, or -1 (built once per CTA)
+  int* zoff = reinterpret_cast<int*>(sm + F::TWSIZE);  // N ints: i3 -> u(i3) * n2, or -1 (built once per CTA)
 #ifdef ABI_EMU
   for (int i3 = 0; i3 < F::N; i3++) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
 #else
   for (int i3 = threadIdx.x; i3 < F::N; i3 += WARPS * 32) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
 #endif
-  double2* E = sm + F::N + F::ZOFF + (size_t)warp * F::ESIZE;
+  double2* E = sm + F::TWSIZE + F::ZOFF + (size_t)warp * F::ESIZE;
   double2* S = P.S + (size_t)blockIdx.x * P.nU * P.n2;
   __syncthreads();
   for (long long unit = blockIdx.x; unit < P.nunits; unit += gridDim.x) {
@@ -368,18 +379,18 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS >= 16 ? 1 : 2)) k_fw_plane_
   double2* tw = sm;
 #ifdef ABI_EMU
   const int warp = 0, nwarps = 1;
-  for (int j = 0; j < F::N; j++) tw[j] = P.tw[j];
+  F::load_tw(tw, P.tw, 0, 1);
 #else
   const int warp = threadIdx.x >> 5, nwarps = WARPS;
-  for (int j = threadIdx.x; j < F::N; j += WARPS * 32) tw[j] = P.tw[j];
+  F::load_tw(tw, P.tw, threadIdx.x, WARPS * 32);
 #endif
-  int* zoff = reinterpret_cast<int*>(sm + F::N);      // N ints: i3 -> u(i3) * n2, or -1 (built once per CTA)
+  int* zoff = reinterpret_cast<int*>(sm + F::TWSIZE);  // N ints: i3 -> u(i3) * n2, or -1 (built once per CTA)
 #ifdef ABI_EMU
   for (int i3 = 0; i3 < F::N; i3++) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
 #else
   for (int i3 = threadIdx.x; i3 < F::N; i3 += WARPS * 32) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
 #endif
-  double2* E = sm + F::N + F::ZOFF + (size_t)warp * F::ESIZE;
+  double2* E = sm + F::TWSIZE + F::ZOFF + (size_t)warp * F::ESIZE;
   double2* S = P.S + (size_t)blockIdx.x * P.nU * P.n2;
   __syncthreads();
   for (long long unit = blockIdx.x; unit < P.nunits; unit += gridDim.x) {
@@ -404,16 +415,16 @@ template <int R1, int R2, int G, int WARPS, int KIND>
 __global__ void __launch_bounds__(WARPS * 32, 2) k_fw_plane_split(PlaneParams P) {
   using F = PlaneFft<R1, R2, G>;
   ABI_DYN_SMEM(double2, sm);
-  double2* tw = sm;                                    // N entries of the length this kernel transforms
+  double2* tw = sm;                                    // twA | twB of the length this kernel transforms
   const double2* twg = (KIND == 1 || KIND == 3) ? P.tw3 : P.tw;
 #ifdef ABI_EMU
   const int warp = 0, nwarps = 1;
-  for (int j = 0; j < F::N; j++) tw[j] = twg[j];
+  F::load_tw(tw, twg, 0, 1);
 #else
   const int warp = threadIdx.x >> 5, nwarps = WARPS;
-  for (int j = threadIdx.x; j < F::N; j += WARPS * 32) tw[j] = twg[j];
+  F::load_tw(tw, twg, threadIdx.x, WARPS * 32);
 #endif
-  int* zoff = reinterpret_cast<int*>(sm + F::N);
+  int* zoff = reinterpret_cast<int*>(sm + F::TWSIZE);
   if (KIND == 1 || KIND == 3) {
 #ifdef ABI_EMU
     for (int i3 = 0; i3 < F::N; i3++) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
@@ -421,7 +432,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_fw_plane_split(PlaneParams P)
     for (int i3 = threadIdx.x; i3 < F::N; i3 += WARPS * 32) { const int u = F::u_of_i3(P, i3); zoff[i3] = u >= 0 ? u * P.n2 : -1; }
 #endif
   }
-  double2* E = sm + F::N + F::ZOFF + (size_t)warp * F::ESIZE;
+  double2* E = sm + F::TWSIZE + F::ZOFF + (size_t)warp * F::ESIZE;
   __syncthreads();
   for (long long unit = blockIdx.x; unit < P.nunits; unit += gridDim.x) {
     const int i1 = (int)(unit / P.nb), b = (int)(unit - (long long)i1 * P.nb);

@@ -14,7 +14,7 @@ template <int R1, int R2, int G, int WARPS>
 void launch_cfg(PlaneParams& P, cudaStream_t st) {
   using F = PlaneFft<R1, R2, G>;
   auto kern = k_fw_plane<R1, R2, G, WARPS>;
-  const size_t smem = sizeof(double2) * ((size_t)F::N + F::ZOFF + (size_t)WARPS * F::ESIZE);
+  const size_t smem = sizeof(double2) * ((size_t)F::TWSIZE + F::ZOFF + (size_t)WARPS * F::ESIZE);
   int cps = 1;
 #ifndef ABI_EMU
   static bool attr_done = false;
@@ -39,7 +39,7 @@ template <int R1, int R2, int G, int WARPS>
 void launch_cfg_rho(PlaneParams& P, cudaStream_t st) {
   using F = PlaneFft<R1, R2, G>;
   auto kern = k_fw_plane_rho<R1, R2, G, WARPS>;
-  const size_t smem = sizeof(double2) * ((size_t)F::N + F::ZOFF + (size_t)WARPS * F::ESIZE);
+  const size_t smem = sizeof(double2) * ((size_t)F::TWSIZE + F::ZOFF + (size_t)WARPS * F::ESIZE);
   int cps = 1;
 #ifndef ABI_EMU
   static bool attr_done = false;
@@ -66,7 +66,7 @@ void launch_split_kind(PlaneParams& P, cudaStream_t st) {
   constexpr int G = 4, WARPS = 8;
   using F = PlaneFft<R1, R2, G>;
   auto kern = k_fw_plane_split<R1, R2, G, WARPS, KIND>;
-  const size_t smem = sizeof(double2) * ((size_t)F::N + F::ZOFF + (size_t)WARPS * F::ESIZE);
+  const size_t smem = sizeof(double2) * ((size_t)F::TWSIZE + F::ZOFF + (size_t)WARPS * F::ESIZE);
   int cps = 1;
 #ifndef ABI_EMU
   static bool attr_done = false;

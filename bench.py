@@ -139,6 +139,16 @@ def algorithmic_units(w, istwfk, ndat):
     return b_fw, f_nl, C
 
 
+def fourwf_flops_per_band(w, istwfk, C):
+    """SURVEY 8d F_fw: pruned zero-padded 3-D FFT pair, nominal 5 n log2 n flops per 1-D transform (x on the C occupied lines,
+    y on the occupied half of the z planes, z on every column) + the V_loc multiply; halved per band at Gamma with a real
+    potential, where two bands ride one complex transform (cwavef_double_rfft_trick, m_getghc.F90:1999-2171)."""
+    n1, n2, n3 = w["ngfft"]
+    l2 = np.log2
+    f = 2.0 * (C * 5.0 * n1 * l2(n1) + n1 * (n3 / 2.0) * 5.0 * n2 * l2(n2) + n1 * n2 * 5.0 * n3 * l2(n3)) + 2.0 * n1 * n2 * n3
+    return f * (0.5 if istwfk == 2 else 1.0)
+
+
 def run_reference(args):
     """The reference's CPU algorithm for the path (oracle port; the Fortran reference cannot be built here: no Fortran
     compiler), all host threads (OpenBLAS + pocketfft workers), each step a bounded sample of `cpu_bands` bands."""
@@ -451,6 +461,11 @@ def main():
         extra["roofline_fourwf"] = {"kernel": "fourwf option 2 (3 fused kernels)", "bound": "hbm", "achieved": ach, "peak": hbm,
                                     "unit": "GB/s", "frac": ach / hbm, "peak_source": hbm_src, "bytes_per_band": b_fw,
                                     "ms_per_step": t_fw, "lines_C": C}
+        # fourwf in FP64 sits above the FP64 ridge of the chip (AI ~ 6-11 flop/B vs 5.4): the FP64 pipe is its other bound
+        f_fw = fourwf_flops_per_band(w, args.istwfk, C)
+        extra["roofline_fourwf"]["fp64"] = {"flops_per_band": f_fw, "achieved": f_fw * ndat / (t_fw * 1e-3) / 1e12, "peak": fp64,
+                                            "unit": "TFLOP/s", "frac": f_fw * ndat / (t_fw * 1e-3) / 1e12 / fp64,
+                                            "note": "nominal 5 n log2 n flops; DADD/DMUL issue at the DFMA rate, so the pipe is busier than this fraction"}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
