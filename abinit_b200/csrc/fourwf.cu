@@ -625,9 +625,16 @@ k_fw_x_forward(const double2* __restrict__ cg, double2* __restrict__ W1, Fft1d p
   __syncthreads();
   fft_lines_dit<+1>(buf, ls, nl, pl, tw, tid, nthr);
   double2* out = W1 + (size_t)b * n * nlines + l0;
-  for (int w = tid; w < nl * n; w += nthr) {
-    const int i1 = w / nl, l = w - i1 * nl;
-    out[(size_t)i1 * nlines + l] = buf[l * ls + i1];
+  {
+    // w = tid + k nthr -> (i1, l) = (w / nl, w % nl) by increments: one division per thread instead of one per element
+    int i1 = tid / nl, l = tid - i1 * nl;
+    const int di = nthr / nl, dl = nthr - di * nl;
+#pragma unroll 4
+    for (int w = tid; w < nl * n; w += nthr) {
+      out[(size_t)i1 * nlines + l] = buf[l * ls + i1];
+      i1 += di; l += dl;
+      if (l >= nl) { l -= nl; i1++; }
+    }
   }
 }
 
@@ -664,9 +671,16 @@ k_fw_x_backward(const double2* __restrict__ W1o, double2* __restrict__ outg, Fft
   const int nl = min(lines_per_cta, nlines - l0);
   for (int j = tid; j < n; j += nthr) tw[j] = pl.tw[j];
   const double2* in = W1o + (size_t)b * n * nlines + l0;
-  for (int w = tid; w < nl * n; w += nthr) {
-    const int i1 = w / nl, l = w - i1 * nl;
-    buf[l * ls + i1] = in[(size_t)i1 * nlines + l];
+  {
+    // (i1, l) = (w / nl, w % nl) by increments; 8 independent 16-byte loads in flight per thread
+    int i1 = tid / nl, l = tid - i1 * nl;
+    const int di = nthr / nl, dl = nthr - di * nl;
+#pragma unroll 8
+    for (int w = tid; w < nl * n; w += nthr) {
+      buf[l * ls + i1] = ldg2(in + (size_t)i1 * nlines + l);
+      i1 += di; l += dl;
+      if (l >= nl) { l -= nl; i1++; }
+    }
   }
   __syncthreads();
   fft_lines_dif<-1>(buf, ls, nl, pl, tw, tid, nthr);
@@ -702,9 +716,16 @@ k_fw_x_backward_packed(const double2* __restrict__ W1o, double2* __restrict__ ou
   const int nl = min(lines_per_cta, nlines - l0);
   for (int j = tid; j < n; j += nthr) tw[j] = pl.tw[j];
   const double2* in = W1o + (size_t)b * n * nlines + l0;
-  for (int w = tid; w < nl * n; w += nthr) {
-    const int i1 = w / nl, l = w - i1 * nl;
-    buf[l * ls + i1] = in[(size_t)i1 * nlines + l];
+  {
+    // (i1, l) = (w / nl, w % nl) by increments; 8 independent 16-byte loads in flight per thread
+    int i1 = tid / nl, l = tid - i1 * nl;
+    const int di = nthr / nl, dl = nthr - di * nl;
+#pragma unroll 8
+    for (int w = tid; w < nl * n; w += nthr) {
+      buf[l * ls + i1] = ldg2(in + (size_t)i1 * nlines + l);
+      i1 += di; l += dl;
+      if (l >= nl) { l -= nl; i1++; }
+    }
   }
   __syncthreads();
   fft_lines_dif<-1>(buf, ls, nl, pl, tw, tid, nthr);
