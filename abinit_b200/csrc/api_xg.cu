@@ -329,13 +329,33 @@ void abi_b200_chebfi_core_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, do
             *lambda_plus, *ndeg_filter, d);
 }
 
+// <psi|Vnl|psi> per band through nonlop(choice=1, signs=1, paw_opt=0) (m_chebfiwf.F90:289-316, m_lobpcgwf.F90:229-236); every
+// (band, spinor) pair is a column of npw coefficients, the two spinor contributions of a band are summed
+static void enl_per_band(abi_b200_ham_t* h, int nband, int nsp, int bandpp, const double* X, double* enl_out, cudaStream_t st) {
+  const size_t colb = 2 * (size_t)h->npw * nsp;             // doubles per band
+  double* d_enl = g_small[1].get((size_t)2 * nband * nsp);
+  for (int b0 = 0; b0 < nband; b0 += bandpp) {
+    const int nd = std::min(bandpp, nband - b0);
+    gemm_nonlop_device(h->P, h->atoms, h->enl, 1, -1, 0, h->me_g0, nullptr, nd * nsp, X + colb * b0, nullptr, nullptr, nullptr, st,
+                       nullptr, 1, d_enl + (size_t)b0 * nsp);
+  }
+  if (nsp == 1) {
+    CUDA_CHECK(cudaMemcpyAsync(enl_out, d_enl, sizeof(double) * nband, cudaMemcpyDeviceToHost, st));
+    return;
+  }
+  std::vector<double> e((size_t)nband * nsp);
+  CUDA_CHECK(cudaMemcpyAsync(e.data(), d_enl, sizeof(double) * e.size(), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int b = 0; b < nband; b++) { double a = 0.0; for (int is = 0; is < nsp; is++) a += e[(size_t)b * nsp + is]; enl_out[b] = a; }
+}
+
 // lobpcgwf2 (src/79_seqpar_mpi/m_lobpcgwf.F90:100-250) -> lobpcg_run (src/48_diago/m_lobpcg2.F90:340-765), nblock_lobpcg
 // blocks of nband / nblock_lobpcg bands (lobpcg_orthoXwrtBlocks against the finished blocks, final Borthonormalize +
 // Rayleigh-Ritz over all bands), paral_kgb = 0
-__global__ void k_build_pcon(int npw, const double* __restrict__ kinpw, double* __restrict__ pcon, double filter) {
+__global__ void k_build_pcon(int npw, int nspinor, const double* __restrict__ kinpw, double* __restrict__ pcon, double filter) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npw) return;
-  const double k = kinpw[i];
+  if (i >= npw * nspinor) return;
+  const double k = kinpw[i % npw];                                                // xgBlock_apply_diag(W, pcond, nspinor)
   if (k > filter) { pcon[i] = 0.0; return; }                                      // m_lobpcgwf.F90:326-331
   const double num = 27 + k * (18 + k * (12 + 8 * k));
   pcon[i] = num / (num + 16 * k * k * k * k);
@@ -349,9 +369,10 @@ void abi_b200_lobpcgwf2_(double* cg, double* eig, double* occ, double* enl_out, 
   Context& c = ctx();
   cudaStream_t st = c.stream;
   abi_b200_ham* h = *gs_hamk;
-  const int nb_all = *nband, np = *npw, nblock = *nblock_lobpcg;
-  ABI_CHECK(*nspinor == 1, "lobpcgwf2: nspinor=2 is not implemented in this build");
-  ABI_CHECK(np == h->npw && h->plan != nullptr, "lobpcgwf2: npw differs from the k-point loaded in gs_hamk");
+  const int nb_all = *nband, nsp = *nspinor, nblock = *nblock_lobpcg;
+  ABI_CHECK(nsp == h->nspinor, "lobpcgwf2: nspinor differs from the Hamiltonian's (abi_b200_ham_set_nspinor)");
+  ABI_CHECK(*npw == h->npw && h->plan != nullptr, "lobpcgwf2: npw differs from the k-point loaded in gs_hamk");
+  const int np = *npw * nsp;                                  // rows of the blocks: npw*nspinor (m_lobpcgwf.F90:192)
   ABI_CHECK(nblock >= 1 && nb_all % nblock == 0, "lobpcgwf2: nband must be a multiple of nblock_lobpcg");   // m_lobpcgwf.F90:133
   ABI_CHECK(*nbdbuf >= 0 || (*nbdbuf == -101 && occ != nullptr), "Bad value of nbdbuf");
   const bool paw = h->usepaw == 1;
@@ -370,7 +391,7 @@ void abi_b200_lobpcgwf2_(double* cg, double* eig, double* occ, double* enl_out, 
   double* AXWP = g_cheb[0].get(3 * blk);
   double* BXWP = paw ? g_cheb[1].get(3 * blk) : nullptr;
   double* d_pcon = g_cheb[2].get((size_t)np + 8);
-  k_build_pcon<<<ceil_div(np, 256), 256, 0, st>>>(np, h->d_kinpw, d_pcon, 1.7976931348623157e308 * 1.0e-11);
+  k_build_pcon<<<ceil_div(np, 256), 256, 0, st>>>(*npw, nsp, h->d_kinpw, d_pcon, 1.7976931348623157e308 * 1.0e-11);
   CUDA_CHECK(cudaGetLastError());
   double* d_eig = g_small[0].get((size_t)4 * n + nb_all);    // 3n eigenvalues + n residuals of a block, nband final eigenvalues
   double* d_res = d_eig + 3 * n;
@@ -445,15 +466,7 @@ void abi_b200_lobpcgwf2_(double* cg, double* eig, double* occ, double* enl_out, 
     CUDA_CHECK(cudaMemcpyAsync(eig, d_eig_all, sizeof(double) * nb_all, cudaMemcpyDeviceToHost, st));
   }
   a_cg.copy_back();
-  if (!paw && enl_out) {
-    double* d_enl = g_small[1].get((size_t)2 * nb_all);
-    for (int b0 = 0; b0 < nb_all; b0 += *bandpp) {
-      const int nd = std::min(*bandpp, nb_all - b0);
-      gemm_nonlop_device(h->P, h->atoms, h->enl, 1, -1, 0, h->me_g0, nullptr, nd, AllX0 + col * b0, nullptr, nullptr, nullptr, st,
-                         nullptr, 1, d_enl + b0);
-    }
-    CUDA_CHECK(cudaMemcpyAsync(enl_out, d_enl, sizeof(double) * nb_all, cudaMemcpyDeviceToHost, st));
-  }
+  if (!paw && enl_out) enl_per_band(h, nb_all, nsp, *bandpp, AllX0, enl_out, st);
   CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
@@ -468,9 +481,10 @@ void abi_b200_chebfiwf2_(double* cg, double* eig, double* occ, double* enl_out, 
   Context& c = ctx();
   cudaStream_t st = c.stream;
   abi_b200_ham* h = *gs_hamk;
-  const int nb = *nband, np = *npw;
-  ABI_CHECK(*nspinor == 1, "chebfiwf2: nspinor=2 is not implemented in this build");
-  ABI_CHECK(np == h->npw, "chebfiwf2: npw differs from the k-point loaded in gs_hamk");
+  const int nb = *nband, nsp = *nspinor;
+  ABI_CHECK(nsp == h->nspinor, "chebfiwf2: nspinor differs from the Hamiltonian's (abi_b200_ham_set_nspinor)");
+  ABI_CHECK(*npw == h->npw, "chebfiwf2: npw differs from the k-point loaded in gs_hamk");
+  const int np = *npw * nsp;                                  // rows of the blocks: npw*nspinor (m_chebfiwf.F90:227)
   ABI_CHECK(h->plan != nullptr, "chebfiwf2: load_k has not been called");
   ABI_CHECK(*bandpp >= 1, "chebfiwf2: bandpp must be >= 1");
   ABI_CHECK(!is_device_ptr(eig) && !is_device_ptr(resid) && (occ == nullptr || !is_device_ptr(occ)), "chebfiwf2: eig, resid, occ are host arrays");
@@ -508,16 +522,7 @@ void abi_b200_chebfiwf2_(double* cg, double* eig, double* occ, double* enl_out, 
   CUDA_CHECK(cudaMemcpyAsync(resid, d_res, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaMemcpyAsync(a_cg.as<double>(), X, sizeof(double) * blk, cudaMemcpyDeviceToDevice, st));   // xgBlock_copy(X, X0) :720
   a_cg.copy_back();
-  if (!paw && enl_out) {
-    // m_chebfiwf.F90:289-316: <psi|Vnl|psi> per band through nonlop(choice=1, signs=1, paw_opt=0)
-    double* d_enl = g_small[1].get((size_t)2 * nb);
-    for (int b0 = 0; b0 < nb; b0 += o.bandpp) {
-      const int nd = std::min(o.bandpp, nb - b0);
-      gemm_nonlop_device(h->P, h->atoms, h->enl, 1, -1, 0, h->me_g0, nullptr, nd, X + 2 * (size_t)np * b0, nullptr, nullptr, nullptr, st,
-                         nullptr, 1, d_enl + b0);
-    }
-    CUDA_CHECK(cudaMemcpyAsync(enl_out, d_enl, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
-  }
+  if (!paw && enl_out) enl_per_band(h, nb, nsp, o.bandpp, X, enl_out, st);   // m_chebfiwf.F90:289-316
   CUDA_CHECK(cudaStreamSynchronize(st));
 }
 #endif   // ABI_EMU
