@@ -15,14 +15,19 @@ from .gsphere import KIN_FILTER
 
 def getghc(cwavef, vlocal, kg, ngfft, kinpw, P, enl, sij, indlmn, nattyp, atindx1, istwf_k=1,
            usepaw=0, sij_opt=0, cpopt=-1, type_calc=0, lambda_=None, ghc_in=None, me_g0=1,
-           filter_dilatmx_loc=True, workers=None):
-    """Returns (ghc, gsc, gvnlxc, projections)."""
+           filter_dilatmx_loc=True, workers=None, local_impl="full"):
+    """Returns (ghc, gsc, gvnlxc, projections).  local_impl: "full" = plain 3-D FFT (the checker of the parity tests),
+    "pad" = the reference's zero-padded passes + Gamma-point band pairing (fourwf_pad.py; same result, the CPU timing arm)."""
     cwavef = np.atleast_2d(cwavef)
     ghc = np.zeros_like(cwavef) if ghc_in is None else np.array(ghc_in, dtype=np.complex128, copy=True)
     gsc = None; gvnlxc = np.zeros_like(cwavef); proj = None
     if type_calc in (0, 1, 3):
         cplex = 2 if np.iscomplexobj(vlocal) else 1
-        ghc, _, _ = fourwf(cplex, vlocal, cwavef, None, kg, kg, ngfft, 2, istwf_k, me_g0=me_g0, workers=workers)
+        if local_impl == "pad":
+            from .fourwf_pad import fourwf_option2_padded
+            ghc = fourwf_option2_padded(cplex, vlocal, cwavef, kg, ngfft, istwf_k, me_g0=me_g0, workers=workers)
+        else:
+            ghc, _, _ = fourwf(cplex, vlocal, cwavef, None, kg, kg, ngfft, 2, istwf_k, me_g0=me_g0, workers=workers)
         if type_calc == 1 and filter_dilatmx_loc:
             ghc[:, kinpw > KIN_FILTER] = 0.0
     if type_calc in (0, 2):

@@ -56,3 +56,25 @@ def test_int8_slicing_is_exact_to_the_advertised_level():
         err[nsl] = np.max(np.linalg.norm(got - ref, axis=0) / np.linalg.norm(ref, axis=0))
         assert nprod == nsl * (nsl + 1) // 2
     assert err[7] < 1e-12 and err[6] > err[7]
+
+
+@pytest.mark.parametrize("istwf_k,kpt", [(1, (.1, .2, .3)), (2, (0, 0, 0)), (3, (.5, 0, 0)), (6, (0, .5, 0)), (9, (.5, .5, .5))])
+@pytest.mark.parametrize("cplex,ndat", [(1, 1), (1, 4), (1, 5), (2, 3)])
+def test_padded_fourwf_equals_full_fft(istwf_k, kpt, cplex, ndat):
+    """oracle/fourwf_pad.py (the reference's zero-padded passes, fftw3_fftpad.finc:14-196, + the Gamma-point band pairing of
+    m_getghc.F90:1999-2171; used by bench.py's CPU arm) gives the result of the plain full-box oracle fourwf, option 2."""
+    from oracle import gsphere as g, fourwf as ofw
+    from oracle.fourwf_pad import fourwf_option2_padded
+    rng = np.random.default_rng(5)
+    _, gmet, _ = g.metric(np.diag([7., 8., 9.]))
+    ng = g.getng(2.0, 6.0, gmet, kpt)
+    kg = g.kpgsph(6.0, gmet, kpt, istwf_k)
+    npw = kg.shape[1]
+    c = rng.standard_normal((ndat, npw)) + 1j * rng.standard_normal((ndat, npw))
+    if istwf_k == 2:
+        c[:, 0] = c[:, 0].real
+    n1, n2, n3 = ng
+    v = rng.standard_normal((n3, n2, n1)) + (1j * rng.standard_normal((n3, n2, n1)) if cplex == 2 else 0)
+    ref, _, _ = ofw.fourwf(cplex, v, c, None, kg, kg, ng, 2, istwf_k)
+    out = fourwf_option2_padded(cplex, v, c, kg, ng, istwf_k, chunk=2)
+    assert np.abs(out - ref).max() < 1e-13 * np.abs(ref).max()
