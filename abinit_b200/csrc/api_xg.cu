@@ -313,9 +313,10 @@ void abi_b200_chebfi_rq_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, doub
   abi_b200_ham* h = *gs_hamk;
   ABI_CHECK(is_device_ptr(x) && is_device_ptr(ax), "chebfi_rq: device blocks required");
   const int space = space_of(h), me_g0 = me_g0_of(h);
-  get_ax_bx(h, space, me_g0, h->npw, *ncols, *bandpp, x, ax, h->usepaw ? bx : nullptr);
+  const int rows = h->npw * h->nspinor;                      // blocks hold npw*nspinor rows per band
+  get_ax_bx(h, space, me_g0, rows, *ncols, *bandpp, x, ax, h->usepaw ? bx : nullptr);
   std::vector<double> d;
-  rr_quotients(space, me_g0, h->npw, *ncols, x, ax, h->usepaw ? bx : nullptr, d, *maxeig, *mineig);
+  rr_quotients(space, me_g0, rows, *ncols, x, ax, h->usepaw ? bx : nullptr, d, *maxeig, *mineig);
   std::copy(d.begin(), d.end(), div);
 }
 
@@ -325,7 +326,7 @@ void abi_b200_chebfi_core_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, do
   AsyncGuard g;
   abi_b200_ham* h = *gs_hamk;
   std::vector<double> d(div, div + *ncols);
-  cheb_core(h, space_of(h), me_g0_of(h), h->npw, *ncols, *bandpp, x, ax, h->usepaw ? bx : nullptr, x_next, x_prev, *lambda_minus,
+  cheb_core(h, space_of(h), me_g0_of(h), h->npw * h->nspinor, *ncols, *bandpp, x, ax, h->usepaw ? bx : nullptr, x_next, x_prev, *lambda_minus,
             *lambda_plus, *ndeg_filter, d);
 }
 
