@@ -159,6 +159,20 @@ def test_option1_split_plane_stage_density(lib, istwf_k, kpt, ndat):
         assert ("fourwf_plane_rho" in prof) == (impl == 0)       # impl 0: fused path (y kernel + z-with-density kernel)
 
 
+@pytest.mark.parametrize("ecut,kpt,istwf_k,ngfft", [(0.01, (0, 0, 0), 2, (24, 24, 24)), (0.01, (0, 0, 0), 1, (24, 24, 24)),
+                                                     (0.01, (0, 0, 0), 2, (24, 30, 36)), (0.3, (.5, .5, .5), 9, (24, 24, 24)),
+                                                     (0.3, (.1, .2, .3), 1, (24, 24, 30))])
+def test_tiny_spheres(lib, ecut, kpt, istwf_k, ngfft):
+    """Degenerate spheres (npw = 1: G = 0 only; npw = 4) on the fused, split and generic paths, options 2 and 1: one occupied
+    line / plane, a single band and an odd band count at Gamma (half-filled packed transform)."""
+    for ndat in (1, 3):
+        p = make_problem(ecut, 8.0, kpt, istwf_k, ndat=ndat, ngfft=ngfft)
+        assert p.npw <= 4
+        for impl in (1, 2):
+            assert _run(lib, p, 2, impl) < TOL
+        assert _run(lib, p, 1, 0) < TOL
+
+
 @pytest.mark.parametrize("ndat", [1, 5, 16])
 def test_option2_ndat_and_clusters(lib, ndat, monkeypatch):
     p = make_problem(8.0, 10.0, (0, 0, 0), 1, ndat=ndat)
