@@ -20,8 +20,12 @@ Pinning status (see DESIGN.md "Oracle"):
     restated in oracle/psp8.py, epsatm 6.67004110 and the Ewald energy reproduced to every printed digit) and
     reproduces tests/tutorial/Refs/tbase3_1.abo: etotal -8.51873906424 Ha to 1.4e-10 Ha, kinetic / local_psp /
     non_local_psp / hartree / xc to < 3e-5 Ha (first order in the reference's own SCF residual) and the five printed
-    eigenvalues at k=(-1/4,1/2,0) to print precision (tests/test_scf_pins.py).  No stored per-vector dumps exist in
-    the reference, so the PAW branches (D_ij / S_ij apply, paw_opt 1-4, cprj) and istwf_k >= 2 remain pinned by
-    invariants only (naive per-atom sum, Hermiticity, istwfk=2 == istwfk=1 on the completed sphere): "parity
-    unpinned" for those branches.
+    eigenvalues at k=(-1/4,1/2,0) to print precision (tests/test_scf_pins.py).
+  * istwf_k = 2 (Gamma point: time-reversal completion of the sphere, G = 0 conventions, real-projection gemm_nonlop,
+    SPACE_CR xgBlock algebra, LOBPCG) -- PINNED on the tutorial test tbase1_1 (H2, Gamma only, istwfk 2, 30^3, npw 1503): the
+    same SCF around getghc(istwf_k=2) reproduces tests/tutorial/Refs/tbase1_1.abo: etotal -1.11718434634432 Ha to 6e-12 Ha,
+    the Ewald / psp-core terms to all digits and both printed eigenvalues (tests/test_scf_pins.py).
+  No stored per-vector dumps exist in the reference, so the PAW branches (D_ij / S_ij apply, paw_opt 1-4, cprj) and the
+  other time-reversal cases (istwf_k 3-9) remain pinned by invariants only (naive per-atom sum, Hermiticity, istwfk>=2 ==
+  istwfk=1 on the completed sphere): "parity unpinned" for those branches.
 """

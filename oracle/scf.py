@@ -343,10 +343,13 @@ def total_energy_scf(s, apply_h, nband=5, nocc=4, tol=1e-11, maxit=60, mix=0.6, 
                 w, v = np.linalg.eigh(H)
                 eig_all.append(w[:nband].copy())
                 c = v[:, :nocc].T                                        # (nocc, npw)
-            ur = _g2r(c, s.kg[ik], s.ngfft)
+            istw = getattr(s, "istwfk", [1] * len(s.kpts))[ik]
+            assert istw == 1 or eigensolver is not None, "istwfk >= 2 needs an iterative eigensolver (H is only R-linear on the half sphere)"
+            ur = _g2r(c, s.kg[ik], s.ngfft, istw)
             rho_new += s.wtk[ik] * 2.0 * np.sum(np.abs(ur) ** 2, axis=0) / s.ucvol
             kin = np.where(s.kinpw[ik] < g.KIN_FILTER, s.kinpw[ik], 0.0)
-            ek += s.wtk[ik] * 2.0 * float(np.sum(kin[None, :] * np.abs(c) ** 2))
+            # istwfk >= 2: every stored G stands for G and -G (G = 0 has zero kinetic energy, so no correction term)
+            ek += s.wtk[ik] * 2.0 * (2.0 if istw >= 2 else 1.0) * float(np.sum(kin[None, :] * np.abs(c) ** 2))
             enl += s.wtk[ik] * 2.0 * float(np.sum(s.enl_of(ik, c)) if enl_bands is None else np.sum(enl_bands[:nocc]))
             res["herm"] = max(res.get("herm", 0.0), herm)
         if getattr(s, "symops", None):
@@ -378,11 +381,16 @@ def total_energy_scf(s, apply_h, nband=5, nocc=4, tol=1e-11, maxit=60, mix=0.6, 
     return res
 
 
-def _g2r(c, kg, ngfft):
-    """psi(r) on the box, unnormalised e^{+iGr} sum (fourwf option 0 convention, m_fft.F90:2201)."""
+def _g2r(c, kg, ngfft, istwf_k=1):
+    """psi(r) on the box, unnormalised e^{+iGr} sum (fourwf option 0 convention, m_fft.F90:2201); istwf_k >= 2: the stored half
+    sphere is completed by time reversal first (sphere, m_fftcore.F90:1624-1650)."""
     n1, n2, n3 = ngfft
-    box = np.zeros((c.shape[0], n3, n2, n1), dtype=np.complex128)
-    box[:, np.mod(kg[2], n3), np.mod(kg[1], n2), np.mod(kg[0], n1)] = c
+    if istwf_k >= 2:
+        from .fourwf import sphere_to_box
+        box = sphere_to_box(c, kg, ngfft, istwf_k, 1)
+    else:
+        box = np.zeros((c.shape[0], n3, n2, n1), dtype=np.complex128)
+        box[:, np.mod(kg[2], n3), np.mod(kg[1], n2), np.mod(kg[0], n1)] = c
     return np.fft.ifftn(box, axes=(1, 2, 3)) * (n1 * n2 * n3)
 
 
@@ -394,9 +402,10 @@ REF_TBASE3_1 = dict(   # tests/tutorial/Refs/tbase3_1.abo:275-288 (EnergyTerms),
     epsatm=6.67004110, ecore_ucvol=1.06720658e+02, boxcut=2.13807, npw_k=(519, 525), ucvol=2.6374446e+02)
 
 
-def setup_from_fixture(fx, irreducible=True):
+def setup_from_fixture(fx, irreducible=True, kpts=None, wtk=None, istwfk=None):
     """fx: dict-like with rprimd, xred, ecut, ngfft, zion, epsatm, ekb, indlmn, qgrid, ffspl_tab (nln, mq), ffspl_yp (nln,2),
-    vpsp, xccc3d (written by tests/golden/make_si2_fixture.py)."""
+    vpsp, xccc3d (written by tests/golden/make_si2_fixture.py / make_h2_fixture.py).  kpts / wtk / istwfk: explicit k-point
+    set (e.g. Gamma with istwfk 2 for tbase1_1); default: the special points of tbase3_1."""
     from . import nonlop as onl
     from .psp8 import ClampedSpline
     s = Setup()
@@ -414,15 +423,18 @@ def setup_from_fixture(fx, irreducible=True):
     s.nattyp = np.array([natom], dtype=np.int32); s.atindx1 = np.arange(natom, dtype=np.int32)
     qg = np.array(fx["qgrid"])
     ffspl = [ClampedSpline(qg, t, yp[0], yp[1]) for t, yp in zip(np.array(fx["ffspl_tab"]), np.array(fx["ffspl_yp"]))]
-    if irreducible:
+    if kpts is not None:
+        s.kpts = np.atleast_2d(np.array(kpts, dtype=np.float64)); s.wtk = np.array(wtk, dtype=np.float64); s.symops = None
+    elif irreducible:
         # the 2 special points and weights of the reference run (tbase3_1.abo:44-45,136) + density symmetrisation
         s.kpts = np.array([[-0.25, 0.5, 0.0], [-0.25, 0.0, 0.0]]); s.wtk = np.array([0.75, 0.25])
         s.symops = find_symmetries(s.rprimd, s.xred)
     else:
         s.kpts, s.wtk = kgrid_tr(); s.symops = None
     s.kg = []; s.kinpw = []; s.ffnl = []; s.ph3d = []; s.P = []
-    for k in s.kpts:
-        kg = g.kpgsph(s.ecut, s.gmet, k, 1)
+    s.istwfk = [1] * len(s.kpts) if istwfk is None else [int(i) for i in istwfk]
+    for k, istw in zip(s.kpts, s.istwfk):
+        kg = g.kpgsph(s.ecut, s.gmet, k, istw)
         s.kg.append(kg)
         s.kinpw.append(np.ascontiguousarray(g.mkkin(s.ecut, 0.0, 1.0, s.gmet, kg, k)))
         ff = mkffnl(kg, k, s.gprimd, s.gmet, s.indlmn[0], ffspl)[None]   # (ntypat, lmnmax, 1, npw)
@@ -433,10 +445,23 @@ def setup_from_fixture(fx, irreducible=True):
     ek_lmn = np.tile(s.ekb[0][iln], natom)
 
     def enl_of(ik, c):
+        if s.istwfk[ik] >= 2:
+            # <c|Vnl|c> on the half sphere: the real-space-real conventions of opernla / xgBlock (factor 2, G=0 once)
+            from . import xg as oxg
+            gv, _, _ = onl.gemm_nonlop(s.P[ik], c, s.ekb, None, s.indlmn, s.nattyp, s.atindx1, s.istwfk[ik], choice=1, paw_opt=0,
+                                       cpopt=-1, me_g0=1)
+            return np.real(oxg.colwise_dot(oxg.SPACE_CR, c, gv, 1 if s.istwfk[ik] == 2 else 0))
         gx = c @ np.conj(s.P[ik]).T
         return np.sum(ek_lmn[None, :] * np.abs(gx) ** 2, axis=1)
     s.enl_of = enl_of
     return s
+
+
+REF_TBASE1_1 = dict(   # tests/tutorial/Refs/tbase1_1.abo:236-245 (EnergyTerms), :224 (eigenvalues), :57 istwfk 2, :63 ngfft, :133 npw
+    kinetic=1.01705426532946, hartree=7.26359620833829e-01, xc=-6.39065298290654e-01, ewald=1.51051118525613e-01,
+    psp_core=1.41966018330111e-03, local_psp=-2.21187993697866, non_local_psp=-1.62123775947208e-01,
+    total=-1.11718434634432, eig=(-0.36942, -0.01446), npw_full=1503, ngfft=(30, 30, 30), istwfk=2,
+    last_deltae=4.681e-10)   # the reference stopped at toldfe 1e-6: its stored etotal is converged to ~5e-10 Ha
 
 
 def apply_h_oracle(s):
@@ -444,6 +469,6 @@ def apply_h_oracle(s):
 
     def apply_h(ik, vloc, c):
         out, _, _, _ = ogh.getghc(c, vloc, s.kg[ik], s.ngfft, s.kinpw[ik], s.P[ik], s.ekb, None, s.indlmn, s.nattyp,
-                                  s.atindx1, istwf_k=1)
+                                  s.atindx1, istwf_k=getattr(s, "istwfk", [1] * len(s.kpts))[ik])
         return out
     return apply_h

@@ -67,3 +67,44 @@ def test_hamiltonian_matrix_cuda_vs_oracle():
         assert np.max(np.abs(wa - wb)) < 1e-10
     for h in hams:
         h.destroy()
+
+
+@pytest.mark.parametrize("solver_name", ["lobpcg", "chebfi"])
+def test_h2_gamma_istwfk2_scf_on_gpu_matches_reference(lib, solver_name):
+    """The Gamma-point path of the bench (istwf_k = 2: packed two-bands-per-transform fourwf, real-projection DMMA GEMMs,
+    SPACE_CR Rayleigh-Ritz) pinned on STORED reference data: the SCF of the reference's tutorial test tbase1_1 (H2, Gamma only)
+    solved by the CUDA LOBPCG / ChebFi2 through the C-ABI reaches tests/tutorial/Refs/tbase1_1.abo's etotal
+    (-1.11718434634432 Ha) within 1e-8 Ha and its printed eigenvalues; enl comes from nonlop(signs=1) on the device."""
+    import os
+    from oracle import scf
+    import abinit_b200 as ab
+    from abinit_b200 import xg
+    R1 = scf.REF_TBASE1_1
+    fix = os.path.join(os.path.dirname(__file__), "golden", "h2_tbase1.npz")
+    s = scf.setup_from_fixture(np.load(fix), kpts=[[0.0, 0.0, 0.0]], wtk=[1.0], istwfk=[2])
+    nband = 4
+    npw = s.kg[0].shape[1]
+    assert 2 * npw - 1 == R1["npw_full"]
+    h = ab.Hamiltonian(s.ngfft, s.xred.shape[1], 1, s.indlmn.shape[1], s.indlmn, s.nattyp, s.atindx1 + 1, 0, s.ucvol)
+    h.load_enl(s.ekb, None)
+    rng = np.random.default_rng(5)
+    cg = (rng.standard_normal((nband, npw)) + 1j * rng.standard_normal((nband, npw))) / (1.0 + s.kinpw[0])[None, :]
+    cg[:, 0] = cg[:, 0].real
+    cg = np.ascontiguousarray(cg)
+
+    def solver(ik, vloc):
+        h.load_spin(np.ascontiguousarray(vloc, dtype=np.float64), 1)
+        h.load_k(2, np.ascontiguousarray(s.kg[0].T), s.kinpw[0], s.ffnl[0], s.ph3d[0], me_g0=1)
+        eig = np.zeros(nband); resid = np.zeros(nband); enl = np.zeros(nband)
+        for _ in range(3):
+            if solver_name == "lobpcg":
+                xg.lobpcgwf2(cg, eig, None, enl, h, nband, npw, 1, resid, 1e-30, 4)
+            else:
+                xg.chebfiwf2(cg, eig, None, enl, h, nband, npw, 1, resid, 1e-22, s.ecut, 6)
+        return eig, cg, enl
+    l0 = ab.kernel_launches()
+    res = scf.total_energy_scf(s, None, eigensolver=solver, nband=2, nocc=1, maxit=60)
+    assert ab.kernel_launches() > l0
+    assert abs(res["energies"]["total"] - R1["total"]) < 1e-8, res["energies"]["total"] - R1["total"]
+    assert np.max(np.abs(np.round(res["eig"][0][:2], 5) - np.array(R1["eig"]))) < 1.5e-5
+    h.destroy()
