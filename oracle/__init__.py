@@ -25,7 +25,9 @@ Pinning status (see DESIGN.md "Oracle"):
     SPACE_CR xgBlock algebra, LOBPCG) -- PINNED on the tutorial test tbase1_1 (H2, Gamma only, istwfk 2, 30^3, npw 1503): the
     same SCF around getghc(istwf_k=2) reproduces tests/tutorial/Refs/tbase1_1.abo: etotal -1.11718434634432 Ha to 6e-12 Ha,
     the Ewald / psp-core terms to all digits and both printed eigenvalues (tests/test_scf_pins.py).
+  * istwf_k = 3 and 7 (k = (1/2,0,0), (1/2,1/2,0)) -- PINNED with istwf_k = 2 on dataset 1 of tests/tutoplugs/Input/tw90_1.abi
+    (Si-2, Gamma-centred 2x2x2 mesh, tolvrs 1e-10): etotal -8.42438318247138 Ha to 3e-12 Ha, components to 4e-7.
   No stored per-vector dumps exist in the reference, so the PAW branches (D_ij / S_ij apply, paw_opt 1-4, cprj) and the
-  other time-reversal cases (istwf_k 3-9) remain pinned by invariants only (naive per-atom sum, Hermiticity, istwfk>=2 ==
+  remaining time-reversal cases (istwf_k 4-6, 8, 9) remain pinned by invariants only (naive per-atom sum, Hermiticity, istwfk>=2 ==
   istwfk=1 on the completed sphere): "parity unpinned" for those branches.
 """

@@ -402,7 +402,7 @@ REF_TBASE3_1 = dict(   # tests/tutorial/Refs/tbase3_1.abo:275-288 (EnergyTerms),
     epsatm=6.67004110, ecore_ucvol=1.06720658e+02, boxcut=2.13807, npw_k=(519, 525), ucvol=2.6374446e+02)
 
 
-def setup_from_fixture(fx, irreducible=True, kpts=None, wtk=None, istwfk=None):
+def setup_from_fixture(fx, irreducible=True, kpts=None, wtk=None, istwfk=None, symmetrize=False):
     """fx: dict-like with rprimd, xred, ecut, ngfft, zion, epsatm, ekb, indlmn, qgrid, ffspl_tab (nln, mq), ffspl_yp (nln,2),
     vpsp, xccc3d (written by tests/golden/make_si2_fixture.py / make_h2_fixture.py).  kpts / wtk / istwfk: explicit k-point
     set (e.g. Gamma with istwfk 2 for tbase1_1); default: the special points of tbase3_1."""
@@ -424,7 +424,8 @@ def setup_from_fixture(fx, irreducible=True, kpts=None, wtk=None, istwfk=None):
     qg = np.array(fx["qgrid"])
     ffspl = [ClampedSpline(qg, t, yp[0], yp[1]) for t, yp in zip(np.array(fx["ffspl_tab"]), np.array(fx["ffspl_yp"]))]
     if kpts is not None:
-        s.kpts = np.atleast_2d(np.array(kpts, dtype=np.float64)); s.wtk = np.array(wtk, dtype=np.float64); s.symops = None
+        s.kpts = np.atleast_2d(np.array(kpts, dtype=np.float64)); s.wtk = np.array(wtk, dtype=np.float64)
+        s.symops = find_symmetries(s.rprimd, s.xred) if symmetrize else None      # irreducible wedge: symmetrise the density
     elif irreducible:
         # the 2 special points and weights of the reference run (tbase3_1.abo:44-45,136) + density symmetrisation
         s.kpts = np.array([[-0.25, 0.5, 0.0], [-0.25, 0.0, 0.0]]); s.wtk = np.array([0.75, 0.25])
@@ -462,6 +463,13 @@ REF_TBASE1_1 = dict(   # tests/tutorial/Refs/tbase1_1.abo:236-245 (EnergyTerms),
     psp_core=1.41966018330111e-03, local_psp=-2.21187993697866, non_local_psp=-1.62123775947208e-01,
     total=-1.11718434634432, eig=(-0.36942, -0.01446), npw_full=1503, ngfft=(30, 30, 30), istwfk=2,
     last_deltae=4.681e-10)   # the reference stopped at toldfe 1e-6: its stored etotal is converged to ~5e-10 Ha
+
+
+REF_TW90_1 = dict(     # tests/tutoplugs/Refs/tw90_1.abo dataset 1: :296-306 (EnergyTerms), :291-292 (eigenvalues at Gamma), :84-86 kpt,
+    kinetic=3.26995439513125, hartree=6.26285762807477e-01, xc=-3.13117901734409, ewald=-8.39800922793231,        # :140 wtk
+    psp_core=3.94898511693256e-01, local_psp=-2.47694075212606, non_local_psp=1.29060714529908,
+    total=-8.42438318247138, eig_gamma=(-0.25879, 0.18379, 0.18379, 0.18379, 0.27224), ngfft=(20, 20, 20), mpw=302,
+    kpts=((0.0, 0.0, 0.0), (0.5, 0.0, 0.0), (0.5, 0.5, 0.0)), wtk=(0.125, 0.5, 0.375), tolvrs=1e-10)
 
 
 def apply_h_oracle(s):

@@ -108,3 +108,44 @@ def test_h2_gamma_istwfk2_scf_on_gpu_matches_reference(lib, solver_name):
     assert abs(res["energies"]["total"] - R1["total"]) < 1e-8, res["energies"]["total"] - R1["total"]
     assert np.max(np.abs(np.round(res["eig"][0][:2], 5) - np.array(R1["eig"]))) < 1.5e-5
     h.destroy()
+
+
+def test_si2_time_reversal_kpoints_scf_on_gpu_matches_reference(lib):
+    """istwf_k = 2, 3, 7 through the C-ABI pinned on stored reference data: the SCF of tests/tutoplugs/Input/tw90_1.abi dataset 1
+    (Si-2, Gamma-centred 2x2x2 mesh: Gamma, (1/2,0,0), (1/2,1/2,0)) with every k-point in its half-sphere storage, solved by
+    the CUDA LOBPCG, reaches tests/tutoplugs/Refs/tw90_1.abo's etotal (-8.42438318247138 Ha, tolvrs 1e-10) within 1e-8 Ha."""
+    import os
+    from oracle import scf
+    import abinit_b200 as ab
+    from abinit_b200 import xg
+    Rw = scf.REF_TW90_1
+    istw = (2, 3, 7)
+    fix = os.path.join(os.path.dirname(__file__), "golden", "si2_tw90.npz")
+    s = scf.setup_from_fixture(np.load(fix), kpts=Rw["kpts"], wtk=Rw["wtk"], istwfk=istw, symmetrize=True)
+    nband = 6
+    hams = []; cgs = []
+    rng = np.random.default_rng(5)
+    for ik in range(3):
+        h = ab.Hamiltonian(s.ngfft, s.xred.shape[1], 1, s.indlmn.shape[1], s.indlmn, s.nattyp, s.atindx1 + 1, 0, s.ucvol)
+        h.load_enl(s.ekb, None)
+        hams.append(h)
+        npw = s.kg[ik].shape[1]
+        c = (rng.standard_normal((nband, npw)) + 1j * rng.standard_normal((nband, npw))) / (1.0 + s.kinpw[ik])[None, :]
+        if istw[ik] == 2:
+            c[:, 0] = c[:, 0].real
+        cgs.append(np.ascontiguousarray(c))
+
+    def solver(ik, vloc):
+        h = hams[ik]
+        h.load_spin(np.ascontiguousarray(vloc, dtype=np.float64), 1)
+        h.load_k(istw[ik], np.ascontiguousarray(s.kg[ik].T), s.kinpw[ik], s.ffnl[ik], s.ph3d[ik], me_g0=1)
+        npw = s.kg[ik].shape[1]
+        eig = np.zeros(nband); resid = np.zeros(nband); enl = np.zeros(nband)
+        for _ in range(3):
+            xg.lobpcgwf2(cgs[ik], eig, None, enl, h, nband, npw, 1, resid, 1e-30, 4)
+        return eig, cgs[ik], enl
+    res = scf.total_energy_scf(s, None, eigensolver=solver, nband=5, nocc=4, maxit=80)
+    assert abs(res["energies"]["total"] - Rw["total"]) < 1e-8, res["energies"]["total"] - Rw["total"]
+    assert np.max(np.abs(np.round(res["eig"][0], 5) - np.array(Rw["eig_gamma"]))) < 1.5e-5
+    for h in hams:
+        h.destroy()

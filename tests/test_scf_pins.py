@@ -105,3 +105,44 @@ def test_h2_gamma_istwfk2_scf_matches_reference():
     for k in ("kinetic", "hartree", "xc", "local_psp", "non_local_psp"):
         assert abs(e[k] - R1[k]) < 1e-5, (k, e[k] - R1[k])              # the reference's components: density converged to ~1e-3
     assert np.max(np.abs(np.round(res["eig"][0][:2], 5) - np.array(R1["eig"]))) < 1.5e-5
+
+
+FIX_W90 = os.path.join(os.path.dirname(__file__), "golden", "si2_tw90.npz")
+
+
+def test_si2_time_reversal_kpoints_scf_matches_reference():
+    """Pins istwf_k = 2, 3 and 7 together: dataset 1 of tests/tutoplugs/Input/tw90_1.abi (Si-2, ecut 8 Ha, Gamma-centred 2x2x2
+    mesh) has the three irreducible k-points Gamma, (1/2,0,0), (1/2,1/2,0), all time-reversal invariant.  The reference ran them
+    with istwfk 1 (forced in the input); the half-sphere storage is the same physics, so the SCF around the oracle's
+    getghc(istwf_k = 2 / 3 / 7) + LOBPCG (SPACE_CR, me_g0 1 / 0 / 0) must reproduce tests/tutoplugs/Refs/tw90_1.abo (tolvrs 1e-10):
+    etotal -8.42438318247138 Ha (measured 3e-12), every energy component to 1e-6, the Gamma eigenvalues, mpw 302."""
+    from oracle import xg as oxg, lobpcg as olb
+    Rw = scf.REF_TW90_1
+    istw = (2, 3, 7)
+    s = scf.setup_from_fixture(np.load(FIX_W90), kpts=Rw["kpts"], wtk=Rw["wtk"], istwfk=istw, symmetrize=True)
+    assert tuple(s.ngfft) == Rw["ngfft"]
+    npw_full = [2 * s.kg[0].shape[1] - 1, 2 * s.kg[1].shape[1], 2 * s.kg[2].shape[1]]
+    assert max(npw_full) == Rw["mpw"]
+    ah = scf.apply_h_oracle(s)
+    rng = np.random.default_rng(1)
+    X = []
+    for ik in range(3):
+        npw = s.kg[ik].shape[1]
+        x = (rng.standard_normal((5, npw)) + 1j * rng.standard_normal((5, npw))) / (1 + s.kinpw[ik])[None, :]
+        if istw[ik] == 2:
+            x[:, 0] = x[:, 0].real
+        X.append(x)
+    pc = [olb.build_pcon(k) for k in s.kinpw]
+
+    def solver(ik, vloc):
+        f = lambda c: (ah(ik, vloc, c), c.copy())
+        for _ in range(3):
+            w, r, X[ik] = olb.lobpcg_run(f, X[ik], pc[ik], oxg.SPACE_CR, 1 if istw[ik] == 2 else 0, nline=4)
+        return w, X[ik], None
+    res = scf.total_energy_scf(s, None, eigensolver=solver, nband=5, nocc=4, maxit=80)
+    e = res["energies"]
+    assert abs(e["total"] - Rw["total"]) < 1e-9
+    for k in ("kinetic", "hartree", "xc", "local_psp", "non_local_psp"):
+        assert abs(e[k] - Rw[k]) < 1e-6, (k, e[k] - Rw[k])
+    assert abs(e["ewald"] - Rw["ewald"]) < 1e-12 and abs(e["psp_core"] - Rw["psp_core"]) < 1e-13
+    assert np.max(np.abs(np.round(res["eig"][0], 5) - np.array(Rw["eig_gamma"]))) < 1.5e-5
