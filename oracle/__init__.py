@@ -27,7 +27,8 @@ Pinning status (see DESIGN.md "Oracle"):
     the Ewald / psp-core terms to all digits and both printed eigenvalues (tests/test_scf_pins.py).
   * istwf_k = 3 and 7 (k = (1/2,0,0), (1/2,1/2,0)) -- PINNED with istwf_k = 2 on dataset 1 of tests/tutoplugs/Input/tw90_1.abi
     (Si-2, Gamma-centred 2x2x2 mesh, tolvrs 1e-10): etotal -8.42438318247138 Ha to 3e-12 Ha, components to 4e-7.
-  No stored per-vector dumps exist in the reference, so the PAW branches (D_ij / S_ij apply, paw_opt 1-4, cprj) and the
-  remaining time-reversal cases (istwf_k 4-6, 8, 9) remain pinned by invariants only (naive per-atom sum, Hermiticity, istwfk>=2 ==
-  istwfk=1 on the completed sphere): "parity unpinned" for those branches.
+    The other representatives of the L and X stars of that mesh carry istwf_k 4, 5, 6, 8, 9 and give the same stored etotal
+    (within 1e-9 Ha) after the density symmetrisation: every time-reversal mode is PINNED (tests/test_scf_pins.py).
+  No stored per-vector dumps exist in the reference, so the PAW branches (D_ij / S_ij apply, paw_opt 1-4, cprj) remain
+  pinned by invariants only (naive per-atom sum, Hermiticity of H and S, S S^-1 = 1): "parity unpinned" for those branches.
 """

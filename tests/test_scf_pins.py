@@ -110,16 +110,20 @@ def test_h2_gamma_istwfk2_scf_matches_reference():
 FIX_W90 = os.path.join(os.path.dirname(__file__), "golden", "si2_tw90.npz")
 
 
-def test_si2_time_reversal_kpoints_scf_matches_reference():
-    """Pins istwf_k = 2, 3 and 7 together: dataset 1 of tests/tutoplugs/Input/tw90_1.abi (Si-2, ecut 8 Ha, Gamma-centred 2x2x2
+@pytest.mark.parametrize("kpts,istw", [(((0, 0, 0), (.5, 0, 0), (.5, .5, 0)), (2, 3, 7)), (((0, 0, 0), (0, 0, .5), (.5, 0, .5)), (2, 4, 5)),
+                                       (((0, 0, 0), (0, .5, 0), (0, .5, .5)), (2, 6, 8)), (((0, 0, 0), (.5, .5, .5), (.5, .5, 0)), (2, 9, 7))])
+def test_si2_time_reversal_kpoints_scf_matches_reference(kpts, istw):
+    """Pins EVERY time-reversal storage mode (istwf_k 2-9): the fcc point group maps the eight mesh points onto Gamma, four L
+    points {(1/2,0,0), (0,1/2,0), (0,0,1/2), (1/2,1/2,1/2)} and three X points {(1/2,1/2,0), (1/2,0,1/2), (0,1/2,1/2)}, so any
+    representative of each star gives the reference's result after the density symmetrisation -- and each representative has
+    its own istwf_k.  First case = the reference's own k-point list.  Original statement for istwf_k = 2, 3 and 7: dataset 1 of tests/tutoplugs/Input/tw90_1.abi (Si-2, ecut 8 Ha, Gamma-centred 2x2x2
     mesh) has the three irreducible k-points Gamma, (1/2,0,0), (1/2,1/2,0), all time-reversal invariant.  The reference ran them
     with istwfk 1 (forced in the input); the half-sphere storage is the same physics, so the SCF around the oracle's
     getghc(istwf_k = 2 / 3 / 7) + LOBPCG (SPACE_CR, me_g0 1 / 0 / 0) must reproduce tests/tutoplugs/Refs/tw90_1.abo (tolvrs 1e-10):
     etotal -8.42438318247138 Ha (measured 3e-12), every energy component to 1e-6, the Gamma eigenvalues, mpw 302."""
     from oracle import xg as oxg, lobpcg as olb
     Rw = scf.REF_TW90_1
-    istw = (2, 3, 7)
-    s = scf.setup_from_fixture(np.load(FIX_W90), kpts=Rw["kpts"], wtk=Rw["wtk"], istwfk=istw, symmetrize=True)
+    s = scf.setup_from_fixture(np.load(FIX_W90), kpts=kpts, wtk=Rw["wtk"], istwfk=istw, symmetrize=True)
     assert tuple(s.ngfft) == Rw["ngfft"]
     npw_full = [2 * s.kg[0].shape[1] - 1, 2 * s.kg[1].shape[1], 2 * s.kg[2].shape[1]]
     assert max(npw_full) == Rw["mpw"]
