@@ -73,13 +73,14 @@ def h2_gamma_scf(solver_factory, **kw):
     return s, scf.total_energy_scf(s, None, eigensolver=solver_factory(s), nband=2, nocc=1, maxit=60, **kw)
 
 
-def test_h2_gamma_istwfk2_scf_matches_reference():
+@pytest.mark.parametrize("solver_name", ["lobpcg", "chebfi"])
+def test_h2_gamma_istwfk2_scf_matches_reference(solver_name):
     """Pins the istwf_k = 2 restatements (time-reversal sphere completion, G = 0 conventions, real-projection gemm_nonlop,
     SPACE_CR xgBlock algebra, LOBPCG) on stored reference data: the SCF of tests/tutorial/Input/tbase1_1.abi through the oracle's
     getghc(istwf_k=2) reproduces tests/tutorial/Refs/tbase1_1.abo -- npw 1503, etotal -1.11718434634432 Ha (the reference
     stopped at toldfe 1e-6 with deltae 4.7e-10, so its etotal is the variational minimum to ~1e-9 while its energy COMPONENTS
     are those of a density converged to ~1e-3 only), eigenvalues -0.36942 / -0.01446, Ewald and psp-core terms to all digits."""
-    from oracle import xg as oxg, lobpcg as olb
+    from oracle import xg as oxg, lobpcg as olb, chebfi as och
     R1 = scf.REF_TBASE1_1
 
     def factory(s):
@@ -87,7 +88,7 @@ def test_h2_gamma_istwfk2_scf_matches_reference():
         ah = scf.apply_h_oracle(s)
         rng = np.random.default_rng(1)
         npw = s.kg[0].shape[1]
-        x = (rng.standard_normal((2, npw)) + 1j * rng.standard_normal((2, npw))) / (1 + s.kinpw[0])[None, :]
+        x = (rng.standard_normal((4, npw)) + 1j * rng.standard_normal((4, npw))) / (1 + s.kinpw[0])[None, :]   # 2 printed + 2 buffer bands
         x[:, 0] = x[:, 0].real
         st = {"x": x}
         pcon = olb.build_pcon(s.kinpw[0])
@@ -95,7 +96,10 @@ def test_h2_gamma_istwfk2_scf_matches_reference():
         def solver(ik, vloc):
             f = lambda c: (ah(ik, vloc, c), c.copy())
             for _ in range(3):
-                w, r, st["x"] = olb.lobpcg_run(f, st["x"], pcon, oxg.SPACE_CR, 1, nline=4)
+                if solver_name == "lobpcg":
+                    w, r, st["x"] = olb.lobpcg_run(f, st["x"], pcon, oxg.SPACE_CR, 1, nline=4)
+                else:
+                    w, r, st["x"] = och.chebfi_run(f, st["x"], oxg.SPACE_CR, 1, s.ecut, nline=6)
             return w, st["x"], None
         return solver
     s, res = h2_gamma_scf(factory)
