@@ -154,3 +154,31 @@ def test_si2_time_reversal_kpoints_scf_matches_reference(kpts, istw):
         assert abs(e[k] - Rw[k]) < 1e-6, (k, e[k] - Rw[k])
     assert abs(e["ewald"] - Rw["ewald"]) < 1e-12 and abs(e["psp_core"] - Rw["psp_core"]) < 1e-13
     assert np.max(np.abs(np.round(res["eig"][0], 5) - np.array(Rw["eig_gamma"]))) < 1.5e-5
+
+
+def test_si2_time_reversal_scf_with_multiblock_lobpcg():
+    """The several-block LOBPCG restatement (blockdim 2 of 6 bands, lobpcg_orthoXwrtBlocks + final Rayleigh-Ritz, SPACE_CR) as
+    the eigensolver of the same tw90_1 SCF: same stored etotal."""
+    from oracle import xg as oxg, lobpcg as olb
+    Rw = scf.REF_TW90_1
+    istw = (2, 3, 7)
+    s = scf.setup_from_fixture(np.load(FIX_W90), kpts=Rw["kpts"], wtk=Rw["wtk"], istwfk=istw, symmetrize=True)
+    ah = scf.apply_h_oracle(s)
+    rng = np.random.default_rng(2)
+    X = []
+    for ik in range(3):
+        npw = s.kg[ik].shape[1]
+        x = (rng.standard_normal((6, npw)) + 1j * rng.standard_normal((6, npw))) / (1 + s.kinpw[ik])[None, :]
+        if istw[ik] == 2:
+            x[:, 0] = x[:, 0].real
+        X.append(x)
+    pc = [olb.build_pcon(k) for k in s.kinpw]
+
+    def solver(ik, vloc):
+        f = lambda c: (ah(ik, vloc, c), c.copy())
+        for _ in range(3):
+            w, r, X[ik] = olb.lobpcg_run(f, X[ik], pc[ik], oxg.SPACE_CR, 1 if istw[ik] == 2 else 0, nline=4, nblock=3)
+        return w, X[ik], None
+    res = scf.total_energy_scf(s, None, eigensolver=solver, nband=5, nocc=4, maxit=80)
+    assert abs(res["energies"]["total"] - Rw["total"]) < 1e-9
+    assert np.max(np.abs(np.round(res["eig"][0], 5) - np.array(Rw["eig_gamma"]))) < 1.5e-5
