@@ -29,6 +29,9 @@ Pinning status (see DESIGN.md "Oracle"):
     (Si-2, Gamma-centred 2x2x2 mesh, tolvrs 1e-10): etotal -8.42438318247138 Ha to 3e-12 Ha, components to 4e-7.
     The other representatives of the L and X stars of that mesh carry istwf_k 4, 5, 6, 8, 9 and give the same stored etotal
     (within 1e-9 Ha) after the density symmetrisation: every time-reversal mode is PINNED (tests/test_scf_pins.py).
+  * nspinor = 2 (getghc_spinor, collinear nvloc = 1 branch) -- PINNED on the same tw90_1 SCF run in spinor form (no spin-orbit:
+    every band becomes a degenerate pair of occupation 1; stored etotal within 1e-9 Ha, tests/test_scf_pins.py).  The
+    non-collinear nvloc = 4 branch has no stored data without the magnetisation machinery: invariants only.
   No stored per-vector dumps exist in the reference, so the PAW branches (D_ij / S_ij apply, paw_opt 1-4, cprj) remain
   pinned by invariants only (naive per-atom sum, Hermiticity of H and S, S S^-1 = 1): "parity unpinned" for those branches.
 """

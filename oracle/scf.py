@@ -308,7 +308,7 @@ def symmetrize_rho(rho, ops, ngfft):
     return out / len(ops)
 
 
-def total_energy_scf(s, apply_h, nband=5, nocc=4, tol=1e-11, maxit=60, mix=0.6, verbose=False, eigensolver=None):
+def total_energy_scf(s, apply_h, nband=5, nocc=4, tol=1e-11, maxit=60, mix=0.6, verbose=False, eigensolver=None, nelect=None):
     """s: Setup with ngfft, gmet, ucvol, gsqcut, vpsp (grid), xccc3d (grid), kpts, wtk, kg[k] (3,npw), kinpw[k], ewald,
     ecore, enl_of(k, c) -> per-band <c|Vnl|c>.  apply_h(ik, vlocal, c(nband_or_npw, npw)) -> H c.
     Dense diagonalisation per k (H built column by column through apply_h on the identity), Anderson mixing on rho.
@@ -317,7 +317,7 @@ def total_energy_scf(s, apply_h, nband=5, nocc=4, tol=1e-11, maxit=60, mix=0.6, 
     n1, n2, n3 = s.ngfft
     nfft = n1 * n2 * n3
     _, gsq = gsq_grid(s.ngfft, s.gmet)
-    nelect = 2.0 * nocc
+    nelect = 2.0 * nocc if nelect is None else float(nelect)    # only the uniform starting density uses it
     rho = np.full((n3, n2, n1), nelect / s.ucvol)
     hist = []
     res = {}

@@ -182,3 +182,36 @@ def test_si2_time_reversal_scf_with_multiblock_lobpcg():
     res = scf.total_energy_scf(s, None, eigensolver=solver, nband=5, nocc=4, maxit=80)
     assert abs(res["energies"]["total"] - Rw["total"]) < 1e-9
     assert np.max(np.abs(np.round(res["eig"][0], 5) - np.array(Rw["eig_gamma"]))) < 1.5e-5
+
+
+def test_si2_spinor_form_scf_matches_reference():
+    """Pins the nspinor = 2 restatement (oracle getghc_spinor, collinear nvloc = 1 branch, m_getghc.F90:555-653) on stored data:
+    without spin-orbit coupling the spinor form of the tw90_1 ground state is the same physics (every band becomes a degenerate
+    pair with occupation 1), so the SCF with 2-component wavefunctions of npw*nspinor rows must give the stored etotal."""
+    from oracle import xg as oxg, lobpcg as olb, getghc as ogh
+    Rw = scf.REF_TW90_1
+    s = scf.setup_from_fixture(np.load(FIX_W90), kpts=Rw["kpts"], wtk=Rw["wtk"], istwfk=(1, 1, 1), symmetrize=True)
+    nb = 10                                                           # 8 occupied spinor bands + 2
+    rng = np.random.default_rng(4)
+    X = []
+    for ik in range(3):
+        npw = s.kg[ik].shape[1]
+        X.append((rng.standard_normal((nb, 2 * npw)) + 1j * rng.standard_normal((nb, 2 * npw))) / np.tile(1 + s.kinpw[ik], 2)[None, :])
+    pc = [np.tile(olb.build_pcon(k), 2) for k in s.kinpw]             # xgBlock_apply_diag(W, pcond, nspinor)
+
+    def solver(ik, vloc):
+        npw = s.kg[ik].shape[1]
+
+        def f(c):
+            out, _ = ogh.getghc_spinor(c.reshape(-1, 2, npw), vloc, s.kg[ik], s.ngfft, s.kinpw[ik], s.P[ik], s.ekb, s.indlmn,
+                                       s.nattyp, s.atindx1)
+            return out.reshape(-1, 2 * npw), c.copy()
+        for _ in range(3):
+            w, r, X[ik] = olb.lobpcg_run(f, X[ik], pc[ik], oxg.SPACE_C, -1, nline=4)
+        # total_energy_scf weights every returned row with occupation 2: hand it the 16 occupied spinor COMPONENTS / sqrt(2)
+        return w, X[ik].reshape(2 * nb, npw) / np.sqrt(2.0), None
+    res = scf.total_energy_scf(s, None, eigensolver=solver, nband=10, nocc=16, nelect=8.0, maxit=80)
+    assert abs(res["energies"]["total"] - Rw["total"]) < 1e-9, res["energies"]["total"] - Rw["total"]
+    e = res["eig"][0]
+    assert np.max(np.abs(e[0::2] - e[1::2])) < 1e-8                   # Kramers-like pairs
+    assert np.max(np.abs(np.round(e[0::2], 5) - np.array(Rw["eig_gamma"]))) < 1.5e-5
