@@ -32,6 +32,9 @@ Pinning status (see DESIGN.md "Oracle"):
   * nspinor = 2 (getghc_spinor, collinear nvloc = 1 branch) -- PINNED on the same tw90_1 SCF run in spinor form (no spin-orbit:
     every band becomes a degenerate pair of occupation 1; stored etotal within 1e-9 Ha, tests/test_scf_pins.py).  The
     non-collinear nvloc = 4 branch has no stored data without the magnetisation machinery: invariants only.
-  No stored per-vector dumps exist in the reference, so the PAW branches (D_ij / S_ij apply, paw_opt 1-4, cprj) remain
+  * PAW application machinery (per-atom packed D_ij with off-diagonal terms, opernlc PAW branch, gsc assembly) -- PINNED through
+    an exact rewriting of the norm-conserving tw90_1 operator (rotated projector pairs p' = R p, D' = R diag(ekb) R^T, S_ij = 0):
+    the SCF through the PAW code path gives the stored etotal within 1e-9 Ha (tests/test_scf_pins.py).
+  No stored per-vector dumps exist in the reference, so a non-trivial S_ij (paw_opt 3-4, apply_invovl) and cprj remain
   pinned by invariants only (naive per-atom sum, Hermiticity of H and S, S S^-1 = 1): "parity unpinned" for those branches.
 """

@@ -149,3 +149,60 @@ def test_si2_time_reversal_kpoints_scf_on_gpu_matches_reference(lib):
     assert np.max(np.abs(np.round(res["eig"][0], 5) - np.array(Rw["eig_gamma"]))) < 1.5e-5
     for h in hams:
         h.destroy()
+
+
+@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on hardware (its CPU twin, "
+                   "tests/test_scf_pins.py::test_si2_scf_through_the_paw_code_path_matches_reference, is green)")
+def test_si2_scf_through_the_cuda_paw_path_matches_reference(lib):
+    """The PAW application path of the CUDA library (k_paw_opernlc on per-atom packed D_ij with off-diagonal terms, gsc assembly,
+    generalised Rayleigh-Ritz) pinned on stored data through an exact rewriting of the norm-conserving tw90_1 operator: p' = R p,
+    D' = R diag(ekb) R^T, S_ij = 0 (see the CPU twin).  Half-sphere storage (istwf_k 2, 3, 7), CUDA LOBPCG."""
+    import os
+    from oracle import scf
+    import abinit_b200 as ab
+    from abinit_b200 import xg
+    Rw = scf.REF_TW90_1
+    istw = (2, 3, 7)
+    fix = os.path.join(os.path.dirname(__file__), "golden", "si2_tw90.npz")
+    s = scf.setup_from_fixture(np.load(fix), kpts=Rw["kpts"], wtk=Rw["wtk"], istwfk=istw, symmetrize=True)
+    ind = s.indlmn[0]
+    nlmn = ind.shape[0]; natom = s.xred.shape[1]
+    rot = np.eye(nlmn)
+    theta = {0: 0.7, 1: -0.4, 2: 1.1}
+    for i in range(nlmn):
+        if ind[i, 2] != 1:
+            continue
+        j = next(q for q in range(nlmn) if ind[q, 0] == ind[i, 0] and ind[q, 1] == ind[i, 1] and ind[q, 2] == 2)
+        c_, s_ = np.cos(theta[int(ind[i, 0])]), np.sin(theta[int(ind[i, 0])])
+        rot[i, i] = c_; rot[i, j] = s_; rot[j, i] = -s_; rot[j, j] = c_
+    dfull = rot @ np.diag(s.ekb[0][ind[:, 4] - 1]) @ rot.T
+    packed = np.array([dfull[i, j] for j in range(nlmn) for i in range(j + 1)])
+    dij = np.ascontiguousarray(np.tile(packed, (natom, 1))); sij = np.zeros((1, packed.size))
+    nband = 6
+    hams = []; cgs = []; ffr = []
+    rng = np.random.default_rng(5)
+    for ik in range(3):
+        h = ab.Hamiltonian(s.ngfft, natom, 1, nlmn, s.indlmn, s.nattyp, s.atindx1 + 1, 1, s.ucvol)
+        h.load_enl(dij, sij)
+        hams.append(h)
+        ffr.append(np.ascontiguousarray(np.einsum("ab,tbdn->tadn", rot, s.ffnl[ik])))
+        npw = s.kg[ik].shape[1]
+        c = (rng.standard_normal((nband, npw)) + 1j * rng.standard_normal((nband, npw))) / (1.0 + s.kinpw[ik])[None, :]
+        if istw[ik] == 2:
+            c[:, 0] = c[:, 0].real
+        cgs.append(np.ascontiguousarray(c))
+
+    def solver(ik, vloc):
+        h = hams[ik]
+        h.load_spin(np.ascontiguousarray(vloc, dtype=np.float64), 1)
+        h.load_k(istw[ik], np.ascontiguousarray(s.kg[ik].T), s.kinpw[ik], ffr[ik], s.ph3d[ik], me_g0=1)
+        npw = s.kg[ik].shape[1]
+        eig = np.zeros(nband); resid = np.zeros(nband)
+        for _ in range(3):
+            xg.lobpcgwf2(cgs[ik], eig, None, None, h, nband, npw, 1, resid, 1e-30, 4)
+        return eig, cgs[ik], None
+    res = scf.total_energy_scf(s, None, eigensolver=solver, nband=5, nocc=4, maxit=80)
+    assert abs(res["energies"]["total"] - Rw["total"]) < 1e-8, res["energies"]["total"] - Rw["total"]
+    assert np.max(np.abs(np.round(res["eig"][0], 5) - np.array(Rw["eig_gamma"]))) < 1.5e-5
+    for h in hams:
+        h.destroy()

@@ -215,3 +215,59 @@ def test_si2_spinor_form_scf_matches_reference():
     e = res["eig"][0]
     assert np.max(np.abs(e[0::2] - e[1::2])) < 1e-8                   # Kramers-like pairs
     assert np.max(np.abs(np.round(e[0::2], 5) - np.array(Rw["eig_gamma"]))) < 1.5e-5
+
+
+def test_si2_scf_through_the_paw_code_path_matches_reference():
+    """Pins the PAW *application machinery* of the oracle (per-atom packed-symmetric D_ij with off-diagonal terms, opernlc PAW
+    branch m_opernlc_ylm_allwf.F90:395-447, gsc = S psi assembly, generalised sub-space problems) on stored data through an
+    exact rewriting of a norm-conserving operator: rotating the two projectors of every (l, m) channel by an angle,
+    p' = R p, and taking D' = R diag(ekb) R^T leaves V_nl = sum_ab D'_ab |p'_a><p'_b| unchanged, but D' is a full 2x2 block per
+    channel stored in the packed j(j+1)/2 + i layout, applied per atom, with S_ij = 0 (S = 1).  The tw90_1 SCF run this way, in
+    the half-sphere storage (istwf_k 2, 3, 7), must give the stored etotal.  (A non-trivial S_ij changes the physics: it stays
+    on invariants -- Hermiticity, S S^-1 = 1.)"""
+    from oracle import xg as oxg, lobpcg as olb, getghc as ogh, nonlop as onl
+    Rw = scf.REF_TW90_1
+    istw = (2, 3, 7)
+    s = scf.setup_from_fixture(np.load(FIX_W90), kpts=Rw["kpts"], wtk=Rw["wtk"], istwfk=istw, symmetrize=True)
+    ind = s.indlmn[0]
+    nlmn = ind.shape[0]; natom = s.xred.shape[1]
+    rot = np.eye(nlmn); dfull = np.zeros((nlmn, nlmn))
+    theta = {0: 0.7, 1: -0.4, 2: 1.1}
+    for i in range(nlmn):
+        if ind[i, 2] != 1:
+            continue
+        j = next(q for q in range(nlmn) if ind[q, 0] == ind[i, 0] and ind[q, 1] == ind[i, 1] and ind[q, 2] == 2)
+        c_, s_ = np.cos(theta[int(ind[i, 0])]), np.sin(theta[int(ind[i, 0])])
+        rot[i, i] = c_; rot[i, j] = s_; rot[j, i] = -s_; rot[j, j] = c_
+    ek = s.ekb[0][ind[:, 4] - 1]
+    dfull = rot @ np.diag(ek) @ rot.T                                  # D' = R diag(ekb) R^T
+    assert np.abs(dfull - np.diag(np.diag(dfull))).max() > 0.5         # genuinely off-diagonal
+    packed = np.array([dfull[i, j] for j in range(nlmn) for i in range(j + 1)])
+    dij = np.tile(packed, (natom, 1)); sij = np.zeros((1, packed.size))
+    P2 = []
+    for ik in range(3):
+        ff = np.einsum("ab,tbdn->tadn", rot, s.ffnl[ik])              # p'_a = sum_b R_ab p_b (same l, m: only the radial part mixes)
+        P2.append(onl.prep_projectors(np.ascontiguousarray(ff), s.ph3d[ik], s.indlmn, s.nattyp, s.ucvol))
+    rng = np.random.default_rng(7)
+    X = []
+    for ik in range(3):
+        npw = s.kg[ik].shape[1]
+        x = (rng.standard_normal((5, npw)) + 1j * rng.standard_normal((5, npw))) / (1 + s.kinpw[ik])[None, :]
+        if istw[ik] == 2:
+            x[:, 0] = x[:, 0].real
+        X.append(x)
+    pc = [olb.build_pcon(k) for k in s.kinpw]
+
+    def solver(ik, vloc):
+        def f(c):
+            ghc, gsc, _, _ = ogh.getghc(c, vloc, s.kg[ik], s.ngfft, s.kinpw[ik], P2[ik], dij, sij, s.indlmn, s.nattyp, s.atindx1,
+                                        istwf_k=istw[ik], usepaw=1, sij_opt=1)
+            assert np.abs(gsc - c).max() < 1e-13                      # S = 1
+            return ghc, gsc
+        for _ in range(3):
+            w, r, X[ik] = olb.lobpcg_run(f, X[ik], pc[ik], oxg.SPACE_CR, 1 if istw[ik] == 2 else 0, nline=4)
+        return w, X[ik], None
+    res = scf.total_energy_scf(s, None, eigensolver=solver, nband=5, nocc=4, maxit=80)
+    assert abs(res["energies"]["total"] - Rw["total"]) < 1e-9, res["energies"]["total"] - Rw["total"]
+    assert abs(res["energies"]["non_local_psp"] - Rw["non_local_psp"]) < 1e-6
+    assert np.max(np.abs(np.round(res["eig"][0], 5) - np.array(Rw["eig_gamma"]))) < 1.5e-5
