@@ -86,7 +86,6 @@ void abi_b200_fourwf_set_tuning(const char* name, int value) {
   else if (k == "plane_split") t.plane_split = value;
   else if (k == "cluster") t.cluster = value;
   else if (k == "lines_x") t.lines_x = value;
-  else if (k == "x_threads") t.x_threads = value;
   else if (k == "smem_kb_mid") t.smem_kb_mid = value;
   else if (k == "band_chunk") t.band_chunk = value;
   else ABI_ERROR("abi_b200_fourwf_set_tuning: unknown knob");

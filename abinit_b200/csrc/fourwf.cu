@@ -934,7 +934,6 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
   int lx = std::max(1, tune.lines_x);
   while (lx > 1 && sizeof(double2) * ((size_t)n1 + (size_t)lx * (n1 | 1)) > 110 * 1024) lx--;
   const size_t smem_x = sizeof(double2) * ((size_t)n1 + (size_t)lx * (n1 | 1));
-  const int xthreads = (tune.x_threads == 64 || tune.x_threads == 128) ? tune.x_threads : 256;   // developer knob: CTA size of the x passes
 #ifndef ABI_EMU
   CUDA_CHECK(cudaFuncSetAttribute(k_fw_x_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
   CUDA_CHECK(cudaFuncSetAttribute(k_fw_x_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
@@ -952,7 +951,7 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
     const int b0 = pack2 ? 2 * t0 : t0;                     // first band of the chunk
     const int nbands = std::min(ndat - b0, pack2 ? 2 * nb : nb);
     { ProfScope ps("fourwf_x_forward");
-    ABI_LAUNCH(k_fw_x_forward, dim3(ceil_div(pl.nlin, lx), nb), dim3(xthreads), smem_x, st,
+    ABI_LAUNCH(k_fw_x_forward, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st,
                d_fofgin + (size_t)b0 * pl.npw_in, W1, t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_in,
                pack2 ? nbands : 0); }
     MidParams P;
@@ -996,11 +995,11 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
     if (e.gsc) e.gsc += (size_t)b0 * pl.npw_out;
     { ProfScope ps("fourwf_x_backward");
     if (pack2) {
-      ABI_LAUNCH(k_fw_x_backward_packed, dim3(ceil_div(pl.nlin, lx), nb), dim3(xthreads), smem_x, st, W1o,
+      ABI_LAUNCH(k_fw_x_backward_packed, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st, W1o,
                  d_fofgout + (size_t)b0 * pl.npw_out, t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_out, nbands,
                  xnorm, e, kin_filter);
     } else {
-      ABI_LAUNCH(k_fw_x_backward, dim3(ceil_div(pl.nlout, lx), nb), dim3(xthreads), smem_x, st, W1o,
+      ABI_LAUNCH(k_fw_x_backward, dim3(ceil_div(pl.nlout, lx), nb), dim3(256), smem_x, st, W1o,
                  d_fofgout + (size_t)b0 * pl.npw_out, t1.plan, pl.d_out_ent, pl.d_lout_estart, pl.nlout, lx, pl.npw_out,
                  xnorm, zero_im, e, kin_filter);
     } }
@@ -1073,7 +1072,6 @@ void fourwf_fused_opt1(const FourwfPlan& pl, const double2* d_fofgin, double* d_
   int lx = std::max(1, tune.lines_x);
   while (lx > 1 && sizeof(double2) * ((size_t)n1 + (size_t)lx * (n1 | 1)) > 110 * 1024) lx--;
   const size_t smem_x = sizeof(double2) * ((size_t)n1 + (size_t)lx * (n1 | 1));
-  const int xthreads = (tune.x_threads == 64 || tune.x_threads == 128) ? tune.x_threads : 256;   // developer knob: CTA size of the x passes
 #ifndef ABI_EMU
   CUDA_CHECK(cudaFuncSetAttribute(k_fw_x_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
 #endif
@@ -1083,7 +1081,7 @@ void fourwf_fused_opt1(const FourwfPlan& pl, const double2* d_fofgin, double* d_
     const int nbands = std::min(ndat - b0, pack2 ? 2 * nb : nb);
     ABI_LAUNCH(k_rho_weights, dim3(ceil_div(nb, 128)), dim3(128), 0, st, wxy, d_wr, d_wi, nb, b0, ndat, pack2 ? 1 : 0);
     { ProfScope ps("fourwf_x_forward");
-    ABI_LAUNCH(k_fw_x_forward, dim3(ceil_div(pl.nlin, lx), nb), dim3(xthreads), smem_x, st, d_fofgin + (size_t)b0 * pl.npw_in, W1,
+    ABI_LAUNCH(k_fw_x_forward, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st, d_fofgin + (size_t)b0 * pl.npw_in, W1,
                t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_in, pack2 ? nbands : 0); }
     { ProfScope ps("fourwf_plane_rho");
     PlaneParams Q;

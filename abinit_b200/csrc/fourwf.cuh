@@ -96,7 +96,6 @@ struct FourwfTuning {
   int plane = 1;               // 1: register-resident two-pass plane stage (plane_stage.cuh) when the box allows it
   int plane_cfg = 0;           // 0 auto, 1: (G=8, 4 warps), 2: (G=4, 8 warps)
   int plane_ctas_per_sm = 0;   // 0: occupancy / L2-budget limited
-  int x_threads = 256;         // threads per CTA of the x passes (64 / 128 / 256; with lines_x 8-16 more CTAs fit per SM)
   int plane_split = 0;         // 1: run the split (three-kernel) plane stage for cubic boxes too (developer comparison)
   int pack2 = 1;               // istwf_k=2: two bands per complex transform (double_rfft_trick, m_getghc.F90:1999-2171)
 };
