@@ -151,9 +151,6 @@ def test_si2_time_reversal_kpoints_scf_on_gpu_matches_reference(lib):
         h.destroy()
 
 
-@pytest.mark.skipif(not os.environ.get("ABI_B200_RUN_UNVALIDATED"),
-                    reason="written after the GPU budget of round 1 was spent: not yet run on hardware (set ABI_B200_RUN_UNVALIDATED=1; "
-                           "its CPU twin, tests/test_scf_pins.py::test_si2_scf_through_the_paw_code_path_matches_reference, is green)")
 def test_si2_scf_through_the_cuda_paw_path_matches_reference(lib):
     """The PAW application path of the CUDA library (k_paw_opernlc on per-atom packed D_ij with off-diagonal terms, gsc assembly,
     generalised Rayleigh-Ritz) pinned on stored data through an exact rewriting of the norm-conserving tw90_1 operator: p' = R p,
