@@ -79,6 +79,8 @@ void abi_b200_fourwf_set_tuning(const char* name, int value) {
   if (k == "plane") t.plane = value;
   else if (k == "plane_cfg") t.plane_cfg = value;
   else if (k == "pack2") t.pack2 = value;
+  else if (k == "half") t.half = value;
+  else if (k == "half_cfg") t.half_cfg = value;
   else if (k == "pipeline") ctx().pipeline = value != 0;
   else if (k == "nonlop_ozaki") ozaki_set_enabled(value);     // EXPERIMENTAL int8-sliced gemm_nonlop (ozaki.cu), default off
   else if (k == "pipe_chunks") ctx().pipe_chunks = std::max(1, value);

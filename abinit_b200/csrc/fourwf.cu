@@ -16,6 +16,7 @@
 //      HBM traffic per band: read psi, write W1, read W1, write W1', read W1', write H psi (+V via L2).
 #include "fourwf.cuh"
 #include "plane_stage.cuh"
+#include "half_stage.cuh"
 #include "context.cuh"
 #include <algorithm>
 #include <cstring>
@@ -44,6 +45,8 @@ FourwfTuning& fourwf_tuning() {
     if (const char* e = getenv("ABI_B200_FOURWF_PLANE_CFG")) t.plane_cfg = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_PLANE_CTAS")) t.plane_ctas_per_sm = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_PACK2")) t.pack2 = atoi(e);
+    if (const char* e = getenv("ABI_B200_FOURWF_HALF")) t.half = atoi(e);
+    if (const char* e = getenv("ABI_B200_FOURWF_HALF_CFG")) t.half_cfg = atoi(e);
   }
   return t;
 }
@@ -172,7 +175,7 @@ struct Workspace {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 static Workspace g_ws[4];
-void fourwf_release_workspace() { for (auto& w : g_ws) w.release(); plane_stage_release(); }
+void fourwf_release_workspace() { for (auto& w : g_ws) w.release(); plane_stage_release(); half_stage_release(); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Planner
@@ -180,6 +183,8 @@ void fourwf_release_workspace() { for (auto& w : g_ws) w.release(); plane_stage_
 void FourwfPlan::release() {
   for (void* p : owned) cudaFree(p);
   owned.clear();
+  for (void* p : owned_lazy) cudaFree(p);
+  owned_lazy.clear();
 }
 
 template <typename T> static T* to_device(const std::vector<T>& v, std::vector<void*>& owned) {
@@ -317,8 +322,26 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
       if (!two_runs(zs, zr)) plane_ok = false;
       pl->za = zr[0]; pl->zla = zr[1]; pl->zb = zr[2]; pl->zlb = zr[3];
     }
+    // half-support form of a sorted index list on an axis of length n = 2m: one run [a, a + la) inside [0, m) and one run
+    // [b, b + lb) inside [m, n) (either may be empty)
+    auto half_runs = [](const std::vector<int>& r, int n, int& a, int& la, int& b, int& lb) {
+      a = la = lb = 0; b = n / 2;
+      if (n % 2) return false;
+      const int m = n / 2;
+      for (int i : r) { if (i < m) la++; else lb++; }
+      if (la > 0) a = r[0];
+      if (lb > 0) b = r[la];
+      for (int q = 0; q < la; q++) if (r[q] != a + q) return false;
+      for (int q = 0; q < lb; q++) if (r[la + q] != b + q) return false;
+      return true;
+    };
+    bool half_ok_in = true, half_ok_out = true;
+    {
+      std::vector<int> zs(u_i3.begin(), u_i3.end());
+      if (!half_runs(zs, n3, pl->h_za, pl->h_zla, pl->h_zb, pl->h_zlb)) half_ok_in = false;
+    }
     auto build = [&](std::vector<Ent>& es, bool dit_positions, int& nlines, int2*& d_ent, int*& d_estart, int*& d_lu,
-                     unsigned short*& d_lpos2, int*& d_plstart, int*& d_pstart, short4*& d_pruns) {
+                     unsigned short*& d_lpos2, int*& d_plstart, int*& d_pstart, short4*& d_pruns, int4*& d_hrows, int& y_amb, bool& half_ok) {
       // sort by (plane u, i2, then original order) -> lines of one plane are contiguous
       std::vector<int> order(es.size());
       for (size_t i = 0; i < es.size(); i++) order[i] = (int)i;
@@ -364,6 +387,16 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
           pruns[u].x = (short)rr[0]; pruns[u].y = (short)rr[1]; pruns[u].z = (short)rr[2]; pruns[u].w = (short)rr[3];
         }
         d_pstart = to_device(pstart, pl->owned); d_pruns = to_device(pruns, pl->owned);
+        std::vector<int4> hrows(pl->nU);
+        y_amb = 0;
+        for (int u = 0; u < pl->nU; u++) {
+          int a = 0, la = 0, b = 0, lb = 0;
+          if (!half_runs(rows[u], n2, a, la, b, lb)) half_ok = false;
+          const int bm = b - n2 / 2;                       // the high run in r = i2 - m coordinates
+          hrows[u].x = plstart[u]; hrows[u].y = a | (la << 16); hrows[u].z = bm | (lb << 16); hrows[u].w = 0;
+          if (la > 0 && lb > 0 && a < bm + lb && bm < a + la) y_amb = 1;
+        }
+        d_hrows = to_device(hrows, pl->owned);
       }
       d_ent = to_device(ent, pl->owned);
       d_estart = to_device(estart, pl->owned);
@@ -373,10 +406,12 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
       (void)dit_positions;
     };
     build(ents, true, pl->nlin, pl->d_in_ent, pl->d_lin_estart, pl->d_lin_u, pl->d_lin_pos2, pl->d_inpl_start,
-          pl->d_pin_start, pl->d_pin_runs);
+          pl->d_pin_start, pl->d_pin_runs, pl->d_hin_rows, pl->y_amb_in, half_ok_in);
     build(oents, false, pl->nlout, pl->d_out_ent, pl->d_lout_estart, pl->d_lout_u, pl->d_lout_pos2, pl->d_outpl_start,
-          pl->d_pout_start, pl->d_pout_runs);
+          pl->d_pout_start, pl->d_pout_runs, pl->d_hout_rows, pl->y_amb_out, half_ok_out);
     pl->plane_ok = plane_ok;
+    pl->half_ok_in = half_ok_in && pl->nU > 0;
+    pl->half_ok_out = half_ok_out;
   }
   FourwfPlan* raw = pl.get();
   cache[key] = std::move(pl);
@@ -921,6 +956,7 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
   const int nlout_eff = pack2 ? pl.nlin : pl.nlout;       // packed: the output lines are the (completed) input lines
   const int ntrans = pack2 ? (ndat + 1) / 2 : ndat;       // transforms to run
 
+  const bool use_half = pl.plane_ok && tune.plane && !tune.plane_split && half_stage_usable(pl, pack2);
   // ---- band chunking bounds the workspace (W1, W1', scratch) ----
   const bool split_plane = pl.plane_ok && tune.plane && (n2 != n3 || tune.plane_split);          // S planes of the chunk live in global memory
   const size_t per_band = sizeof(double2) * (size_t)n1 * ((size_t)pl.nlin + nlout_eff + (split_plane ? (size_t)pl.nU * n2 : 0));
@@ -961,8 +997,13 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
     P.inpl_start = pl.d_inpl_start; P.lin_u = pl.d_lin_u; P.lin_pos2 = pl.d_lin_pos2;
     P.outpl_start = pl.d_outpl_start; P.lout_u = pl.d_lout_u; P.lout_pos2 = pl.d_lout_pos2;
     P.u_i3 = pl.d_u_i3; P.u_flags = pl.d_u_flags; P.p2 = t2.plan; P.p3 = t3.plan;
-    if (getenv("ABI_B200_DEBUG")) fprintf(stderr, "abinit_b200: fourwf fused: plane_ok=%d tune.plane=%d nU=%d z=[%d,+%d)U[%d,+%d)\n", (int)pl.plane_ok, tune.plane, pl.nU, pl.za, pl.zla, pl.zb, pl.zlb);
-    if (pl.plane_ok && tune.plane) {
+    if (getenv("ABI_B200_DEBUG")) fprintf(stderr, "abinit_b200: fourwf fused: plane_ok=%d tune.plane=%d half=%d (half_ok=%d/%d amb=%d/%d) nU=%d z=[%d,+%d)U[%d,+%d)\n", (int)pl.plane_ok, tune.plane, (int)use_half, (int)pl.half_ok_in, (int)pl.half_ok_out, pl.y_amb_in, pl.y_amb_out, pl.nU, pl.za, pl.zla, pl.zb, pl.zlb);
+    if (use_half) {
+      ProfScope ps("fourwf_plane_stage");
+      HalfLaunch L;
+      L.nb = nb; L.W1 = W1; L.W1o = W1o; L.nlin = pl.nlin; L.nlout = nlout_eff; L.out_is_in = pack2;
+      half_stage_launch(pl, v, L, st);
+    } else if (pl.plane_ok && tune.plane) {
       ProfScope ps("fourwf_plane_stage");
       PlaneParams Q;
       Q.n1 = n1; Q.n2 = n2; Q.n3 = n3; Q.nb = nb; Q.nU = pl.nU; Q.cplex = v.cplex; Q.za = pl.za; Q.zla = pl.zla; Q.zb = pl.zb; Q.zlb = pl.zlb;

@@ -58,6 +58,15 @@ struct FourwfPlan {
   int za = 0, zla = 0, zb = 0, zlb = 0;
   int* d_pin_start = nullptr; short4* d_pin_runs = nullptr;      // nU each
   int* d_pout_start = nullptr; short4* d_pout_runs = nullptr;
+  // ---- half-support plane stage (half_stage.cuh): every row / the occupied z planes are [0, la) U [n - lb, n), la, lb <= n/2
+  bool half_ok_in = false, half_ok_out = false;   // input rows + occupied z planes / output rows
+  int h_za = 0, h_zla = 0, h_zb = 0, h_zlb = 0;   // occupied z planes [za, za + zla) U [zb, zb + zlb), zb >= n3 / 2
+  int y_amb_in = 0, y_amb_out = 0;
+  int4* d_hin_rows = nullptr; int4* d_hout_rows = nullptr;       // nU each: {first line, a | la << 16, (b - n2/2) | lb << 16, 0}
+  // per-configuration z tables, built by the launcher at first use (mutable cache; the plan is otherwise immutable)
+  mutable int h_cfg_key = -1; mutable int h_z_has_ov = 0;
+  mutable int* d_hz_rowoff = nullptr; mutable int* d_hz_ovoff = nullptr; mutable int* d_hz_sign = nullptr; mutable int* d_hu_row = nullptr;
+  mutable std::vector<void*> owned_lazy;
   std::vector<void*> owned;      // device allocations to free
   void release();
 };
@@ -74,6 +83,8 @@ struct VlocDev {
   double* d_v = nullptr;
   double* d_vT = nullptr;
   uint64_t stamp = 0;
+  // V_loc in the register order of the half-support z pass (half_stage.cuh), built at first use per (stamp, configuration)
+  mutable double* d_vP = nullptr; mutable size_t vP_cap = 0; mutable uint64_t vP_stamp = ~0ULL; mutable int vP_key = -1;
 };
 void vloc_upload(VlocDev& v, const double* denpot, bool on_device, int cplex, int n1, int n2, int n3,
                  cudaStream_t st);
@@ -97,6 +108,8 @@ struct FourwfTuning {
   int plane_cfg = 0;           // 0 auto, 1: (G=8, 4 warps), 2: (G=4, 8 warps)
   int plane_ctas_per_sm = 0;   // 0: occupancy / L2-budget limited
   int plane_split = 0;         // 1: run the split (three-kernel) plane stage for cubic boxes too (developer comparison)
+  int half = 1;                // 1: half-support plane stage (half_stage.cuh) when the sphere fits in half of the box axes
+  int half_cfg = 0;            // 0: 8 warps x 2 CTAs/SM, 1: 16 warps x 1 CTA/SM
   int pack2 = 1;               // istwf_k=2: two bands per complex transform (double_rfft_trick, m_getghc.F90:1999-2171)
 };
 FourwfTuning& fourwf_tuning();

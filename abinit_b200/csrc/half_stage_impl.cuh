@@ -1,0 +1,46 @@
+// Launcher templates of the half-support plane stage (included by the half_inst_*.cu instantiation units).
+#pragma once
+#include "half_stage.cuh"
+#include "fourwf.cuh"
+#include "context.cuh"
+#include <algorithm>
+
+namespace abi {
+void* plane_scratch_get(size_t bytes);
+
+// kind 0: fused option 2, kind 1: fused option 1 (density)
+template <int A, int B, int G, int WARPS, int MINB, int KIND>
+void half_launch_cfg(HalfParams& P, cudaStream_t st) {
+  auto kern = KIND == 0 ? k_hw_plane<A, B, G, WARPS, MINB> : k_hw_plane_rho<A, B, G, WARPS, MINB>;
+  const size_t smem = half_smem_bytes<A, B, G>(WARPS, P.nU);
+  ABI_CHECK(smem <= kMaxSmemPerCta, "half-support plane stage: too many occupied z planes for the shared-memory tables");
+  int cps = 1;
+#ifndef ABI_EMU
+  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, WARPS * 32, smem));
+  ABI_CHECK(cps >= 1, "half-support plane stage: kernel does not fit on an SM");
+#endif
+  const FourwfTuning& tune = fourwf_tuning();
+  cps = std::min(cps, MINB);
+  if (tune.plane_ctas_per_sm > 0) cps = std::min(cps, tune.plane_ctas_per_sm);
+  long long grid = std::min<long long>(P.nunits, (long long)kNumSM * cps);
+#ifdef ABI_EMU
+  grid = std::min<long long>(grid, 3);
+#endif
+  const size_t sbytes = sizeof(double2) * (size_t)P.ng2 * P.nU * G;
+  P.S = (double2*)plane_scratch_get(sbytes * (size_t)grid);
+  ABI_LAUNCH(kern, dim3((unsigned)grid), dim3(WARPS * 32), smem, st, P);
+}
+
+template <int A, int B, int G>
+void half_launch_n(int kind, HalfParams& P, cudaStream_t st) {
+  const int cfg = fourwf_tuning().half_cfg;
+  if (kind == 0) {
+    if (cfg == 1) half_launch_cfg<A, B, G, 16, 1, 0>(P, st);
+    else half_launch_cfg<A, B, G, 8, 2, 0>(P, st);
+  } else {
+    half_launch_cfg<A, B, G, 8, 2, 1>(P, st);
+  }
+}
+
+}  // namespace abi

@@ -19,6 +19,7 @@ struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 struct int2 { int x, y; };
 struct short4 { short x, y, z, w; };
+struct int4 { int x, y, z, w; };
 inline int2 make_int2(int x, int y) { return int2{x, y}; }
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 typedef int cudaError_t; typedef void* cudaStream_t;
