@@ -395,6 +395,7 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
           const int bm = b - n2 / 2;                       // the high run in r = i2 - m coordinates
           hrows[u].x = plstart[u]; hrows[u].y = a | (la << 16); hrows[u].z = bm | (lb << 16); hrows[u].w = 0;
           if (la > 0 && lb > 0 && a < bm + lb && bm < a + la) y_amb = 1;
+          if (la + lb > n2 / 2 + 2) half_ok = false;     // staging buffer of the plane stage: rows of at most m + kHalfOV entries
         }
         d_hrows = to_device(hrows, pl->owned);
       }

@@ -64,8 +64,8 @@ struct FourwfPlan {
   int y_amb_in = 0, y_amb_out = 0;
   int4* d_hin_rows = nullptr; int4* d_hout_rows = nullptr;       // nU each: {first line, a | la << 16, (b - n2/2) | lb << 16, 0}
   // per-configuration z tables, built by the launcher at first use (mutable cache; the plan is otherwise immutable)
-  mutable int h_cfg_key = -1; mutable int h_z_has_ov = 0;
-  mutable int* d_hz_rowoff = nullptr; mutable int* d_hz_ovoff = nullptr; mutable int* d_hz_sign = nullptr; mutable int* d_hu_row = nullptr;
+  mutable int h_cfg_key = -1; mutable bool h_z_ok = false;
+  mutable int* d_hz_ovoff = nullptr; mutable int* d_hz_sign = nullptr; mutable int* d_hu_row = nullptr;
   mutable std::vector<void*> owned_lazy;
   std::vector<void*> owned;      // device allocations to free
   void release();
@@ -109,6 +109,7 @@ struct FourwfTuning {
   int plane_ctas_per_sm = 0;   // 0: occupancy / L2-budget limited
   int plane_split = 0;         // 1: run the split (three-kernel) plane stage for cubic boxes too (developer comparison)
   int half = 1;                // 1: half-support plane stage (half_stage.cuh) when the sphere fits in half of the box axes
+  int half_skip = 0;           // developer timing aid (phase mask), see HalfParams::dbg_skip
   int half_cfg = 0;            // 0: 8 warps x 2 CTAs/SM, 1: 16 warps x 1 CTA/SM
   int pack2 = 1;               // istwf_k=2: two bands per complex transform (double_rfft_trick, m_getghc.F90:1999-2171)
 };

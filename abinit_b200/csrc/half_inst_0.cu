@@ -2,5 +2,5 @@
 #include "half_stage_impl.cuh"
 namespace abi {
 template void half_launch_n<9, 10, 3>(int, HalfParams&, cudaStream_t);
-template void half_launch_n<3, 4, 8>(int, HalfParams&, cudaStream_t);
+template void half_launch_n<4, 3, 8>(int, HalfParams&, cudaStream_t);
 }  // namespace abi

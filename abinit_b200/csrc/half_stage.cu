@@ -14,8 +14,8 @@ typedef void (*HalfFn)(int, HalfParams&, cudaStream_t);
 struct Entry { HalfCfg cfg; HalfFn fn; };
 #define HALF_ENTRY(A, B, G) {{2 * (A) * (B), A, B, G}, &half_launch_n<A, B, G>}
 const Entry kEntries[] = {
-    HALF_ENTRY(3, 4, 8), HALF_ENTRY(3, 5, 5), HALF_ENTRY(4, 4, 8), HALF_ENTRY(2, 9, 7), HALF_ENTRY(5, 4, 8), HALF_ENTRY(3, 8, 8),
-    HALF_ENTRY(8, 8, 4), HALF_ENTRY(9, 10, 3),
+    HALF_ENTRY(4, 3, 8), HALF_ENTRY(5, 3, 10), HALF_ENTRY(4, 4, 8), HALF_ENTRY(9, 2, 9), HALF_ENTRY(4, 5, 8), HALF_ENTRY(8, 3, 8),
+    HALF_ENTRY(4, 8, 4), HALF_ENTRY(8, 8, 4), HALF_ENTRY(9, 10, 3),
 };
 const Entry* find_entry(int n) {
   for (const Entry& e : kEntries) if (e.cfg.n == n) return &e;
@@ -35,6 +35,8 @@ template <typename T> T* upload(const std::vector<T>& v, std::vector<void*>& own
   owned.push_back(d);
   return d;
 }
+struct HScratch { void* p = nullptr; size_t cap = 0; uint64_t key = 0; } g_hscratch;
+
 // permutation tables of one (n2, n3) pair: grid index of every slot of the vP / rhoP layout
 struct PermTab { int* d_i2_of_cid = nullptr; int* d_i3_of_slot = nullptr; };
 std::map<std::pair<int, int>, PermTab>& perm_cache() { static std::map<std::pair<int, int>, PermTab> c; return c; }
@@ -101,54 +103,63 @@ __global__ void k_rho_unpermute_add(const double* __restrict__ rhoP, double* __r
 }
 
 // z tables of the plan for one configuration (cached in the plan)
-void ensure_z_tables(const FourwfPlan& pl, const HalfCfg& c3, int G) {
+bool ensure_z_tables(const FourwfPlan& pl, const HalfCfg& c3, int G) {
   const int key = c3.n * 1000 + c3.A * 32 + G;
-  if (pl.h_cfg_key == key) return;
+  if (pl.h_cfg_key == key) return pl.h_z_ok;
   for (void* p : pl.owned_lazy) cudaFree(p);
   pl.owned_lazy.clear();
   const int M = c3.A * c3.B, za = pl.h_za, zla = pl.h_zla, zbm = pl.h_zb - M, zlb = pl.h_zlb;
-  std::vector<int> rowoff(M, -1), ovoff(M, -1), sign(M, 1), urow(pl.nU, 0);
-  int row = 0, has_ov = 0;
+  std::vector<int> sign(M, 0), ovrow(M, -1), urow(pl.nU, 0);
+  int nov = 0, nplanes = 0;
   for (int t = 0; t < c3.A; t++) for (int j = 0; j < c3.B; j++) {
     const int q = t * c3.B + j, r = rin_rt(c3, t, j);
     const bool lo = r >= za && r < za + zla, hi = r >= zbm && r < zbm + zlb;
     const int u_lo = r - za, u_hi = zla + r - zbm;
-    if (lo) { rowoff[q] = row * G; urow[u_lo] = row * G; row++; sign[q] = 1; }
+    if (lo) { sign[q] = 1; urow[u_lo] = q * G; nplanes++; }
     if (hi) {
-      if (lo) { ovoff[q] = row * G; has_ov = 1; }
-      else { rowoff[q] = row * G; sign[q] = -1; }
-      urow[u_hi] = row * G; row++;
+      if (lo) { ovrow[q] = M + nov; urow[u_hi] = (M + nov) * G; nov++; }
+      else { sign[q] = -1; urow[u_hi] = q * G; }
+      nplanes++;
     }
   }
-  ABI_CHECK(row == pl.nU, "half-support plane stage: inconsistent z-plane table");
-  pl.d_hz_rowoff = upload(rowoff, pl.owned_lazy);
-  pl.d_hz_ovoff = upload(ovoff, pl.owned_lazy);
-  pl.d_hz_sign = upload(sign, pl.owned_lazy);
-  pl.d_hu_row = upload(urow, pl.owned_lazy);
-  pl.h_z_has_ov = has_ov;
   pl.h_cfg_key = key;
+  pl.h_z_ok = nplanes == pl.nU && nov <= kHalfOV;
+  if (!pl.h_z_ok) return false;
+  pl.d_hz_sign = upload(sign, pl.owned_lazy);
+  pl.d_hz_ovoff = upload(ovrow, pl.owned_lazy);
+  pl.d_hu_row = upload(urow, pl.owned_lazy);
+  return true;
 }
 
 void fill_params(const FourwfPlan& pl, const HalfCfg& c2, const HalfCfg& c3, const HalfLaunch& L, HalfParams& P) {
-  ensure_z_tables(pl, c3, c2.G);
+  ABI_CHECK(ensure_z_tables(pl, c3, c2.G), "half-support plane stage: unsupported occupied z planes");
   P.n1 = pl.n1; P.n2 = pl.n2; P.n3 = pl.n3; P.nb = L.nb; P.nU = pl.nU; P.cplex = 1;
   P.nlin = L.nlin; P.nlout = L.nlout; P.nunits = (long long)L.nb * pl.n1;
   P.W1 = L.W1; P.W1o = L.W1o; P.S = nullptr; P.vP = nullptr;
   P.tw2 = fft_tables(pl.n2).plan.tw; P.tw3 = fft_tables(pl.n3).plan.tw;
   P.in_rows = pl.d_hin_rows; P.out_rows = L.out_is_in ? pl.d_hin_rows : pl.d_hout_rows;
   P.y_amb_in = pl.y_amb_in; P.y_amb_out = L.out_is_in ? pl.y_amb_in : pl.y_amb_out;
-  P.z_rowoff = pl.d_hz_rowoff; P.z_ovoff = pl.d_hz_ovoff; P.z_sign = pl.d_hz_sign; P.u_row = pl.d_hu_row;
-  P.z_has_ov = pl.h_z_has_ov;
+  P.z_sign = pl.d_hz_sign; P.z_ovrow = pl.d_hz_ovoff; P.u_row = pl.d_hu_row;
+  P.layout_key = pl.key ^ ((unsigned long long)pl.h_cfg_key << 40) ^ 0x9e3779b97f4a7c15ULL;
   P.ng2 = (pl.n2 + c2.G - 1) / c2.G;
   P.rhoP = L.rhoP; P.wxy = L.wxy;
+  P.dbg_skip = fourwf_tuning().half_skip;
 }
 }  // namespace
 
 const HalfCfg* half_stage_cfg(int n) { const Entry* e = find_entry(n); return e ? &e->cfg : nullptr; }
 
+void* half_scratch_get(size_t bytes, uint64_t layout_key, cudaStream_t st) {
+  HScratch& h = g_hscratch;
+  if (bytes > h.cap) { if (h.p) CUDA_CHECK(cudaFree(h.p)); CUDA_CHECK(cudaMalloc(&h.p, bytes)); h.cap = bytes; h.key = 0; }
+  if (h.key != layout_key) { CUDA_CHECK(cudaMemsetAsync(h.p, 0, h.cap, st)); h.key = layout_key; }   // the whole buffer: later launches of this plan may use more of it
+  return h.p;
+}
+
 bool half_stage_usable(const FourwfPlan& pl, bool out_is_in) {
-  return pl.fused_ok && pl.half_ok_in && (out_is_in || pl.half_ok_out) && fourwf_tuning().half && pl.n2 == pl.n3 &&
-         find_entry(pl.n2) != nullptr;
+  if (!(pl.fused_ok && pl.half_ok_in && (out_is_in || pl.half_ok_out) && fourwf_tuning().half && pl.n2 == pl.n3)) return false;
+  const Entry* e = find_entry(pl.n2);
+  return e != nullptr && ensure_z_tables(pl, e->cfg, e->cfg.G);
 }
 
 void half_stage_launch(const FourwfPlan& pl, const VlocDev& v, const HalfLaunch& L, cudaStream_t st) {
@@ -203,6 +214,8 @@ void half_rho_unpermute_add(const FourwfPlan& pl, const double* rhoP, double* de
 }
 
 void half_stage_release() {
+  if (g_hscratch.p) cudaFree(g_hscratch.p);
+  g_hscratch = HScratch();
   for (void* p : perm_owned()) cudaFree(p);
   perm_owned().clear(); perm_cache().clear();
 }

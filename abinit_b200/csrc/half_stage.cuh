@@ -26,6 +26,7 @@
 // density accumulation :2338-2384.
 #pragma once
 #include "plane_stage.cuh"
+#include "hdft.cuh"
 
 namespace abi {
 
@@ -34,7 +35,7 @@ struct HalfParams {
   int nlin, nlout;                    // lines per (band, i1) plane of W1 / W1o
   long long nunits;                   // nb * n1
   const double2* W1; double2* W1o;    // [b][i1][line]
-  double2* S;                         // fused: [gridDim.x][ng2][nU][G]; split: [nunits][ng2][nU][G]
+  double2* S;                         // fused: [gridDim.x][ng2][ROWS][G]; split: [nunits][ng2][ROWS][G]
   const double* vP;                   // V_loc permuted [i1][ng2][B3][G][2 A3] (cplex doubles per point)
   const double2* tw2;                 // exp(-2 pi i q / n2), q < n2
   const double2* tw3;                 // exp(-2 pi i q / n3)
@@ -42,12 +43,14 @@ struct HalfParams {
   // lb entries i2 in [b, b + lb) (b >= m2):  rows[u] = {first line of the plane, a | la << 16, (b - m2) | lb << 16, 0}
   const int4* in_rows; const int4* out_rows;
   int y_amb_in, y_amb_out;            // 1 if some row holds both i2 = r and i2 = r + m2 for some r (overlap of the two runs)
-  const int* z_rowoff;                // [m3] in pass-1 order (t * B + j): row * G of the plane holding v[r], or -1
-  const int* z_ovoff;                 // [m3] row * G of the high partner where both r and r + m3 are occupied, else -1
-  const int* z_sign;                  // [m3] +1 / -1: s_r of the plane behind z_rowoff
+  // z direction, in pass-1 order q = t * B + j (r = rin(t, j)): S row q holds the occupied plane behind v[r]; where both i3 = r and
+  // i3 = r + m3 are occupied the high partner sits in one of the OV extra rows m3 + idx
+  const int* z_sign;                  // [m3] +1 / -1: s_r of the plane in row q (high planes carry -1); 0: no plane (row stays zero)
+  const int* z_ovrow;                 // [m3] extra row (>= m3) of the high partner, or -1
   const int* u_row;                   // [nU] row * G of plane u
-  int z_has_ov;
   int ng2;                            // column batches: ceil(n2 / G)
+  int dbg_skip = 0;                   // developer timing aid: bit 0 / 1 / 2 skips the y / z / y^-1 phase (results are then wrong)
+  unsigned long long layout_key = 0;  // identifies (plan, configuration): the scratch is cleared when it changes
   // option 1 (density accumulation): rhoP[i1][ng2][B3][G][2 A3] += wxy[b].x Re(psi)^2 + wxy[b].y Im(psi)^2
   double* rhoP = nullptr; const double2* wxy = nullptr;
 };
@@ -66,19 +69,25 @@ ABI_DEV double2 ld_keep(const double2* a, unsigned long long pol) {
 ABI_DEV void st_keep(double2* a, double2 v, unsigned long long pol) {
   asm volatile("st.global.cg.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(a), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
 }
-ABI_DEV double2 ld_stream(const double2* a, unsigned long long pol) {
-  double2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol)); return v;
-}
 ABI_DEV void st_stream(double2* a, double2 v, unsigned long long pol) {
   asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(a), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS), L1 bypassed, with an L2 policy
+ABI_DEV void cp_async16(double2* sdst, const double2* gsrc, unsigned long long pol) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "l"(pol) : "memory");
+}
+ABI_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+ABI_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #else
 inline unsigned long long policy_evict_last() { return 0; }
 inline unsigned long long policy_evict_first() { return 0; }
 inline double2 ld_keep(const double2* a, unsigned long long) { return *a; }
 inline void st_keep(double2* a, double2 v, unsigned long long) { *a = v; }
-inline double2 ld_stream(const double2* a, unsigned long long) { return *a; }
 inline void st_stream(double2* a, double2 v, unsigned long long) { *a = v; }
+inline void cp_async16(double2* sdst, const double2* gsrc, unsigned long long) { *sdst = *gsrc; }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
 #endif
 
 ABI_HD constexpr int h_gcd(int a, int b) { return b == 0 ? a : h_gcd(b, a % b); }
@@ -94,27 +103,34 @@ template <int A, int B> struct HalfMap {
   }
 };
 
+constexpr int kHalfOV = 2;   // extra S rows for planes / row entries present at both r and r + m (exact boxcut-2 boxes: one)
+
 template <int A, int B, int G>
 struct HalfFft {
+  static_assert((2 * A) % G == 0, "the column-batch width must divide 2A (compile-time S strides)");
   using Map = HalfMap<A, B>;
   static constexpr int M = A * B, N = 2 * M;
   static constexpr bool PFA = Map::PFA;
+  static constexpr int ROWS = M + kHalfOV;               // rows of one column batch of S
   static constexpr int ZK = (B * G) | 1;                 // odd stride between the (half, k1) slabs of the exchange buffer
-  static constexpr int ESIZE = 2 * A * ZK;               // double2 per warp
+  static constexpr int ESIZE = 2 * A * ZK;               // exchange buffer, double2 per warp
+  static constexpr int STG = ROWS * G;                   // staging buffer (prefetched W1 rows / S block), double2 per warp
+  static constexpr int WSIZE = ESIZE + STG + 1;          // + one slot that always holds zero (reads of absent row entries)
   static constexpr int NG = (N + G - 1) / G;             // column batches of a length-N axis
+  static constexpr int GSTR = ROWS * G;                  // double2 between consecutive column batches of S
   // shared-memory tables (double2 slots): Ty[M] | Tz[M] | ctwA[M] | ctwB[M] (Cooley-Tukey only) | ints
   static constexpr int TW_SLOTS = 2 * M + (PFA ? 0 : 2 * M);
-  ABI_HD static constexpr int int_slots(int nU) { return (2 * M + nU + 3) / 4; }   // z_rowoff, z_ovoff, u_row
+  ABI_HD static constexpr int int_slots(int nU) { return (B + M + nU + 3) / 4; }   // zmask[B], zov[M], u_row[nU]
 
   struct Tables {
     const double2* Ty; const double2* Tz; const double2* ctwA; const double2* ctwB;
-    const int* zrow; const int* zov; const int* urow;
+    const int* zmask; const int* zov; const int* urow;
   };
 
-  // tid/nthr: the whole CTA fills the tables once
+  // tid/nthr: the whole CTA fills the tables once (ends without a barrier: the caller synchronises)
   ABI_DEV static Tables load_tables(double2* sm, const HalfParams& P, bool ytab, bool ztab, int tid, int nthr) {
     double2* Ty = sm; double2* Tz = sm + M; double2* cA = sm + 2 * M; double2* cB = cA + M;
-    int* zrow = reinterpret_cast<int*>(sm + TW_SLOTS); int* zov = zrow + M; int* urow = zov + M;
+    int* zmask = reinterpret_cast<int*>(sm + TW_SLOTS); int* zov = zmask + B; int* urow = zov + M;
     for (int q = tid; q < M; q += nthr) {
       const int t = q / B, j = q - t * B;
       const int r = Map::rin(t, j);
@@ -122,7 +138,7 @@ struct HalfFft {
       if (ztab) {
         double2 w = P.tw3[r];
         if (P.z_sign[q] < 0) { w.x = -w.x; w.y = -w.y; }
-        Tz[q] = w; zrow[q] = P.z_rowoff[q]; zov[q] = P.z_ovoff[q];
+        Tz[q] = w; zov[q] = P.z_ovrow[q];
       }
       if (!PFA) {
         // inter-pass twiddle w_m^(j k1): element q = k1 * B + j of ctwA, j * A + k1 of ctwB
@@ -131,15 +147,21 @@ struct HalfFft {
         cA[q] = w; cB[jj * A + k1] = w;
       }
     }
+    // per j: bit t = row (t, j) holds a plane; bit 16 + t = it also has a high partner in an extra row
+    if (ztab) for (int j = tid; j < B; j += nthr) {
+      int m = 0;
+      for (int t = 0; t < A; t++) { if (P.z_sign[t * B + j] != 0) m |= 1 << t; if (P.z_ovrow[t * B + j] >= 0) m |= 1 << (16 + t); }
+      zmask[j] = m;
+    }
     for (int u = tid; u < P.nU; u += nthr) urow[u] = P.u_row[u];
-    Tables T; T.Ty = Ty; T.Tz = Tz; T.ctwA = cA; T.ctwB = cB; T.zrow = zrow; T.zov = zov; T.urow = urow;
+    Tables T; T.Ty = Ty; T.Tz = Tz; T.ctwA = cA; T.ctwB = cB; T.zmask = zmask; T.zov = zov; T.urow = urow;
     return T;
   }
 
   // ---- pass 1 (forward) on registers: x = even-half input, xo = odd-half input already multiplied by s_r w^r ----
   ABI_DEV static void fwd1_store(double2* x, double2* xo, double2* e, const Tables& T, int j) {
-    Dft<A, +1>::run(x);
-    Dft<A, +1>::run(xo);
+    HDft<A, +1>::run(x);
+    HDft<A, +1>::run(xo);
     if (!PFA) {
 #pragma unroll
       for (int k1 = 1; k1 < A; k1++) { const double2 w = T.ctwA[k1 * B + j]; x[k1] = cmulc(x[k1], w); xo[k1] = cmulc(xo[k1], w); }
@@ -151,14 +173,31 @@ struct HalfFft {
   ABI_DEV static void inv1_load(double2* ye, double2* yo, const double2* e) {
 #pragma unroll
     for (int k1 = 0; k1 < A; k1++) { ye[k1] = e[k1 * ZK]; yo[k1] = e[(A + k1) * ZK]; }
-    Dft<A, -1>::run(ye);
-    Dft<A, -1>::run(yo);
+    HDft<A, -1>::run(ye);
+    HDft<A, -1>::run(yo);
+  }
+  // ye + yo * tw as four fused multiply-adds per element
+  ABI_DEV static double2 comb(double2 ye, double2 yo, double2 tw) {
+    return make_double2(fma(yo.x, tw.x, fma(-yo.y, tw.y, ye.x)), fma(yo.x, tw.y, fma(yo.y, tw.x, ye.y)));
   }
 
   // ---------------- phase Y: compact rows of W1 -> S ----------------
-  ABI_DEV static void phase_y(const HalfParams& P, const Tables& T, const double2* __restrict__ w1, double2* __restrict__ S,
-                              double2* E, int u0, unsigned long long pkeep, unsigned long long pstream) {
+  // asynchronous copy of the W1 rows of the line batch [u0, u0 + nl) (one contiguous piece of W1) into the warp's staging buffer
+  ABI_DEV static void y_prefetch(const HalfParams& P, const double2* __restrict__ w1, double2* stg, int u0, unsigned long long pstream) {
     const int nl = min(G, P.nU - u0);
+    if (nl <= 0) return;
+    const int4 r0 = P.in_rows[u0], r1 = P.in_rows[u0 + nl - 1];
+    const int first = r0.x, count = r1.x + (r1.y >> 16) + (r1.z >> 16) - r0.x;
+    ABI_FOR_LANES {
+      for (int q = lane; q < count; q += 32) cp_async16(stg + q, w1 + first + q, pstream);
+    }
+    cp_async_commit();
+  }
+
+  ABI_DEV static void y_batch(const HalfParams& P, const Tables& T, double2* __restrict__ S, double2* E, const double2* stg, int u0,
+                              unsigned long long pkeep) {
+    const int nl = min(G, P.nU - u0);
+    const int first = P.in_rows[u0].x;
     for (int w0 = 0; w0 < G * B; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
@@ -166,21 +205,20 @@ struct HalfFft {
         if (w < G * B && line < nl) {
           const int4 row = P.in_rows[u0 + line];
           const int a = row.y & 0xffff, la = row.y >> 16, bm = row.z & 0xffff, lb = row.z >> 16;
-          const double2* slo = w1 + row.x - a;                 // slo[r] = x[r]      for r in [a, a + la)
-          const double2* shi = w1 + row.x + (la - bm);         // shi[r] = x[r + m]  for r in [bm, bm + lb)
+          const int olo = (row.x - first) - a, ohi = (row.x - first) + (la - bm);   // stg[olo + r] = x[r], stg[ohi + r] = x[r + m]
           double2 x[A], xo[A];
           int r = PFA ? (A * j) % M : j;
 #pragma unroll
           for (int t = 0; t < A; t++) {
             const bool lo = (unsigned)(r - a) < (unsigned)la, hi = (unsigned)(r - bm) < (unsigned)lb;
-            double2 v = make_double2(0.0, 0.0);
-            if (lo) v = ld_stream(slo + r, pstream);
-            else if (hi) v = ld_stream(shi + r, pstream);
-            double2 tw = T.Ty[t * B + j];
-            if (!lo) { tw.x = -tw.x; tw.y = -tw.y; }
-            double2 vo = v;
-            if (P.y_amb_in && lo && hi) { const double2 h = ld_stream(shi + r, pstream); vo = csub(v, h); v = cadd(v, h); }
-            x[t] = v; xo[t] = cmulc(vo, tw);
+            // absent entries read the zero slot; the odd half of a high-run entry carries s_r = -1 (sign bit flipped on the way)
+            const double2 v = stg[lo ? olo + r : (hi ? ohi + r : STG)];
+            const int flip = lo ? 0 : (int)0x80000000;
+            double2 vo = make_double2(__hiloint2double(__double2hiint(v.x) ^ flip, __double2loint(v.x)),
+                                      __hiloint2double(__double2hiint(v.y) ^ flip, __double2loint(v.y)));
+            x[t] = v;
+            if (P.y_amb_in && lo && hi) { const double2 h = stg[ohi + r]; vo = csub(v, h); x[t] = cadd(v, h); }
+            xo[t] = cmulc(vo, T.Ty[t * B + j]);
             r += B; if (PFA && r >= M) r -= M;
           }
           fwd1_store(x, xo, E + j * G + line, T, j);
@@ -188,6 +226,11 @@ struct HalfFft {
       }
     }
     ABI_SYNCWARP();
+  }
+
+  ABI_DEV static void y_pass2(const HalfParams& P, const Tables& T, double2* __restrict__ S, const double2* E, int u0,
+                              unsigned long long pkeep) {
+    const int nl = min(G, P.nU - u0);
     for (int w0 = 0; w0 < 2 * A * G; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
@@ -197,44 +240,60 @@ struct HalfFft {
           double2 v[B];
 #pragma unroll
           for (int j = 0; j < B; j++) v[j] = e[j * G];
-          Dft<B, +1>::run(v);
-          double2* dst = S + T.urow[u0 + line];
-          int g = hk1 / G, c = hk1 - g * G;
+          HDft<B, +1>::run(v);
+          // column id k2 * 2A + hk1 -> batch g = g0 + k2 * (2A / G), c = hk1 % G
+          double2* dst = S + T.urow[u0 + line] + (hk1 / G) * GSTR + (hk1 % G);
 #pragma unroll
-          for (int k2 = 0; k2 < B; k2++) {
-            st_keep(dst + (size_t)g * (P.nU * G) + c, v[k2], pkeep);
-            g += (2 * A) / G; c += (2 * A) % G;
-            if ((2 * A) % G != 0 && c >= G) { c -= G; g++; }
-          }
+          for (int k2 = 0; k2 < B; k2++) st_keep(dst + k2 * ((2 * A / G) * GSTR), v[k2], pkeep);
         }
       }
     }
     ABI_SYNCWARP();
   }
 
+  // all line batches of one plane that belong to this warp; the first batch must already be in flight (y_prefetch)
+  ABI_DEV static void phase_y(const HalfParams& P, const Tables& T, const double2* __restrict__ w1, double2* __restrict__ S,
+                              double2* E, double2* stg, int warp, int nwarps, unsigned long long pkeep, unsigned long long pstream) {
+    for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) {
+      cp_async_wait_all();
+      ABI_SYNCWARP();
+      y_batch(P, T, S, E, stg, u0, pkeep);
+      if (u0 + nwarps * G < P.nU) y_prefetch(P, w1, stg, u0 + nwarps * G, pstream);   // flies during pass 2
+      y_pass2(P, T, S, E, u0, pkeep);
+    }
+  }
+
   // ---------------- phase Z: one column batch of S -> z FFT, * V_loc, z FFT^-1 -> S (in place) ----------------
-  ABI_DEV static void z_pass1(const HalfParams& P, const Tables& T, const double2* __restrict__ Sg, double2* E, int nl,
-                              unsigned long long pkeep) {
+  ABI_DEV static void z_prefetch(const double2* __restrict__ S, double2* stg, int g, unsigned long long pkeep) {
+    const double2* src = S + (size_t)g * GSTR;
+    ABI_FOR_LANES {
+#pragma unroll
+      for (int q = 0; q < (STG + 31) / 32; q++) if (q * 32 + lane < STG) cp_async16(stg + q * 32 + lane, src + q * 32 + lane, pkeep);
+    }
+    cp_async_commit();
+  }
+
+  ABI_DEV static void z_pass1(const Tables& T, const double2* stg, double2* E, int nl) {
     for (int w0 = 0; w0 < G * B; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
         const int j = w / G, c = w - j * G;
         if (w < G * B && c < nl) {
-          const double2* src = Sg + c;
+          const double2* src = stg + j * G + c;
           double2 x[A], xo[A];
 #pragma unroll
-          for (int t = 0; t < A; t++) {
-            const int o = T.zrow[t * B + j];
-            x[t] = (o >= 0) ? ld_keep(src + o, pkeep) : make_double2(0.0, 0.0);
-          }
+          for (int t = 0; t < A; t++) x[t] = src[t * (B * G)];
+          const int zm = T.zmask[j];
+          if (zm >> 16) {                     // a plane pair (r, r + m) in this lane's column: rare, one or two lanes of a warp
 #pragma unroll
-          for (int t = 0; t < A; t++) {
-            double2 vo = x[t];
-            if (P.z_has_ov) {
-              const int o2 = T.zov[t * B + j];
-              if (o2 >= 0) { const double2 h = ld_keep(src + o2, pkeep); vo = csub(x[t], h); x[t] = cadd(x[t], h); }
+            for (int t = 0; t < A; t++) {
+              double2 vo = x[t];
+              if ((zm >> (16 + t)) & 1) { const double2 h = stg[T.zov[t * B + j] * G + c]; vo = csub(x[t], h); x[t] = cadd(x[t], h); }
+              xo[t] = cmulc(vo, T.Tz[t * B + j]);
             }
-            xo[t] = cmulc(vo, T.Tz[t * B + j]);
+          } else {
+#pragma unroll
+            for (int t = 0; t < A; t++) xo[t] = cmulc(x[t], T.Tz[t * B + j]);
           }
           fwd1_store(x, xo, E + j * G + c, T, j);
         }
@@ -243,48 +302,64 @@ struct HalfFft {
     ABI_SYNCWARP();
   }
 
-  ABI_DEV static void phase_z(const HalfParams& P, const Tables& T, double2* __restrict__ S, const double* __restrict__ vunit,
-                              double2* E, int g, unsigned long long pkeep) {
+  template <bool RHO>
+  ABI_DEV static void z_batch(const HalfParams& P, const Tables& T, double2* __restrict__ S, const double* __restrict__ vunit,
+                              double* __restrict__ runit, double2 wxy, double2* E, double2* stg, int g, int gnext,
+                              unsigned long long pkeep) {
     const int nl = min(G, P.n2 - g * G);
-    double2* Sg = S + (size_t)g * (P.nU * G);
-    z_pass1(P, T, Sg, E, nl, pkeep);
+    double2* Sg = S + (size_t)g * GSTR;
+    cp_async_wait_all();
+    ABI_SYNCWARP();
+    z_pass1(T, stg, E, nl);
+    if (gnext < P.ng2) z_prefetch(S, stg, gnext, pkeep);       // flies during pass 2 and pass 1'
     for (int w0 = 0; w0 < 2 * A * G; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
         const int c = w / (2 * A), hk1 = w - c * (2 * A);
         if (w < 2 * A * G && c < nl) {
           double2* e = E + hk1 * ZK + c;
-          // V_loc of this lane's B grid points first: the loads fly while the exchange buffer is read and transformed
-          double2 vv[B];
-          if (P.cplex == 1) {
-            const double* vp = vunit + (size_t)g * (B * G * 2 * A) + c * (2 * A) + hk1;
+          if (RHO) {
+            double2 v[B];
 #pragma unroll
-            for (int k2 = 0; k2 < B; k2++) vv[k2] = make_double2(ldg1(vp + k2 * (G * 2 * A)), 0.0);
+            for (int j = 0; j < B; j++) v[j] = e[j * G];
+            HDft<B, +1>::run(v);
+            double* rp = runit + (size_t)g * (B * G * 2 * A) + c * (2 * A) + hk1;
+#pragma unroll
+            for (int k2 = 0; k2 < B; k2++) ABI_RED_ADD(rp + k2 * (G * 2 * A), wxy.x * v[k2].x * v[k2].x + wxy.y * v[k2].y * v[k2].y);
           } else {
-            const double2* vp = reinterpret_cast<const double2*>(vunit) + (size_t)g * (B * G * 2 * A) + c * (2 * A) + hk1;
+            // V_loc of this lane's B grid points first: the loads fly while the exchange buffer is read and transformed
+            double2 vv[B];
+            if (P.cplex == 1) {
+              const double* vp = vunit + (size_t)g * (B * G * 2 * A) + c * (2 * A) + hk1;
 #pragma unroll
-            for (int k2 = 0; k2 < B; k2++) vv[k2] = ldg2(vp + k2 * (G * 2 * A));
+              for (int k2 = 0; k2 < B; k2++) vv[k2] = make_double2(ldg1(vp + k2 * (G * 2 * A)), 0.0);
+            } else {
+              const double2* vp = reinterpret_cast<const double2*>(vunit) + (size_t)g * (B * G * 2 * A) + c * (2 * A) + hk1;
+#pragma unroll
+              for (int k2 = 0; k2 < B; k2++) vv[k2] = ldg2(vp + k2 * (G * 2 * A));
+            }
+            double2 v[B];
+#pragma unroll
+            for (int j = 0; j < B; j++) v[j] = e[j * G];
+            HDft<B, +1>::run(v);
+            if (P.cplex == 1) {
+#pragma unroll
+              for (int k2 = 0; k2 < B; k2++) { v[k2].x *= vv[k2].x; v[k2].y *= vv[k2].x; }
+            } else {
+#pragma unroll
+              for (int k2 = 0; k2 < B; k2++) v[k2] = cmul(v[k2], vv[k2]);
+            }
+            HDft<B, -1>::run(v);
+            const int k1 = hk1 >= A ? hk1 - A : hk1;
+            e[0] = v[0];
+#pragma unroll
+            for (int j = 1; j < B; j++) e[j * G] = PFA ? v[j] : cmul(v[j], T.ctwB[j * A + k1]);
           }
-          double2 v[B];
-#pragma unroll
-          for (int j = 0; j < B; j++) v[j] = e[j * G];
-          Dft<B, +1>::run(v);
-          if (P.cplex == 1) {
-#pragma unroll
-            for (int k2 = 0; k2 < B; k2++) { v[k2].x *= vv[k2].x; v[k2].y *= vv[k2].x; }
-          } else {
-#pragma unroll
-            for (int k2 = 0; k2 < B; k2++) v[k2] = cmul(v[k2], vv[k2]);
-          }
-          Dft<B, -1>::run(v);
-          const int k1 = hk1 >= A ? hk1 - A : hk1;
-          e[0] = v[0];
-#pragma unroll
-          for (int j = 1; j < B; j++) e[j * G] = PFA ? v[j] : cmul(v[j], T.ctwB[j * A + k1]);
         }
       }
     }
     ABI_SYNCWARP();
+    if (RHO) return;
     for (int w0 = 0; w0 < G * B; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
@@ -292,16 +367,13 @@ struct HalfFft {
         if (w < G * B && c < nl) {
           double2 ye[A], yo[A];
           inv1_load(ye, yo, E + j * G + c);
-          double2* dst = Sg + c;
+          double2* dst = Sg + j * G + c;
+          const int zm = T.zmask[j];
 #pragma unroll
           for (int t = 0; t < A; t++) {
-            const int o = T.zrow[t * B + j];
-            const double2 to = cmul(yo[t], T.Tz[t * B + j]);
-            if (o >= 0) st_keep(dst + o, cadd(ye[t], to), pkeep);
-            if (P.z_has_ov) {
-              const int o2 = T.zov[t * B + j];
-              if (o2 >= 0) st_keep(dst + o2, csub(ye[t], to), pkeep);
-            }
+            const double2 tw = T.Tz[t * B + j];
+            if ((zm >> t) & 1) st_keep(dst + t * (B * G), comb(ye[t], yo[t], tw), pkeep);
+            if ((zm >> (16 + t)) & 1) st_keep(Sg + T.zov[t * B + j] * G + c, comb(ye[t], yo[t], make_double2(-tw.x, -tw.y)), pkeep);
           }
         }
       }
@@ -309,29 +381,12 @@ struct HalfFft {
     ABI_SYNCWARP();
   }
 
-  // ---------------- phase Z (option 1): z FFT of one column batch -> rhoP += w |psi(r)|^2 ----------------
-  ABI_DEV static void phase_z_rho(const HalfParams& P, const Tables& T, const double2* __restrict__ S, double* __restrict__ runit,
-                                  double2 wxy, double2* E, int g, unsigned long long pkeep) {
-    const int nl = min(G, P.n2 - g * G);
-    const double2* Sg = S + (size_t)g * (P.nU * G);
-    z_pass1(P, T, Sg, E, nl, pkeep);
-    for (int w0 = 0; w0 < 2 * A * G; w0 += 32) {
-      ABI_FOR_LANES {
-        const int w = w0 + lane;
-        const int c = w / (2 * A), hk1 = w - c * (2 * A);
-        if (w < 2 * A * G && c < nl) {
-          const double2* e = E + hk1 * ZK + c;
-          double2 v[B];
-#pragma unroll
-          for (int j = 0; j < B; j++) v[j] = e[j * G];
-          Dft<B, +1>::run(v);
-          double* rp = runit + (size_t)g * (B * G * 2 * A) + c * (2 * A) + hk1;
-#pragma unroll
-          for (int k2 = 0; k2 < B; k2++) ABI_RED_ADD(rp + k2 * (G * 2 * A), wxy.x * v[k2].x * v[k2].x + wxy.y * v[k2].y * v[k2].y);
-        }
-      }
-    }
-    ABI_SYNCWARP();
+  template <bool RHO>
+  ABI_DEV static void phase_z(const HalfParams& P, const Tables& T, double2* __restrict__ S, const double* __restrict__ vunit,
+                              double* __restrict__ runit, double2 wxy, double2* E, double2* stg, int warp, int nwarps,
+                              unsigned long long pkeep) {
+    if (warp < P.ng2) z_prefetch(S, stg, warp, pkeep);
+    for (int g = warp; g < P.ng2; g += nwarps) z_batch<RHO>(P, T, S, vunit, runit, wxy, E, stg, g, g + nwarps, pkeep);
   }
 
   // ---------------- phase Y': S -> y FFT^-1 -> compact output rows of W1o ----------------
@@ -343,16 +398,11 @@ struct HalfFft {
         const int w = w0 + lane;
         const int line = w / (2 * A), hk1 = w - line * (2 * A);
         if (w < 2 * A * G && line < nl) {
-          const double2* src = S + T.urow[u0 + line];
+          const double2* src = S + T.urow[u0 + line] + (hk1 / G) * GSTR + (hk1 % G);
           double2 v[B];
-          int g = hk1 / G, c = hk1 - g * G;
 #pragma unroll
-          for (int k2 = 0; k2 < B; k2++) {
-            v[k2] = ld_keep(src + (size_t)g * (P.nU * G) + c, pkeep);
-            g += (2 * A) / G; c += (2 * A) % G;
-            if ((2 * A) % G != 0 && c >= G) { c -= G; g++; }
-          }
-          Dft<B, -1>::run(v);
+          for (int k2 = 0; k2 < B; k2++) v[k2] = ld_keep(src + k2 * ((2 * A / G) * GSTR), pkeep);
+          HDft<B, -1>::run(v);
           const int k1 = hk1 >= A ? hk1 - A : hk1;
           double2* e = E + hk1 * ZK + line;
           e[0] = v[0];
@@ -376,9 +426,9 @@ struct HalfFft {
           int r = PFA ? (A * j) % M : j;
 #pragma unroll
           for (int t = 0; t < A; t++) {
-            const double2 to = cmul(yo[t], T.Ty[t * B + j]);
-            if ((unsigned)(r - a) < (unsigned)la) st_stream(dlo + r, cadd(ye[t], to), pstream);
-            if ((unsigned)(r - bm) < (unsigned)lb) st_stream(dhi + r, csub(ye[t], to), pstream);
+            const double2 tw = T.Ty[t * B + j];
+            if ((unsigned)(r - a) < (unsigned)la) st_stream(dlo + r, comb(ye[t], yo[t], tw), pstream);
+            if ((unsigned)(r - bm) < (unsigned)lb) st_stream(dhi + r, comb(ye[t], yo[t], make_double2(-tw.x, -tw.y)), pstream);
             r += B; if (PFA && r >= M) r -= M;
           }
         }
@@ -391,11 +441,12 @@ struct HalfFft {
 // dynamic shared memory of the kernels below (bytes)
 template <int A, int B, int G> ABI_HD constexpr size_t half_smem_bytes(int warps, int nU) {
   using F = HalfFft<A, B, G>;
-  return sizeof(double2) * ((size_t)F::TW_SLOTS + F::int_slots(nU) + (size_t)warps * F::ESIZE);
+  return sizeof(double2) * ((size_t)F::TW_SLOTS + F::int_slots(nU) + (size_t)warps * F::WSIZE);
 }
 
 // one CTA = one (transform, i1) plane at a time; warps take line / column batches round-robin inside each phase
-template <int A, int B, int G, int WARPS, int MINB>
+// KIND 0: option 2 (y, z * V_loc, y^-1), KIND 1: option 1 (y, z, density accumulation)
+template <int A, int B, int G, int WARPS, int MINB, int KIND>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_hw_plane(HalfParams P) {
   using F = HalfFft<A, B, G>;
   ABI_DYN_SMEM(double2, sm);
@@ -405,89 +456,42 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_hw_plane(HalfParams P) {
   const int warp = threadIdx.x >> 5, nwarps = WARPS, tid = threadIdx.x, nthr = WARPS * 32;
 #endif
   const typename F::Tables T = F::load_tables(sm, P, true, true, tid, nthr);
-  double2* E = sm + F::TW_SLOTS + F::int_slots(P.nU) + (size_t)warp * F::ESIZE;
-  double2* S = P.S + (size_t)blockIdx.x * P.ng2 * P.nU * G;
+  double2* E = sm + F::TW_SLOTS + F::int_slots(P.nU) + (size_t)warp * F::WSIZE;
+  double2* stg = E + F::ESIZE;
+  stg[F::STG] = make_double2(0.0, 0.0);                  // the zero slot (every lane writes the same value)
+  double2* S = P.S + (size_t)blockIdx.x * P.ng2 * F::GSTR;
   const unsigned long long pkeep = policy_evict_last(), pstream = policy_evict_first();
-  const size_t vplane = (size_t)P.cplex * P.ng2 * (B * G * 2 * A);
+  const size_t vplane = (size_t)P.ng2 * (B * G * 2 * A);
   __syncthreads();
+  if (blockIdx.x < P.nunits) {
+    const int i1 = (int)(blockIdx.x / P.nb), b = (int)(blockIdx.x - (long long)i1 * P.nb);
+    F::y_prefetch(P, P.W1 + ((size_t)b * P.n1 + i1) * P.nlin, stg, warp * G, pstream);
+  }
   for (long long unit = blockIdx.x; unit < P.nunits; unit += gridDim.x) {
     const int i1 = (int)(unit / P.nb), b = (int)(unit - (long long)i1 * P.nb);
     const double2* w1 = P.W1 + ((size_t)b * P.n1 + i1) * P.nlin;
-    double2* w1o = P.W1o + ((size_t)b * P.n1 + i1) * P.nlout;
-    const double* vunit = P.vP + (size_t)i1 * vplane;
-    for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_y(P, T, w1, S, E, u0, pkeep, pstream);
+    if (!(P.dbg_skip & 1)) F::phase_y(P, T, w1, S, E, stg, warp, nwarps, pkeep, pstream);
     __syncthreads();
-    for (int g = warp; g < P.ng2; g += nwarps) F::phase_z(P, T, S, vunit, E, g, pkeep);
+    if (P.dbg_skip & 2) {
+    } else if (KIND == 0) {
+      F::template phase_z<false>(P, T, S, P.vP + (size_t)P.cplex * i1 * vplane, nullptr, make_double2(0.0, 0.0), E, stg, warp, nwarps, pkeep);
+    } else {
+      F::template phase_z<true>(P, T, S, nullptr, P.rhoP + (size_t)i1 * vplane, P.wxy[b], E, stg, warp, nwarps, pkeep);
+    }
+    // the staging buffer is idle from here on: fetch the first line batch of the next plane
+    const long long next = unit + gridDim.x;
+    if (next < P.nunits) {
+      const int i1n = (int)(next / P.nb), bn = (int)(next - (long long)i1n * P.nb);
+      F::y_prefetch(P, P.W1 + ((size_t)bn * P.n1 + i1n) * P.nlin, stg, warp * G, pstream);
+    }
     __syncthreads();
-    for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_yinv(P, T, S, w1o, E, u0, pkeep, pstream);
-    __syncthreads();
-  }
-}
-
-// option 1: y FFT, z FFT, density accumulation (no way back)
-template <int A, int B, int G, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) k_hw_plane_rho(HalfParams P) {
-  using F = HalfFft<A, B, G>;
-  ABI_DYN_SMEM(double2, sm);
-#ifdef ABI_EMU
-  const int warp = 0, nwarps = 1, tid = 0, nthr = 1;
-#else
-  const int warp = threadIdx.x >> 5, nwarps = WARPS, tid = threadIdx.x, nthr = WARPS * 32;
-#endif
-  const typename F::Tables T = F::load_tables(sm, P, true, true, tid, nthr);
-  double2* E = sm + F::TW_SLOTS + F::int_slots(P.nU) + (size_t)warp * F::ESIZE;
-  double2* S = P.S + (size_t)blockIdx.x * P.ng2 * P.nU * G;
-  const unsigned long long pkeep = policy_evict_last(), pstream = policy_evict_first();
-  const size_t rplane = (size_t)P.ng2 * (B * G * 2 * A);
-  __syncthreads();
-  for (long long unit = blockIdx.x; unit < P.nunits; unit += gridDim.x) {
-    const int i1 = (int)(unit / P.nb), b = (int)(unit - (long long)i1 * P.nb);
-    const double2* w1 = P.W1 + ((size_t)b * P.n1 + i1) * P.nlin;
-    double* runit = P.rhoP + (size_t)i1 * rplane;
-    const double2 wxy = P.wxy[b];
-    for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_y(P, T, w1, S, E, u0, pkeep, pstream);
-    __syncthreads();
-    for (int g = warp; g < P.ng2; g += nwarps) F::phase_z_rho(P, T, S, runit, wxy, E, g, pkeep);
-    __syncthreads();
-  }
-}
-
-// Split plane stage for n2 != n3: the same phases as three kernels, each templated on ONE half-length, with the S planes of
-// all units of the chunk in global memory.  kind: 0 = y, 1 = z (* V_loc), 2 = y^-1, 3 = z + density accumulation.
-// G is the column-batch width of S and must be the same for the y and z kernels of one launch (the host picks it).
-template <int A, int B, int G, int WARPS, int KIND>
-__global__ void __launch_bounds__(WARPS * 32, 2) k_hw_plane_split(HalfParams P) {
-  using F = HalfFft<A, B, G>;
-  ABI_DYN_SMEM(double2, sm);
-#ifdef ABI_EMU
-  const int warp = 0, nwarps = 1, tid = 0, nthr = 1;
-#else
-  const int warp = threadIdx.x >> 5, nwarps = WARPS, tid = threadIdx.x, nthr = WARPS * 32;
-#endif
-  constexpr bool ZK_ = (KIND == 1 || KIND == 3);
-  const typename F::Tables T = F::load_tables(sm, P, !ZK_, ZK_, tid, nthr);
-  double2* E = sm + F::TW_SLOTS + F::int_slots(P.nU) + (size_t)warp * F::ESIZE;
-  const unsigned long long pkeep = policy_evict_last(), pstream = policy_evict_first();
-  const size_t vplane = (size_t)(KIND == 1 ? P.cplex : 1) * P.ng2 * (B * G * 2 * A);
-  __syncthreads();
-  for (long long unit = blockIdx.x; unit < P.nunits; unit += gridDim.x) {
-    const int i1 = (int)(unit / P.nb), b = (int)(unit - (long long)i1 * P.nb);
-    double2* S = P.S + (size_t)unit * P.ng2 * P.nU * G;
-    if (KIND == 0) {
-      const double2* w1 = P.W1 + ((size_t)b * P.n1 + i1) * P.nlin;
-      for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_y(P, T, w1, S, E, u0, pkeep, pstream);
-    } else if (KIND == 1) {
-      const double* vunit = P.vP + (size_t)i1 * vplane;
-      for (int g = warp; g < P.ng2; g += nwarps) F::phase_z(P, T, S, vunit, E, g, pkeep);
-    } else if (KIND == 2) {
+    if (KIND == 0 && !(P.dbg_skip & 4)) {
       double2* w1o = P.W1o + ((size_t)b * P.n1 + i1) * P.nlout;
       for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_yinv(P, T, S, w1o, E, u0, pkeep, pstream);
-    } else {
-      double* runit = P.rhoP + (size_t)i1 * vplane;
-      const double2 wxy = P.wxy[b];
-      for (int g = warp; g < P.ng2; g += nwarps) F::phase_z_rho(P, T, S, runit, wxy, E, g, pkeep);
+      __syncthreads();
     }
   }
+  cp_async_wait_all();
 }
 
 // ---- host interface (half_stage.cu) ----

@@ -6,12 +6,12 @@
 #include <algorithm>
 
 namespace abi {
-void* plane_scratch_get(size_t bytes);
+void* half_scratch_get(size_t bytes, uint64_t layout_key, cudaStream_t st);
 
 // kind 0: fused option 2, kind 1: fused option 1 (density)
 template <int A, int B, int G, int WARPS, int MINB, int KIND>
 void half_launch_cfg(HalfParams& P, cudaStream_t st) {
-  auto kern = KIND == 0 ? k_hw_plane<A, B, G, WARPS, MINB> : k_hw_plane_rho<A, B, G, WARPS, MINB>;
+  auto kern = k_hw_plane<A, B, G, WARPS, MINB, KIND>;
   const size_t smem = half_smem_bytes<A, B, G>(WARPS, P.nU);
   ABI_CHECK(smem <= kMaxSmemPerCta, "half-support plane stage: too many occupied z planes for the shared-memory tables");
   int cps = 1;
@@ -27,13 +27,15 @@ void half_launch_cfg(HalfParams& P, cudaStream_t st) {
 #ifdef ABI_EMU
   grid = std::min<long long>(grid, 3);
 #endif
-  const size_t sbytes = sizeof(double2) * (size_t)P.ng2 * P.nU * G;
-  P.S = (double2*)plane_scratch_get(sbytes * (size_t)grid);
+  const size_t sbytes = sizeof(double2) * (size_t)P.ng2 * HalfFft<A, B, G>::GSTR;
+  // rows without a plane must read as zero: the scratch is cleared whenever the plan (layout key) changes
+  P.S = (double2*)half_scratch_get(sbytes * (size_t)grid, P.layout_key, st);
   ABI_LAUNCH(kern, dim3((unsigned)grid), dim3(WARPS * 32), smem, st, P);
 }
 
 template <int A, int B, int G>
 void half_launch_n(int kind, HalfParams& P, cudaStream_t st) {
+  static_assert(HalfFft<A, B, G>::ROWS * G * 16 + HalfFft<A, B, G>::ESIZE * 16 <= 14 * 1024, "per-warp shared memory too large for 16 warps per SM");
   const int cfg = fourwf_tuning().half_cfg;
   if (kind == 0) {
     if (cfg == 1) half_launch_cfg<A, B, G, 16, 1, 0>(P, st);

@@ -60,3 +60,6 @@ inline void __syncthreads() {}
 #include <algorithm>
 using std::min; using std::max;
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+inline int __double2hiint(double x) { long long b; memcpy(&b, &x, 8); return (int)(b >> 32); }
+inline int __double2loint(double x) { long long b; memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL); }
+inline double __hiloint2double(int hi, int lo) { long long b = ((long long)(unsigned)hi << 32) | (unsigned)lo; double x; memcpy(&x, &b, 8); return x; }
