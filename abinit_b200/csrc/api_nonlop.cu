@@ -31,7 +31,15 @@ static const NonlopAtoms& call_atoms(int natom, int ntypat, int lmnmax, const in
   if (atindx1) k = hash_ints(atindx1, natom, k);
   int meta[3] = {natom, ntypat, lmnmax};
   k = hash_ints(meta, 3, k);
-  if (k != g_call_atoms_key || g_call_atoms.d_proj_typ == nullptr) {
+  // the hash only short-cuts the comparison: a hit must also match the stored tables themselves
+  const bool same = k == g_call_atoms_key && g_call_atoms.d_proj_typ != nullptr && g_call_atoms.natom == natom &&
+                    g_call_atoms.ntypat == ntypat && g_call_atoms.lmnmax == lmnmax &&
+                    g_call_atoms.indlmn.size() == (size_t)6 * lmnmax * ntypat &&
+                    memcmp(g_call_atoms.indlmn.data(), indlmn, sizeof(int) * 6 * (size_t)lmnmax * ntypat) == 0 &&
+                    g_call_atoms.nattyp.size() == (size_t)ntypat && memcmp(g_call_atoms.nattyp.data(), nattyp, sizeof(int) * ntypat) == 0 &&
+                    (atindx1 == nullptr || (g_call_atoms.atindx1.size() == (size_t)natom &&
+                                            memcmp(g_call_atoms.atindx1.data(), atindx1, sizeof(int) * natom) == 0));
+  if (!same) {
     std::vector<int> ident(natom);
     for (int i = 0; i < natom; i++) ident[i] = i + 1;
     g_call_atoms.build(natom, ntypat, lmnmax, indlmn, nattyp, atindx1 ? atindx1 : ident.data());
@@ -328,7 +336,8 @@ void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_
   h->istwf_k = istwf_k; h->npw = npw; h->me_g0 = me_g0;
   h->invovl.release();
   h->kg.assign(kg_k, kg_k + (size_t)3 * npw);
-  h->plan = fourwf_get_plan(h->kg.data(), npw, h->kg.data(), npw, h->ngfft, istwf_k, me_g0);
+  h->plan_ref = fourwf_get_plan_shared(h->kg.data(), npw, h->kg.data(), npw, h->ngfft, istwf_k, me_g0);
+  h->plan = h->plan_ref.get();
   if (h->d_kinpw) cudaFree(h->d_kinpw);
   CUDA_CHECK(cudaMalloc(&h->d_kinpw, sizeof(double) * std::max(1, npw)));
   CUDA_CHECK(cudaMemcpyAsync(h->d_kinpw, kinpw, sizeof(double) * npw, cudaMemcpyDefault, c.stream));
@@ -423,7 +432,7 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
   DevArg a_gv(3, gvnlxc, nv, false);
   const int cpopt_here = (h->usepaw == 1) ? *cpopt : -1;                                 // m_getghc.F90:1046
   DevArg a_prj(4, (cpopt_here >= 0) ? cwaveprj : nullptr, sizeof(double) * (size_t)cplex * h->atoms.nprojs * nd, cpopt_here >= 2);
-  DevArg a_lam(5, lambda, sizeof(double) * nd, true);
+  DevArg a_lam(5, lambda, sizeof(double) * (*ndat), true);     // the reference passes lambda(ndat): one value per band, spinors share it
   const double kin_filter = 1.7976931348623157e308 * 1.0e-11;
   int paw_opt = h->usepaw; if (*sij_opt != 0) paw_opt = *sij_opt + 3;                    // m_getghc.F90:1067
   if (nonlocal)

@@ -314,6 +314,7 @@ void abi_b200_chebfi_rq_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, doub
   ABI_CHECK(is_device_ptr(x) && is_device_ptr(ax), "chebfi_rq: device blocks required");
   const int space = space_of(h), me_g0 = me_g0_of(h);
   const int rows = h->npw * h->nspinor;                      // blocks hold npw*nspinor rows per band
+  ABI_CHECK(!(h->usepaw && bx == nullptr), "chebfi_rq: a PAW Hamiltonian needs the BX block (S X)");
   get_ax_bx(h, space, me_g0, rows, *ncols, *bandpp, x, ax, h->usepaw ? bx : nullptr);
   std::vector<double> d;
   rr_quotients(space, me_g0, rows, *ncols, x, ax, h->usepaw ? bx : nullptr, d, *maxeig, *mineig);
@@ -326,6 +327,7 @@ void abi_b200_chebfi_core_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, do
   AsyncGuard g;
   abi_b200_ham* h = *gs_hamk;
   std::vector<double> d(div, div + *ncols);
+  ABI_CHECK(!(h->usepaw && bx == nullptr), "chebfi_core: a PAW Hamiltonian needs the BX block (S X)");
   cheb_core(h, space_of(h), me_g0_of(h), h->npw * h->nspinor, *ncols, *bandpp, x, ax, h->usepaw ? bx : nullptr, x_next, x_prev, *lambda_minus,
             *lambda_plus, *ndeg_filter, d);
 }

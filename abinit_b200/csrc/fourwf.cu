@@ -17,6 +17,7 @@
 #include "fourwf.cuh"
 #include "plane_stage.cuh"
 #include "half_stage.cuh"
+#include "x_stage.cuh"
 #include "context.cuh"
 #include <algorithm>
 #include <cstring>
@@ -46,6 +47,7 @@ FourwfTuning& fourwf_tuning() {
     if (const char* e = getenv("ABI_B200_FOURWF_PLANE_CTAS")) t.plane_ctas_per_sm = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_PACK2")) t.pack2 = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_HALF")) t.half = atoi(e);
+    if (const char* e = getenv("ABI_B200_FOURWF_XHALF")) t.xhalf = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_HALF_CFG")) t.half_cfg = atoi(e);
   }
   return t;
@@ -185,6 +187,7 @@ void FourwfPlan::release() {
   owned.clear();
   for (void* p : owned_lazy) cudaFree(p);
   owned_lazy.clear();
+  if (xh) { xh_tabs_free(xh); xh = nullptr; }
 }
 
 template <typename T> static T* to_device(const std::vector<T>& v, std::vector<void*>& owned) {
@@ -201,19 +204,25 @@ static uint64_t fnv1a(const void* data, size_t n, uint64_t h = 14695981039346656
   return h;
 }
 
-static std::unordered_map<uint64_t, std::unique_ptr<FourwfPlan>>& plan_cache() {
-  static std::unordered_map<uint64_t, std::unique_ptr<FourwfPlan>> c;
+// Plans are shared: the cache holds one reference, every Hamiltonian handle that loaded the k-point holds another
+// (fourwf_get_plan_shared), so clearing or trimming the cache never frees tables a handle still uses; the device tables go
+// away with the last reference (FourwfPlan::~FourwfPlan).
+static std::unordered_map<uint64_t, std::shared_ptr<FourwfPlan>>& plan_cache() {
+  static std::unordered_map<uint64_t, std::shared_ptr<FourwfPlan>> c;
   return c;
 }
-void fourwf_clear_plans() {
-  for (auto& kv : plan_cache()) kv.second->release();
-  plan_cache().clear();
-}
+FourwfPlan::~FourwfPlan() { release(); }
+void fourwf_clear_plans() { plan_cache().clear(); }
 
 static inline int wrapi(int g, int n) { return g < 0 ? g + n : g; }
 
 FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int npw_out, const int* ngfft,
                             int istwf_k, int me_g0) {
+  return fourwf_get_plan_shared(kg_in, npw_in, kg_out, npw_out, ngfft, istwf_k, me_g0).get();
+}
+
+std::shared_ptr<FourwfPlan> fourwf_get_plan_shared(const int* kg_in, int npw_in, const int* kg_out, int npw_out, const int* ngfft,
+                                                   int istwf_k, int me_g0) {
   const int n1 = ngfft[0], n2 = ngfft[1], n3 = ngfft[2];
   uint64_t key = fnv1a(kg_in, sizeof(int) * 3 * (size_t)npw_in);
   if (kg_out != kg_in) key = fnv1a(kg_out, sizeof(int) * 3 * (size_t)npw_out, key);
@@ -221,11 +230,24 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
   key = fnv1a(meta, sizeof meta, key);
   auto& cache = plan_cache();
   auto it = cache.find(key);
-  if (it != cache.end()) return it->second.get();
-  if (cache.size() > 64) fourwf_clear_plans();   // bound device memory held by stale k-points
+  if (it != cache.end()) {
+    // the 64-bit hash only finds the candidate: the spheres themselves must match
+    FourwfPlan& c = *it->second;
+    const bool same = c.npw_in == npw_in && c.npw_out == npw_out && c.h_kg_in.size() == (size_t)3 * npw_in &&
+                      memcmp(c.h_kg_in.data(), kg_in, sizeof(int) * 3 * (size_t)npw_in) == 0 &&
+                      (c.h_kg_out.empty() ? kg_out == kg_in || memcmp(kg_in, kg_out, sizeof(int) * 3 * (size_t)npw_in) == 0
+                                          : (c.h_kg_out.size() == (size_t)3 * npw_out && memcmp(c.h_kg_out.data(), kg_out, sizeof(int) * 3 * (size_t)npw_out) == 0));
+    if (same) return it->second;
+    cache.erase(it);                               // hash collision: rebuild (the old plan lives on in the handles that hold it)
+  }
+  if (cache.size() > 64) {                         // bound device memory held by stale k-points: drop the plans nobody holds
+    for (auto q = cache.begin(); q != cache.end();) { if (q->second.use_count() == 1) q = cache.erase(q); else ++q; }
+  }
 
   ABI_CHECK(istwf_k >= 1 && istwf_k <= 9, "istwf_k must be between 1 and 9");
-  auto pl = std::make_unique<FourwfPlan>();
+  auto pl = std::make_shared<FourwfPlan>();
+  pl->h_kg_in.assign(kg_in, kg_in + 3 * (size_t)npw_in);
+  if (kg_out != kg_in) pl->h_kg_out.assign(kg_out, kg_out + 3 * (size_t)npw_out);
   pl->n1 = n1; pl->n2 = n2; pl->n3 = n3; pl->istwf_k = istwf_k; pl->me_g0 = me_g0;
   pl->npw_in = npw_in; pl->npw_out = npw_out; pl->key = key;
   pl->same_sphere = (kg_out == kg_in) || (npw_in == npw_out && memcmp(kg_in, kg_out, sizeof(int) * 3 * (size_t)npw_in) == 0);
@@ -359,6 +381,7 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
         if (kk != prev) {
           prev = kk; line++;
           estart.push_back((int)k);
+          if (dit_positions) pl->h_lin_i2i3.push_back(make_int2(e.i2, e.i3));
           lu.push_back(u_of_i3[e.i3]);
           lpos2.push_back(t2.pos_of_idx[e.i2]);
           plstart[u_of_i3[e.i3] + 1]++;
@@ -401,6 +424,7 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
       }
       d_ent = to_device(ent, pl->owned);
       d_estart = to_device(estart, pl->owned);
+      if (dit_positions) { pl->h_in_ent = ent; pl->h_in_estart = estart; } else { pl->h_out_ent = ent; pl->h_out_estart = estart; }
       d_lu = to_device(lu, pl->owned);
       d_lpos2 = to_device(lpos2, pl->owned);
       d_plstart = to_device(plstart, pl->owned);
@@ -414,9 +438,8 @@ FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int
     pl->half_ok_in = half_ok_in && pl->nU > 0;
     pl->half_ok_out = half_ok_out;
   }
-  FourwfPlan* raw = pl.get();
-  cache[key] = std::move(pl);
-  return raw;
+  cache[key] = pl;
+  return pl;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -672,24 +695,6 @@ k_fw_x_forward(const double2* __restrict__ cg, double2* __restrict__ W1, Fft1d p
       if (l >= nl) { l -= nl; i1++; }
     }
   }
-}
-
-// fused getghc assembly of one output coefficient (m_getghc.F90:1266-1280, type_calc=1 filter :1003-1031)
-ABI_DEV bool fw_epilogue(const FourwfEpilogue& epi, double kin_filter, int ipw, size_t o, double2& v) {
-  if (epi.mode == 1) {
-    const double k = epi.kinpw[ipw];
-    if (k < kin_filter) {
-      const double2 c = epi.cwavef[o];
-      v.x = v.x + k * c.x; v.y = v.y + k * c.y;
-      if (epi.gvnlxc) { const double2 g = epi.gvnlxc[o]; v.x += g.x; v.y += g.y; }
-    } else {
-      if (epi.gsc) epi.gsc[o] = make_double2(0.0, 0.0);
-      return false;
-    }
-  } else if (epi.mode == 2) {
-    if (epi.kinpw[ipw] > kin_filter) return false;
-  }
-  return true;
 }
 
 // K3: W1out[b][i1][line] -> x FFT (e^{-i}) -> gather to the sphere * xnorm (+ fused getghc assembly)
@@ -982,13 +987,15 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
   const int zero_im = (pl.istwf_k == 2 && pl.me_g0 == 1) ? 1 : 0;
   const double kin_filter = 1.7976931348623157e308 * 1.0e-11;   // huge(0d0)*1d-11, m_getghc.F90:1272
 
-  if (pack2) CUDA_CHECK(cudaMemsetAsync(d_fofgout, 0, sizeof(double2) * (size_t)pl.npw_out * ndat, st));
+  const bool use_xh = x_stage_usable(pl, pack2);
+  if (pack2 && !(use_xh && (tune.xhalf & 2))) CUDA_CHECK(cudaMemsetAsync(d_fofgout, 0, sizeof(double2) * (size_t)pl.npw_out * ndat, st));
   for (int t0 = 0; t0 < ntrans; t0 += chunk) {
     const int nb = std::min(chunk, ntrans - t0);            // transforms in this chunk
     const int b0 = pack2 ? 2 * t0 : t0;                     // first band of the chunk
     const int nbands = std::min(ndat - b0, pack2 ? 2 * nb : nb);
     { ProfScope ps("fourwf_x_forward");
-    ABI_LAUNCH(k_fw_x_forward, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st,
+    if (use_xh && (tune.xhalf & 1)) x_stage_forward(pl, d_fofgin + (size_t)b0 * pl.npw_in, W1, nb, pack2 ? nbands : 0, st);
+    else ABI_LAUNCH(k_fw_x_forward, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st,
                d_fofgin + (size_t)b0 * pl.npw_in, W1, t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_in,
                pack2 ? nbands : 0); }
     MidParams P;
@@ -1036,7 +1043,9 @@ void fourwf_fused_opt2(const FourwfPlan& pl, const VlocDev& v, const double2* d_
     if (e.gvnlxc) e.gvnlxc += (size_t)b0 * pl.npw_out;
     if (e.gsc) e.gsc += (size_t)b0 * pl.npw_out;
     { ProfScope ps("fourwf_x_backward");
-    if (pack2) {
+    if (use_xh && (tune.xhalf & 2)) {
+      x_stage_backward(pl, W1o, d_fofgout + (size_t)b0 * pl.npw_out, nb, pack2 ? nbands : 0, xnorm, zero_im, e, kin_filter, st);
+    } else if (pack2) {
       ABI_LAUNCH(k_fw_x_backward_packed, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st, W1o,
                  d_fofgout + (size_t)b0 * pl.npw_out, t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_out, nbands,
                  xnorm, e, kin_filter);
@@ -1107,10 +1116,14 @@ void fourwf_fused_opt1(const FourwfPlan& pl, const double2* d_fofgin, double* d_
   int chunk = tune.band_chunk > 0 ? tune.band_chunk : (int)std::max<size_t>(1, ((size_t)3 << 30) / per_band);
   chunk = std::min(chunk, ntrans);
   double2* W1 = (double2*)g_ws[1].get(sizeof(double2) * (size_t)n1 * pl.nlin * chunk);
-  // rhoT (N doubles) followed by the per-transform weights
-  double2* wxy = (double2*)g_ws[2].get(sizeof(double2) * (size_t)ntrans + sizeof(double) * N);
+  // half-support plane stage: the density is accumulated in the register order of its z pass (rhoP) and un-permuted at the end
+  const bool use_half = half_stage_usable(pl, true);
+  const bool use_xh = x_stage_usable(pl, pl.istwf_k == 2 && pl.same_sphere) && (tune.xhalf & 1);
+  const size_t nrho = use_half ? half_rho_elems(pl) : N;
+  // rhoT / rhoP (nrho doubles) followed by the per-transform weights
+  double2* wxy = (double2*)g_ws[2].get(sizeof(double2) * (size_t)ntrans + sizeof(double) * nrho);
   double* rhoT = reinterpret_cast<double*>(wxy + ntrans);
-  CUDA_CHECK(cudaMemsetAsync(rhoT, 0, sizeof(double) * N, st));
+  CUDA_CHECK(cudaMemsetAsync(rhoT, 0, sizeof(double) * nrho, st));
   int lx = std::max(1, tune.lines_x);
   while (lx > 1 && sizeof(double2) * ((size_t)n1 + (size_t)lx * (n1 | 1)) > 110 * 1024) lx--;
   const size_t smem_x = sizeof(double2) * ((size_t)n1 + (size_t)lx * (n1 | 1));
@@ -1123,18 +1136,27 @@ void fourwf_fused_opt1(const FourwfPlan& pl, const double2* d_fofgin, double* d_
     const int nbands = std::min(ndat - b0, pack2 ? 2 * nb : nb);
     ABI_LAUNCH(k_rho_weights, dim3(ceil_div(nb, 128)), dim3(128), 0, st, wxy, d_wr, d_wi, nb, b0, ndat, pack2 ? 1 : 0);
     { ProfScope ps("fourwf_x_forward");
-    ABI_LAUNCH(k_fw_x_forward, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st, d_fofgin + (size_t)b0 * pl.npw_in, W1,
+    if (use_xh) x_stage_forward(pl, d_fofgin + (size_t)b0 * pl.npw_in, W1, nb, pack2 ? nbands : 0, st);
+    else ABI_LAUNCH(k_fw_x_forward, dim3(ceil_div(pl.nlin, lx), nb), dim3(256), smem_x, st, d_fofgin + (size_t)b0 * pl.npw_in, W1,
                t1.plan, pl.d_in_ent, pl.d_lin_estart, pl.nlin, lx, pl.npw_in, pack2 ? nbands : 0); }
     { ProfScope ps("fourwf_plane_rho");
+    if (use_half) {
+      HalfLaunch L;
+      L.nb = nb; L.W1 = W1; L.W1o = nullptr; L.nlin = pl.nlin; L.nlout = pl.nlin; L.out_is_in = true; L.rhoP = rhoT; L.wxy = wxy;
+      half_stage_launch_rho(pl, L, st);
+    } else {
     PlaneParams Q;
     Q.n1 = n1; Q.n2 = n2; Q.n3 = n3; Q.nb = nb; Q.nU = pl.nU; Q.cplex = 1; Q.za = pl.za; Q.zla = pl.zla; Q.zb = pl.zb; Q.zlb = pl.zlb;
     Q.nlin = pl.nlin; Q.nlout = pl.nlin; Q.nunits = (long long)nb * n1;
     Q.W1 = W1; Q.W1o = nullptr; Q.S = nullptr; Q.vT = nullptr; Q.tw = t2.plan.tw; Q.tw3 = t3.plan.tw;
     Q.in_start = pl.d_pin_start; Q.in_runs = pl.d_pin_runs; Q.out_start = pl.d_pin_start; Q.out_runs = pl.d_pin_runs;
     Q.rhoT = rhoT; Q.wxy = wxy;
-    plane_stage_launch_rho(Q, st); }
+    plane_stage_launch_rho(Q, st); } }
     g_kernel_launches += (n2 != n3) ? 4 : 3;
   }
+  if (use_half) {
+    half_rho_unpermute_add(pl, rhoT, d_denpot, st);
+  } else {
 #ifndef ABI_EMU
   k_rho_untranspose_add<<<dim3(ceil_div(n1, 32), ceil_div(n2, 32), n3), dim3(32, 8), 0, st>>>(rhoT, d_denpot, n1, n2, n3);
   CUDA_CHECK(cudaGetLastError());
@@ -1142,6 +1164,7 @@ void fourwf_fused_opt1(const FourwfPlan& pl, const double2* d_fofgin, double* d_
   k_rho_untranspose_add(rhoT, d_denpot, n1, n2, n3);
 #endif
   g_kernel_launches++;
+  }
 }
 
 }  // namespace abi

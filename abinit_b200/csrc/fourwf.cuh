@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "fft_engine.cuh"
 #include <vector>
+#include <memory>
 
 namespace abi {
 
@@ -26,6 +27,28 @@ struct FourwfEpilogue {
   const double2* gvnlxc = nullptr;  // device or null
   double2* gsc = nullptr;        // device or null: zeroed where filtered (sij_opt==1)
 };
+
+// fused getghc assembly of one output coefficient (m_getghc.F90:1266-1280, type_calc=1 filter :1003-1031)
+ABI_DEV bool fw_epilogue(const FourwfEpilogue& epi, double kin_filter, int ipw, size_t o, double2& v) {
+  if (epi.mode == 1) {
+    const double k = epi.kinpw[ipw];
+    if (k < kin_filter) {
+      const double2 c = epi.cwavef[o];
+      v.x = v.x + k * c.x; v.y = v.y + k * c.y;
+      if (epi.gvnlxc) { const double2 g = epi.gvnlxc[o]; v.x += g.x; v.y += g.y; }
+    } else {
+      if (epi.gsc) epi.gsc[o] = make_double2(0.0, 0.0);
+      return false;
+    }
+  } else if (epi.mode == 2) {
+    if (epi.kinpw[ipw] > kin_filter) return false;
+  }
+  return true;
+}
+
+
+struct XhTabs;
+void xh_tabs_free(XhTabs* t);
 
 struct FourwfPlan {
   int n1 = 0, n2 = 0, n3 = 0, istwf_k = 1, me_g0 = 1;
@@ -67,13 +90,25 @@ struct FourwfPlan {
   mutable int h_cfg_key = -1; mutable bool h_z_ok = false;
   mutable int* d_hz_ovoff = nullptr; mutable int* d_hz_sign = nullptr; mutable int* d_hu_row = nullptr;
   mutable std::vector<void*> owned_lazy;
+  // host copies of the line / entry tables (the half-support x kernels derive their own tables from them at first use)
+  std::vector<int2> h_in_ent, h_out_ent; std::vector<int> h_in_estart, h_out_estart; std::vector<int2> h_lin_i2i3;
+  mutable XhTabs* xh = nullptr;
+  std::vector<int> h_kg_in, h_kg_out;   // the spheres the plan was built for (compared on a cache hit; h_kg_out empty = same array)
   std::vector<void*> owned;      // device allocations to free
   void release();
+  FourwfPlan() = default;
+  FourwfPlan(const FourwfPlan&) = delete;
+  FourwfPlan& operator=(const FourwfPlan&) = delete;
+  ~FourwfPlan();
 };
 
 // Build (or fetch from the cache) the plan for (kg_in, kg_out). kg arrays are HOST pointers, Fortran layout kg(3,npw).
 FourwfPlan* fourwf_get_plan(const int* kg_in, int npw_in, const int* kg_out, int npw_out, const int* ngfft,
                             int istwf_k, int me_g0);
+// same, returning a reference the caller keeps for as long as it uses the plan (Hamiltonian handles): the plan then survives
+// fourwf_clear_plans / free_gpu_fourwf_ / cache trimming
+std::shared_ptr<FourwfPlan> fourwf_get_plan_shared(const int* kg_in, int npw_in, const int* kg_out, int npw_out, const int* ngfft,
+                                                   int istwf_k, int me_g0);
 void fourwf_clear_plans();
 
 // V_loc on the device: natural layout [i3][i2][i1] (cplex doubles per point) and the x-slowest transpose
@@ -109,8 +144,9 @@ struct FourwfTuning {
   int plane_ctas_per_sm = 0;   // 0: occupancy / L2-budget limited
   int plane_split = 0;         // 1: run the split (three-kernel) plane stage for cubic boxes too (developer comparison)
   int half = 1;                // 1: half-support plane stage (half_stage.cuh) when the sphere fits in half of the box axes
+  int xhalf = 3;               // half-support x passes (x_stage.cuh) when the plan allows them: bit 0 forward (K1), bit 1 backward (K3)
   int half_skip = 0;           // developer timing aid (phase mask), see HalfParams::dbg_skip
-  int half_cfg = 0;            // 0: 8 warps x 2 CTAs/SM, 1: 16 warps x 1 CTA/SM
+  int half_cfg = 1;            // 0: 8 warps x 2 CTAs/SM, 1: 16 warps x 1 CTA/SM (measured on B200, Si-512: 3.55 vs 3.44 ms)
   int pack2 = 1;               // istwf_k=2: two bands per complex transform (double_rfft_trick, m_getghc.F90:1999-2171)
 };
 FourwfTuning& fourwf_tuning();

@@ -109,16 +109,16 @@ bool ensure_z_tables(const FourwfPlan& pl, const HalfCfg& c3, int G) {
   for (void* p : pl.owned_lazy) cudaFree(p);
   pl.owned_lazy.clear();
   const int M = c3.A * c3.B, za = pl.h_za, zla = pl.h_zla, zbm = pl.h_zb - M, zlb = pl.h_zlb;
-  std::vector<int> sign(M, 0), ovrow(M, -1), urow(pl.nU, 0);
+  std::vector<int> sign(M, 0), ovrow(M, -1), rowu(M + kHalfOV, -1);
   int nov = 0, nplanes = 0;
   for (int t = 0; t < c3.A; t++) for (int j = 0; j < c3.B; j++) {
     const int q = t * c3.B + j, r = rin_rt(c3, t, j);
     const bool lo = r >= za && r < za + zla, hi = r >= zbm && r < zbm + zlb;
     const int u_lo = r - za, u_hi = zla + r - zbm;
-    if (lo) { sign[q] = 1; urow[u_lo] = q * G; nplanes++; }
+    if (lo) { sign[q] = 1; rowu[q] = u_lo; nplanes++; }
     if (hi) {
-      if (lo) { ovrow[q] = M + nov; urow[u_hi] = (M + nov) * G; nov++; }
-      else { sign[q] = -1; urow[u_hi] = q * G; }
+      if (lo) { ovrow[q] = M + nov; if (nov < kHalfOV) rowu[M + nov] = u_hi; nov++; }
+      else { sign[q] = -1; rowu[q] = u_hi; }
       nplanes++;
     }
   }
@@ -127,7 +127,7 @@ bool ensure_z_tables(const FourwfPlan& pl, const HalfCfg& c3, int G) {
   if (!pl.h_z_ok) return false;
   pl.d_hz_sign = upload(sign, pl.owned_lazy);
   pl.d_hz_ovoff = upload(ovrow, pl.owned_lazy);
-  pl.d_hu_row = upload(urow, pl.owned_lazy);
+  pl.d_hu_row = upload(rowu, pl.owned_lazy);
   return true;
 }
 
@@ -139,7 +139,7 @@ void fill_params(const FourwfPlan& pl, const HalfCfg& c2, const HalfCfg& c3, con
   P.tw2 = fft_tables(pl.n2).plan.tw; P.tw3 = fft_tables(pl.n3).plan.tw;
   P.in_rows = pl.d_hin_rows; P.out_rows = L.out_is_in ? pl.d_hin_rows : pl.d_hout_rows;
   P.y_amb_in = pl.y_amb_in; P.y_amb_out = L.out_is_in ? pl.y_amb_in : pl.y_amb_out;
-  P.z_sign = pl.d_hz_sign; P.z_ovrow = pl.d_hz_ovoff; P.u_row = pl.d_hu_row;
+  P.z_sign = pl.d_hz_sign; P.z_ovrow = pl.d_hz_ovoff; P.row_u = pl.d_hu_row;
   P.layout_key = pl.key ^ ((unsigned long long)pl.h_cfg_key << 40) ^ 0x9e3779b97f4a7c15ULL;
   P.ng2 = (pl.n2 + c2.G - 1) / c2.G;
   P.rhoP = L.rhoP; P.wxy = L.wxy;

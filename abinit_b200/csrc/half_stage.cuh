@@ -47,7 +47,7 @@ struct HalfParams {
   // i3 = r + m3 are occupied the high partner sits in one of the OV extra rows m3 + idx
   const int* z_sign;                  // [m3] +1 / -1: s_r of the plane in row q (high planes carry -1); 0: no plane (row stays zero)
   const int* z_ovrow;                 // [m3] extra row (>= m3) of the high partner, or -1
-  const int* u_row;                   // [nU] row * G of plane u
+  const int* row_u;                   // [m3 + kHalfOV] the occupied plane u stored in S row q, or -1
   int ng2;                            // column batches: ceil(n2 / G)
   int dbg_skip = 0;                   // developer timing aid: bit 0 / 1 / 2 skips the y / z / y^-1 phase (results are then wrong)
   unsigned long long layout_key = 0;  // identifies (plan, configuration): the scratch is cleared when it changes
@@ -120,17 +120,17 @@ struct HalfFft {
   static constexpr int GSTR = ROWS * G;                  // double2 between consecutive column batches of S
   // shared-memory tables (double2 slots): Ty[M] | Tz[M] | ctwA[M] | ctwB[M] (Cooley-Tukey only) | ints
   static constexpr int TW_SLOTS = 2 * M + (PFA ? 0 : 2 * M);
-  ABI_HD static constexpr int int_slots(int nU) { return (B + M + nU + 3) / 4; }   // zmask[B], zov[M], u_row[nU]
+  ABI_HD static constexpr int int_slots() { return (B + M + ROWS + 3) / 4; }   // zmask[B], zov[M], rowu[ROWS]
 
   struct Tables {
     const double2* Ty; const double2* Tz; const double2* ctwA; const double2* ctwB;
-    const int* zmask; const int* zov; const int* urow;
+    const int* zmask; const int* zov; const int* rowu;
   };
 
   // tid/nthr: the whole CTA fills the tables once (ends without a barrier: the caller synchronises)
   ABI_DEV static Tables load_tables(double2* sm, const HalfParams& P, bool ytab, bool ztab, int tid, int nthr) {
     double2* Ty = sm; double2* Tz = sm + M; double2* cA = sm + 2 * M; double2* cB = cA + M;
-    int* zmask = reinterpret_cast<int*>(sm + TW_SLOTS); int* zov = zmask + B; int* urow = zov + M;
+    int* zmask = reinterpret_cast<int*>(sm + TW_SLOTS); int* zov = zmask + B; int* rowu = zov + M;
     for (int q = tid; q < M; q += nthr) {
       const int t = q / B, j = q - t * B;
       const int r = Map::rin(t, j);
@@ -153,8 +153,8 @@ struct HalfFft {
       for (int t = 0; t < A; t++) { if (P.z_sign[t * B + j] != 0) m |= 1 << t; if (P.z_ovrow[t * B + j] >= 0) m |= 1 << (16 + t); }
       zmask[j] = m;
     }
-    for (int u = tid; u < P.nU; u += nthr) urow[u] = P.u_row[u];
-    Tables T; T.Ty = Ty; T.Tz = Tz; T.ctwA = cA; T.ctwB = cB; T.zmask = zmask; T.zov = zov; T.urow = urow;
+    for (int q = tid; q < ROWS; q += nthr) rowu[q] = P.row_u[q];
+    Tables T; T.Ty = Ty; T.Tz = Tz; T.ctwA = cA; T.ctwB = cB; T.zmask = zmask; T.zov = zov; T.rowu = rowu;
     return T;
   }
 
@@ -182,30 +182,41 @@ struct HalfFft {
   }
 
   // ---------------- phase Y: compact rows of W1 -> S ----------------
-  // asynchronous copy of the W1 rows of the line batch [u0, u0 + nl) (one contiguous piece of W1) into the warp's staging buffer
-  ABI_DEV static void y_prefetch(const HalfParams& P, const double2* __restrict__ w1, double2* stg, int u0, unsigned long long pstream) {
-    const int nl = min(G, P.nU - u0);
-    if (nl <= 0) return;
-    const int4 r0 = P.in_rows[u0], r1 = P.in_rows[u0 + nl - 1];
-    const int first = r0.x, count = r1.x + (r1.y >> 16) + (r1.z >> 16) - r0.x;
-    ABI_FOR_LANES {
-      for (int q = lane; q < count; q += 32) cp_async16(stg + q, w1 + first + q, pstream);
+  // A line batch is G consecutive ROWS of S (rows q0 .. q0 + G - 1 in pass-1 order of the z transform; rowu[q] = the occupied
+  // plane stored in row q, or -1): the y-side stores / loads of S then touch G adjacent rows of every column batch, i.e.
+  // runs of G * G * 16 bytes instead of G * 16.  The W1 rows of a batch are fetched separately (they are not neighbours in W1).
+  static constexpr int RS = M + kHalfOV;                 // staging slots per line
+  static constexpr int NBY = (ROWS + G - 1) / G;         // line batches of a plane
+
+  ABI_DEV static void y_prefetch(const HalfParams& P, const Tables& T, const double2* __restrict__ w1, double2* stg, int b,
+                                 unsigned long long pstream) {
+    if (b >= NBY) return;
+#pragma unroll
+    for (int line = 0; line < G; line++) {
+      const int q = b * G + line;
+      const int u = q < ROWS ? T.rowu[q] : -1;
+      if (u >= 0) {
+        const int4 row = P.in_rows[u];
+        const int len = (row.y >> 16) + (row.z >> 16);
+        ABI_FOR_LANES {
+          for (int p = lane; p < len; p += 32) cp_async16(stg + line * RS + p, w1 + row.x + p, pstream);
+        }
+      }
     }
     cp_async_commit();
   }
 
-  ABI_DEV static void y_batch(const HalfParams& P, const Tables& T, double2* __restrict__ S, double2* E, const double2* stg, int u0,
-                              unsigned long long pkeep) {
-    const int nl = min(G, P.nU - u0);
-    const int first = P.in_rows[u0].x;
+  ABI_DEV static void y_pass1(const HalfParams& P, const Tables& T, double2* E, const double2* stg, int b) {
     for (int w0 = 0; w0 < G * B; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
         const int j = w / G, line = w - j * G;
-        if (w < G * B && line < nl) {
-          const int4 row = P.in_rows[u0 + line];
+        const int q = b * G + line;
+        const int u = (w < G * B && q < ROWS) ? T.rowu[q] : -1;
+        if (u >= 0) {
+          const int4 row = P.in_rows[u];
           const int a = row.y & 0xffff, la = row.y >> 16, bm = row.z & 0xffff, lb = row.z >> 16;
-          const int olo = (row.x - first) - a, ohi = (row.x - first) + (la - bm);   // stg[olo + r] = x[r], stg[ohi + r] = x[r + m]
+          const int olo = line * RS - a, ohi = line * RS + (la - bm);   // stg[olo + r] = x[r], stg[ohi + r] = x[r + m]
           double2 x[A], xo[A];
           int r = PFA ? (A * j) % M : j;
 #pragma unroll
@@ -228,21 +239,20 @@ struct HalfFft {
     ABI_SYNCWARP();
   }
 
-  ABI_DEV static void y_pass2(const HalfParams& P, const Tables& T, double2* __restrict__ S, const double2* E, int u0,
-                              unsigned long long pkeep) {
-    const int nl = min(G, P.nU - u0);
+  ABI_DEV static void y_pass2(const Tables& T, double2* __restrict__ S, const double2* E, int b, unsigned long long pkeep) {
     for (int w0 = 0; w0 < 2 * A * G; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
         const int line = w / (2 * A), hk1 = w - line * (2 * A);
-        if (w < 2 * A * G && line < nl) {
+        const int q = b * G + line;
+        if (w < 2 * A * G && q < ROWS && T.rowu[q] >= 0) {
           const double2* e = E + hk1 * ZK + line;
           double2 v[B];
 #pragma unroll
           for (int j = 0; j < B; j++) v[j] = e[j * G];
           HDft<B, +1>::run(v);
           // column id k2 * 2A + hk1 -> batch g = g0 + k2 * (2A / G), c = hk1 % G
-          double2* dst = S + T.urow[u0 + line] + (hk1 / G) * GSTR + (hk1 % G);
+          double2* dst = S + q * G + (hk1 / G) * GSTR + (hk1 % G);
 #pragma unroll
           for (int k2 = 0; k2 < B; k2++) st_keep(dst + k2 * ((2 * A / G) * GSTR), v[k2], pkeep);
         }
@@ -254,41 +264,32 @@ struct HalfFft {
   // all line batches of one plane that belong to this warp; the first batch must already be in flight (y_prefetch)
   ABI_DEV static void phase_y(const HalfParams& P, const Tables& T, const double2* __restrict__ w1, double2* __restrict__ S,
                               double2* E, double2* stg, int warp, int nwarps, unsigned long long pkeep, unsigned long long pstream) {
-    for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) {
+    for (int b = warp; b < NBY; b += nwarps) {
       cp_async_wait_all();
       ABI_SYNCWARP();
-      y_batch(P, T, S, E, stg, u0, pkeep);
-      if (u0 + nwarps * G < P.nU) y_prefetch(P, w1, stg, u0 + nwarps * G, pstream);   // flies during pass 2
-      y_pass2(P, T, S, E, u0, pkeep);
+      y_pass1(P, T, E, stg, b);
+      y_prefetch(P, T, w1, stg, b + nwarps, pstream);   // flies during pass 2
+      y_pass2(T, S, E, b, pkeep);
     }
   }
 
   // ---------------- phase Z: one column batch of S -> z FFT, * V_loc, z FFT^-1 -> S (in place) ----------------
-  ABI_DEV static void z_prefetch(const double2* __restrict__ S, double2* stg, int g, unsigned long long pkeep) {
-    const double2* src = S + (size_t)g * GSTR;
-    ABI_FOR_LANES {
-#pragma unroll
-      for (int q = 0; q < (STG + 31) / 32; q++) if (q * 32 + lane < STG) cp_async16(stg + q * 32 + lane, src + q * 32 + lane, pkeep);
-    }
-    cp_async_commit();
-  }
-
-  ABI_DEV static void z_pass1(const Tables& T, const double2* stg, double2* E, int nl) {
+  ABI_DEV static void z_pass1(const Tables& T, const double2* __restrict__ Sg, double2* E, int nl, unsigned long long pkeep) {
     for (int w0 = 0; w0 < G * B; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
         const int j = w / G, c = w - j * G;
         if (w < G * B && c < nl) {
-          const double2* src = stg + j * G + c;
+          const double2* src = Sg + j * G + c;
           double2 x[A], xo[A];
 #pragma unroll
-          for (int t = 0; t < A; t++) x[t] = src[t * (B * G)];
+          for (int t = 0; t < A; t++) x[t] = ld_keep(src + t * (B * G), pkeep);
           const int zm = T.zmask[j];
           if (zm >> 16) {                     // a plane pair (r, r + m) in this lane's column: rare, one or two lanes of a warp
 #pragma unroll
             for (int t = 0; t < A; t++) {
               double2 vo = x[t];
-              if ((zm >> (16 + t)) & 1) { const double2 h = stg[T.zov[t * B + j] * G + c]; vo = csub(x[t], h); x[t] = cadd(x[t], h); }
+              if ((zm >> (16 + t)) & 1) { const double2 h = ld_keep(Sg + T.zov[t * B + j] * G + c, pkeep); vo = csub(x[t], h); x[t] = cadd(x[t], h); }
               xo[t] = cmulc(vo, T.Tz[t * B + j]);
             }
           } else {
@@ -304,14 +305,10 @@ struct HalfFft {
 
   template <bool RHO>
   ABI_DEV static void z_batch(const HalfParams& P, const Tables& T, double2* __restrict__ S, const double* __restrict__ vunit,
-                              double* __restrict__ runit, double2 wxy, double2* E, double2* stg, int g, int gnext,
-                              unsigned long long pkeep) {
+                              double* __restrict__ runit, double2 wxy, double2* E, int g, unsigned long long pkeep) {
     const int nl = min(G, P.n2 - g * G);
     double2* Sg = S + (size_t)g * GSTR;
-    cp_async_wait_all();
-    ABI_SYNCWARP();
-    z_pass1(T, stg, E, nl);
-    if (gnext < P.ng2) z_prefetch(S, stg, gnext, pkeep);       // flies during pass 2 and pass 1'
+    z_pass1(T, Sg, E, nl, pkeep);
     for (int w0 = 0; w0 < 2 * A * G; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
@@ -383,22 +380,20 @@ struct HalfFft {
 
   template <bool RHO>
   ABI_DEV static void phase_z(const HalfParams& P, const Tables& T, double2* __restrict__ S, const double* __restrict__ vunit,
-                              double* __restrict__ runit, double2 wxy, double2* E, double2* stg, int warp, int nwarps,
-                              unsigned long long pkeep) {
-    if (warp < P.ng2) z_prefetch(S, stg, warp, pkeep);
-    for (int g = warp; g < P.ng2; g += nwarps) z_batch<RHO>(P, T, S, vunit, runit, wxy, E, stg, g, g + nwarps, pkeep);
+                              double* __restrict__ runit, double2 wxy, double2* E, int warp, int nwarps, unsigned long long pkeep) {
+    for (int g = warp; g < P.ng2; g += nwarps) z_batch<RHO>(P, T, S, vunit, runit, wxy, E, g, pkeep);
   }
 
   // ---------------- phase Y': S -> y FFT^-1 -> compact output rows of W1o ----------------
-  ABI_DEV static void phase_yinv(const HalfParams& P, const Tables& T, const double2* __restrict__ S, double2* __restrict__ w1o,
-                                 double2* E, int u0, unsigned long long pkeep, unsigned long long pstream) {
-    const int nl = min(G, P.nU - u0);
+  ABI_DEV static void yinv_batch(const HalfParams& P, const Tables& T, const double2* __restrict__ S, double2* __restrict__ w1o,
+                                 double2* E, double2* stg, int b, unsigned long long pkeep, unsigned long long pstream) {
     for (int w0 = 0; w0 < 2 * A * G; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
         const int line = w / (2 * A), hk1 = w - line * (2 * A);
-        if (w < 2 * A * G && line < nl) {
-          const double2* src = S + T.urow[u0 + line] + (hk1 / G) * GSTR + (hk1 % G);
+        const int q = b * G + line;
+        if (w < 2 * A * G && q < ROWS && T.rowu[q] >= 0) {
+          const double2* src = S + q * G + (hk1 / G) * GSTR + (hk1 % G);
           double2 v[B];
 #pragma unroll
           for (int k2 = 0; k2 < B; k2++) v[k2] = ld_keep(src + k2 * ((2 * A / G) * GSTR), pkeep);
@@ -412,25 +407,42 @@ struct HalfFft {
       }
     }
     ABI_SYNCWARP();
+    // pass 1': the wanted outputs of each line go to the staging buffer in compact row order ...
     for (int w0 = 0; w0 < G * B; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
         const int j = w / G, line = w - j * G;
-        if (w < G * B && line < nl) {
-          const int4 row = P.out_rows[u0 + line];
+        const int q = b * G + line;
+        const int u = (w < G * B && q < ROWS) ? T.rowu[q] : -1;
+        if (u >= 0) {
+          const int4 row = P.out_rows[u];
           const int a = row.y & 0xffff, la = row.y >> 16, bm = row.z & 0xffff, lb = row.z >> 16;
-          double2* dlo = w1o + row.x - a;
-          double2* dhi = w1o + row.x + (la - bm);
+          double2* dlo = stg + line * RS - a;
+          double2* dhi = stg + line * RS + (la - bm);
           double2 ye[A], yo[A];
           inv1_load(ye, yo, E + j * G + line);
           int r = PFA ? (A * j) % M : j;
 #pragma unroll
           for (int t = 0; t < A; t++) {
             const double2 tw = T.Ty[t * B + j];
-            if ((unsigned)(r - a) < (unsigned)la) st_stream(dlo + r, comb(ye[t], yo[t], tw), pstream);
-            if ((unsigned)(r - bm) < (unsigned)lb) st_stream(dhi + r, comb(ye[t], yo[t], make_double2(-tw.x, -tw.y)), pstream);
+            if ((unsigned)(r - a) < (unsigned)la) dlo[r] = comb(ye[t], yo[t], tw);
+            if ((unsigned)(r - bm) < (unsigned)lb) dhi[r] = comb(ye[t], yo[t], make_double2(-tw.x, -tw.y));
             r += B; if (PFA && r >= M) r -= M;
           }
+        }
+      }
+    }
+    ABI_SYNCWARP();
+    // ... and leave as whole rows (coalesced 16-byte stores)
+#pragma unroll
+    for (int line = 0; line < G; line++) {
+      const int q = b * G + line;
+      const int u = q < ROWS ? T.rowu[q] : -1;
+      if (u >= 0) {
+        const int4 row = P.out_rows[u];
+        const int len = (row.y >> 16) + (row.z >> 16);
+        ABI_FOR_LANES {
+          for (int p = lane; p < len; p += 32) st_stream(w1o + row.x + p, stg[line * RS + p], pstream);
         }
       }
     }
@@ -441,7 +453,7 @@ struct HalfFft {
 // dynamic shared memory of the kernels below (bytes)
 template <int A, int B, int G> ABI_HD constexpr size_t half_smem_bytes(int warps, int nU) {
   using F = HalfFft<A, B, G>;
-  return sizeof(double2) * ((size_t)F::TW_SLOTS + F::int_slots(nU) + (size_t)warps * F::WSIZE);
+  (void)nU; return sizeof(double2) * ((size_t)F::TW_SLOTS + F::int_slots() + (size_t)warps * F::WSIZE);
 }
 
 // one CTA = one (transform, i1) plane at a time; warps take line / column batches round-robin inside each phase
@@ -456,7 +468,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_hw_plane(HalfParams P) {
   const int warp = threadIdx.x >> 5, nwarps = WARPS, tid = threadIdx.x, nthr = WARPS * 32;
 #endif
   const typename F::Tables T = F::load_tables(sm, P, true, true, tid, nthr);
-  double2* E = sm + F::TW_SLOTS + F::int_slots(P.nU) + (size_t)warp * F::WSIZE;
+  double2* E = sm + F::TW_SLOTS + F::int_slots() + (size_t)warp * F::WSIZE;
   double2* stg = E + F::ESIZE;
   stg[F::STG] = make_double2(0.0, 0.0);                  // the zero slot (every lane writes the same value)
   double2* S = P.S + (size_t)blockIdx.x * P.ng2 * F::GSTR;
@@ -465,7 +477,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_hw_plane(HalfParams P) {
   __syncthreads();
   if (blockIdx.x < P.nunits) {
     const int i1 = (int)(blockIdx.x / P.nb), b = (int)(blockIdx.x - (long long)i1 * P.nb);
-    F::y_prefetch(P, P.W1 + ((size_t)b * P.n1 + i1) * P.nlin, stg, warp * G, pstream);
+    F::y_prefetch(P, T, P.W1 + ((size_t)b * P.n1 + i1) * P.nlin, stg, warp, pstream);
   }
   for (long long unit = blockIdx.x; unit < P.nunits; unit += gridDim.x) {
     const int i1 = (int)(unit / P.nb), b = (int)(unit - (long long)i1 * P.nb);
@@ -474,22 +486,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_hw_plane(HalfParams P) {
     __syncthreads();
     if (P.dbg_skip & 2) {
     } else if (KIND == 0) {
-      F::template phase_z<false>(P, T, S, P.vP + (size_t)P.cplex * i1 * vplane, nullptr, make_double2(0.0, 0.0), E, stg, warp, nwarps, pkeep);
+      F::template phase_z<false>(P, T, S, P.vP + (size_t)P.cplex * i1 * vplane, nullptr, make_double2(0.0, 0.0), E, warp, nwarps, pkeep);
     } else {
-      F::template phase_z<true>(P, T, S, nullptr, P.rhoP + (size_t)i1 * vplane, P.wxy[b], E, stg, warp, nwarps, pkeep);
-    }
-    // the staging buffer is idle from here on: fetch the first line batch of the next plane
-    const long long next = unit + gridDim.x;
-    if (next < P.nunits) {
-      const int i1n = (int)(next / P.nb), bn = (int)(next - (long long)i1n * P.nb);
-      F::y_prefetch(P, P.W1 + ((size_t)bn * P.n1 + i1n) * P.nlin, stg, warp * G, pstream);
+      F::template phase_z<true>(P, T, S, nullptr, P.rhoP + (size_t)i1 * vplane, P.wxy[b], E, warp, nwarps, pkeep);
     }
     __syncthreads();
     if (KIND == 0 && !(P.dbg_skip & 4)) {
       double2* w1o = P.W1o + ((size_t)b * P.n1 + i1) * P.nlout;
-      for (int u0 = warp * G; u0 < P.nU; u0 += nwarps * G) F::phase_yinv(P, T, S, w1o, E, u0, pkeep, pstream);
-      __syncthreads();
+      for (int bb = warp; bb < F::NBY; bb += nwarps) F::yinv_batch(P, T, S, w1o, E, stg, bb, pkeep, pstream);
     }
+    // the staging buffer is idle again: fetch this warp's first line batch of the next plane while the others finish
+    const long long next = unit + gridDim.x;
+    if (next < P.nunits) {
+      const int i1n = (int)(next / P.nb), bn = (int)(next - (long long)i1n * P.nb);
+      F::y_prefetch(P, T, P.W1 + ((size_t)bn * P.n1 + i1n) * P.nlin, stg, warp, pstream);
+    }
+    if (KIND == 0) __syncthreads();
   }
   cp_async_wait_all();
 }

@@ -32,6 +32,7 @@ struct abi_b200_ham {
   int istwf_k = 1, npw = 0, me_g0 = 1;
   std::vector<int> kg;
   double* d_kinpw = nullptr;
+  std::shared_ptr<abi::FourwfPlan> plan_ref;   // keeps the plan alive whatever happens to the plan cache
   abi::FourwfPlan* plan = nullptr;
   double* d_gvnlxc = nullptr; size_t gvnlxc_cap = 0;
   abi::Invovl invovl;                 // built lazily by apply_invovl, dropped by load_k / load_enl / set_projectors

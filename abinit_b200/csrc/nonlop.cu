@@ -564,20 +564,29 @@ void NonlopAtoms::release() {
 }
 
 void NonlopEnl::load(const double* enl, int d1, int d2, const double* sij, int ntypat, cudaStream_t st) {
-  release();
+  // gemm_nonlop passes enl on every call (m_nonlop.F90:800-808): keep the device buffers while the sizes fit
+  const size_t ne = std::max<size_t>(1, (size_t)d1 * d2), ns = std::max<size_t>(1, (size_t)d1 * ntypat);
   dimenl1 = d1; dimenl2 = d2;
-  CUDA_CHECK(cudaMalloc(&d_enl, sizeof(double) * std::max<size_t>(1, (size_t)d1 * d2)));
+  if (ne > enl_cap || d_enl == nullptr) {
+    if (d_enl) CUDA_CHECK(cudaFree(d_enl));
+    CUDA_CHECK(cudaMalloc(&d_enl, sizeof(double) * ne)); enl_cap = ne;
+  }
   CUDA_CHECK(cudaMemcpyAsync(d_enl, enl, sizeof(double) * (size_t)d1 * d2, cudaMemcpyDefault, st));
   if (sij) {
-    CUDA_CHECK(cudaMalloc(&d_sij, sizeof(double) * std::max<size_t>(1, (size_t)d1 * ntypat)));
+    if (ns > sij_cap || d_sij == nullptr) {
+      if (d_sij) CUDA_CHECK(cudaFree(d_sij));
+      CUDA_CHECK(cudaMalloc(&d_sij, sizeof(double) * ns)); sij_cap = ns;
+    }
     CUDA_CHECK(cudaMemcpyAsync(d_sij, sij, sizeof(double) * (size_t)d1 * ntypat, cudaMemcpyDefault, st));
+  } else if (d_sij) {
+    CUDA_CHECK(cudaFree(d_sij)); d_sij = nullptr; sij_cap = 0;
   }
-  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(cudaStreamSynchronize(st));     // the caller owns enl / sij and may change them after the call returns
 }
 void NonlopEnl::release() {
   if (d_enl) cudaFree(d_enl);
   if (d_sij) cudaFree(d_sij);
-  d_enl = d_sij = nullptr;
+  d_enl = d_sij = nullptr; enl_cap = sij_cap = 0;
 }
 
 struct NlWorkspace {
@@ -860,6 +869,9 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
     zs = gx;                                   // s_projections = projections (m_gemm_nonlop.F90:856-861)
   } else if (paw_opt != 0) {
     ABI_CHECK(enl.d_enl != nullptr, "gemm_nonlop: D_ij not loaded");
+    // k_paw_opernlc indexes real packed-symmetric D_ij / S_ij (m_opernlc_ylm_allwf.F90:395-447): cplex_dij = 2 or a
+    // q-dependent layout (dimekbq = 2) would be read as something else
+    ABI_CHECK(enl.dimenl1 == at.lmnmax * (at.lmnmax + 1) / 2, "gemm_nonlop: PAW D_ij must be real packed symmetric, dimenl1 = lmnmax*(lmnmax+1)/2");
     ABI_CHECK(!(paw_opt >= 2) || enl.d_sij != nullptr, "gemm_nonlop: S_ij not loaded");
     k_paw_opernlc<<<dim3(at.natom, ndat), 64, 0, st>>>(gx, gxfac, gxs, ldg, cplex, at.d_atom_first, at.d_atom_typ, at.d_atom_enl,
                                                        enl.d_enl, enl.d_sij, enl.dimenl1, paw_opt, d_lambda);

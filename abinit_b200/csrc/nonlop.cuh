@@ -54,6 +54,7 @@ struct NonlopEnl {
   int dimenl1 = 0, dimenl2 = 0;
   double* d_enl = nullptr;        // dimenl1 * dimenl2
   double* d_sij = nullptr;        // dimenl1 * ntypat or null
+  size_t enl_cap = 0, sij_cap = 0; // allocated doubles (the buffers are reused while the dimensions do not grow)
   void load(const double* enl, int dimenl1, int dimenl2, const double* sij, int ntypat, cudaStream_t st);
   void release();
 };

@@ -125,6 +125,11 @@ def chebfi_band_parallel(gs_hamk, cg_cols, nband: int, ecut: float, nline: int, 
     if ncols != l - f:
         raise ValueError("cg_cols does not hold this rank's band block")
     istwf_k = gs_hamk.istwf_k
+    if getattr(gs_hamk, "usepaw", 0):
+        # the PAW filter needs S X (Rayleigh quotients), S^-1 (apply_invovl) and X^H S X as the B matrix of the Rayleigh-Ritz
+        # step: the BX blocks are not transposed in this driver yet -- refuse instead of solving the wrong problem
+        raise NotImplementedError("chebfi_band_parallel: PAW Hamiltonians (B = S) are not supported by the band-parallel driver; "
+                                  "use xg.chebfiwf2 on one GPU")
     space = xg.SPACE_CR if istwf_k > 1 else xg.SPACE_C
     x = cg_cols.clone(); ax = torch.empty_like(x); xn = torch.empty_like(x); xp = torch.empty_like(x)
     sync()
