@@ -55,11 +55,101 @@ def _setup(name, istwfk, ndat, usepaw=0, seed=0, sentinel=True):
 
 
 def _gram(space, a, b, npw, me_g0):
-    na, nb = a.shape[0], b.shape[0]
-    w = torch.zeros((nb, na), dtype=torch.complex128 if space == xg.SPACE_C else torch.float64, device=a.device)
+    """<a_i|b_j> in the block metric of src/45_xgTools/m_xg.F90:1802-1882, computed in NumPy on the HOST (not with the
+    library's own xg_gram: a symmetric bug of its long-K GEMM must not be able to hide behind the Hermiticity checks).
+    SPACE_CR: 2 Re(a^H b) minus the doubly counted G = 0 term when this rank holds G = 0."""
+    ca, cb = _c(a), _c(b)
+    g = ca.conj() @ cb.T
+    if space == xg.SPACE_C:
+        return g
+    g = 2.0 * g.real
+    if me_g0 == 1:
+        g -= np.outer(ca[:, 0].real, cb[:, 0].real)
+    return g
+
+
+def _oracle_getghc(cfg, istwfk, kg, kinpw, cw, P, enl, sij, usepaw, sij_opt, atindx1, nattyp, indlmn):
+    from oracle import getghc as ogh
+    Ph = P.cpu().numpy()
+    if istwfk >= 2:
+        class SplitP:            # P_r / P_i as the reference keeps them for istwf_k > 1 (m_gemm_nonlop_projectors.F90:889-969)
+            real = np.ascontiguousarray(Ph[..., 0]); imag = np.ascontiguousarray(Ph[..., 1])
+        Pin = SplitP
+    else:
+        Pin = np.ascontiguousarray(Ph[..., 0]) + 1j * np.ascontiguousarray(Ph[..., 1])
+    del Ph
+    vloc = wl.smooth_potential(cfg["ngfft"], seed=5)
+    return ogh.getghc(_c(cw), vloc, np.ascontiguousarray(kg.T), cfg["ngfft"], kinpw, Pin, enl, sij, indlmn, nattyp, atindx1 - 1,
+                      istwf_k=istwfk, usepaw=usepaw, sij_opt=sij_opt)
+
+
+def _rel(a, b):
+    return float(np.max(np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)))
+
+
+def test_si512_getghc_matches_oracle_at_full_size(lib):
+    """The bench configuration itself (BASELINE configs[1]: box 180^3, Gamma, npw 144 057, nprojs 9216, P = 21 GB) against the
+    ORACLE on 8 bands: the same seeded P is generated once on the device and shared with the CPU restatement."""
+    ndat = 8
+    cfg = wl.CONFIGS["si512"]
+    kg, kin = wl.gsphere_orthorhombic(cfg["ecut"], cfg["L"], (0.0, 0.0, 0.0), 2)
+    npw = kg.shape[0]
+    kinpw = kin.copy(); kinpw[kin >= np.quantile(kin, 0.995)] = wl.HUGE * 1e-10
+    indlmn, lnmax = wl.nc_indlmn(cfg["lmax"], cfg["nproj_per_l"])
+    nlmn = indlmn.shape[1]; natom = cfg["natom"]; nprojs = natom * nlmn
+    nattyp = np.array([natom], dtype=np.int32); atindx1 = np.arange(1, natom + 1, dtype=np.int32)
+    rng = np.random.Generator(np.random.PCG64(2024))
+    ekb = rng.standard_normal((1, lnmax))
+    h = ab.Hamiltonian(cfg["ngfft"], natom, 1, nlmn, indlmn, nattyp, atindx1, 0, float(cfg["L"]) ** 3)
+    h.load_spin(wl.smooth_potential(cfg["ngfft"], seed=5), 1)
+    h.load_enl(ekb, None)
+    h.load_k(2, kg, kinpw, None, None, me_g0=1)
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev).manual_seed(77)
+    P = torch.randn((nprojs, npw, 2), generator=gen, device=dev, dtype=torch.float64) / np.sqrt(npw)
+    cw = torch.randn((ndat, npw, 2), generator=gen, device=dev, dtype=torch.float64)
+    P[:, 0, 1] = 0.0; cw[:, 0, 1] = 0.0
     torch.cuda.synchronize()
-    xg.xg_gram(space, npw, na, nb, a, npw, b, npw, w, na, me_g0)
-    return w.cpu().numpy().T
+    ref, _, _, _ = _oracle_getghc(cfg, 2, kg, kinpw, cw, P, ekb, None, 0, 0, atindx1, nattyp, indlmn)
+    h.set_projectors(P, nprojs)
+    del P
+    torch.cuda.empty_cache()
+    ghc = torch.zeros_like(cw)
+    torch.cuda.synchronize()
+    ab.getghc(-1, cw, None, ghc, None, h, None, None, None, ndat)
+    assert _rel(_c(ghc), ref) < 1e-11                       # north-star tolerance: 1e-11 relative per band
+    # odd block (the last band rides a half-empty packed transform) and the band-by-band path
+    g3 = torch.zeros((3, npw, 2), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    ab.getghc(-1, cw[:3].contiguous(), None, g3, None, h, None, None, None, 3)
+    assert _rel(_c(g3), ref[:3]) < 1e-11
+    h.destroy()
+
+
+def test_au108_paw_getghc_matches_oracle_at_full_size(lib):
+    """BASELINE configs[3] shape (box 96^3, istwf_k 1, npw 52 923, nprojs 1944, PAW with S): ghc AND gsc against the oracle."""
+    ndat = 6
+    cfg, h, cw, kg, kinpw, npw, nprojs = _setup("au108", 1, ndat, usepaw=1, seed=11)
+    # _setup loaded random D_ij / S_ij and projectors; rebuild the same operands for the oracle from the same seeds
+    indlmn, lnmax = wl.nc_indlmn(cfg["lmax"], cfg["nproj_per_l"])
+    nlmn = indlmn.shape[1]; natom = cfg["natom"]
+    rng = np.random.Generator(np.random.PCG64(100 + 11))
+    lmn2 = nlmn * (nlmn + 1) // 2
+    dij = 0.3 * rng.standard_normal((natom, lmn2))
+    a = 0.1 * rng.standard_normal((nlmn, nlmn)); a = a @ a.T
+    sij = np.array([[a[i, j] for j in range(nlmn) for i in range(j + 1)]])
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev).manual_seed(4321 + 11)
+    P = torch.randn((nprojs, npw, 2), generator=gen, device=dev, dtype=torch.float64) / np.sqrt(npw)
+    nattyp = np.array([natom], dtype=np.int32); atindx1 = np.arange(1, natom + 1, dtype=np.int32)
+    ref, refs, _, _ = _oracle_getghc(cfg, 1, kg, kinpw, cw, P, dij, sij, 1, 1, atindx1, nattyp, indlmn)
+    del P
+    ghc = torch.zeros_like(cw); gsc = torch.zeros_like(cw)
+    torch.cuda.synchronize()
+    ab.getghc(-1, cw, None, ghc, gsc, h, None, None, None, ndat, sij_opt=1)
+    assert _rel(_c(ghc), ref) < 1e-11
+    assert _rel(_c(gsc), refs) < 1e-11
+    h.destroy()
 
 
 def test_si512_getghc_properties(lib):
