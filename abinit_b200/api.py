@@ -211,6 +211,22 @@ def getghc(cpopt, cwavef, cwaveprj, ghc, gsc, gs_ham: Hamiltonian, gvnlxc, lambd
                          _iref(prtvol), _iref(sij_opt), _iref(tim_getghc), _iref(type_calc))
 
 
+def getghc_batch(hams, cwavefs, ghcs, gscs=None, ndat=1, sij_opt=0, type_calc=0, use_graphs=True):
+    """nk independent getghc calls on nk handles (one per (k, spin) pair) with device-resident blocks, overlapped on
+    concurrent streams and replayed from CUDA graphs (abi_b200_getghc_batch_; the (k, spin) loop of m_vtorho.F90:789-1045).
+    Identical results to a loop over getghc; gscs may be None (sij_opt = 0)."""
+    nk = len(hams)
+    Hp = (C.c_void_p * nk)(*[h.h for h in hams])
+    Cp = (C.c_void_p * nk)(*[_ptr(c, _F, "cwavef") for c in cwavefs])
+    Gp = (C.c_void_p * nk)(*[_ptr(g, _F, "ghc") for g in ghcs])
+    Sp = (C.c_void_p * nk)(*[_ptr(g, _F, "gsc") for g in gscs]) if gscs is not None else None
+    L().abi_b200_getghc_batch_(_iref(nk), Hp, Cp, Gp, Sp, _iref(ndat), _iref(sij_opt), _iref(type_calc), _iref(1 if use_graphs else 0))
+
+
+def graphs_clear():
+    L().abi_b200_graphs_clear()
+
+
 _nonlop_slot_npw = {}
 
 

@@ -1,6 +1,8 @@
 // C-ABI entry points: gemm_nonlop life cycle + apply, Hamiltonian handle, fused getghc, Gram matrices.
 // See include/abinit_b200.h for the reference interfaces replaced.
 #include "../../include/abinit_b200.h"
+#include <tuple>
+#include <map>
 #include "context.cuh"
 #include "fourwf.cuh"
 #include "nonlop.cuh"
@@ -273,6 +275,7 @@ void abi_b200_ham_destroy(abi_b200_ham_t* h) {
 }
 
 void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_vloc, int n4, int n5, int n6) {
+  h->epoch++;
   ensure_init();
   ABI_CHECK(n4 == h->ngfft[0] && n5 == h->ngfft[1] && n6 == h->ngfft[2],
             "FFT SIZE ERROR: when gpu mode is on the fft grid must not be augmented (n4,n5,n6 must equal n1,n2,n3)");
@@ -283,6 +286,7 @@ void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_v
 }
 
 void abi_b200_ham_set_nspinor(abi_b200_ham_t* h, int nspinor) {
+  h->epoch++;
   ABI_CHECK(nspinor == 1 || nspinor == 2, "nspinor must be 1 or 2");
   ABI_CHECK(!(nspinor == 2 && h->usepaw == 1), "nspinor=2 with PAW (spinor-mixing D_ij) is not implemented in this build");
   h->nspinor = nspinor;
@@ -298,6 +302,7 @@ __global__ void k_pack_vud(const double* __restrict__ v3, const double* __restri
 #endif
 
 void abi_b200_ham_load_spin_nvloc(abi_b200_ham_t* h, const double* vlocal, int nvloc, int n4, int n5, int n6) {
+  h->epoch++;
   ensure_init();
   ABI_CHECK(nvloc == 1 || nvloc == 4, "nvloc must be 1 or 4");
   if (nvloc == 1) { abi_b200_ham_load_spin(h, vlocal, 1, n4, n5, n6); h->nvloc = 1; return; }
@@ -323,6 +328,7 @@ void abi_b200_ham_load_spin_nvloc(abi_b200_ham_t* h, const double* vlocal, int n
 }
 
 void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, const double* sij) {
+  h->epoch++;
   ensure_init();
   h->enl.load(enl, dimenl1, dimenl2, sij, h->ntypat, ctx().stream);
   h->invovl.release();
@@ -330,6 +336,7 @@ void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, in
 
 void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw, const double* ffnl,
                          int dimffnl, const double* ph3d, int matblk, int me_g0) {
+  h->epoch++;
   ensure_init();
   Context& c = ctx();
   ABI_CHECK(!is_device_ptr(kg_k), "kg_k must be a host array");
@@ -354,6 +361,7 @@ void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_
 
 void abi_b200_ham_load_k_xred(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw, const double* ffnl,
                               int dimffnl, const double* kpt, const double* xred, int me_g0) {
+  h->epoch++;
   ABI_CHECK(ffnl != nullptr && kpt != nullptr && xred != nullptr, "load_k_xred: ffnl, kpt and xred are required");
   abi_b200_ham_load_k(h, istwf_k, npw, kg_k, kinpw, nullptr, 0, nullptr, 0, me_g0);
   Context& c = ctx();
@@ -366,6 +374,7 @@ void abi_b200_ham_load_k_xred(abi_b200_ham_t* h, int istwf_k, int npw, const int
 }
 
 void abi_b200_ham_set_projectors(abi_b200_ham_t* h, const double* projs, int nprojs) {
+  h->epoch++;
   ensure_init();
   ABI_CHECK(nprojs == h->atoms.nprojs, "set_projectors: nprojs differs from sum(nlmn*nattyp)");
   h->P.alloc(h->npw, nprojs, h->istwf_k);
@@ -547,6 +556,107 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     if (pipe) CUDA_CHECK(cudaStreamSynchronize(c.copy_stream));
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// Batched getghc for the many-small-k-points regime (BASELINE configs[2]: Fe-2 PAW, hundreds of (k, spin) pairs of ~24 bands and
+// ~700 plane waves: 6-9 kernels of a few microseconds per call, i.e. launch-latency bound on one stream).
+//   * the calls of a batch are dealt round-robin to kMaxLanes streams, each with its own set of internal workspaces, so the
+//     kernels of different k-points overlap on the device;
+//   * the kernel sequence of one (handle, arrays, ndat) combination is captured into a CUDA graph the second time it is seen
+//     and replayed afterwards (one launch per call instead of 6-9); any load_* / set_* on the handle bumps its epoch and
+//     drops the graph.
+// Reference: the (k, spin) loop of src/79_seqpar_mpi/m_vtorho.F90:789-1045 around the eigensolver's getghc calls.
+// ------------------------------------------------------------------------------------------------------
+namespace {
+struct GraphEntry { int state = 0; cudaGraphExec_t exec = nullptr; };
+struct GraphKey {
+  const void* h; unsigned epoch; const void* c; const void* g; const void* s; int ndat, sij, tc, lane;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(h, epoch, c, g, s, ndat, sij, tc, lane) < std::tie(o.h, o.epoch, o.c, o.g, o.s, o.ndat, o.sij, o.tc, o.lane);
+  }
+};
+std::map<GraphKey, GraphEntry>& graph_cache() { static std::map<GraphKey, GraphEntry> c; return c; }
+cudaEvent_t g_lane_ev[kMaxLanes + 1] = {};
+}  // namespace
+
+void abi_b200_graphs_clear(void) {
+#ifndef ABI_EMU
+  for (auto& kv : graph_cache()) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+#endif
+  graph_cache().clear();
+}
+
+void abi_b200_getghc_batch_(int* nk, abi_b200_ham_t** hams, double** cwavef, double** ghc, double** gsc, int* ndat, int* sij_opt,
+                            int* type_calc, int* use_graphs) {
+  ensure_init();
+  Context& c = ctx();
+  ABI_CHECK(*nk >= 0, "getghc_batch: nk must be >= 0");
+#ifdef ABI_EMU
+  for (int i = 0; i < *nk; i++) {
+    int cpopt = -1, prtvol = 0, tim = 0;
+    abi_b200_getghc_(&cpopt, cwavef[i], nullptr, ghc[i], gsc ? gsc[i] : nullptr, &hams[i], nullptr, nullptr, ndat, &prtvol, sij_opt, &tim, type_calc);
+  }
+  (void)use_graphs;
+#else
+  const bool was_async = c.async;
+  cudaStream_t main_stream = c.stream;
+  const int nlanes = std::min(kMaxLanes, std::max(1, *nk));
+  for (int l = 0; l < nlanes; l++) {
+    if (!c.lane_stream[l]) CUDA_CHECK(cudaStreamCreateWithFlags(&c.lane_stream[l], cudaStreamNonBlocking));
+    if (!g_lane_ev[l]) CUDA_CHECK(cudaEventCreateWithFlags(&g_lane_ev[l], cudaEventDisableTiming));
+  }
+  if (!g_lane_ev[kMaxLanes]) CUDA_CHECK(cudaEventCreateWithFlags(&g_lane_ev[kMaxLanes], cudaEventDisableTiming));
+  // the lanes start behind whatever the caller queued on the library stream (the blocks may have been produced there)
+  CUDA_CHECK(cudaEventRecord(g_lane_ev[kMaxLanes], main_stream));
+  for (int l = 0; l < nlanes; l++) CUDA_CHECK(cudaStreamWaitEvent(c.lane_stream[l], g_lane_ev[kMaxLanes], 0));
+  c.async = true;
+  for (int i = 0; i < *nk; i++) {
+    abi_b200_ham* h = hams[i];
+    double* gs = gsc ? gsc[i] : nullptr;
+    ABI_CHECK(is_device_ptr(cwavef[i]) && is_device_ptr(ghc[i]) && (gs == nullptr || is_device_ptr(gs)),
+              "getghc_batch: the wavefunction blocks must be device-resident");
+    const int lane = i % nlanes;
+    c.lane = lane; c.stream = c.lane_stream[lane];
+    int cpopt = -1, prtvol = 0, tim = 0;
+    auto eager = [&]() {
+      abi_b200_getghc_(&cpopt, cwavef[i], nullptr, ghc[i], gs, &hams[i], nullptr, nullptr, ndat, &prtvol, sij_opt, &tim, type_calc);
+    };
+    if (!*use_graphs) { eager(); continue; }
+    GraphKey key{h, h->epoch, cwavef[i], ghc[i], gs, *ndat, *sij_opt, *type_calc, lane};
+    GraphEntry& ge = graph_cache()[key];
+    if (ge.state == 0) {                       // first sight: run eagerly (plans, V_loc permutation, workspaces get allocated)
+      eager(); ge.state = 1;
+    } else if (ge.state == 1) {                // second sight: capture the same call into a graph
+      const long long fw0 = c.fourwf_counter, nl0 = c.nonlop_counter, kl0 = g_kernel_launches;
+      c.force_scratch_clear = true;
+      CUDA_CHECK(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed));
+      eager();
+      cudaGraph_t graph = nullptr;
+      CUDA_CHECK(cudaStreamEndCapture(c.stream, &graph));
+      c.force_scratch_clear = false;
+      CUDA_CHECK(cudaGraphInstantiate(&ge.exec, graph, 0));
+      CUDA_CHECK(cudaGraphDestroy(graph));
+      ge.state = 2;
+      // the captured call did not run: undo its bookkeeping, the launch below redoes it
+      c.fourwf_counter = fw0; c.nonlop_counter = nl0; g_kernel_launches = kl0;
+      ge.state = 2;
+      CUDA_CHECK(cudaGraphLaunch(ge.exec, c.stream));
+      c.fourwf_counter += 2 * (*ndat); c.nonlop_counter += *ndat; g_kernel_launches += 1;
+    } else {
+      CUDA_CHECK(cudaGraphLaunch(ge.exec, c.stream));
+      c.fourwf_counter += 2 * (*ndat); c.nonlop_counter += *ndat; g_kernel_launches += 1;
+    }
+  }
+  // join: the library stream continues behind every lane
+  c.lane = 0; c.stream = main_stream; c.async = was_async;
+  for (int l = 0; l < nlanes; l++) {
+    CUDA_CHECK(cudaEventRecord(g_lane_ev[l], c.lane_stream[l]));
+    CUDA_CHECK(cudaStreamWaitEvent(main_stream, g_lane_ev[l], 0));
+  }
+  if (!c.async) CUDA_CHECK(cudaStreamSynchronize(main_stream));
+#endif
 }
 
 }  // extern "C"

@@ -11,6 +11,8 @@ struct Staging {             // grow-only device buffer used to mirror one host 
   void release();
 };
 
+constexpr int kMaxLanes = 8;    // concurrent streams of the batched small-system path (getghc_batch); lane 0 = the library stream
+
 struct Context {
   bool initialized = false;
   int device = 0;
@@ -25,6 +27,10 @@ struct Context {
   long long fourwf_counter = 0; // m_fft.F90:2333-2336
   long long nonlop_counter = 0; // m_nonlop.F90:389-392
   Staging stage[16];
+  // lanes: every internal workspace exists once per lane, so calls issued on different lanes may overlap on the device
+  int lane = 0;
+  cudaStream_t lane_stream[kMaxLanes] = {};
+  bool force_scratch_clear = false;   // set while a call is captured into a CUDA graph (see half_scratch_get)
 };
 Context& ctx();
 void ensure_init();

@@ -176,8 +176,9 @@ struct Workspace {
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
-static Workspace g_ws[4];
-void fourwf_release_workspace() { for (auto& w : g_ws) w.release(); plane_stage_release(); half_stage_release(); }
+static Workspace g_ws_all[kMaxLanes][4];
+#define g_ws g_ws_all[ctx().lane]
+void fourwf_release_workspace() { for (auto& l : g_ws_all) for (auto& w : l) w.release(); plane_stage_release(); half_stage_release(); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Planner

@@ -35,7 +35,8 @@ template <typename T> T* upload(const std::vector<T>& v, std::vector<void*>& own
   owned.push_back(d);
   return d;
 }
-struct HScratch { void* p = nullptr; size_t cap = 0; uint64_t key = 0; } g_hscratch;
+struct HScratch { void* p = nullptr; size_t cap = 0; uint64_t key = 0; } g_hscratch_all[kMaxLanes];
+#define g_hscratch g_hscratch_all[ctx().lane]
 
 // permutation tables of one (n2, n3) pair: grid index of every slot of the vP / rhoP layout
 struct PermTab { int* d_i2_of_cid = nullptr; int* d_i3_of_slot = nullptr; };
@@ -152,7 +153,8 @@ const HalfCfg* half_stage_cfg(int n) { const Entry* e = find_entry(n); return e 
 void* half_scratch_get(size_t bytes, uint64_t layout_key, cudaStream_t st) {
   HScratch& h = g_hscratch;
   if (bytes > h.cap) { if (h.p) CUDA_CHECK(cudaFree(h.p)); CUDA_CHECK(cudaMalloc(&h.p, bytes)); h.cap = bytes; h.key = 0; }
-  if (h.key != layout_key) { CUDA_CHECK(cudaMemsetAsync(h.p, 0, h.cap, st)); h.key = layout_key; }   // the whole buffer: later launches of this plan may use more of it
+  // (a call being captured into a CUDA graph always clears: at replay time another plan may have used the buffer in between)
+  if (h.key != layout_key || ctx().force_scratch_clear) { CUDA_CHECK(cudaMemsetAsync(h.p, 0, h.cap, st)); h.key = layout_key; }   // the whole buffer: later launches of this plan may use more of it
   return h.p;
 }
 
@@ -214,8 +216,7 @@ void half_rho_unpermute_add(const FourwfPlan& pl, const double* rhoP, double* de
 }
 
 void half_stage_release() {
-  if (g_hscratch.p) cudaFree(g_hscratch.p);
-  g_hscratch = HScratch();
+  for (auto& g : g_hscratch_all) { if (g.p) cudaFree(g.p); g = HScratch(); }
   for (void* p : perm_owned()) cudaFree(p);
   perm_owned().clear(); perm_cache().clear();
 }

@@ -35,13 +35,20 @@ void half_launch_cfg(HalfParams& P, cudaStream_t st) {
 
 template <int A, int B, int G>
 void half_launch_n(int kind, HalfParams& P, cudaStream_t st) {
-  static_assert(HalfFft<A, B, G>::ROWS * G * 16 + HalfFft<A, B, G>::ESIZE * 16 <= 14 * 1024, "per-warp shared memory too large for 16 warps per SM");
+  using F = HalfFft<A, B, G>;
+  static_assert(F::ROWS * G * 16 + F::ESIZE * 16 <= 14 * 1024, "per-warp shared memory too large for 16 warps per SM");
   const int cfg = fourwf_tuning().half_cfg;
-  if (kind == 0) {
-    if (cfg == 1) half_launch_cfg<A, B, G, 16, 1, 0>(P, st);
-    else half_launch_cfg<A, B, G, 8, 2, 0>(P, st);
+  // warps that can be busy at once in a phase: line batches (y) or column batches (z) of ONE plane.  Small boxes have only a
+  // few, so they run as small CTAs, several per SM (many planes in flight), instead of one 16-warp CTA per SM.
+  constexpr int kBusy = F::NBY > F::NG ? F::NBY : F::NG;
+  if (kBusy <= 4) {
+    if (kind == 0) half_launch_cfg<A, B, G, 4, 6, 0>(P, st);
+    else half_launch_cfg<A, B, G, 4, 6, 1>(P, st);
+  } else if (kBusy <= 8 || cfg == 0 || kind != 0) {
+    if (kind == 0) half_launch_cfg<A, B, G, 8, 2, 0>(P, st);
+    else half_launch_cfg<A, B, G, 8, 2, 1>(P, st);
   } else {
-    half_launch_cfg<A, B, G, 8, 2, 1>(P, st);
+    half_launch_cfg<A, B, G, 16, 1, 0>(P, st);
   }
 }
 

@@ -35,6 +35,7 @@ struct abi_b200_ham {
   std::shared_ptr<abi::FourwfPlan> plan_ref;   // keeps the plan alive whatever happens to the plan cache
   abi::FourwfPlan* plan = nullptr;
   double* d_gvnlxc = nullptr; size_t gvnlxc_cap = 0;
+  unsigned epoch = 0;                 // bumped by every load_* / set_*: invalidates the CUDA graphs captured for this handle
   abi::Invovl invovl;                 // built lazily by apply_invovl, dropped by load_k / load_enl / set_projectors
 };
 

@@ -597,8 +597,9 @@ struct NlWorkspace {
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
-static NlWorkspace g_nlws[4];   // 0: partials, 1: gx, 2: gxfac, 3: gxs
-void nonlop_release_workspace() { for (auto& w : g_nlws) w.release(); ozaki_release_workspace(); }
+static NlWorkspace g_nlws_all[kMaxLanes][4];   // per lane: 0: partials, 1: gx, 2: gxfac, 3: gxs
+#define g_nlws g_nlws_all[ctx().lane]
+void nonlop_release_workspace() { for (auto& l : g_nlws_all) for (auto& w : l) w.release(); ozaki_release_workspace(); }
 
 #ifndef ABI_EMU
 void prep_projectors_device(Projectors& P, const NonlopAtoms& at, const double* d_ffnl, int dimffnl, const double* d_ph3d,
@@ -658,12 +659,59 @@ static void launch_gemm(const GemmParams& p, int nblocks, cudaStream_t st) {
   g_kernel_launches++;
 }
 
+// Small-system TN product (Si-2 / Fe-2 per k-point: M = nprojs <= 64, N <= 64 effective columns, K = 2 npw ~ 10^3): one CTA per
+// K chunk holds its slices of A and B in shared memory and every thread accumulates a few of the M x N outputs with plain
+// FP64 FMAs -- the 128-wide DMMA tiles above would be 90 % padding here and cost the latency of their cp.async pipeline.
+// Same partial-buffer layout [z][n][m] and the same reduction kernel as the tiled path.
+constexpr int kSmallK = 32;
+template <bool CPLX>
+__global__ void __launch_bounds__(256) k_small_tn(GemmParams p) {
+  __shared__ double As[64][kSmallK + 1];
+  __shared__ double Bs[64][kSmallK + 2];
+  const int z = blockIdx.x, k0 = z * p.kchunk, kc = min(p.kchunk, p.K - k0);
+  const int nrows_b = CPLX ? p.N / 2 : p.N;
+  for (int w = threadIdx.x; w < p.M * kSmallK; w += 256) {
+    const int m = w / kSmallK, k = w - m * kSmallK;
+    As[m][k] = k < kc ? p.A[(size_t)m * p.lda + k0 + k] : 0.0;
+  }
+  for (int w = threadIdx.x; w < nrows_b * kSmallK; w += 256) {
+    const int n = w / kSmallK, k = w - n * kSmallK;
+    Bs[n][k] = k < kc ? p.B[(size_t)n * p.ldb + k0 + k] : 0.0;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < p.M * p.N; o += 256) {
+    const int m = o % p.M, n = o / p.M;
+    double acc = 0.0;
+    if (!CPLX || !(n & 1)) {
+      const double* b = Bs[CPLX ? n >> 1 : n];
+#pragma unroll 8
+      for (int k = 0; k < kSmallK; k++) acc = fma(As[m][k], b[k], acc);
+    } else {
+      // column (-i psi): real view (Im psi, -Re psi) -- k chunks are even, so pairs never straddle a chunk
+      const double* b = Bs[n >> 1];
+#pragma unroll 8
+      for (int k = 0; k < kSmallK; k += 2) { acc = fma(As[m][k], b[k + 1], acc); acc = fma(-As[m][k + 1], b[k], acc); }
+    }
+    p.C[((size_t)z * p.N + n) * p.M + m] = acc;
+  }
+}
+
 // split-K TN GEMM into partial buffers; returns nsplit
 static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long long lda, const double* B, long long ldb,
                      double*& part, cudaStream_t st, const char* prof_name = "dgemm_tn_opernla") {
   const int BN = Neff <= 32 ? 32 : (Neff <= 64 ? 64 : 128), BM = 128 * 128 / BN;
   GemmParams p{};
   p.M = M; p.N = Neff; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.add = nullptr; p.ldc = 0;
+  if (M <= 64 && Neff <= 64 && K <= 128 * kSmallK && K % 2 == 0) {
+    p.kchunk = kSmallK; p.nsplit = ceil_div(K, kSmallK);
+    part = g_nlws[0].get((size_t)p.nsplit * Neff * M);
+    p.C = part;
+    ProfScope ps(prof_name);
+    if (cplx) k_small_tn<true><<<p.nsplit, 256, 0, st>>>(p); else k_small_tn<false><<<p.nsplit, 256, 0, st>>>(p);
+    CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+    return p.nsplit;
+  }
   p.tiles_m = ceil_div(M, BM); p.tiles_n = ceil_div(Neff, BN);
   const int tiles = p.tiles_m * p.tiles_n;
   // pick the split count that minimises the makespan (waves of 148 CTAs per unit of work)

@@ -16,7 +16,8 @@ struct Scratch {
     if (bytes > cap) { if (p) CUDA_CHECK(cudaFree(p)); CUDA_CHECK(cudaMalloc(&p, bytes)); cap = bytes; }
     return p;
   }
-} g_scratch;
+} g_scratch_all[kMaxLanes];
+#define g_scratch g_scratch_all[ctx().lane]
 
 typedef void (*LaunchFn)(PlaneParams&, cudaStream_t);
 typedef void (*SplitFn)(int, PlaneParams&, cudaStream_t);
@@ -62,6 +63,6 @@ void plane_stage_launch_rho(PlaneParams& P, cudaStream_t st) {
   e3->fn_split(3, P, st);          // z + density accumulation
 }
 
-void plane_stage_release() { if (g_scratch.p) cudaFree(g_scratch.p); g_scratch.p = nullptr; g_scratch.cap = 0; }
+void plane_stage_release() { for (auto& g : g_scratch_all) { if (g.p) cudaFree(g.p); g.p = nullptr; g.cap = 0; } }
 
 }  // namespace abi

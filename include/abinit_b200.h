@@ -150,6 +150,15 @@ int abi_b200_ham_nprojs(const abi_b200_ham_t* h);
 void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc, double* gsc,
                       abi_b200_ham_t** gs_ham, double* gvnlxc, double* lambda, int* ndat, int* prtvol,
                       int* sij_opt, int* tim_getghc, int* type_calc);
+/* Batched getghc for the many-small-k-points regime (the (k, spin) loop of src/79_seqpar_mpi/m_vtorho.F90:789-1045 around the
+ * eigensolver's getghc calls): nk independent applications, call i on handle hams[i] (one handle per (k, spin) pair: its own
+ * load_spin / load_k) with DEVICE-resident blocks cwavef[i] -> ghc[i] (, gsc[i]; gsc may be NULL), cpopt = -1, no gvnlxc / lambda.
+ * The calls are dealt to concurrent streams with private workspaces and, when *use_graphs != 0, replayed from CUDA graphs
+ * captured on their second occurrence (dropped when the handle is reloaded).  Results are identical to nk calls of
+ * abi_b200_getghc_.  abi_b200_graphs_clear drops every captured graph (call it before freeing the arrays they refer to). */
+void abi_b200_getghc_batch_(int* nk, abi_b200_ham_t** hams, double** cwavef, double** ghc, double** gsc, int* ndat,
+                            int* sij_opt, int* type_calc, int* use_graphs);
+void abi_b200_graphs_clear(void);
 
 /* ------------------------------------------------------------------------------------------------------
  * nonlop dispatcher on the Hamiltonian handle (src/66_nonlocal/m_nonlop.F90:336-976, gemm_nonlop route :782-811):
