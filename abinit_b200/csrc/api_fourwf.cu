@@ -83,6 +83,7 @@ void abi_b200_fourwf_set_tuning(const char* name, int value) {
   else if (k == "half_cfg") t.half_cfg = value;
   else if (k == "half_skip") t.half_skip = value;
   else if (k == "xhalf") t.xhalf = value;
+  else if (k == "xh_order") t.xh_order = value;
   else if (k == "pipeline") ctx().pipeline = value != 0;
   else if (k == "nonlop_ozaki") ozaki_set_enabled(value);     // EXPERIMENTAL int8-sliced gemm_nonlop (ozaki.cu), default off
   else if (k == "pipe_chunks") ctx().pipe_chunks = std::max(1, value);

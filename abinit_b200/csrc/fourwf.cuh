@@ -145,6 +145,7 @@ struct FourwfTuning {
   int plane_split = 0;         // 1: run the split (three-kernel) plane stage for cubic boxes too (developer comparison)
   int half = 1;                // 1: half-support plane stage (half_stage.cuh) when the sphere fits in half of the box axes
   int xhalf = 3;               // half-support x passes (x_stage.cuh) when the plan allows them: bit 0 forward (K1), bit 1 backward (K3)
+  int xh_order = 1;            // x passes: bit 0 = batch index fastest (neighbouring warps touch neighbouring runs), bit 1 = evict_first on the W1o strip
   int half_skip = 0;           // developer timing aid (phase mask), see HalfParams::dbg_skip
   int half_cfg = 1;            // 0: 8 warps x 2 CTAs/SM, 1: 16 warps x 1 CTA/SM (measured on B200, Si-512: 3.55 vs 3.44 ms)
   int pack2 = 1;               // istwf_k=2: two bands per complex transform (double_rfft_trick, m_getghc.F90:1999-2171)

@@ -63,6 +63,9 @@ ABI_DEV unsigned long long policy_evict_last() {
 ABI_DEV unsigned long long policy_evict_first() {
   unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
 }
+ABI_DEV unsigned long long policy_evict_normal() {
+  unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p;
+}
 ABI_DEV double2 ld_keep(const double2* a, unsigned long long pol) {
   double2 v; asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol)); return v;
 }
@@ -77,15 +80,21 @@ ABI_DEV void cp_async16(double2* sdst, const double2* gsrc, unsigned long long p
   const unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "l"(pol) : "memory");
 }
+ABI_DEV void cp_async16_plain(double2* sdst, const double2* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
 ABI_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 ABI_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #else
 inline unsigned long long policy_evict_last() { return 0; }
 inline unsigned long long policy_evict_first() { return 0; }
+inline unsigned long long policy_evict_normal() { return 0; }
 inline double2 ld_keep(const double2* a, unsigned long long) { return *a; }
 inline void st_keep(double2* a, double2 v, unsigned long long) { *a = v; }
 inline void st_stream(double2* a, double2 v, unsigned long long) { *a = v; }
 inline void cp_async16(double2* sdst, const double2* gsrc, unsigned long long) { *sdst = *gsrc; }
+inline void cp_async16_plain(double2* sdst, const double2* gsrc) { *sdst = *gsrc; }
 inline void cp_async_commit() {}
 inline void cp_async_wait_all() {}
 #endif

@@ -187,7 +187,7 @@ static void fill_common(const FourwfPlan& pl, const XhSet& s, XhParams& P, int n
   P.n1 = pl.n1; P.nb = nb; P.nlines = s.nlines; P.pack_ndat = pack_ndat;
   P.tw1 = fft_tables(pl.n1).plan.tw; P.x_sign = s.d_sign; P.x_ovslot = s.d_ovslot;
   P.cg = nullptr; P.out = nullptr; P.W1in = nullptr; P.W1 = nullptr; P.ent = nullptr; P.estart = nullptr;
-  P.batches = nullptr; P.oent = nullptr; P.bstart = nullptr; P.xnorm = 1.0; P.kin_filter = 0.0; P.zero_im_g0 = 0;
+  P.batches = nullptr; P.oent = nullptr; P.bstart = nullptr; P.xnorm = 1.0; P.kin_filter = 0.0; P.zero_im_g0 = 0; P.order = fourwf_tuning().xh_order;
 }
 
 void x_stage_forward(const FourwfPlan& pl, const double2* cg, double2* W1, int nb, int pack_ndat, cudaStream_t st) {

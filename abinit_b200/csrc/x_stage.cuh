@@ -33,6 +33,7 @@ struct XhParams {
   //     {ipw | g0flag << 30, slotD | lineD << 8 | slotI << 12 | lineI << 20 | has_image << 24}; bstart[batch]
   const int4* batches; const int2* oent; const int* bstart;
   double xnorm; double kin_filter; int zero_im_g0;
+  int order;                          // unit order: 0 transform fastest, 1 batch fastest (neighbouring warps touch neighbouring 128-byte runs)
   FourwfEpilogue epi;
 };
 
@@ -47,13 +48,18 @@ struct XHalf {
   static constexpr int STG = GL * RS;
   static constexpr int WSIZE = ESIZE + STG;
   static constexpr int TW_SLOTS = M + (PFA ? 0 : 2 * M);
-  ABI_HD static constexpr int int_slots() { return (B + M + 3) / 4; }   // xmask[B], xov[M]
+  ABI_HD static constexpr int int_slots() { return (B + M + 2 * M + 3) / 4; }   // xmask[B], xov[M], i1row[2M]
 
-  struct Tables { const double2* Tx; const double2* ctwA; const double2* ctwB; const int* xmask; const int* xov; };
+  struct Tables { const double2* Tx; const double2* ctwA; const double2* ctwB; const int* xmask; const int* xov; const int* i1row; };
 
   ABI_DEV static Tables load_tables(double2* sm, const XhParams& P, int tid, int nthr) {
     double2* Tx = sm; double2* cA = sm + M; double2* cB = cA + M;
-    int* xmask = reinterpret_cast<int*>(sm + TW_SLOTS); int* xov = xmask + B;
+    int* xmask = reinterpret_cast<int*>(sm + TW_SLOTS); int* xov = xmask + B; int* i1row = xov + M;
+    // row = (h * A + k1) * B + k2 of the exchange buffer <-> i1 = 2 kout(k1, k2) + h
+    for (int q = tid; q < 2 * M; q += nthr) {
+      const int hk1 = q / B, k2 = q - hk1 * B, h = hk1 >= A ? 1 : 0;
+      i1row[q] = 2 * Map::kout(hk1 - h * A, k2) + h;
+    }
     for (int q = tid; q < M; q += nthr) {
       const int t = q / B, j = q - t * B;
       double2 w = P.tw1[Map::rin(t, j)];
@@ -70,49 +76,68 @@ struct XHalf {
       for (int t = 0; t < A; t++) if (P.x_ovslot[t * B + j] >= 0) m |= 1 << t;
       xmask[j] = m;
     }
-    Tables T; T.Tx = Tx; T.ctwA = cA; T.ctwB = cB; T.xmask = xmask; T.xov = xov;
+    Tables T; T.Tx = Tx; T.ctwA = cA; T.ctwB = cB; T.xmask = xmask; T.xov = xov; T.i1row = i1row;
     return T;
   }
 
   // ---------------- K1: one batch of lines, sphere -> W1 ----------------
-  ABI_DEV static void forward(const XhParams& P, const Tables& T, double2* E, double2* stg, int b, int batch) {
+  // The coefficients of a batch are gathered into the staging buffer ONE UNIT AHEAD: the loads of the next batch are issued
+  // inside pass 2 of the current one (UG entries per lane and pass-2 iteration, their table entries one iteration earlier), so
+  // that a warp never sits on the table -> coefficient -> shared-memory chain with nothing else to do (ncu r02e: 56 % of the
+  // warp stalls were long-scoreboard waits with 6 warps per SM).
+  static constexpr int UG = 4;
+  struct Gather {                       // where the coefficients of one unit come from
+    const double2* c0; const double2* c1; bool pack, has_d; int l0, e0, e1;
+  };
+  ABI_DEV static Gather gather_of(const XhParams& P, int b, int batch) {
+    Gather g;
+    g.pack = P.pack_ndat != 0;
+    g.c0 = P.cg + (size_t)(g.pack ? 2 * b : b) * P.npw; g.c1 = g.c0 + P.npw;
+    g.has_d = g.pack && 2 * b + 1 < P.pack_ndat;
+    g.l0 = batch * GL;
+    const int nl = min(GL, P.nlines - g.l0);
+    g.e0 = P.estart[g.l0]; g.e1 = P.estart[g.l0 + nl];
+    return g;
+  }
+  ABI_DEV static void g_load(const Gather& g, int2 en, double2& c, double2& d) {
+    const int ipw = en.x & 0x3fffffff;
+    c = g.c0[ipw];
+    d = g.has_d ? g.c1[ipw] : make_double2(0.0, 0.0);
+  }
+  // E(G) = C(G) + i D(G), E(-G) = conj(C(G)) + i conj(D(G)) (image entries: bit 31; G = 0: bit 30, imaginary parts dropped)
+  ABI_DEV static void g_store(const Gather& g, double2* stg, int2 en, double2 c, double2 d) {
+    if (en.x < 0) { c.y = -c.y; d.y = -d.y; }
+    if (en.x & (1 << 30)) { c.y = 0.0; d.y = 0.0; }
+    stg[((en.y >> 10) - g.l0) * RS + (en.y & 1023)] = g.pack ? make_double2(c.x - d.y, c.y + d.x) : c;
+  }
+  ABI_DEV static void zero_stg(double2* stg) {
+    ABI_FOR_LANES {
+      for (int q = lane; q < STG; q += 32) stg[q] = make_double2(0.0, 0.0);
+    }
+    ABI_SYNCWARP();
+  }
+  // un-pipelined gather (first unit of a warp)
+  ABI_DEV static void gather_plain(const XhParams& P, double2* stg, int b, int batch) {
+    zero_stg(stg);
+    const Gather g = gather_of(P, b, batch);
+    ABI_FOR_LANES {
+      for (int e = g.e0 + lane; e < g.e1; e += 32) {
+        const int2 en = P.ent[e];
+        double2 c, d;
+        g_load(g, en, c, d);
+        g_store(g, stg, en, c, d);
+      }
+    }
+    ABI_SYNCWARP();
+  }
+
+  // stg holds the coefficients of (b, batch) on entry and those of (bn, batchn) on exit (when have_next)
+  ABI_DEV static void forward(const XhParams& P, const Tables& T, double2* E, double2* stg, int b, int batch, bool have_next, int bn,
+                              int batchn) {
     const int l0 = batch * GL, nl = min(GL, P.nlines - l0);
-    {
-      ABI_FOR_LANES {
-        for (int q = lane; q < STG; q += 32) stg[q] = make_double2(0.0, 0.0);
-      }
-    }
-    ABI_SYNCWARP();
-    const int e0 = P.estart[l0], e1 = P.estart[l0 + nl];
-    {
-      ABI_FOR_LANES {
-        if (P.pack_ndat == 0) {
-          const double2* cgb = P.cg + (size_t)b * P.npw;
-          for (int e = e0 + lane; e < e1; e += 32) {
-            const int2 en = P.ent[e];
-            double2 v = cgb[en.x & 0x3fffffff];
-            if (en.x < 0) v.y = -v.y;
-            if (en.x & (1 << 30)) v.y = 0.0;
-            stg[((en.y >> 10) - l0) * RS + (en.y & 1023)] = v;
-          }
-        } else {
-          // E(G) = C(G) + i D(G), E(-G) = conj(C(G)) + i conj(D(G))
-          const double2* c0 = P.cg + (size_t)(2 * b) * P.npw;
-          const bool has_d = 2 * b + 1 < P.pack_ndat;
-          const double2* c1 = c0 + P.npw;
-          for (int e = e0 + lane; e < e1; e += 32) {
-            const int2 en = P.ent[e];
-            const int ipw = en.x & 0x3fffffff;
-            double2 c = c0[ipw];
-            double2 d = has_d ? c1[ipw] : make_double2(0.0, 0.0);
-            if (en.x < 0) { c.y = -c.y; d.y = -d.y; }
-            if (en.x & (1 << 30)) { c.y = 0.0; d.y = 0.0; }
-            stg[((en.y >> 10) - l0) * RS + (en.y & 1023)] = make_double2(c.x - d.y, c.y + d.x);
-          }
-        }
-      }
-    }
-    ABI_SYNCWARP();
+    Gather g;
+    if (have_next) g = gather_of(P, bn, batchn);         // estart loads fly during pass 1
+    else { g.e0 = g.e1 = 0; g.l0 = 0; g.pack = false; g.has_d = false; g.c0 = g.c1 = nullptr; }
     for (int w0 = 0; w0 < B * GL; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
@@ -147,26 +172,53 @@ struct XHalf {
       }
     }
     ABI_SYNCWARP();
+    if (have_next) zero_stg(stg);                        // the staging buffer is free: it receives the next unit during pass 2
     double2* outb = P.W1 + (size_t)b * P.n1 * P.nlines + l0;
-    for (int w0 = 0; w0 < 2 * A * GL; w0 += 32) {
+    {
       ABI_FOR_LANES {
-        const int w = w0 + lane;
-        const int hk1 = w / GL, line = w - hk1 * GL;
-        if (w < 2 * A * GL && line < nl) {
-          const double2* e = E + hk1 * ZK + line;
-          double2 v[B];
+        int2 en[UG];
+        int ecur = g.e0 + lane;
 #pragma unroll
-          for (int j = 0; j < B; j++) v[j] = e[j * GL];
-          HDft<B, +1>::run(v);
-          const int h = hk1 >= A ? 1 : 0, k1 = hk1 - h * A;
-          // i1 = 2 kout(k1, k2) + h; kout(k1, k2) = (kout(k1, 0) + kout(0, k2)) mod M for both index maps
-          const int kb = Map::kout(0, 0) + (PFA ? (k1 * (B * h_inv_mod(B % A, A))) % M : k1);
+        for (int u = 0; u < UG; u++) en[u] = ecur + 32 * u < g.e1 ? P.ent[ecur + 32 * u] : make_int2(0, -1);
 #pragma unroll
-          for (int k2 = 0; k2 < B; k2++) {
-            int kk = kb + Map::kout(0, k2);
-            if (PFA && kk >= M) kk -= M;
-            outb[(size_t)(2 * kk + h) * P.nlines + line] = v[k2];
+        for (int w0 = 0; w0 < 2 * A * GL; w0 += 32) {
+          // coefficients of this iteration's entries and the table entries of the next iteration: all in flight during the DFT
+          double2 cv[UG], dv[UG]; int2 enn[UG];
+#pragma unroll
+          for (int u = 0; u < UG; u++) { cv[u] = dv[u] = make_double2(0.0, 0.0); if (en[u].y >= 0) g_load(g, en[u], cv[u], dv[u]); }
+          ecur += 32 * UG;
+#pragma unroll
+          for (int u = 0; u < UG; u++) enn[u] = ecur + 32 * u < g.e1 ? P.ent[ecur + 32 * u] : make_int2(0, -1);
+          const int w = w0 + lane;
+          const int hk1 = w / GL, line = w - hk1 * GL;
+          if (w < 2 * A * GL && line < nl) {
+            const double2* e = E + hk1 * ZK + line;
+            double2 v[B];
+#pragma unroll
+            for (int j = 0; j < B; j++) v[j] = e[j * GL];
+            HDft<B, +1>::run(v);
+            const int h = hk1 >= A ? 1 : 0, k1 = hk1 - h * A;
+            // i1 = 2 kout(k1, k2) + h; kout(k1, k2) = (kout(k1, 0) + kout(0, k2)) mod M for both index maps
+            const int kb = Map::kout(0, 0) + (PFA ? (k1 * (B * h_inv_mod(B % A, A))) % M : k1);
+#pragma unroll
+            for (int k2 = 0; k2 < B; k2++) {
+              int kk = kb + Map::kout(0, k2);
+              if (PFA && kk >= M) kk -= M;
+              outb[(size_t)(2 * kk + h) * P.nlines + line] = v[k2];
+            }
           }
+#pragma unroll
+          for (int u = 0; u < UG; u++) { if (en[u].y >= 0) g_store(g, stg, en[u], cv[u], dv[u]); en[u] = enn[u]; }
+        }
+        // long batches: what the pass-2 iterations did not cover
+        for (;;) {
+          bool any = false;
+#pragma unroll
+          for (int u = 0; u < UG; u++) if (en[u].y >= 0) { double2 c, d; g_load(g, en[u], c, d); g_store(g, stg, en[u], c, d); any = true; }
+          if (!any) break;
+          ecur += 32 * UG;
+#pragma unroll
+          for (int u = 0; u < UG; u++) en[u] = ecur + 32 * u < g.e1 ? P.ent[ecur + 32 * u] : make_int2(0, -1);
         }
       }
     }
@@ -174,27 +226,46 @@ struct XHalf {
   }
 
   // ---------------- K3: one batch of lines (+ mirror lines), W1o -> sphere ----------------
-  ABI_DEV static void backward(const XhParams& P, const Tables& T, double2* E, double2* stg, int b, int batch) {
+  // The (2M x GL) strip of W1o of a batch is copied into the exchange buffer with cp.async (every 16-byte word straight to the
+  // slot pass 2' reads it from: the pass then works in place), ONE UNIT AHEAD: the copy of the next strip is issued as soon as
+  // pass 1' has emptied the buffer and flies during the scatter / getghc assembly of the current unit.
+  ABI_DEV static void prefetch_strip(const XhParams& P, const Tables& T, double2* E, int b, int batch, unsigned long long pol) {
     const int4 bd = P.batches[batch];
     const int nl = bd.y + bd.w;
     const double2* inb = P.W1in + (size_t)b * P.n1 * P.nlines;
+    ABI_FOR_LANES {
+#pragma unroll 5
+      for (int idx = lane; idx < 2 * M * GL; idx += 32) {
+        const int row = idx / GL, line = idx - row * GL;           // row = hk1 * B + k2
+        if (line < nl) {
+          const int gl = line < bd.y ? bd.x + line : bd.z + (line - bd.y);
+          const int hk1 = row / B, k2 = row - hk1 * B;
+          // default L2 policy: a 64-byte half-run that straddles a sector shares it with the neighbouring batch, which must find it
+          // in L2 (evict_first here: 1.8 GB of DRAM reads per launch instead of 1.0)
+          cp_async16(E + hk1 * ZK + k2 * GL + line, inb + (size_t)T.i1row[row] * P.nlines + gl, pol);
+        }
+      }
+    }
+    cp_async_commit();
+  }
+
+  ABI_DEV static void backward(const XhParams& P, const Tables& T, double2* E, double2* stg, int b, int batch, bool have_next, int bn,
+                               int batchn, unsigned long long pol) {
+    const int4 bd = P.batches[batch];
+    const int nl = bd.y + bd.w;
+    cp_async_wait_all();
+    ABI_SYNCWARP();
     for (int w0 = 0; w0 < 2 * A * GL; w0 += 32) {
       ABI_FOR_LANES {
         const int w = w0 + lane;
         const int hk1 = w / GL, line = w - hk1 * GL;
         if (w < 2 * A * GL && line < nl) {
-          const int gl = line < bd.y ? bd.x + line : bd.z + (line - bd.y);
           const int h = hk1 >= A ? 1 : 0, k1 = hk1 - h * A;
-          double2 v[B];
-          const int kb = PFA ? (k1 * (B * h_inv_mod(B % A, A))) % M : k1;
-#pragma unroll
-          for (int k2 = 0; k2 < B; k2++) {
-            int kk = kb + Map::kout(0, k2);
-            if (PFA && kk >= M) kk -= M;
-            v[k2] = ldg2(inb + (size_t)(2 * kk + h) * P.nlines + gl);
-          }
-          HDft<B, -1>::run(v);
           double2* e = E + hk1 * ZK + line;
+          double2 v[B];
+#pragma unroll
+          for (int k2 = 0; k2 < B; k2++) v[k2] = e[k2 * GL];
+          HDft<B, -1>::run(v);
           e[0] = v[0];
 #pragma unroll
           for (int j = 1; j < B; j++) e[j * GL] = PFA ? v[j] : cmul(v[j], T.ctwB[j * A + k1]);
@@ -227,6 +298,7 @@ struct XHalf {
       }
     }
     ABI_SYNCWARP();
+    if (have_next) prefetch_strip(P, T, E, bn, batchn, pol);
     const int e0 = P.bstart[batch], e1 = P.bstart[batch + 1];
     {
       ABI_FOR_LANES {
@@ -331,11 +403,26 @@ __global__ void __launch_bounds__(WARPS * 32) k_xh(XhParams P) {
   double2* stg = E + F::ESIZE;
   __syncthreads();
   const long long nunits = (long long)P.nbatch * P.nb;
-  for (long long unit = gw; unit < nunits; unit += nw) {
-    const int batch = (int)(unit / P.nb), b = (int)(unit - (long long)batch * P.nb);
-    if (DIR == 0) F::forward(P, T, E, stg, b, batch);
-    else F::backward(P, T, E, stg, b, batch);
+  auto decode = [&](long long unit, int& b, int& batch) {
+    if ((P.order & 1) == 0) { batch = (int)(unit / P.nb); b = (int)(unit - (long long)batch * P.nb); }
+    else { b = (int)(unit / P.nbatch); batch = (int)(unit - (long long)b * P.nbatch); }
+  };
+  const unsigned long long pol = (P.order & 2) ? policy_evict_first() : policy_evict_normal();
+  int b = 0, batch = 0;
+  if (gw < nunits) {
+    decode(gw, b, batch);
+    if (DIR == 0) F::gather_plain(P, stg, b, batch);
+    else F::prefetch_strip(P, T, E, b, batch, pol);
   }
+  for (long long unit = gw; unit < nunits; unit += nw) {
+    const bool have_next = unit + nw < nunits;
+    int bn = 0, batchn = 0;
+    if (have_next) decode(unit + nw, bn, batchn);
+    if (DIR == 0) F::forward(P, T, E, stg, b, batch, have_next, bn, batchn);
+    else F::backward(P, T, E, stg, b, batch, have_next, bn, batchn, pol);
+    b = bn; batch = batchn;
+  }
+  cp_async_wait_all();
 }
 
 // ---- host interface (x_stage.cu) ----

@@ -6,7 +6,7 @@
 
 namespace abi {
 
-constexpr int kXhGL = 8;        // lines per warp batch: runs of 8 * 16 = 128 bytes at every i1 of W1 / W1o
+constexpr int kXhGL = 8;        // lines per warp batch: runs of 8 * 16 = 128 bytes at every i1 of W1 / W1o (4-line batches: 12 warps per SM but 64-byte runs, K3 0.66 -> 0.93 ms)
 
 template <int A, int B, int DIR>
 void xh_launch_dir(XhParams& P, cudaStream_t st) {
