@@ -98,6 +98,13 @@ def profile_enable(on: bool):
     L().abi_b200_profile_enable(1 if on else 0)
 
 
+def probe_fp64_peak() -> dict:
+    """FP64 pipe peak of the current device measured now: {"dfma": TFLOP/s, "dmma": TFLOP/s} (abi_b200_probe_fp64_peak)."""
+    a = C.c_double(); b = C.c_double()
+    L().abi_b200_probe_fp64_peak(C.byref(a), C.byref(b))
+    return {"dfma": a.value, "dmma": b.value}
+
+
 def profile_collect() -> dict:
     """{kernel class: (total ms, launches)} since profile_enable(True)."""
     names = C.create_string_buffer(4096)

@@ -70,6 +70,7 @@ void abi_b200_profile_enable(int on) { ensure_init(); prof_enable(on != 0); }
 int abi_b200_profile_collect(char* names, int names_cap, double* ms, long long* counts, int cap) {
   ensure_init(); return prof_collect(names, names_cap, ms, counts, cap);
 }
+void abi_b200_probe_fp64_peak(double* dfma_tflops, double* dmma_tflops) { probe_fp64_peak(dfma_tflops, dmma_tflops); }
 void abi_b200_set_me_g0(int me_g0) { ctx().me_g0 = me_g0; }
 void abi_b200_fourwf_set_impl(int impl) { ctx().fourwf_impl = impl; }
 long long abi_b200_fourwf_counter(void) { return ctx().fourwf_counter; }
@@ -109,6 +110,7 @@ void abi_b200_fourwf_(int* cplex, double* denpot, double* fofgin, double* fofgou
                       int* tim_fourwf, double* weight_r, double* weight_i) {
   (void)gboundin; (void)gboundout; (void)mgfft; (void)mpi_enreg; (void)paral_kgb; (void)tim_fourwf;
   ensure_init();
+  NvtxRange nvtx("FOURWF");                               // NVTX_FOURWF
   Context& c = ctx();
   const int n1 = ngfft[0], n2 = ngfft[1], n3 = ngfft[2];
   const int opt = *option, nd = *ndat;

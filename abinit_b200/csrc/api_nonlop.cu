@@ -414,6 +414,7 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
                       double* gvnlxc, double* lambda, int* ndat, int* prtvol, int* sij_opt, int* tim_getghc, int* type_calc) {
   (void)prtvol; (void)tim_getghc;
   ensure_init();
+  NvtxRange nvtx_getghc("GETGHC");                       // NVTX_GETGHC, m_getghc.F90:264
   Context& c = ctx();
   abi_b200_ham* h = *gs_ham;
   // nspinor = 2 (NC, istwf_k = 1): the block is cwavef(2, npw*nspinor*ndat) -- every (band, spinor) pair is a column of npw
@@ -474,6 +475,8 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
 #endif
   if (local) {
     // ---- local part first: ghc = V_loc psi + T psi (filtered); the non-local term is added by the last GEMM's epilogue
+    NvtxRange nvtx_loc("LOCPOT");                        // NVTX_GETGHC_LOCPOT, m_getghc.F90:400
+    NvtxRange nvtx_kin("KINETIC");                       // NVTX_GETGHC_KIN (m_getghc.F90:1162): fused into the last fourwf kernel here
     c.fourwf_counter += 2 * nd;
     FourwfEpilogue epi;
     if (tc == 1) { epi.mode = 2; epi.kinpw = h->d_kinpw; }
@@ -514,6 +517,7 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
   }
 #ifndef ABI_EMU
   if (nonlocal) {
+    NvtxRange nvtx_nl("NLOCPOT");                        // NVTX_GETGHC_NLOCPOT, m_getghc.F90:1042
     c.nonlop_counter += nd;
     if (tc == 0) {
       NonlopFusion fuse;

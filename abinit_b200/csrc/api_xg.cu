@@ -56,6 +56,7 @@ struct AsyncGuard {   // inner calls must not synchronise per block
 // getAX_BX bound to getghc (getghc_gsc1, m_chebfiwf.F90:341-385): AX = H X, BX = S X (PAW) in band blocks of `bandpp`,
 // followed by xgBlock_zero_im_g0 on AX and BX (m_chebfi2.F90:580-581).  BX == nullptr for norm-conserving (BX = X).
 void get_ax_bx(abi_b200_ham_t* h, int space, int me_g0, int npw, int ncols, int bandpp, double* X, double* AX, double* BX) {
+  NvtxRange nvtx("GET_AX_BX");                            // NVTX_CHEBFI2_GET_AX_BX / NVTX_LOBPCG2_GET_AX_BX
   int cpopt = -1, prtvol = 0, tim = 0, type_calc = 0, sij_opt = BX ? 1 : 0;
   const size_t col = 2 * (size_t)npw;
   for (int b0 = 0; b0 < ncols; b0 += bandpp) {
@@ -183,6 +184,7 @@ void abi_b200_nonlop_(int* choice, int* cpopt, double* cprjin, double* enlout, a
                       double* vectout) {
   (void)idir; (void)tim_nonlop;
   ensure_init();
+  NvtxRange nvtx("NONLOP");                               // NVTX_NONLOP
   Context& c = ctx();
   abi_b200_ham* h = *hamk;
   const int nd = *ndat;
@@ -290,6 +292,7 @@ void abi_b200_apply_invovl_(abi_b200_ham_t** ham, double* cwavef, double* sm1cwa
                             int* nspinor, int* block_sliced) {
   (void)block_sliced;
   ensure_init();
+  NvtxRange nvtx("INVOVL");                               // NVTX_INVOVL, m_invovl.F90:790
   Context& c = ctx();
   abi_b200_ham* h = *ham;
   ABI_CHECK(*nspinor == 1, "apply_invovl: nspinor=2 is not implemented in this build");
@@ -369,6 +372,7 @@ void abi_b200_lobpcgwf2_(double* cg, double* eig, double* occ, double* enl_out, 
                          int* bandpp) {
   (void)prtvol;
   ensure_init();
+  NvtxRange nvtx("LOBPCG2");                              // NVTX_LOBPCG2, m_lobpcgwf.F90
   Context& c = ctx();
   cudaStream_t st = c.stream;
   abi_b200_ham* h = *gs_hamk;
@@ -481,6 +485,7 @@ void abi_b200_chebfiwf2_(double* cg, double* eig, double* occ, double* enl_out, 
                          int* chebfi_oracle, double* oracle_factor, double* oracle_min_occ, int* bandpp) {
   (void)prtvol;
   ensure_init();
+  NvtxRange nvtx("CHEBFI2");                              // NVTX_CHEBFI2, m_chebfiwf.F90
   Context& c = ctx();
   cudaStream_t st = c.stream;
   abi_b200_ham* h = *gs_hamk;
@@ -508,13 +513,14 @@ void abi_b200_chebfiwf2_(double* cg, double* eig, double* occ, double* enl_out, 
   // caller passes the array it wants compared with oracle_min_occ)
   get_ax_bx(h, space, me_g0, np, nb, o.bandpp, X, AX, BX);                          // m_chebfi2.F90:578-581
   std::vector<double> div; double maxeig, mineig;
-  rr_quotients(space, me_g0, np, nb, X, AX, BX, div, maxeig, mineig);               // :613
+  { NvtxRange nq("RAYLRITZ_Q"); rr_quotients(space, me_g0, np, nb, X, AX, BX, div, maxeig, mineig); }   // :613
   const double lambda_minus = maxeig, lambda_plus = o.ecut;                         // :547, :619
   const int ndeg_max = cheb_oracle1(mineig, lambda_minus, lambda_plus, 1e-16, 40);  // :625
   int ndeg = std::min(ndeg_max, o.ndeg_filter);
   if (o.oracle > 0) ndeg = ndeg_from_residu(o, space, me_g0, np, nb, lambda_minus, lambda_plus, occ, div, ndeg_max, AX, BX ? BX : X, Xn);
-  cheb_core(h, space, me_g0, np, nb, o.bandpp, &X, AX, BX, &Xn, &Xp, lambda_minus, lambda_plus, ndeg, div);
+  { NvtxRange nc("CHEBFI2_CORE"); cheb_core(h, space, me_g0, np, nb, o.bandpp, &X, AX, BX, &Xn, &Xp, lambda_minus, lambda_plus, ndeg, div); }
   // Rayleigh-Ritz (:705) and residuals (:709-716)
+  NvtxRange nrr("RAYLRITZ");
   double* d_eig = g_small[0].get((size_t)2 * nb);
   double* d_res = d_eig + nb;
   const int info = xg_rayleigh_ritz(space, np, nb, X, np, AX, np, BX, np, d_eig, true, me_g0, st);

@@ -1,6 +1,9 @@
 #include "context.cuh"
 #include "fourwf.cuh"
 #include <string>
+#ifndef ABI_EMU
+#include <nvtx3/nvToolsExt.h>
+#endif
 
 namespace abi {
 
@@ -87,7 +90,11 @@ static void prof_drain() {
   }
   g_prof_open.clear();
 }
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
+
 ProfScope::ProfScope(const char* name) : id(-1) {
+  nvtxRangePushA(name);
   if (!g_prof_on) return;
   if (g_prof_open.size() >= 4096) prof_drain();
   id = prof_id(name);
@@ -96,8 +103,56 @@ ProfScope::ProfScope(const char* name) : id(-1) {
   g_prof_open.push_back(r); slot = (int)g_prof_open.size() - 1;
 }
 ProfScope::~ProfScope() {
+  nvtxRangePop();
   if (id < 0 || slot < 0 || slot >= (int)g_prof_open.size()) return;
   cudaEventRecord(g_prof_open[slot].b, ctx().stream);
+}
+
+// ---- FP64 pipe probe (bench.py measures its roofline denominator in the run it reports) ----
+__global__ void __launch_bounds__(256) k_probe_dfma(double* out, int iters) {
+  double a[16]; const double x = threadIdx.x * 1e-9 + 1.0, y = 0.999999;
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = i * 0.5;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = fma(a[i], x, y);
+  }
+  double s = 0; for (int i = 0; i < 16; i++) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) k_probe_dmma(double* out, int iters) {
+  double c[8][2]; const double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c[i][0] = i; c[i][1] = -i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0; for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+void probe_fp64_peak(double* dfma_tflops, double* dmma_tflops) {
+  ensure_init();
+  cudaStream_t st = ctx().stream;
+  const int grid = kNumSM * 4, block = 256, iters = 20000;
+  double* d = nullptr;
+  CUDA_CHECK(cudaMalloc(&d, sizeof(double) * grid * block));
+  cudaEvent_t e0, e1; CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+  double best[2] = {0.0, 0.0};
+  for (int kind = 0; kind < 2; kind++)
+    for (int rep = 0; rep < 4; rep++) {
+      CUDA_CHECK(cudaEventRecord(e0, st));
+      if (kind == 0) k_probe_dfma<<<grid, block, 0, st>>>(d, iters); else k_probe_dmma<<<grid, block, 0, st>>>(d, iters);
+      CUDA_CHECK(cudaEventRecord(e1, st));
+      CUDA_CHECK(cudaEventSynchronize(e1));
+      float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      // DFMA: 16 FMAs per thread and iteration; DMMA m8n8k4: 8 x 8 x 4 FMAs per warp instruction, 8 instructions per iteration
+      const double flops = kind == 0 ? 2.0 * 16 * (double)iters * grid * block : 2.0 * 256 * 8 * (double)iters * grid * (block / 32);
+      if (rep > 0) best[kind] = std::max(best[kind], flops / (ms * 1e-3) / 1e12);
+    }
+  CUDA_CHECK(cudaEventDestroy(e0)); CUDA_CHECK(cudaEventDestroy(e1)); CUDA_CHECK(cudaFree(d));
+  *dfma_tflops = best[0]; *dmma_tflops = best[1];
 }
 void prof_enable(bool on) {
   if (!on) prof_drain();
@@ -115,6 +170,9 @@ int prof_collect(char* names, int names_cap, double* ms, long long* counts, int 
   return n;
 }
 #else
+NvtxRange::NvtxRange(const char*) {}
+NvtxRange::~NvtxRange() {}
+void probe_fp64_peak(double* a, double* b) { *a = 0.0; *b = 0.0; }
 ProfScope::ProfScope(const char*) : id(-1) {}
 ProfScope::~ProfScope() {}
 void prof_enable(bool) {}

@@ -53,7 +53,16 @@ struct ProfScope {
   explicit ProfScope(const char* name);
   ~ProfScope();
 };
+// NVTX range on the calling thread, named like the reference's regions (src/44_abitools/m_nvtx_data.F90:157-240: "GETGHC",
+// "LOCPOT", "NLOCPOT", "KINETIC", "CHEBFI2", "RAYLRITZ", ...; pushed at the same places, m_getghc.F90:264,400,1042,1162) so that an
+// Nsight Systems timeline of this library lines up with one of the reference.  Every ProfScope (one per kernel class) is a range too.
+struct NvtxRange {
+  explicit NvtxRange(const char* name);
+  ~NvtxRange();
+};
 void prof_enable(bool on);
+// FP64 pipe peak of the current device measured now (register-resident DFMA / DMMA m8n8k4 loops, best of 3): TFLOP/s
+void probe_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 int prof_collect(char* names, int names_cap, double* ms, long long* counts, int cap);   // syncs; returns #classes
 
 }  // namespace abi

@@ -19,7 +19,7 @@ def library_path() -> str:
 # every symbol include/abinit_b200.h declares (checked by tests/test_abi_symbols.py)
 SYMBOLS = [
     "abi_b200_init", "abi_b200_finalize", "abi_b200_set_stream", "abi_b200_set_async", "abi_b200_synchronize",
-    "abi_b200_kernel_launches", "abi_b200_version", "abi_b200_profile_enable", "abi_b200_profile_collect",
+    "abi_b200_kernel_launches", "abi_b200_version", "abi_b200_profile_enable", "abi_b200_profile_collect", "abi_b200_probe_fp64_peak",
     "abi_b200_fourwf_", "abi_b200_alloc_fourwf_", "abi_b200_free_fourwf_", "gpu_fourwf_", "alloc_gpu_fourwf_",
     "free_gpu_fourwf_", "abi_b200_set_me_g0", "abi_b200_fourwf_set_impl", "abi_b200_fourwf_set_tuning", "abi_b200_fourwf_counter",
     "abi_b200_init_gemm_nonlop_", "abi_b200_destroy_gemm_nonlop_", "abi_b200_prep_projectors_",
@@ -55,6 +55,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.abi_b200_profile_collect.argtypes = [vp, C.c_int, vp, vp, C.c_int]
     lib.abi_b200_profile_collect.restype = C.c_int
     lib.abi_b200_version.restype = C.c_char_p
+    lib.abi_b200_probe_fp64_peak.argtypes = [vp, vp]
     lib.abi_b200_set_me_g0.argtypes = [C.c_int]
     lib.abi_b200_fourwf_set_impl.argtypes = [C.c_int]
     lib.abi_b200_fourwf_set_tuning.argtypes = [C.c_char_p, C.c_int]

@@ -43,6 +43,9 @@ const char* abi_b200_version(void);
  * and returns the number of classes; names are ';'-separated, ms are summed durations, counts are launches. */
 void abi_b200_profile_enable(int on);
 int abi_b200_profile_collect(char* names, int names_cap, double* ms, long long* counts, int cap);
+/* FP64 pipe peak of the current device, measured now (register-resident DFMA and DMMA m8n8k4 loops, TFLOP/s): the roofline
+ * denominator bench.py reports is measured in the run it belongs to. */
+void abi_b200_probe_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 
 /* ------------------------------------------------------------------------------------------------------
  * fourwf.  Same symbol shape as the legacy CUDA plug point
