@@ -166,10 +166,13 @@ class Hamiltonian:
         L().abi_b200_ham_load_spin_nvloc(self.h, _ptr(vlocal, _F, "vlocal"), int(nvloc), n1, n2, n3)
 
     def load_enl(self, enl, sij=None):
-        enl = np.ascontiguousarray(enl, dtype=np.float64)              # (dimenl2, dimenl1) == Fortran (dimenl1,dimenl2)
+        """enl (dimenl2, dimenl1) == Fortran enl(dimenl1, dimenl2), or (nspinortot**2, dimenl2, dimenl1) for the four spinor blocks
+        [up-up, dn-dn, up-dn, dn-up] of a PAW spinor Hamiltonian; PAW dimenl1 = cplex_dij * lmn2 ((re, im) pairs when complex)."""
+        enl = np.ascontiguousarray(enl, dtype=np.float64)
         sij_a = None if sij is None else np.ascontiguousarray(sij, dtype=np.float64)
-        L().abi_b200_ham_load_enl(self.h, enl.ctypes.data, int(enl.shape[1]), int(enl.shape[0]),
-                                  None if sij_a is None else sij_a.ctypes.data)
+        nblk = 1 if enl.ndim == 2 else int(enl.shape[0])
+        L().abi_b200_ham_load_enl_spinor(self.h, enl.ctypes.data, int(enl.shape[-1]), int(enl.shape[-2]), nblk,
+                                         None if sij_a is None else sij_a.ctypes.data)
 
     def load_k(self, istwf_k, kg_k, kinpw, ffnl=None, ph3d=None, me_g0=1):
         kg_k = np.ascontiguousarray(kg_k, dtype=np.int32)
@@ -267,7 +270,7 @@ def gemm_nonlop(atindx1, choice, cpopt, vectproj, enl, indlmn, istwf_k, lambda_,
     lam = np.ascontiguousarray(np.broadcast_to(np.asarray(0.0 if lambda_ is None else lambda_, dtype=np.float64), (ndat,)))
     lmnmax = indlmn.shape[1]
     L().abi_b200_gemm_nonlop_(atindx1.ctypes.data, _iref(choice), _iref(cpopt), _ptr(vectproj, _F, "vectproj"),
-                              _iref(enl.shape[1]), _iref(enl.shape[0]), _iref(dimekbq), enl.ctypes.data,
+                              _iref(enl.shape[-1]), _iref(enl.shape[-2]), _iref(dimekbq), enl.ctypes.data,
                               indlmn.ctypes.data, _iref(istwf_k), lam.ctypes.data, _iref(lmnmax), _iref(natom),
                               nattyp.ctypes.data, _iref(ndat), _iref(nnlout), _iref(npwin), _iref(npwout),
                               _iref(nspinor), _iref(nspinor), _iref(ntypat), _iref(paw_opt),

@@ -218,8 +218,9 @@ void abi_b200_gemm_nonlop_(int* atindx1, int* choice, int* cpopt, double* vectpr
   c.nonlop_counter += *ndat;                               // m_nonlop.F90:389-392
   ABI_CHECK(*signs == 2, "gemm_nonlop: only signs=2 is on the getghc path (signs=1 contractions are out of scope)");
   ABI_CHECK(*useylm == 1, "gemm_nonlop requires useylm=1 (m_invars2.F90:2829)");
-  ABI_CHECK(*nspinor == 1 && *nspinortot == 1, "gemm_nonlop: nspinor=2 is not implemented in this build");
-  ABI_CHECK(*dimekbq == 1, "gemm_nonlop: dimekbq=2 (q-dependent D_ij) is not implemented");
+  ABI_CHECK((*nspinor == 1 || *nspinor == 2) && *nspinor == *nspinortot,
+            "gemm_nonlop: nspinor must be 1 or 2 and equal to nspinortot (no parallelisation over spinors, as in the reference's GPU paths)");
+  ABI_CHECK(*dimekbq == 1, "gemm_nonlop: dimekbq=2 (q-dependent D_ij, DFPT) is outside the getghc path");
   ABI_CHECK(*npwin == *npwout, "gemm_nonlop: k/=k' is not implemented");
   auto it = g_slots.find(g_cur_slot);
   ABI_CHECK(it != g_slots.end() && it->second->P.d_p != nullptr, "gemm_nonlop: projectors not prepared for the current ikpt");
@@ -229,17 +230,25 @@ void abi_b200_gemm_nonlop_(int* atindx1, int* choice, int* cpopt, double* vectpr
   const NonlopAtoms& at = call_atoms(*natom, *ntypat, *lmnmax, indlmn, nattyp, atindx1);
   if (*choice != 0 && *choice != 7) {
     ABI_CHECK(enl != nullptr, "gemm_nonlop: enl is required");
-    g_call_enl.load(enl, *dimenl1, *dimenl2, (*paw_opt >= 2) ? sij : nullptr, *ntypat, c.stream);
+    // enl(dimenl1, dimenl2, nspinortot**2): NC ekb(lnmax, ntypat, nspinortot**2) uses its first block (identical for both spinor
+    // components without spin-orbit); PAW D_ij real or complex (cplex_dij = dimenl1 / lmn2), four blocks with spinors
+    const int lmn2 = *lmnmax * (*lmnmax + 1) / 2;
+    const int nblk = (*paw_opt == 0) ? 1 : (*nspinortot) * (*nspinortot);
+    g_call_enl.load(enl, *dimenl1, *dimenl2, (*paw_opt >= 2) ? sij : nullptr, *ntypat, c.stream, nblk, *paw_opt == 0 ? 0 : lmn2);
+    g_call_enl.cplex_enl = (*paw_opt != 0 && *dimenl1 == 2 * lmn2) ? 2 : 1;
   }
+  g_call_enl.nspinor = (*paw_opt == 0) ? 1 : *nspinor;       // NC: every (band, spinor) column is independent
   const int cplex = (*istwf_k == 1) ? 2 : 1;
-  const size_t nv = sizeof(double) * 2 * (size_t)P.npw * (*ndat);
-  const size_t np = sizeof(double) * (size_t)cplex * P.nprojs * (*ndat);
+  const int ncol = *ndat * *nspinor;                         // vectin(2, npw*nspinor*ndat)
+  const size_t nv = sizeof(double) * 2 * (size_t)P.npw * ncol;
+  const size_t np = sizeof(double) * (size_t)cplex * P.nprojs * ncol;
   DevArg a_in(0, vectin, nv, true);
   DevArg a_out(1, vectout, nv, false);
   DevArg a_sout(2, svectout, nv, false);
   DevArg a_proj(3, vectproj, np, *cpopt >= 2);
   DevArg a_lam(4, lambda, sizeof(double) * (*ndat), true);
-  gemm_nonlop_device(P, at, g_call_enl, *choice, *cpopt, *paw_opt, c.me_g0, a_lam.as<double>(), *ndat, a_in.as<double>(),
+  ABI_CHECK(!(*nspinor == 2 && *paw_opt == 2), "gemm_nonlop: paw_opt=2 with nspinor=2 needs lambda per band; use the handle-based nonlop");
+  gemm_nonlop_device(P, at, g_call_enl, *choice, *cpopt, *paw_opt, c.me_g0, a_lam.as<double>(), ncol, a_in.as<double>(),
                      a_out.as<double>(), a_sout.as<double>(), a_proj.as<double>(), c.stream);
   const bool want_v = *choice == 1 && (*paw_opt == 0 || *paw_opt == 1 || *paw_opt == 2 || *paw_opt == 4);
   const bool want_s = *choice == 7 || (*choice == 1 && (*paw_opt == 3 || *paw_opt == 4));
@@ -288,8 +297,9 @@ void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_v
 void abi_b200_ham_set_nspinor(abi_b200_ham_t* h, int nspinor) {
   h->epoch++;
   ABI_CHECK(nspinor == 1 || nspinor == 2, "nspinor must be 1 or 2");
-  ABI_CHECK(!(nspinor == 2 && h->usepaw == 1), "nspinor=2 with PAW (spinor-mixing D_ij) is not implemented in this build");
+  // PAW spinors: D_ij comes as four complex blocks (abi_b200_ham_load_enl_spinor), m_opernlc_ylm_allwf.F90:660-737
   h->nspinor = nspinor;
+  h->enl.nspinor = h->usepaw ? nspinor : 1;
 }
 
 #ifndef ABI_EMU
@@ -327,11 +337,24 @@ void abi_b200_ham_load_spin_nvloc(abi_b200_ham_t* h, const double* vlocal, int n
   h->nvloc = 4;
 }
 
-void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, const double* sij) {
+void abi_b200_ham_load_enl_spinor(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, int nspinortot2, const double* sij) {
   h->epoch++;
   ensure_init();
-  h->enl.load(enl, dimenl1, dimenl2, sij, h->ntypat, ctx().stream);
+  ABI_CHECK(nspinortot2 == 1 || nspinortot2 == 4, "load_enl: enl(dimenl1, dimenl2, nspinortot**2) needs nspinortot**2 = 1 or 4");
+  const int lmn2 = h->lmnmax * (h->lmnmax + 1) / 2;
+  int cplex_enl = 1;
+  if (h->usepaw) {
+    ABI_CHECK(dimenl1 == lmn2 || dimenl1 == 2 * lmn2, "load_enl: PAW D_ij must be packed, dimenl1 = cplex_dij * lmnmax*(lmnmax+1)/2");
+    cplex_enl = dimenl1 / lmn2;
+    ABI_CHECK(nspinortot2 == 1 || cplex_enl == 2, "load_enl: spinor D_ij blocks must be complex (m_opernlc_ylm_allwf.F90:665)");
+  }
+  h->enl.load(enl, dimenl1, dimenl2, sij, h->ntypat, ctx().stream, h->usepaw ? nspinortot2 : 1, h->usepaw ? lmn2 : 0);
+  h->enl.cplex_enl = cplex_enl;
+  h->enl.nspinor = h->usepaw ? h->nspinor : 1;
   h->invovl.release();
+}
+void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, const double* sij) {
+  abi_b200_ham_load_enl_spinor(h, enl, dimenl1, dimenl2, 1, sij);
 }
 
 void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw, const double* ffnl,
@@ -421,8 +444,10 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
   // coefficients on which the kinetic and non-local terms act separately (m_getghc.F90:1266-1280, opernlc NC branch with
   // ekb(:,:,ispinor) equal for both components); only the local part couples them, and only when nvloc = 4.
   if (h->nspinor == 2) {
-    ABI_CHECK(h->usepaw == 0, "getghc: nspinor=2 with PAW is not implemented in this build");
     ABI_CHECK(h->istwf_k == 1, "getghc: nspinor=2 requires istwf_k=1");
+    ABI_CHECK(h->usepaw == 0 || (h->enl.nblk == 4 && h->enl.cplex_enl == 2),
+              "getghc: nspinor=2 with PAW needs the four complex D_ij blocks (abi_b200_ham_load_enl_spinor)");
+    ABI_CHECK(!(h->usepaw == 1 && *sij_opt == -1), "getghc: sij_opt=-1 (H - lambda S) with nspinor=2 is not implemented");
   }
   const int tc = *type_calc, nd = *ndat * h->nspinor, npw = h->npw;
   ABI_CHECK(tc >= 0 && tc <= 3, "getghc: type_calc must be 0, 1, 2 or 3");

@@ -133,7 +133,7 @@ void make_invovl(abi_b200_ham* h, cudaStream_t st) {
   const int me_g0 = cplx == 2 ? -1 : ((h->istwf_k == 2 && h->me_g0 == 1) ? 1 : 0);
   xg_gram(space, h->npw, nprojs, nprojs, h->P.d_p, h->npw, h->P.d_p, h->npw, iv.d_gram, iv.ldgram, me_g0, st);
   // s_ij per type -> inv_sij ; inv_s_approx = (inv_sij + Gram of the first atom of the type)^-1 (:560-700)
-  const int dimenl1 = h->enl.dimenl1;
+  const int dimenl1 = h->enl.sij_dim1 > 0 ? h->enl.sij_dim1 : h->enl.dimenl1;       // S_ij is real whatever cplex_dij is
   ABI_CHECK(dimenl1 == lmnmax * (lmnmax + 1) / 2, "make_invovl: sij size not recognized (real packed sij only)");
   std::vector<double> sij((size_t)dimenl1 * ntypat);
   CUDA_CHECK(cudaMemcpyAsync(sij.data(), h->enl.d_sij, sizeof(double) * sij.size(), cudaMemcpyDeviceToHost, st));

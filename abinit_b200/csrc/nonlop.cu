@@ -389,6 +389,57 @@ __global__ void k_paw_opernlc(const double* __restrict__ gx, double* __restrict_
   }
 }
 
+// PAW with complex Hermitian D_ij (cplex_enl = 2) and / or spinor wavefunctions (nspinortot = 2), complex gx (istwf_k = 1):
+//   gxfac_s = M^{ss} gx_s + M^{ss'} gx_s'      (m_opernlc_ylm_allwf.F90:453-655 spin-diagonal, :660-737 off-diagonal blocks)
+// with the packed upper triangles E_b(i <= j) of the blocks b = [up-up, dn-dn, up-dn, dn-up]:
+//   M^{ss}[j,i]  = conj(E_s[i,j]) (i < j),  Re E_s[j,j] (i = j: the stored imaginary part is not used),  E_s[j,i] (i > j)
+//   M^{ud}[j,i]  = E_ud[j,i] (i > j),  conj(E_du[i,j]) (i <= j);      M^{du}[j,i] = E_du[j,i] (i > j),  conj(E_ud[i,j]) (i <= j)
+// paw_opt = 2 subtracts lambda S_ij from the spin-diagonal blocks; gxs = S_ij gx per spinor component (S real, :1253-1295).
+// One block per (sorted atom, band); work items (j, spinor).
+__global__ void k_paw_opernlc_cplx(const double* __restrict__ gx, double* __restrict__ gxfac, double* __restrict__ gxs, long long ldg,
+                                   const int* __restrict__ atom_first, const int* __restrict__ atom_typ,
+                                   const int* __restrict__ atom_enl, const double* __restrict__ enl, const double* __restrict__ sij,
+                                   int dimenl1, int sij_dim1, int cplex_enl, int nspinor, long long blk_stride, int paw_opt,
+                                   const double* __restrict__ lambda) {
+  const int a = blockIdx.x, b = blockIdx.y;
+  const int first = atom_first[a], nlmn = atom_first[a + 1] - first;
+  const double* S = sij ? sij + (size_t)sij_dim1 * atom_typ[a] : nullptr;
+  const double lam = (paw_opt == 2) ? lambda[b] : 0.0;
+  const bool want_d = paw_opt == 1 || paw_opt == 2 || paw_opt == 4, want_s = paw_opt == 3 || paw_opt == 4;
+  auto elem = [&](int blk, int pk) {      // packed element pk of spin block blk as a complex number
+    const double* D = enl + blk_stride * blk + (size_t)dimenl1 * atom_enl[a];
+    return cplex_enl == 2 ? make_double2(D[2 * pk], D[2 * pk + 1]) : make_double2(D[pk], 0.0);
+  };
+  for (int w = threadIdx.x; w < nlmn * nspinor; w += blockDim.x) {
+    const int s = w / nlmn, j = w - s * nlmn;
+    const double2* xs = reinterpret_cast<const double2*>(gx + (size_t)(b * nspinor + s) * ldg) + first;
+    const double2* xo = reinterpret_cast<const double2*>(gx + (size_t)(b * nspinor + (1 - s)) * ldg) + first;   // other spinor
+    double2 sd = make_double2(0.0, 0.0), ss = make_double2(0.0, 0.0);
+    for (int i = 0; i < nlmn; i++) {
+      const int hi = max(i, j), lo = min(i, j);
+      const int pk = hi * (hi + 1) / 2 + lo;
+      const double2 x = xs[i];
+      if (want_d) {
+        double2 m = elem(s, pk);
+        if (i < j) m.y = -m.y; else if (i == j) m.y = 0.0;
+        if (paw_opt == 2) m.x -= lam * S[pk];
+        sd.x += m.x * x.x - m.y * x.y; sd.y += m.x * x.y + m.y * x.x;
+        if (nspinor == 2) {
+          // s = 0 (up): upper triangle from the up-dn block, lower + diagonal from conj(dn-up); s = 1 (dn): the other way round
+          double2 mo = (i > j) ? elem(2 + s, pk) : elem(2 + (1 - s), pk);
+          if (i <= j) mo.y = -mo.y;
+          const double2 y = xo[i];
+          sd.x += mo.x * y.x - mo.y * y.y; sd.y += mo.x * y.y + mo.y * y.x;
+        }
+      }
+      if (want_s) { ss.x += S[pk] * x.x; ss.y += S[pk] * x.y; }
+    }
+    const size_t o = (size_t)(b * nspinor + s) * ldg + 2 * (size_t)(first + j);
+    if (gxfac && want_d) { gxfac[o] = sd.x; gxfac[o + 1] = sd.y; }
+    if (gxs && want_s) { gxs[o] = ss.x; gxs[o + 1] = ss.y; }
+  }
+}
+
 // prep_projectors: P = 4 pi / sqrt(ucvol) * ffnl(:,1,ilmn,itypat) * (-i)^l * conj(ph3d(:,ia))
 __global__ void k_prep_projectors(double2* __restrict__ P, int npw, int nprojs, const double* __restrict__ ffnl, int dimffnl,
                                   int lmnmax, const double2* __restrict__ ph3d, const int* __restrict__ proj_typ,
@@ -571,21 +622,22 @@ void NonlopAtoms::release() {
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
 }
 
-void NonlopEnl::load(const double* enl, int d1, int d2, const double* sij, int ntypat, cudaStream_t st) {
+void NonlopEnl::load(const double* enl, int d1, int d2, const double* sij, int ntypat, cudaStream_t st, int nb, int sd1) {
   // gemm_nonlop passes enl on every call (m_nonlop.F90:800-808): keep the device buffers while the sizes fit
-  const size_t ne = std::max<size_t>(1, (size_t)d1 * d2), ns = std::max<size_t>(1, (size_t)d1 * ntypat);
-  dimenl1 = d1; dimenl2 = d2;
+  if (sd1 <= 0) sd1 = d1;
+  const size_t ne = std::max<size_t>(1, (size_t)d1 * d2 * nb), ns = std::max<size_t>(1, (size_t)sd1 * ntypat);
+  dimenl1 = d1; dimenl2 = d2; nblk = nb; sij_dim1 = sd1;
   if (ne > enl_cap || d_enl == nullptr) {
     if (d_enl) CUDA_CHECK(cudaFree(d_enl));
     CUDA_CHECK(cudaMalloc(&d_enl, sizeof(double) * ne)); enl_cap = ne;
   }
-  CUDA_CHECK(cudaMemcpyAsync(d_enl, enl, sizeof(double) * (size_t)d1 * d2, cudaMemcpyDefault, st));
+  CUDA_CHECK(cudaMemcpyAsync(d_enl, enl, sizeof(double) * (size_t)d1 * d2 * nb, cudaMemcpyDefault, st));
   if (sij) {
     if (ns > sij_cap || d_sij == nullptr) {
       if (d_sij) CUDA_CHECK(cudaFree(d_sij));
       CUDA_CHECK(cudaMalloc(&d_sij, sizeof(double) * ns)); sij_cap = ns;
     }
-    CUDA_CHECK(cudaMemcpyAsync(d_sij, sij, sizeof(double) * (size_t)d1 * ntypat, cudaMemcpyDefault, st));
+    CUDA_CHECK(cudaMemcpyAsync(d_sij, sij, sizeof(double) * (size_t)sd1 * ntypat, cudaMemcpyDefault, st));
   } else if (d_sij) {
     CUDA_CHECK(cudaFree(d_sij)); d_sij = nullptr; sij_cap = 0;
   }
@@ -931,10 +983,22 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
     ABI_CHECK(enl.d_enl != nullptr, "gemm_nonlop: D_ij not loaded");
     // k_paw_opernlc indexes real packed-symmetric D_ij / S_ij (m_opernlc_ylm_allwf.F90:395-447): cplex_dij = 2 or a
     // q-dependent layout (dimekbq = 2) would be read as something else
-    ABI_CHECK(enl.dimenl1 == at.lmnmax * (at.lmnmax + 1) / 2, "gemm_nonlop: PAW D_ij must be real packed symmetric, dimenl1 = lmnmax*(lmnmax+1)/2");
+    const int lmn2 = at.lmnmax * (at.lmnmax + 1) / 2;
+    ABI_CHECK(enl.dimenl1 == enl.cplex_enl * lmn2, "gemm_nonlop: PAW D_ij must be packed symmetric / Hermitian, dimenl1 = cplex_dij * lmnmax*(lmnmax+1)/2");
     ABI_CHECK(!(paw_opt >= 2) || enl.d_sij != nullptr, "gemm_nonlop: S_ij not loaded");
-    k_paw_opernlc<<<dim3(at.natom, ndat), 64, 0, st>>>(gx, gxfac, gxs, ldg, cplex, at.d_atom_first, at.d_atom_typ, at.d_atom_enl,
-                                                       enl.d_enl, enl.d_sij, enl.dimenl1, paw_opt, d_lambda);
+    if (enl.cplex_enl == 1 && enl.nspinor == 1) {
+      k_paw_opernlc<<<dim3(at.natom, ndat), 64, 0, st>>>(gx, gxfac, gxs, ldg, cplex, at.d_atom_first, at.d_atom_typ, at.d_atom_enl,
+                                                         enl.d_enl, enl.d_sij, enl.dimenl1, paw_opt, d_lambda);
+    } else {
+      // complex Hermitian D_ij and / or spinor-mixing blocks (m_opernlc_ylm_allwf.F90:453-737): complex projections only
+      ABI_CHECK(cplex == 2, "gemm_nonlop: complex D_ij / spinor blocks need istwf_k = 1 (cplex_fac = cplex = 2)");
+      ABI_CHECK(enl.nspinor == 1 || (enl.nblk == 4 && enl.cplex_enl == 2),
+                "gemm_nonlop: nspinor = 2 with PAW needs enl(cplex_dij*lmn2, natom, 4) with cplex_dij = 2 (m_opernlc_ylm_allwf.F90:665)");
+      ABI_CHECK(ndat % enl.nspinor == 0, "gemm_nonlop: the column count is not a multiple of nspinor");
+      k_paw_opernlc_cplx<<<dim3(at.natom, ndat / enl.nspinor), 64, 0, st>>>(
+          gx, gxfac, gxs, ldg, at.d_atom_first, at.d_atom_typ, at.d_atom_enl, enl.d_enl, enl.d_sij, enl.dimenl1,
+          enl.sij_dim1 > 0 ? enl.sij_dim1 : lmn2, enl.cplex_enl, enl.nspinor, (long long)enl.dimenl1 * enl.dimenl2, paw_opt, d_lambda);
+    }
     CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }

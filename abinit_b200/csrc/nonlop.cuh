@@ -52,10 +52,15 @@ struct NonlopAtoms {
 
 struct NonlopEnl {
   int dimenl1 = 0, dimenl2 = 0;
-  double* d_enl = nullptr;        // dimenl1 * dimenl2
-  double* d_sij = nullptr;        // dimenl1 * ntypat or null
+  int nblk = 1;                   // spin blocks of enl(dimenl1, dimenl2, nspinortot**2): 1, or 4 = [up-up, dn-dn, up-dn, dn-up]
+  int cplex_enl = 1;              // 2: complex Hermitian D_ij stored as (re, im) pairs of the packed upper triangle
+  int sij_dim1 = 0;               // leading dimension of sij (lmn2_size: S_ij is always real)
+  int nspinor = 1;                // spinor components per band in the blocks handed to gemm_nonlop (columns = ndat * nspinor)
+  double* d_enl = nullptr;        // dimenl1 * dimenl2 * nblk
+  double* d_sij = nullptr;        // sij_dim1 * ntypat or null
   size_t enl_cap = 0, sij_cap = 0; // allocated doubles (the buffers are reused while the dimensions do not grow)
-  void load(const double* enl, int dimenl1, int dimenl2, const double* sij, int ntypat, cudaStream_t st);
+  void load(const double* enl, int dimenl1, int dimenl2, const double* sij, int ntypat, cudaStream_t st, int nblk = 1,
+            int sij_dim1 = 0);
   void release();
 };
 

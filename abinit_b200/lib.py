@@ -25,7 +25,7 @@ SYMBOLS = [
     "abi_b200_init_gemm_nonlop_", "abi_b200_destroy_gemm_nonlop_", "abi_b200_prep_projectors_",
     "abi_b200_set_projectors_", "abi_b200_set_gemm_nonlop_ikpt_", "abi_b200_initylmg_k_", "abi_b200_mkffnl_", "abi_b200_gemm_nonlop_",
     "abi_b200_nonlop_counter",
-    "abi_b200_ham_create", "abi_b200_ham_destroy", "abi_b200_ham_load_spin", "abi_b200_ham_set_nspinor", "abi_b200_ham_load_spin_nvloc", "abi_b200_ham_load_enl",
+    "abi_b200_ham_create", "abi_b200_ham_destroy", "abi_b200_ham_load_spin", "abi_b200_ham_set_nspinor", "abi_b200_ham_load_spin_nvloc", "abi_b200_ham_load_enl", "abi_b200_ham_load_enl_spinor",
     "abi_b200_ham_load_k", "abi_b200_ham_load_k_xred", "abi_b200_ham_set_projectors", "abi_b200_ham_nprojs", "abi_b200_getghc_", "abi_b200_getghc_batch_", "abi_b200_graphs_clear",
     "abi_b200_nonlop_",
     "abi_b200_xg_gram_", "abi_b200_xg_rotate_", "abi_b200_xg_hegvd_", "abi_b200_xg_gemm_nn_", "abi_b200_xg_chol_inverse_", "abi_b200_xg_colwise_", "abi_b200_xg_rayleigh_ritz_",
@@ -78,6 +78,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         lib.abi_b200_ham_set_nspinor.argtypes = [vp, C.c_int]
         lib.abi_b200_ham_load_spin_nvloc.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
         lib.abi_b200_ham_load_enl.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        lib.abi_b200_ham_load_enl_spinor.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
         lib.abi_b200_ham_load_k.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int]
         lib.abi_b200_ham_load_k_xred.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int]
         lib.abi_b200_ham_set_projectors.argtypes = [vp, vp, C.c_int]

@@ -134,11 +134,16 @@ void abi_b200_ham_destroy(abi_b200_ham_t* h);
 void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_vloc, int n4, int n5, int n6);
 /* nspinor = 2 (gs_hamk%nspinor, norm-conserving, istwf_k = 1): blocks are cwavef(2, npw*nspinor*ndat); ndat keeps counting bands.
  * load_spin_nvloc: vlocal(n4,n5,n6,nvloc), nvloc = 4 = [V11, V22, Re V12, Im V12] (non-collinear magnetism): the four local
- * applications of src/66_wfs/m_getghc.F90:655-830.  Spin-orbit projectors and PAW spinors are rejected. */
+ * applications of src/66_wfs/m_getghc.F90:655-830.  PAW spinors take their D_ij through abi_b200_ham_load_enl_spinor. */
 void abi_b200_ham_set_nspinor(abi_b200_ham_t* h, int nspinor);
 void abi_b200_ham_load_spin_nvloc(abi_b200_ham_t* h, const double* vlocal, int nvloc, int n4, int n5, int n6);
-/* enl: NC ekb(dimenl1=lnmax, ntypat); PAW dij(dimenl1=lmn2_size, natom).  sij(dimenl1, ntypat) (PAW) or NULL */
+/* enl: NC ekb(dimenl1=lnmax, ntypat); PAW dij(dimenl1=cplex_dij*lmn2_size, natom): real packed symmetric (cplex_dij = 1) or
+ * complex Hermitian, (re, im) pairs of the packed upper triangle (cplex_dij = 2, istwf_k = 1 only;
+ * src/66_nonlocal/m_opernlc_ylm_allwf.F90:453-576).  sij(lmn2_size, ntypat) (PAW, always real) or NULL.
+ * load_enl_spinor: enl(dimenl1, dimenl2, nspinortot**2) with the four blocks [up-up, dn-dn, up-dn, dn-up] of a spinor
+ * Hamiltonian (gs_hamk%ekb, nspinor = 2 with PAW; off-diagonal blocks :660-737); nspinortot2 = 1 is load_enl. */
 void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, const double* sij);
+void abi_b200_ham_load_enl_spinor(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, int nspinortot2, const double* sij);
 void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw,
                          const double* ffnl, int dimffnl, const double* ph3d, int matblk, int me_g0);
 /* load_k with the structure-factor phases built on the device: ph3d(G,ia) = exp(2 pi i (k+G).xred_ia) is what load_k computes

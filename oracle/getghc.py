@@ -46,6 +46,32 @@ def getghc(cwavef, vlocal, kg, ngfft, kinpw, P, enl, sij, indlmn, nattyp, atindx
     return ghc, gsc, gvnlxc, proj
 
 
+def getghc_paw_general(cwavef, vlocal, kg, ngfft, kinpw, P, enl, sij, indlmn, nattyp, atindx1, nspinor=1, cplex_enl=1, sij_opt=1,
+                       workers=None):
+    """getghc, type_calc 0, istwf_k = 1, PAW with complex Hermitian D_ij and / or spinor wavefunctions (collinear local potential
+    nvloc = 1 or the four-component nvloc = 4): local part as getghc / getghc_spinor, non-local part through
+    nonlop.gemm_nonlop_general.  cwavef: (ndat, nspinor, npw).  Returns (ghc, gsc)."""
+    from .nonlop import gemm_nonlop_general
+    cw = np.asarray(cwavef, dtype=np.complex128)
+    ndat, nsp, npw = cw.shape
+    v = np.asarray(vlocal)
+    f = lambda vv, c: fourwf(2 if np.iscomplexobj(vv) else 1, vv, np.ascontiguousarray(c), None, kg, kg, ngfft, 2, 1, workers=workers)[0]
+    ghc = np.zeros_like(cw)
+    if nsp == 1:
+        ghc[:, 0] = f(v, cw[:, 0])
+    elif v.ndim == 3:
+        ghc[:, 0] = f(v, cw[:, 0]); ghc[:, 1] = f(v, cw[:, 1])
+    else:
+        ghc[:, 0] = f(v[0], cw[:, 0]) + f(v[2] + 1j * v[3], cw[:, 1])
+        ghc[:, 1] = f(v[2] - 1j * v[3], cw[:, 0]) + f(v[1], cw[:, 1])
+    gv, gs = gemm_nonlop_general(P, cw, enl, sij, indlmn, nattyp, atindx1, 4 if sij_opt == 1 else 1, nsp, cplex_enl)
+    ok = kinpw < KIN_FILTER
+    kin = np.where(ok, kinpw, 0.0)
+    ghc = np.where(ok[None, None, :], ghc + kin[None, None, :] * cw + gv, 0.0)
+    gsc = np.where(ok[None, None, :], gs, 0.0) if gs is not None else None
+    return ghc, gsc
+
+
 def getghc_spinor(cwavef, vlocal, kg, ngfft, kinpw, P, enl, indlmn, nattyp, atindx1, type_calc=0, workers=None):
     """nspinor = 2 (norm-conserving, istwf_k = 1, no spin-orbit): restates the spinor branches of m_getghc.F90
       nvloc = 1  :555-653   the same real potential on both spinor components

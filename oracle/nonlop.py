@@ -96,6 +96,88 @@ def opernlc(gx, enl, sij, indlmn, nattyp, atindx1, paw_opt, lambda_=None):
     return gxfac, gxs
 
 
+def _hermitian_from_packed(packed, nlmn, cplex_enl, diag_real=True):
+    """Full matrix M[j, i] the reference applies for one spin-DIAGONAL block (m_opernlc_ylm_allwf.F90:453-655):
+    M[j,i] = conj(E[i,j]) for i < j, Re E[j,j] on the diagonal (the stored imaginary part is never read), E[j,i] for i > j,
+    E = packed upper triangle, (re, im) pairs when cplex_enl = 2."""
+    E = np.zeros((nlmn, nlmn), dtype=np.complex128)
+    for j in range(nlmn):
+        for i in range(j + 1):
+            pk = j * (j + 1) // 2 + i
+            E[i, j] = packed[2 * pk] + 1j * packed[2 * pk + 1] if cplex_enl == 2 else packed[pk]
+    M = np.zeros_like(E)
+    for j in range(nlmn):
+        for i in range(nlmn):
+            if i < j:
+                M[j, i] = np.conj(E[i, j])
+            elif i == j:
+                M[j, i] = E[j, j].real if diag_real else E[j, j]
+            else:
+                M[j, i] = E[j, i]
+    return M, E
+
+
+def opernlc_general(gx, enl, sij, indlmn, nattyp, atindx1, paw_opt, nspinor=1, cplex_enl=1, lambda_=None):
+    """opernlc_ylm_allwf with complex Hermitian D_ij (cplex_enl = 2, m_opernlc_ylm_allwf.F90:453-576) and / or spinor
+    wavefunctions (nspinortot = 2: spin-diagonal blocks :578-655, off-diagonal blocks :660-737), complex gx (cplex = 2).
+      gx  : (ndat, nspinor, nprojs) complex   == Fortran gx(2, nprojs, nspinor, ndat)
+      enl : (nblk, natom, dimenl1) real       == Fortran enl(dimenl1, natom, nspinortot**2), blocks [uu, dd, ud, du],
+            dimenl1 = cplex_enl * lmn2 ((re, im) pairs of the packed upper triangle when complex); nblk = 1 without spinors
+      sij : (ntypat, lmn2) real packed
+    Returns gxfac, gxfac_sij in the layout of gx.  "parity unpinned": no stored reference data reaches these branches; checked by
+    reduction to the pinned real-D_ij path and by Hermiticity of the assembled operator (tests/test_oracle_invariants.py)."""
+    gx = np.asarray(gx, dtype=np.complex128)
+    ndat, nsp, nprojs = gx.shape
+    assert nsp == nspinor
+    enl = np.asarray(enl)
+    if enl.ndim == 2:
+        enl = enl[None]
+    want_d = paw_opt in (1, 2, 4); want_s = paw_opt in (3, 4)
+    gxfac = np.zeros_like(gx); gxs = np.zeros_like(gx) if want_s else None
+    shift = 0; iatm = 0
+    for t in range(indlmn.shape[0]):
+        nlmn = nlmn_of_types(indlmn)[t]
+        S = _unpack_sym(sij[t], nlmn) if paw_opt in (2, 3, 4) else None
+        for ia in range(int(nattyp[t])):
+            sl = slice(shift, shift + nlmn)
+            ie = atindx1[iatm + ia]
+            if want_d:
+                for isp in range(nspinor):
+                    M, _ = _hermitian_from_packed(enl[isp, ie], nlmn, cplex_enl)
+                    for idat in range(ndat):
+                        Md = M - (lambda_[idat] * S if paw_opt == 2 else 0.0)
+                        gxfac[idat, isp, sl] += Md @ gx[idat, isp, sl]
+                if nspinor == 2:
+                    # :660-737  ispinor = 1: gxfac(j, dn) += sum_{i<=j} conj(E_ud[i,j]) gx(i, up); gxfac(j, up) += sum_{i>j} E_ud[j,i] gx(i, dn)
+                    #           ispinor = 2: the same with up <-> dn and E_du
+                    for isp in range(2):
+                        jsp = 1 - isp
+                        _, E = _hermitian_from_packed(enl[2 + isp, ie], nlmn, cplex_enl)
+                        lower = np.conj(np.triu(E)).T                    # [j, i] = conj(E[i, j]) for i <= j
+                        upper = np.triu(E, 1)                            # [j, i] = E[j, i] for i > j
+                        for idat in range(ndat):
+                            gxfac[idat, jsp, sl] += lower @ gx[idat, isp, sl]
+                            gxfac[idat, isp, sl] += upper @ gx[idat, jsp, sl]
+            if want_s:
+                for isp in range(nspinor):
+                    gxs[:, isp, sl] = gx[:, isp, sl] @ S.T
+            shift += nlmn
+        iatm += int(nattyp[t])
+    return gxfac, gxs
+
+
+def gemm_nonlop_general(P, vectin, enl, sij, indlmn, nattyp, atindx1, paw_opt, nspinor=1, cplex_enl=1, lambda_=None):
+    """gemm_nonlop choice 1, signs 2, istwf_k = 1 with complex D_ij and / or spinors: vectin (ndat, nspinor, npw).
+    Returns (vectout, svectout)."""
+    v = np.asarray(vectin, dtype=np.complex128)
+    ndat, nsp, npw = v.shape
+    gx = (v.reshape(ndat * nsp, npw) @ np.conj(P).T).reshape(ndat, nsp, -1)
+    gxfac, gxs = opernlc_general(gx, enl, sij, indlmn, nattyp, atindx1, paw_opt, nspinor, cplex_enl, lambda_)
+    vectout = (gxfac.reshape(ndat * nsp, -1) @ P).reshape(ndat, nsp, npw) if paw_opt in (1, 2, 4) else None
+    svectout = (gxs.reshape(ndat * nsp, -1) @ P).reshape(ndat, nsp, npw) + v if paw_opt in (3, 4) else None
+    return vectout, svectout
+
+
 def opernlb(P, gxfac, istwf_k):
     """vect(ndat, npw) = P . gxfac ; istwf_k>=2: (P_r z, P_i z) interleaved (m_opernlb_gemm.F90:700-706, 804-833)."""
     if istwf_k == 1:

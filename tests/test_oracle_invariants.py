@@ -78,3 +78,47 @@ def test_padded_fourwf_equals_full_fft(istwf_k, kpt, cplex, ndat):
     ref, _, _ = ofw.fourwf(cplex, v, c, None, kg, kg, ng, 2, istwf_k)
     out = fourwf_option2_padded(cplex, v, c, kg, ng, istwf_k, chunk=2)
     assert np.abs(out - ref).max() < 1e-13 * np.abs(ref).max()
+
+
+def _cplx_paw_problem(nspinor, seed=21):
+    from problems import make_problem
+    p = make_problem(7.0, 8.0, (0.2, -0.1, 0.3), 1, ndat=3, seed=seed, natom_per_type=(2, 1), lmax_per_type=(1, 2), usepaw=1)
+    rng = np.random.default_rng(seed)
+    lmn2 = p.lmnmax * (p.lmnmax + 1) // 2
+    nblk = 4 if nspinor == 2 else 1
+    enl = 0.4 * rng.standard_normal((nblk, p.natom, 2 * lmn2))
+    if nblk == 4:
+        # the packed upper triangles of D^{ud} and D^{du} are independent data except on the diagonal, D^{du}_jj = conj(D^{ud}_jj)
+        for j in range(p.lmnmax):
+            pk = j * (j + 1) // 2 + j
+            enl[3, :, 2 * pk] = enl[2, :, 2 * pk]; enl[3, :, 2 * pk + 1] = -enl[2, :, 2 * pk + 1]
+    c = rng.standard_normal((p.ndat, nspinor, p.npw)) + 1j * rng.standard_normal((p.ndat, nspinor, p.npw))
+    return p, enl, c
+
+
+def test_complex_dij_reduces_to_the_pinned_real_path():
+    """cplex_dij = 2 with zero imaginary parts (and spinors with empty off-diagonal blocks and equal diagonal blocks) must give the
+    real packed-symmetric result of nonlop.opernlc, which the tw90_1 SCF pins (m_opernlc_ylm_allwf.F90:336-447 vs :453-737)."""
+    from oracle import nonlop as onl
+    p, enl, c = _cplx_paw_problem(2)
+    lmn2 = p.lmnmax * (p.lmnmax + 1) // 2
+    real_d = enl[0, :, 0::2].copy()
+    e = np.zeros_like(enl); e[0, :, 0::2] = real_d; e[1, :, 0::2] = real_d
+    P = onl.prep_projectors(p.ffnl, p.ph3d, p.indlmn, p.nattyp, p.ucvol)
+    vo, so = onl.gemm_nonlop_general(P, c, e, p.sij, p.indlmn, p.nattyp, p.atindx1 - 1, 4, nspinor=2, cplex_enl=2)
+    for isp in range(2):
+        ro, rs, _ = onl.gemm_nonlop(P, c[:, isp], real_d, p.sij, p.indlmn, p.nattyp, p.atindx1 - 1, 1, choice=1, paw_opt=4)
+        assert np.abs(vo[:, isp] - ro).max() < 1e-13 * np.abs(ro).max()
+        assert np.abs(so[:, isp] - rs).max() < 1e-13 * np.abs(rs).max()
+
+
+def test_complex_and_spinor_dij_operator_is_hermitian():
+    """<a| Vnl b> = conj(<b| Vnl a>) for complex Hermitian D_ij (nspinor 1) and for the four spinor blocks (nspinor 2)."""
+    from oracle import nonlop as onl
+    for nspinor in (1, 2):
+        p, enl, c = _cplx_paw_problem(nspinor, seed=30 + nspinor)
+        P = onl.prep_projectors(p.ffnl, p.ph3d, p.indlmn, p.nattyp, p.ucvol)
+        vo, _ = onl.gemm_nonlop_general(P, c, enl, p.sij, p.indlmn, p.nattyp, p.atindx1 - 1, 1, nspinor=nspinor, cplex_enl=2)
+        a = c.reshape(p.ndat, -1); hb = vo.reshape(p.ndat, -1)
+        g = a.conj() @ hb.T
+        assert np.abs(g - g.conj().T).max() < 1e-12 * np.abs(g).max()
