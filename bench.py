@@ -439,7 +439,8 @@ def run_fe2(args, env):
     # parity: every 6th pair of this rank against the CPU restatement, both outputs
     parity = None
     if not args.no_parity and rank == 0:
-        step_dev(); barrier()
+        step_dev()
+        stream.synchronize(); torch.cuda.synchronize()           # rank 0 only: NO collective in this block
         errs = []
         for i in range(0, len(hams), 6):
             q = probs[i]
@@ -534,10 +535,12 @@ class Block:
             self.ham.load_enl(w["ekb"], None)
         self.ham.load_k(args.istwfk, w["kg"], w["kinpw"], None, None, me_g0=1)
         with torch.cuda.stream(stream):
-            gen = torch.Generator(device=dev).manual_seed(seed + rank)
+            # ONE operator for the whole job (the band-sharded ChebFi2 leg needs the same P on every rank), rank-specific bands
+            gen = torch.Generator(device=dev).manual_seed(seed)
             P = torch.randn((nprojs, npw, 2), generator=gen, device=dev, dtype=torch.float64) / np.sqrt(npw)
             if args.istwfk == 2:
                 P[:, 0, 1] = 0.0
+            gen = torch.Generator(device=dev).manual_seed(seed + 1000 + rank)
             self.cw = torch.randn((ndat, npw, 2), generator=gen, device=dev, dtype=torch.float64)
             if args.istwfk == 2:
                 self.cw[:, 0, 1] = 0.0
