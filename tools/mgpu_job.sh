@@ -9,9 +9,9 @@ for w in fe2 au108; do
 done
 run --workload sweep ${SWEEP_ARGS:-} --out gpurun_out/sweep_${TAG}_${N}gpu.jsonl > gpurun_out/bench_sweep_${TAG}_${N}gpu.json 2> gpurun_out/bench_sweep_${TAG}_${N}gpu.err
 cut -c1-200 gpurun_out/bench_sweep_${TAG}_${N}gpu.json; PORT=$((PORT+1))
-run > gpurun_out/bench_${TAG}_${N}gpu.json 2> gpurun_out/bench_${TAG}_${N}gpu.err
+run ${SI_ARGS:-} > gpurun_out/bench_${TAG}_${N}gpu.json 2> gpurun_out/bench_${TAG}_${N}gpu.err
 cut -c1-300 gpurun_out/bench_${TAG}_${N}gpu.json
-if [ "$N" != 1 ]; then
+if [ "$N" != 1 ] && [ -z "${SKIP_EXTRA:-}" ]; then
   timeout 600 python -m pytest tests/test_chebfi_mgpu.py -m gpu -x -q > gpurun_out/mgpu_tests_${TAG}_${N}gpu.log 2>&1; tail -2 gpurun_out/mgpu_tests_${TAG}_${N}gpu.log
   run --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_${TAG}_${N}gpu.json 2> gpurun_out/bench_ref_${TAG}_${N}gpu.err; cut -c1-200 gpurun_out/bench_ref_${TAG}_${N}gpu.json
 fi
