@@ -125,36 +125,39 @@ def chebfi_band_parallel(gs_hamk, cg_cols, nband: int, ecut: float, nline: int, 
     if ncols != l - f:
         raise ValueError("cg_cols does not hold this rank's band block")
     istwf_k = gs_hamk.istwf_k
-    if getattr(gs_hamk, "usepaw", 0):
-        # the PAW filter needs S X (Rayleigh quotients), S^-1 (apply_invovl) and X^H S X as the B matrix of the Rayleigh-Ritz
-        # step: the BX blocks are not transposed in this driver yet -- refuse instead of solving the wrong problem
-        raise NotImplementedError("chebfi_band_parallel: PAW Hamiltonians (B = S) are not supported by the band-parallel driver; "
-                                  "use xg.chebfiwf2 on one GPU")
+    # PAW: B = S.  The filter needs S X for the Rayleigh quotients and S^-1 (apply_invovl) per band -- both local to the rank's
+    # band block -- and the Rayleigh-Ritz step needs X^H S X as its B matrix, so the BX block is transposed, rotated and
+    # transposed back with X and AX (m_chebfi2.F90:687-705 with paw = .true.).
+    paw = bool(getattr(gs_hamk, "usepaw", 0))
     space = xg.SPACE_CR if istwf_k > 1 else xg.SPACE_C
     x = cg_cols.clone(); ax = torch.empty_like(x); xn = torch.empty_like(x); xp = torch.empty_like(x)
+    bx = torch.empty_like(x) if paw else None
     sync()
-    div, mx, mn = xg.chebfi_rq(gs_hamk, ncols, bandpp, x, ax)
+    div, mx, mn = xg.chebfi_rq(gs_hamk, ncols, bandpp, x, ax, bx)
     if world > 1:
         t = torch.tensor([mx, -mn], dtype=torch.float64, device=x.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         mx, mn = float(t[0]), -float(t[1])
     lambda_minus, lambda_plus = mx, float(ecut)
     ndeg = min(xg.cheb_oracle1(mn, lambda_minus, lambda_plus, 1e-16, 40), int(nline))
-    x, xn, xp = xg.chebfi_core(gs_hamk, ncols, bandpp, x, ax, None, xn, xp, lambda_minus, lambda_plus, ndeg, div)
+    x, xn, xp = xg.chebfi_core(gs_hamk, ncols, bandpp, x, ax, bx, xn, xp, lambda_minus, lambda_plus, ndeg, div)
     del xn, xp
     # ---- Rayleigh-Ritz in the row-sharded layout
     xr = transpose_cols_to_rows(x, nband, npw, group); axr = transpose_cols_to_rows(ax, nband, npw, group)
+    bxr = transpose_cols_to_rows(bx, nband, npw, group) if paw else None
     nrows = int(xr.shape[1])
     sync()
     me_g0 = (1 if (istwf_k == 2 and rank == 0 and gs_hamk.me_g0 == 1) else 0) if space == xg.SPACE_CR else -1
     xg.xg_colwise("zero_im_g0", space, nrows, nband, xr, nrows, me_g0=me_g0)
     xg.xg_colwise("zero_im_g0", space, nrows, nband, axr, nrows, me_g0=me_g0)
+    if paw:
+        xg.xg_colwise("zero_im_g0", space, nrows, nband, bxr, nrows, me_g0=me_g0)
     ldw = (nband + 1) & ~1
     sdt = torch.complex128 if space == xg.SPACE_C else torch.float64
     sub = torch.zeros((2, nband, ldw), dtype=sdt, device=x.device)
     sync()
     xg.xg_gram(space, nrows, nband, nband, xr, nrows, axr, nrows, sub[0], ldw, me_g0)
-    xg.xg_gram(space, nrows, nband, nband, xr, nrows, xr, nrows, sub[1], ldw, me_g0)
+    xg.xg_gram(space, nrows, nband, nband, xr, nrows, bxr if paw else xr, nrows, sub[1], ldw, me_g0)
     if world > 1:
         dist.all_reduce(torch.view_as_real(sub) if sub.is_complex() else sub, op=dist.ReduceOp.SUM, group=group)   # xgBlock_mpi_sum
     w = torch.empty(nband, dtype=torch.float64, device=x.device)
@@ -164,14 +167,18 @@ def chebfi_band_parallel(gs_hamk, cg_cols, nband: int, ecut: float, nline: int, 
         raise RuntimeError(f"chebfi: hegvd failed with info={info}")
     xg.xg_rotate(space, nrows, nband, nband, xr, nrows, sub[0], ldw)
     xg.xg_rotate(space, nrows, nband, nband, axr, nrows, sub[0], ldw)
+    if paw:
+        xg.xg_rotate(space, nrows, nband, nband, bxr, nrows, sub[0], ldw)
     x = transpose_rows_to_cols(xr, nband, npw, group); ax = transpose_rows_to_cols(axr, nband, npw, group)
-    del xr, axr
-    # ---- residuals of my bands: |AX - eig X|^2 (m_chebfi2.F90:709-716)
+    if paw:
+        bx = transpose_rows_to_cols(bxr, nband, npw, group)
+    del xr, axr, bxr
+    # ---- residuals of my bands: |AX - eig BX|^2 (m_chebfi2.F90:709-716)
     me_g0_cols = (1 if (istwf_k == 2 and gs_hamk.me_g0 == 1) else 0) if space == xg.SPACE_CR else -1
     w_loc = w[f:l].contiguous()
     res = torch.empty(ncols, dtype=torch.float64, device=x.device)
     sync()
-    xg.xg_colwise("cymax", space, npw, ncols, ax, npw, x, npw, ax, npw, da=w_loc)
+    xg.xg_colwise("cymax", space, npw, ncols, ax, npw, bx if paw else x, npw, ax, npw, da=w_loc)
     xg.xg_colwise("norm2", space, npw, ncols, ax, npw, out=res, me_g0=me_g0_cols)
     cg_cols.copy_(x)
     return w.cpu().numpy(), res.cpu().numpy()

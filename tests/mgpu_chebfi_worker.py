@@ -47,6 +47,23 @@ def main():
         print(f"rank {rank} istwf_k {istwf_k}: lobpcg eig {le_err:.2e} resid {lr_ok} vec {lv_ok}", flush=True)
         ok = ok and le_err < 1e-8 and lr_ok and lv_ok
         h.destroy()
+    # PAW (B = S): S X in the Rayleigh quotients, apply_invovl in the filter, X^H S X in the Rayleigh-Ritz step, BX transposed too
+    for istwf_k, kpt, nband in ((2, (0, 0, 0), 11), (1, (-.25, .5, 0), 10)):
+        p = make_problem(7.0, (8.0, 9.0, 7.5), kpt, istwf_k, ndat=nband, natom_per_type=(2,), lmax_per_type=(1,), filter_shell=False, usepaw=1)
+        h = ab.Hamiltonian(p.ngfft, p.natom, p.ntypat, p.lmnmax, p.indlmn, p.nattyp, p.atindx1, 1, p.ucvol)
+        h.load_spin(p.vlocal, p.cplex); h.load_enl(p.enl, p.sij); h.load_k(istwf_k, p.kgF, p.kinpw, p.ffnl, p.ph3d, me_g0=1)
+        cg1 = p.cwavef.copy(); eig1 = np.zeros(nband); res1 = np.zeros(nband)
+        xg.chebfiwf2(cg1, eig1, None, None, h, nband, p.npw, 1, res1, 1e-16, p.ecut, 5, bandpp=4)
+        f, l = par.band_block(nband, world, rank)
+        cg = torch.from_numpy(np.ascontiguousarray(p.cwavef[f:l]).view(np.float64).reshape(l - f, p.npw, 2)).cuda()
+        eig, res = par.chebfi_band_parallel(h, cg, nband, p.ecut, 5, bandpp=4)
+        e_err = float(np.max(np.abs(eig - eig1))); e_ok = e_err < 1e-8
+        r_ok = np.max(np.abs(res - res1[f:l]) / (np.abs(res1[f:l]) + 1e-12)) < 1e-5
+        c = cg.cpu().numpy(); c = c[..., 0] + 1j * c[..., 1]
+        v_ok = np.max(np.abs(np.abs(c) - np.abs(cg1[f:l]))) < 1e-8
+        print(f"rank {rank} istwf_k {istwf_k} PAW: eig {e_ok} ({e_err:.2e}) resid {r_ok} vec {v_ok}", flush=True)
+        ok = ok and e_ok and r_ok and v_ok
+        h.destroy()
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
