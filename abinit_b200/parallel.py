@@ -186,7 +186,8 @@ def chebfi_band_parallel(gs_hamk, cg_cols, nband: int, ecut: float, nline: int, 
 
 def lobpcg_band_parallel(gs_hamk, cg_cols, nband: int, nline: int, kinpw, tolwfr_diago: float = 1e-30, bandpp: int = 128, group=None):
     """lobpcg_run with paral_kgb=1, npband = world size, one block of all bands (src/48_diago/m_lobpcg2.F90:340-765),
-    norm-conserving: getAX_BX on the rank's own band block (band-sharded layout), everything else -- B-orthonormalisation,
+    norm-conserving or PAW (B = S: the [BX | BW | BP] blocks travel with the A blocks): getAX_BX on the rank's own band block
+    (band-sharded layout), everything else -- B-orthonormalisation,
     X / XW / XWP Rayleigh-Ritz, residuals, preconditioner -- on the rank's plane-wave rows (row-sharded layout) with the Gram
     matrices summed over ranks by NCCL allreduce and the small dense problems solved redundantly on every rank; per LOBPCG
     iteration one all-to-all out (W) and one back (AW), as the reference's xgTransposer does.
@@ -195,8 +196,7 @@ def lobpcg_band_parallel(gs_hamk, cg_cols, nband: int, nline: int, kinpw, tolwfr
     import torch
     import torch.distributed as dist
     from . import xg, api
-    if gs_hamk.usepaw:
-        raise NotImplementedError("lobpcg_band_parallel: norm-conserving only in this build (PAW needs the BX blocks transposed too)")
+    paw = bool(gs_hamk.usepaw)      # PAW: B = S, the [BX | BW | BP] blocks are carried (and transposed) like the A blocks
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     api.set_async(False)
@@ -223,20 +223,28 @@ def lobpcg_band_parallel(gs_hamk, cg_cols, nband: int, nline: int, kinpw, tolwfr
     # [X | W | P] and [AX | AW | AP] on my rows; B blocks alias the X blocks (norm-conserving)
     xwp = torch.zeros((3 * n, nr, 2), dtype=torch.float64, device=dev)
     axwp = torch.zeros_like(xwp)
-    X, W, AX, AW = xwp[:n], xwp[n:2 * n], axwp[:n], axwp[n:2 * n]
+    bxwp = torch.zeros_like(xwp) if paw else xwp
+    blocks = (xwp, axwp, bxwp) if paw else (xwp, axwp)
+    X, W, AX, AW, BX, BW = xwp[:n], xwp[n:2 * n], axwp[:n], axwp[n:2 * n], bxwp[:n], bxwp[n:2 * n]
 
     def allsum(t):
         if world > 1:
             dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t, op=dist.ReduceOp.SUM, group=group)
 
-    def apply_h(src_rows, dst_rows):
+    def apply_h(src_rows, dst_rows, dst_b_rows=None):
         cols = transpose_rows_to_cols(src_rows.contiguous(), n, npw, group).contiguous()
         out = torch.empty_like(cols)
+        outs = torch.empty_like(cols) if paw else None
         sync()
-        api.getghc(-1, cols, None, out, None, gs_hamk, None, None, None, ncols)
+        api.getghc(-1, cols, None, out, outs, gs_hamk, None, None, None, ncols, sij_opt=1 if paw else 0)
         if space == xg.SPACE_CR:
-            xg.xg_colwise("zero_im_g0", space, npw, ncols, out, npw, me_g0=1 if (istwf_k == 2 and gs_hamk.me_g0 == 1) else 0)
+            g0 = 1 if (istwf_k == 2 and gs_hamk.me_g0 == 1) else 0
+            xg.xg_colwise("zero_im_g0", space, npw, ncols, out, npw, me_g0=g0)
+            if paw:
+                xg.xg_colwise("zero_im_g0", space, npw, ncols, outs, npw, me_g0=g0)
         dst_rows.copy_(transpose_cols_to_rows(out, n, npw, group))
+        if paw:
+            dst_b_rows.copy_(transpose_cols_to_rows(outs, n, npw, group))
         return cols
 
     def gram(a, b, na, nb, w):                       # w: column block view of a (.., ldw) tensor, written in place
@@ -246,15 +254,15 @@ def lobpcg_band_parallel(gs_hamk, cg_cols, nband: int, nline: int, kinpw, tolwfr
     def b_orthonormalize(m):
         ldw = (m + 1) & ~1
         buf = torch.zeros((m, ldw), dtype=sdt, device=dev)
-        for blk in (xwp, axwp):
+        for blk in blocks:
             xg.xg_colwise("zero_im_g0", space, nr, m, blk, nr, me_g0=me_g0)
-        gram(xwp, xwp, m, m, buf)
+        gram(xwp, bxwp, m, m, buf)
         allsum(buf)
         sync()
         info = xg.xg_chol_inverse(sub_space, m, buf, ldw)
         if info != 0:
             return info
-        for blk in (xwp, axwp):
+        for blk in blocks:
             xg.xg_gemm_nn(space, nr, m, m, blk, nr, buf, ldw, blk, nr, upper=True)
         return 0
 
@@ -262,12 +270,12 @@ def lobpcg_band_parallel(gs_hamk, cg_cols, nband: int, nline: int, kinpw, tolwfr
         sub = nvar * n
         ldw = (sub + 1) & ~1
         ab = torch.zeros((2, sub, ldw), dtype=sdt, device=dev)
-        for blk in (xwp, axwp):
+        for blk in blocks:
             xg.xg_colwise("zero_im_g0", space, nr, sub, blk, nr, me_g0=me_g0)
         for v in range(nvar):
             gram(xwp, axwp[v * n:], (v + 1) * n, n, ab[0, v * n:])
             if nvar > 1:
-                gram(xwp, xwp[v * n:], (v + 1) * n, n, ab[1, v * n:])
+                gram(xwp, bxwp[v * n:], (v + 1) * n, n, ab[1, v * n:])
         allsum(ab)
         w = torch.empty(sub, dtype=torch.float64, device=dev)
         sync()
@@ -280,7 +288,7 @@ def lobpcg_band_parallel(gs_hamk, cg_cols, nband: int, nline: int, kinpw, tolwfr
             c1 = torch.zeros((n, ldc1), dtype=sdt, device=dev)
             c1[:, :sub - n] = vec[:n, n:sub]
         sync()
-        for blk in (xwp, axwp):
+        for blk in blocks:
             xg.xg_rotate(space, nr, n, n, blk, nr, vec, ldw)
             if nvar > 1:
                 xg.xg_gemm_nn(space, nr, sub - n, n, blk[n:], nr, c1, ldc1, blk[2 * n:], nr)
@@ -288,14 +296,14 @@ def lobpcg_band_parallel(gs_hamk, cg_cols, nband: int, nline: int, kinpw, tolwfr
         return w
 
     X.copy_(transpose_cols_to_rows(cg_cols, n, npw, group))
-    apply_h(X, AX)
+    apply_h(X, AX, BX)
     b_orthonormalize(n)
     eig = rayleigh_ritz(1)[:n].clone()
     res = torch.zeros(n, dtype=torch.float64, device=dev)
 
     def residuals():
         sync()
-        xg.xg_colwise("cymax", space, nr, n, W, nr, X, nr, AX, nr, da=eig)       # W = AX - eig BX, BX = X
+        xg.xg_colwise("cymax", space, nr, n, W, nr, BX, nr, AX, nr, da=eig)      # W = AX - eig BX (BX = X when norm-conserving)
         xg.xg_colwise("norm2", space, nr, n, W, nr, out=res, me_g0=me_g0)
         allsum(res)
         xg.xg_colwise("apply_diag", space, nr, n, W, nr, da=pcon)
@@ -308,13 +316,14 @@ def lobpcg_band_parallel(gs_hamk, cg_cols, nband: int, nline: int, kinpw, tolwfr
         if max_res < tolwfr_diago:
             compute_residu = False
             break
-        apply_h(W, AW)
+        apply_h(W, AW, BW)
         use_xw = iline == 1 or min_res < 1e-27
         if not use_xw and b_orthonormalize(3 * n) != 0:
             use_xw = True
         if use_xw:
             b_orthonormalize(2 * n)
-            xwp[2 * n:].zero_(); axwp[2 * n:].zero_()
+            for blk in blocks:
+                blk[2 * n:].zero_()
         eig = rayleigh_ritz(2 if use_xw else 3)[:n].clone()
     if compute_residu:
         r, _, _ = residuals()

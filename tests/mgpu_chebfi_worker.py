@@ -63,6 +63,15 @@ def main():
         v_ok = np.max(np.abs(np.abs(c) - np.abs(cg1[f:l]))) < 1e-8
         print(f"rank {rank} istwf_k {istwf_k} PAW: eig {e_ok} ({e_err:.2e}) resid {r_ok} vec {v_ok}", flush=True)
         ok = ok and e_ok and r_ok and v_ok
+        cgl1 = p.cwavef.copy(); eigl1 = np.zeros(nband); resl1 = np.zeros(nband)
+        xg.lobpcgwf2(cgl1, eigl1, None, None, h, nband, p.npw, 1, resl1, 1e-30, 3, bandpp=4)
+        cgl = torch.from_numpy(np.ascontiguousarray(p.cwavef[f:l]).view(np.float64).reshape(l - f, p.npw, 2)).cuda()
+        eigl, resl = par.lobpcg_band_parallel(h, cgl, nband, 3, p.kinpw, bandpp=4)
+        le_err = float(np.max(np.abs(eigl - eigl1))); lr_ok = np.max(np.abs(resl - resl1) / (np.abs(resl1) + 1e-12)) < 1e-4
+        cl = cgl.cpu().numpy(); cl = cl[..., 0] + 1j * cl[..., 1]
+        lv_ok = np.max(np.abs(np.abs(cl) - np.abs(cgl1[f:l]))) < 1e-7
+        print(f"rank {rank} istwf_k {istwf_k} PAW: lobpcg eig {le_err:.2e} resid {lr_ok} vec {lv_ok}", flush=True)
+        ok = ok and le_err < 1e-8 and lr_ok and lv_ok
         h.destroy()
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
