@@ -4,8 +4,8 @@ import os, subprocess, sys, hashlib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["fourwf.cu", "plane_stage.cu", "plane_inst_0.cu", "plane_inst_1.cu", "plane_inst_2.cu", "plane_inst_3.cu", "half_stage.cu", "half_inst_0.cu", "half_inst_1.cu", "half_inst_2.cu", "x_stage.cu", "x_inst_0.cu", "x_inst_1.cu", "nonlop.cu", "context.cu", "api_fourwf.cu", "api_nonlop.cu", "xg.cu", "api_xg.cu", "invovl.cu", "ozaki.cu"]
-HEADERS = ["common.cuh", "fft_engine.cuh", "plane_stage.cuh", "plane_stage_impl.cuh", "half_stage.cuh", "half_stage_impl.cuh", "hdft.cuh", "x_stage.cuh", "x_stage_impl.cuh", "roots.inc", "fourwf.cuh", "nonlop.cuh", "context.cuh", "ham.cuh", "xg.cuh",
+SOURCES = ["fourwf.cu", "plane_stage.cu", "plane_inst_0.cu", "plane_inst_1.cu", "plane_inst_2.cu", "plane_inst_3.cu", "half_stage.cu", "half_inst_0.cu", "half_inst_1.cu", "half_inst_2.cu", "x_stage.cu", "x_inst_0.cu", "x_inst_1.cu", "nonlop.cu", "context.cu", "api_fourwf.cu", "api_nonlop.cu", "xg.cu", "api_xg.cu", "invovl.cu", "ozaki.cu", "comm.cu"]
+HEADERS = ["common.cuh", "fft_engine.cuh", "plane_stage.cuh", "plane_stage_impl.cuh", "half_stage.cuh", "half_stage_impl.cuh", "hdft.cuh", "x_stage.cuh", "x_stage_impl.cuh", "roots.inc", "fourwf.cuh", "nonlop.cuh", "context.cuh", "ham.cuh", "xg.cuh", "comm.cuh",
            os.path.join("..", "..", "include", "abinit_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]

@@ -5,6 +5,7 @@
 #include "context.cuh"
 #include "ham.cuh"
 #include "xg.cuh"
+#include "comm.cuh"
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -47,6 +48,7 @@ struct Buf {
 };
 Buf g_cheb[6];      // AX, BX, X_next, X_prev, X (work copy), LOBPCG AllBX0
 Buf g_small[2];     // device scalars per band
+Buf g_par[4];       // band-parallel drivers: transposer pack buffer, BX (row layout), sub-space matrices, scalars
 
 struct AsyncGuard {   // inner calls must not synchronise per block
   bool old; AsyncGuard() : old(ctx().async) { ctx().async = true; }
@@ -174,7 +176,12 @@ int me_g0_of(const abi_b200_ham_t* h) { return h->istwf_k > 1 ? ((h->istwf_k == 
 }  // namespace
 
 namespace abi {
-void chebfi_release_workspace() { for (auto& b : g_cheb) b.release(); for (auto& b : g_small) b.release(); invovl_release_workspace(); }
+void chebfi_release_workspace() {
+  for (auto& b : g_cheb) b.release();
+  for (auto& b : g_small) b.release();
+  for (auto& b : g_par) b.release();
+  invovl_release_workspace();
+}
 }
 
 extern "C" {
@@ -534,6 +541,129 @@ void abi_b200_chebfiwf2_(double* cg, double* eig, double* occ, double* enl_out, 
   if (!paw && enl_out) enl_per_band(h, nb, nsp, o.bandpp, X, enl_out, st);   // m_chebfiwf.F90:289-316
   CUDA_CHECK(cudaStreamSynchronize(st));
 }
+// ---- band-parallel ChebFi2 inside the library (paral_kgb = 1, npband = ranks of the library communicator) ----
+void abi_b200_comm_get_unique_id_(char* id128) { ensure_init(); comm_get_unique_id(id128); }
+void abi_b200_comm_init_rank_(const char* id128, int* nranks, int* rank) { comm_init(id128, *nranks, *rank); }
+void abi_b200_comm_adopt_(void* nccl_comm, int* nranks, int* rank) { ensure_init(); comm_adopt(nccl_comm, *nranks, *rank); }
+void abi_b200_comm_destroy_(void) { comm_destroy(); }
+
+void abi_b200_xg_transpose_(int* to_rows, double* cols, double* lin, int* rows, int* nband) {
+  ensure_init();
+  cudaStream_t st = ctx().stream;
+  ABI_CHECK(is_device_ptr(cols) && is_device_ptr(lin), "xg_transpose: device blocks required");
+  long long f, l;
+  block_range(*nband, comm_state().nranks, comm_state().rank, &f, &l);
+  double* pack = g_par[0].get(2 * (size_t)(*rows) * std::max<long long>(l - f, 1));
+  if (*to_rows) transpose_cols_to_rows(cols, lin, pack, *rows, *nband, st);
+  else transpose_rows_to_cols(lin, cols, pack, *rows, *nband, st);
+  if (!ctx().async) CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+void abi_b200_chebfiwf2_paral_(double* cg, double* eig, double* resid, abi_b200_ham_t** gs_hamk, int* nband, int* ncols_mine, int* npw,
+                               int* nspinor, double* ecut, int* nline, int* bandpp) {
+  ensure_init();
+  NvtxRange nvtx("CHEBFI2");
+  Context& c = ctx();
+  cudaStream_t st = c.stream;
+  abi_b200_ham* h = *gs_hamk;
+  const CommState& cm = comm_state();
+  const int R = cm.nranks, nb = *nband, nsp = *nspinor;
+  ABI_CHECK(nsp == h->nspinor, "chebfiwf2_paral: nspinor differs from the Hamiltonian's (abi_b200_ham_set_nspinor)");
+  ABI_CHECK(*npw == h->npw && h->plan != nullptr, "chebfiwf2_paral: npw differs from the k-point loaded in gs_hamk");
+  ABI_CHECK(!is_device_ptr(eig) && !is_device_ptr(resid), "chebfiwf2_paral: eig, resid are host arrays");
+  const int np = *npw * nsp;
+  long long f, l, lo, hi;
+  block_range(nb, R, cm.rank, &f, &l);
+  block_range(np, R, cm.rank, &lo, &hi);
+  const int ncols = (int)(l - f), nrows = (int)(hi - lo);
+  ABI_CHECK(*ncols_mine == ncols, "chebfiwf2_paral: cg does not hold this rank's band block (contiguous blocks, larger ones first)");
+  const bool paw = h->usepaw == 1;
+  const int space = space_of(h), me_g0 = me_g0_of(h);
+  AsyncGuard g;
+  const size_t blk_c = 2 * (size_t)np * std::max(ncols, 1), blk_r = 2 * (size_t)std::max(nrows, 1) * nb;
+  const size_t blk = std::max(blk_c, blk_r);
+  DevArg a_cg(10, cg, sizeof(double) * 2 * (size_t)np * ncols, true);
+  double* X = g_cheb[4].get(blk);
+  double* AX = g_cheb[0].get(blk);
+  double* BX = paw ? g_cheb[1].get(blk) : nullptr;
+  double* Xn = g_cheb[2].get(blk);
+  double* Xp = g_cheb[3].get(blk);
+  CUDA_CHECK(cudaMemcpyAsync(X, a_cg.as<double>(), sizeof(double) * 2 * (size_t)np * ncols, cudaMemcpyDeviceToDevice, st));
+  // ---- filter on my band block: no communication except the extrema of the Rayleigh quotients (m_chebfi2.F90:606-611)
+  get_ax_bx(h, space, me_g0, np, ncols, *bandpp, X, AX, BX);
+  std::vector<double> div; double maxeig, mineig;
+  rr_quotients(space, me_g0, np, ncols, X, AX, BX, div, maxeig, mineig);
+  if (R > 1) {
+    double* d_mm = g_par[3].get(8);
+    double mm[2] = {maxeig, -mineig};
+    CUDA_CHECK(cudaMemcpyAsync(d_mm, mm, sizeof(mm), cudaMemcpyHostToDevice, st));
+    comm_allreduce(d_mm, 2, true, st);
+    CUDA_CHECK(cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    maxeig = mm[0]; mineig = -mm[1];
+  }
+  const double lambda_minus = maxeig, lambda_plus = *ecut;
+  const int ndeg = std::min(cheb_oracle1(mineig, lambda_minus, lambda_plus, 1e-16, 40), *nline);
+  { NvtxRange nc("CHEBFI2_CORE"); cheb_core(h, space, me_g0, np, ncols, *bandpp, &X, AX, BX, &Xn, &Xp, lambda_minus, lambda_plus, ndeg, div); }
+  // ---- Rayleigh-Ritz in the row-sharded layout (m_chebfi2.F90:687-705): all bands, my rows
+  NvtxRange nrr("RAYLRITZ");
+  ProfScope* ps_rr = new ProfScope("rr_paral");
+  double *Xr = X, *AXr = AX, *BXr = BX;
+  double* pack = nullptr;
+  if (R > 1) {
+    pack = g_par[0].get(blk_c);
+    Xr = Xn; AXr = Xp; BXr = paw ? g_par[1].get(blk_r) : nullptr;    // the filter's X_next / X_prev blocks are free now
+    transpose_cols_to_rows(X, Xr, pack, np, nb, st);
+    transpose_cols_to_rows(AX, AXr, pack, np, nb, st);
+    if (paw) transpose_cols_to_rows(BX, BXr, pack, np, nb, st);
+  }
+  const int me_g0_rows = space == SPACE_CR ? ((h->istwf_k == 2 && cm.rank == 0 && h->me_g0 == 1) ? 1 : 0) : -1;   // row 0 lives on rank 0
+  xg_zero_im_g0(space, nb, Xr, nrows, me_g0_rows, st);
+  xg_zero_im_g0(space, nb, AXr, nrows, me_g0_rows, st);
+  if (paw) xg_zero_im_g0(space, nb, BXr, nrows, me_g0_rows, st);
+  const int sc = sub_cplex(space);
+  const long long ldw = (nb + 1) & ~1LL;
+  const size_t nsub = (size_t)sc * ldw * nb;
+  double* subA = g_par[2].get(2 * nsub + nb);
+  double* subB = subA + nsub;
+  double* d_eig = subB + nsub;
+  CUDA_CHECK(cudaMemsetAsync(subA, 0, sizeof(double) * 2 * nsub, st));
+  static cudaStream_t cs = nullptr; static cudaEvent_t evA = nullptr, evB = nullptr, evC = nullptr;
+  if (!cs) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&evA, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&evB, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&evC, cudaEventDisableTiming));
+  }
+  // X^H A X, then its allreduce on the side stream while X^H B X is computed (xgBlock_gemm(..., comm=), m_xg.F90:1969-1974)
+  xg_gram(space, nrows, nb, nb, Xr, nrows, AXr, nrows, subA, ldw, me_g0_rows, st);
+  if (R > 1) { CUDA_CHECK(cudaEventRecord(evA, st)); CUDA_CHECK(cudaStreamWaitEvent(cs, evA, 0)); comm_allreduce(subA, nsub, false, cs); }
+  xg_gram(space, nrows, nb, nb, Xr, nrows, paw ? BXr : Xr, nrows, subB, ldw, me_g0_rows, st);
+  if (R > 1) {
+    CUDA_CHECK(cudaEventRecord(evB, st)); CUDA_CHECK(cudaStreamWaitEvent(cs, evB, 0)); comm_allreduce(subB, nsub, false, cs);
+    CUDA_CHECK(cudaEventRecord(evC, cs)); CUDA_CHECK(cudaStreamWaitEvent(st, evC, 0));
+  }
+  const int info = xg_hegvd(space == SPACE_C ? SPACE_C : SPACE_R, nb, subA, ldw, subB, ldw, d_eig, st);   // replicated on every rank
+  ABI_CHECK(info == 0, "chebfi: the sub-space eigenproblem failed (hegvd info /= 0)");
+  xg_rotate(space, nrows, nb, nb, Xr, nrows, subA, ldw, st);
+  xg_rotate(space, nrows, nb, nb, AXr, nrows, subA, ldw, st);
+  if (paw) xg_rotate(space, nrows, nb, nb, BXr, nrows, subA, ldw, st);
+  if (R > 1) {
+    transpose_rows_to_cols(Xr, X, pack, np, nb, st);
+    transpose_rows_to_cols(AXr, AX, pack, np, nb, st);
+    if (paw) transpose_rows_to_cols(BXr, BX, pack, np, nb, st);
+  }
+  delete ps_rr;
+  // ---- residuals of my bands (m_chebfi2.F90:709-716)
+  double* d_res = g_small[0].get((size_t)2 * std::max(ncols, 1));
+  xg_colwise_cymax(space, np, ncols, AX, np, d_eig + f, BX ? BX : X, np, AX, np, st);
+  xg_colwise_norm2(space, np, ncols, AX, np, d_res, me_g0, st);
+  CUDA_CHECK(cudaMemcpyAsync(eig, d_eig, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+  if (ncols) CUDA_CHECK(cudaMemcpyAsync(resid, d_res, sizeof(double) * ncols, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaMemcpyAsync(a_cg.as<double>(), X, sizeof(double) * 2 * (size_t)np * ncols, cudaMemcpyDeviceToDevice, st));
+  a_cg.copy_back();
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
 #endif   // ABI_EMU
+
 
 }  // extern "C"

@@ -31,6 +31,8 @@ SYMBOLS = [
     "abi_b200_xg_gram_", "abi_b200_xg_rotate_", "abi_b200_xg_hegvd_", "abi_b200_xg_gemm_nn_", "abi_b200_xg_chol_inverse_", "abi_b200_xg_colwise_", "abi_b200_xg_rayleigh_ritz_",
     "abi_b200_chebfiwf2_", "abi_b200_lobpcgwf2_", "abi_b200_chebfi_rq_", "abi_b200_chebfi_core_", "abi_b200_cheb_oracle1_", "abi_b200_cheb_poly1_",
     "abi_b200_make_invovl_", "abi_b200_apply_invovl_",
+    "abi_b200_comm_get_unique_id_", "abi_b200_comm_init_rank_", "abi_b200_comm_adopt_", "abi_b200_comm_destroy_", "abi_b200_xg_transpose_",
+    "abi_b200_chebfiwf2_paral_",
 ]
 
 
@@ -104,6 +106,11 @@ def load_library(path: str | None = None) -> C.CDLL:
         lib.abi_b200_cheb_poly1_.restype = C.c_double
         lib.abi_b200_make_invovl_.argtypes = [vp]
         lib.abi_b200_apply_invovl_.argtypes = [vp] * 8
+        lib.abi_b200_comm_get_unique_id_.argtypes = [vp]
+        lib.abi_b200_comm_init_rank_.argtypes = [vp] * 3
+        lib.abi_b200_comm_adopt_.argtypes = [vp] * 3
+        lib.abi_b200_xg_transpose_.argtypes = [vp] * 5
+        lib.abi_b200_chebfiwf2_paral_.argtypes = [vp] * 11
     if path is None:
         _LIB = lib
     return lib

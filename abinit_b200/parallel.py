@@ -104,6 +104,47 @@ def transpose_rows_to_cols(x_rows, nband: int, npw: int, group=None):
     return out
 
 
+_LIB_COMM = {"world": 0}
+
+
+def init_library_comm(group=None):
+    """Create the NCCL communicator owned by libabinit_b200.so for the ranks of `group` (ncclCommInitRank): rank 0 draws the
+    ncclUniqueId, torch.distributed only carries its 128 bytes.  After this call the band-parallel drivers run entirely inside
+    the library (abi_b200_chebfiwf2_paral_): NCCL on the library stream, no torch tensors on the data path."""
+    import torch
+    import torch.distributed as dist
+    from . import xg
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if _LIB_COMM["world"] == world:
+        return
+    if world == 1:
+        xg.comm_init_rank(bytes(128), 1, 0)
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(xg.comm_get_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        xg.comm_init_rank(bytes(t.cpu().numpy().tobytes()), world, rank)
+    _LIB_COMM["world"] = world
+
+
+def chebfi_band_parallel_native(gs_hamk, cg_cols, nband: int, ecut: float, nline: int, bandpp: int = 128, group=None):
+    """chebfi_band_parallel through the library's own driver (abi_b200_chebfiwf2_paral_, include/abinit_b200.h): same arguments
+    and results; the all-to-all re-layouts, the Gram allreduce (overlapped with the second Gram product) and the MAX reduction
+    run on the library stream without host synchronisation in between."""
+    import numpy as np
+    import torch
+    from . import xg
+    init_library_comm(group)
+    ncols, npw = int(cg_cols.shape[0]), int(cg_cols.shape[1])
+    eig = np.zeros(nband); res = np.zeros(max(ncols, 1))
+    torch.cuda.current_stream(cg_cols.device).synchronize()
+    xg.chebfiwf2_paral(cg_cols, eig, res, gs_hamk, nband, ncols, npw, 1, float(ecut), int(nline), bandpp=bandpp)
+    return eig, res[:ncols]
+
+
 def chebfi_band_parallel(gs_hamk, cg_cols, nband: int, ecut: float, nline: int, bandpp: int = 128, group=None):
     """chebfi_run with paral_kgb=1, npband = world size (src/48_diago/m_chebfi2.F90:466-735): every rank filters its own
     band block (no communication), the Rayleigh quotient extrema are reduced over ranks (:606-611), the blocks are

@@ -115,3 +115,35 @@ def lobpcgwf2(cg, eig, occ, enl_out, gs_hamk: Hamiltonian, nband, npw, nspinor, 
     L().abi_b200_lobpcgwf2_(_ptr(cg, _F, "cg"), _ptr(eig, _F, "eig"), _ptr(occ, _F, "occ"), _ptr(enl_out, _F, "enl_out"),
                             C.byref(hp), _iref(nband), _iref(npw), _iref(nspinor), _iref(prtvol), _ptr(resid, _F, "resid"),
                             _dref(tolwfr_diago), _iref(nline), _iref(nblock_lobpcg), _iref(nbdbuf), _iref(bp))
+
+
+# ---- band-parallel ChebFi2 inside the library (NCCL communicator owned by libabinit_b200.so) ----
+def comm_get_unique_id() -> bytes:
+    """ncclGetUniqueId (128 bytes): call on rank 0 and broadcast with the application's own transport."""
+    buf = C.create_string_buffer(128)
+    L().abi_b200_comm_get_unique_id_(buf)
+    return buf.raw
+
+
+def comm_init_rank(uid: bytes, nranks: int, rank: int):
+    if len(uid) != 128:
+        raise ValueError("the ncclUniqueId is 128 bytes")
+    L().abi_b200_comm_init_rank_(C.create_string_buffer(uid, 128), _iref(nranks), _iref(rank))
+
+
+def comm_destroy():
+    L().abi_b200_comm_destroy_()
+
+
+def xg_transpose(to_rows: bool, cols, lin, rows, nband):
+    """xgTransposer_transpose between cols (2, rows, my_ncols) and lin (2, my_nrows, nband), device blocks."""
+    L().abi_b200_xg_transpose_(_iref(1 if to_rows else 0), _ptr(cols), _ptr(lin), _iref(rows), _iref(nband))
+
+
+def chebfiwf2_paral(cg, eig, resid, gs_hamk: Hamiltonian, nband, ncols_mine, npw, nspinor, ecut, nline, bandpp=None):
+    """chebfiwf2 with paral_kgb = 1 over the ranks of the library communicator: cg holds this rank's band block (in/out), eig
+    (nband, replicated) and resid (ncols_mine) are host float64 arrays."""
+    hp = C.c_void_p(gs_hamk.h)
+    bp = int(max(ncols_mine, 1) if bandpp is None else bandpp)
+    L().abi_b200_chebfiwf2_paral_(_ptr(cg, _F, "cg"), _ptr(eig, _F, "eig"), _ptr(resid, _F, "resid"), C.byref(hp), _iref(nband),
+                                  _iref(ncols_mine), _iref(npw), _iref(nspinor), _dref(ecut), _iref(nline), _iref(bp))

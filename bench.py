@@ -57,6 +57,7 @@ def parse(argv=None):
     ap.add_argument("--ndat", type=int, default=None, help="band block per GPU (default 128; fe2: 24 bands per (k, spin))")
     ap.add_argument("--istwfk", type=int, default=None, help="default: 2 for si512 / sweep, 1 for au108 / fe2")
     ap.add_argument("--au-lmax", type=int, default=2, help="au108: 2 = 18 projectors per atom (nprojs 1944), 3 = 32 (nprojs 3456)")
+    ap.add_argument("--scf-driver", choices=("native", "python"), default="native", help="band-parallel ChebFi2 of the scf_step leg: the library's own NCCL driver or the torch.distributed one")
     ap.add_argument("--cpu-bands", type=int, default=32, help="bands in the bounded CPU sample (one block: amortises the stream of P like bandpp does)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -736,6 +737,9 @@ def run_block_workload(args, env):
     if extras:
         from abinit_b200 import parallel as par
         api.set_async(False)
+        # "native": abi_b200_chebfiwf2_paral_ (NCCL inside the library, collectives on the library stream); "python": the same
+        # scheme strung together from the xg_* entries with torch.distributed (abinit_b200/parallel.py)
+        cheb_paral = par.chebfi_band_parallel_native if args.scf_driver == "native" else par.chebfi_band_parallel
         f, l = par.band_block(args.nband, world, rank)
         with torch.cuda.stream(stream):
             damp = torch.from_numpy(1.0 / (1.0 + np.minimum(w["kinpw"], 1e6))).to(dev)
@@ -751,7 +755,7 @@ def run_block_workload(args, env):
                 barrier()
                 t0 = time.perf_counter()
                 l1 = ab.kernel_launches()
-                eig, resid = par.chebfi_band_parallel(ham, cg, args.nband, float(w["cfg"]["ecut"]), args.nline, bandpp=ndat)
+                eig, resid = cheb_paral(ham, cg, args.nband, float(w["cfg"]["ecut"]), args.nline, bandpp=ndat)
                 barrier()
                 times.append(time.perf_counter() - t0)
             dtm = torch.tensor([times[-1]], device=dev, dtype=torch.float64)
@@ -759,12 +763,12 @@ def run_block_workload(args, env):
                 dist.all_reduce(dtm, op=dist.ReduceOp.MAX)
         api.profile_enable(True)
         with torch.cuda.stream(stream):
-            par.chebfi_band_parallel(ham, cg, args.nband, float(w["cfg"]["ecut"]), args.nline, bandpp=ndat)
+            cheb_paral(ham, cg, args.nband, float(w["cfg"]["ecut"]), args.nline, bandpp=ndat)
         prof_scf = api.profile_collect()
         api.profile_enable(False)
         eig = np.asarray(eig)
         scf_step = {"value": float(dtm.item()), "unit": "s per ChebFi2 call (one k-point, SCF-step-equivalent)", "nband": args.nband,
-                    "nline": args.nline, "bands_per_gpu": l - f, "launches": int(ab.kernel_launches() - l1),
+                    "nline": args.nline, "bands_per_gpu": l - f, "driver": args.scf_driver, "launches": int(ab.kernel_launches() - l1),
                     "eig_min_max": [float(np.min(eig)), float(np.max(eig))], "resid_max": float(np.max(resid)),
                     "cross_n_invariant": {"what": "eigenvalues after two ChebFi2 calls from a start block seeded per GLOBAL band index: identical input on every "
                                                   "GPU count, results must agree to 1e-8 Ha between the N = 1, 2, 4, 8 lines",

@@ -237,6 +237,29 @@ void abi_b200_chebfi_rq_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, doub
 void abi_b200_chebfi_core_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, double** x, double* ax, double* bx,
                            double** x_next, double** x_prev, double* lambda_minus, double* lambda_plus,
                            int* ndeg_filter, double* div);
+/* ------------------------------------------------------------------------------------------------------
+ * Band-parallel ChebFi2 inside the library: chebfi_run with paral_kgb = 1, npband = the ranks of the library communicator
+ * (src/48_diago/m_chebfi2.F90:466-735 with xmpi_max/xmpi_min of the Rayleigh quotients :606-611, xgTransposer
+ * src/45_xgTools/m_xgTransposer.F90:640-900 (TRANS_ALL2ALL) :687-689, xgBlock_gemm(..., comm=) -> xgBlock_mpi_sum
+ * src/45_xgTools/m_xg.F90:1969-1974, 3636-3663).  One process per GPU; NCCL (dlopen'ed libnccl.so.2) carries the three collectives
+ * on the library stream, so a Fortran caller reaches the multi-GPU solver without Python:
+ *   comm_get_unique_id : rank 0 obtains the 128-byte ncclUniqueId and broadcasts it with the application's own MPI (xmpi_bcast)
+ *   comm_init_rank     : every rank joins (ncclCommInitRank); nranks = 1 needs no id and no NCCL
+ *   comm_adopt         : alternative: hand in an ncclComm_t the application already owns (not destroyed by the library)
+ *   xg_transpose       : xgTransposer_transpose on device blocks: to_rows = 1: cols(2, rows, my_ncols) -> lin(2, my_nrows, nband),
+ *                        to_rows = 0 the inverse.  Bands and rows are distributed in contiguous blocks whose sizes differ by at
+ *                        most one, the larger blocks on the lower ranks.
+ *   chebfiwf2_paral    : cg(2, npw*nspinor*ncols_mine): this rank's band block (host or device, in/out); eig(nband): all
+ *                        eigenvalues (host, replicated); resid(ncols_mine): residuals of the rank's bands (host).
+ *                        chebfi_oracle = 0 (fixed degree nline, capped by cheb_oracle1 like the serial entry).  NC and PAW.
+ * ---------------------------------------------------------------------------------------------------- */
+void abi_b200_comm_get_unique_id_(char* id128);
+void abi_b200_comm_init_rank_(const char* id128, int* nranks, int* rank);
+void abi_b200_comm_adopt_(void* nccl_comm, int* nranks, int* rank);
+void abi_b200_comm_destroy_(void);
+void abi_b200_xg_transpose_(int* to_rows, double* cols, double* lin, int* rows, int* nband);
+void abi_b200_chebfiwf2_paral_(double* cg, double* eig, double* resid, abi_b200_ham_t** gs_hamk, int* nband, int* ncols_mine,
+                               int* npw, int* nspinor, double* ecut, int* nline, int* bandpp);
 /* LOBPCG (src/48_diago/m_lobpcg2.F90:340-765 lobpcg_run) driven as lobpcgwf2 drives it (src/79_seqpar_mpi/m_lobpcgwf.F90:
  * 100-250): getAX_BX = fused getghc, preconditioner = build_pcon(kinpw) (:316-334), xg_Borthonormalize (Cholesky) and the
  * X / XW / XWP Rayleigh-Ritz of src/45_xgTools/m_xg_ortho_RR.F90:86-150, 251-571.  nblock_lobpcg blocks of

@@ -36,6 +36,15 @@ def main():
         v_ok = np.max(np.abs(np.abs(c) - np.abs(cg1[f:l]))) < 1e-8
         print(f"rank {rank} istwf_k {istwf_k}: eig {e_ok} ({e_err:.2e}) resid {r_ok} vec {v_ok}", flush=True)
         ok = ok and e_ok and r_ok and v_ok
+        # the same through the library's own driver (NCCL inside libabinit_b200.so, abi_b200_chebfiwf2_paral_)
+        cgn = torch.from_numpy(np.ascontiguousarray(p.cwavef[f:l]).view(np.float64).reshape(l - f, p.npw, 2)).cuda()
+        eign, resn = par.chebfi_band_parallel_native(h, cgn, nband, p.ecut, 5, bandpp=4)
+        ne_err = float(np.max(np.abs(eign - eig1)))
+        nr_ok = np.max(np.abs(resn - res1[f:l]) / (np.abs(res1[f:l]) + 1e-12)) < 1e-5
+        cn = cgn.cpu().numpy(); cn = cn[..., 0] + 1j * cn[..., 1]
+        nv_ok = np.max(np.abs(np.abs(cn) - np.abs(cg1[f:l]))) < 1e-8
+        print(f"rank {rank} istwf_k {istwf_k}: native eig {ne_err:.2e} resid {nr_ok} vec {nv_ok}", flush=True)
+        ok = ok and ne_err < 1e-8 and nr_ok and nv_ok
         # band-parallel LOBPCG (row-sharded linear algebra, Gram allreduce) vs the single-GPU lobpcgwf2
         cgl1 = p.cwavef.copy(); eigl1 = np.zeros(nband); resl1 = np.zeros(nband)
         xg.lobpcgwf2(cgl1, eigl1, None, None, h, nband, p.npw, 1, resl1, 1e-30, 3, bandpp=4)
@@ -63,6 +72,14 @@ def main():
         v_ok = np.max(np.abs(np.abs(c) - np.abs(cg1[f:l]))) < 1e-8
         print(f"rank {rank} istwf_k {istwf_k} PAW: eig {e_ok} ({e_err:.2e}) resid {r_ok} vec {v_ok}", flush=True)
         ok = ok and e_ok and r_ok and v_ok
+        cgn = torch.from_numpy(np.ascontiguousarray(p.cwavef[f:l]).view(np.float64).reshape(l - f, p.npw, 2)).cuda()
+        eign, resn = par.chebfi_band_parallel_native(h, cgn, nband, p.ecut, 5, bandpp=4)
+        ne_err = float(np.max(np.abs(eign - eig1)))
+        nr_ok = np.max(np.abs(resn - res1[f:l]) / (np.abs(res1[f:l]) + 1e-12)) < 1e-5
+        cn = cgn.cpu().numpy(); cn = cn[..., 0] + 1j * cn[..., 1]
+        nv_ok = np.max(np.abs(np.abs(cn) - np.abs(cg1[f:l]))) < 1e-8
+        print(f"rank {rank} istwf_k {istwf_k} PAW: native eig {ne_err:.2e} resid {nr_ok} vec {nv_ok}", flush=True)
+        ok = ok and ne_err < 1e-8 and nr_ok and nv_ok
         cgl1 = p.cwavef.copy(); eigl1 = np.zeros(nband); resl1 = np.zeros(nband)
         xg.lobpcgwf2(cgl1, eigl1, None, None, h, nband, p.npw, 1, resl1, 1e-30, 3, bandpp=4)
         cgl = torch.from_numpy(np.ascontiguousarray(p.cwavef[f:l]).view(np.float64).reshape(l - f, p.npw, 2)).cuda()

@@ -115,3 +115,35 @@ def test_scf_with_cuda_chebfi2_reaches_reference_etotal(lib):
     assert abs(res["energies"]["non_local_psp"] - ref["energies"]["non_local_psp"]) < 1e-7
     for h in hams:
         h.destroy()
+
+
+@pytest.mark.parametrize("istwf_k,kpt,usepaw", [(1, (-.25, .5, 0), 0), (2, (0, 0, 0), 0), (2, (0, 0, 0), 1)])
+def test_chebfiwf2_paral_on_one_rank_equals_chebfiwf2(lib, istwf_k, kpt, usepaw):
+    """The library's band-parallel driver (abi_b200_chebfiwf2_paral_, NCCL inside the library) on a one-rank communicator: no
+    collective is issued and the result is the serial chebfiwf2's (the 2-GPU comparison is tests/test_chebfi_mgpu.py); the
+    transposer on one rank is the identity."""
+    torch = pytest.importorskip("torch")
+    nband = 9
+    p = make_problem(7.0, (8.0, 9.0, 7.5), kpt, istwf_k, ndat=nband, natom_per_type=(2,), lmax_per_type=(1,), filter_shell=False, usepaw=usepaw)
+    h = _ham(p)
+    cg1 = p.cwavef.copy(); eig1 = np.zeros(nband); res1 = np.zeros(nband)
+    xg.chebfiwf2(cg1, eig1, None, None, h, nband, p.npw, 1, res1, 1e-16, p.ecut, 5, bandpp=4)
+    xg.comm_init_rank(bytes(128), 1, 0)
+    for on_dev in (False, True):
+        cg = p.cwavef.copy(); eig = np.zeros(nband); res = np.zeros(nband)
+        if on_dev:
+            d = torch.from_numpy(cg).cuda()
+            xg.chebfiwf2_paral(d, eig, res, h, nband, nband, p.npw, 1, p.ecut, 5, bandpp=4)
+            cg = d.cpu().numpy()
+        else:
+            xg.chebfiwf2_paral(cg, eig, res, h, nband, nband, p.npw, 1, p.ecut, 5, bandpp=4)
+        assert np.max(np.abs(eig - eig1)) < 1e-10
+        assert np.max(np.abs(res - res1) / (np.abs(res1) + 1e-12)) < 1e-5
+        assert np.max(np.abs(np.abs(cg) - np.abs(cg1))) < 1e-8
+    a = torch.randn((nband, p.npw, 2), dtype=torch.float64, device="cuda"); b = torch.zeros_like(a); c = torch.zeros_like(a)
+    xg.xg_transpose(True, a, b, p.npw, nband)
+    xg.xg_transpose(False, c, b, p.npw, nband)
+    ab.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    xg.comm_destroy()
+    h.destroy()
