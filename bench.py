@@ -603,9 +603,13 @@ def measure_block(args, env, blk, steps, warmup, want_e2e=True):
     if want_e2e:
         api.set_async(False)
         ngs = 2 if blk.sij_opt else 1
+        numa = numa_prefer_gpu_node(dev)              # pinned pages on the GPU's own NUMA node (round-1 e2e limit at N = 8)
         h_c = torch.empty((ndat, npw, 2), dtype=torch.float64).pin_memory(); h_c.copy_(blk.cw.cpu())
-        h_g = torch.empty((ndat, npw, 2), dtype=torch.float64).pin_memory()
+        h_g = torch.empty((ndat, npw, 2), dtype=torch.float64).pin_memory(); h_g.zero_()
         h_s = torch.empty((ndat, npw, 2), dtype=torch.float64).pin_memory() if blk.sij_opt else None
+        if h_s is not None:
+            h_s.zero_()
+        numa_reset_policy()
         hc, hg, hs = h_c.numpy(), h_g.numpy(), (h_s.numpy() if h_s is not None else None)
         for _ in range(2):
             blk.step(hc, hg, hs)
@@ -618,9 +622,44 @@ def measure_block(args, env, blk, steps, warmup, want_e2e=True):
         if dist is not None:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         res["e2e"] = {"value": world * ndat * steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(ndat * npw * 16),
-                      "d2h_bytes_per_step": int(ngs * ndat * npw * 16)}
+                      "d2h_bytes_per_step": int(ngs * ndat * npw * 16), "host_numa": numa}
         api.set_async(True)
     return res
+
+
+def _set_mempolicy(mode, node):
+    """set_mempolicy(2) through libc.syscall (no libnuma in the image); returns True on success."""
+    import ctypes
+    libc = ctypes.CDLL(None, use_errno=True)
+    if node is None:
+        return libc.syscall(238, 0, None, 0) == 0                       # MPOL_DEFAULT
+    mask = (ctypes.c_ulong * 16)()
+    mask[node // 64] = 1 << (node % 64)
+    return libc.syscall(238, mode, mask, 16 * 64 + 1) == 0
+
+
+def numa_prefer_gpu_node(dev):
+    """Host buffers of the e2e leg: prefer the NUMA node the GPU hangs off (sysfs numa_node of its PCI function) for the pages
+    allocated next -- first touch happens right after the allocation.  Anything unexpected leaves the policy unchanged."""
+    info = {"gpu_node": None, "policy": "default"}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        info["gpu_node"] = node
+        if node >= 0 and os.path.isdir("/sys/devices/system/node/node%d" % node) and _set_mempolicy(1, node):   # MPOL_PREFERRED
+            info["policy"] = "preferred"
+    except Exception as e:                                                  # noqa: BLE001
+        info["error"] = str(e)[:80]
+    return info
+
+
+def numa_reset_policy():
+    try:
+        _set_mempolicy(0, None)
+    except Exception:                                                       # noqa: BLE001
+        pass
 
 
 def rooflines(args, blk, res, steps, fp64):
