@@ -146,7 +146,7 @@ void cheb_core(abi_b200_ham_t* h, int space, int me_g0, int npw, int ncols, int 
     // X_next = (AX - center X) * (1/r | 2/r) [- X_prev]   (chebfi_computeNextOrderChebfiPolynom, one pass)
     const double* src = AX;
     if (BX) {                                  // PAW: X_next = getBm1X(AX) = S^-1 AX (apply_invovl, m_chebfiwf.F90:390-440)
-      apply_invovl_device(h, AX, Xn, nullptr, ncols, st);
+      apply_invovl_device(h, AX, Xn, nullptr, ncols * h->nspinor, st);   // spinor components are separate columns of npw rows
       src = Xn;
     }
     xg_cheb_next(space, npw, ncols, Xn, npw, src, npw, X, npw, ideg == 0 ? nullptr : Xp, npw, center,
@@ -302,15 +302,17 @@ void abi_b200_apply_invovl_(abi_b200_ham_t** ham, double* cwavef, double* sm1cwa
   NvtxRange nvtx("INVOVL");                               // NVTX_INVOVL, m_invovl.F90:790
   Context& c = ctx();
   abi_b200_ham* h = *ham;
-  ABI_CHECK(*nspinor == 1, "apply_invovl: nspinor=2 is not implemented in this build");
+  ABI_CHECK(*nspinor == h->nspinor, "apply_invovl: nspinor differs from the Hamiltonian's (abi_b200_ham_set_nspinor)");
   ABI_CHECK(*npw == h->npw, "apply_invovl: npw differs from the k-point loaded in ham");
   ABI_CHECK(h->usepaw == 1, "apply_invovl: PAW only");
-  const size_t nv = sizeof(double) * 2 * (size_t)h->npw * (*ndat);
+  // S has no spin structure: every spinor component is a column of npw coefficients (ndat*nspinor columns, m_invovl.F90:851-958)
+  const int ncol = *ndat * *nspinor;
+  const size_t nv = sizeof(double) * 2 * (size_t)h->npw * ncol;
   const int cplex = h->istwf_k == 1 ? 2 : 1;
   DevArg a_c(0, cwavef, nv, true);
   DevArg a_s(1, sm1cwavef, nv, false);
-  DevArg a_p(3, cwaveprj, sizeof(double) * (size_t)cplex * h->atoms.nprojs * (*ndat), false);
-  apply_invovl_device(h, a_c.as<double>(), a_s.as<double>(), a_p.as<double>(), *ndat, c.stream);
+  DevArg a_p(3, cwaveprj, sizeof(double) * (size_t)cplex * h->atoms.nprojs * ncol, false);
+  apply_invovl_device(h, a_c.as<double>(), a_s.as<double>(), a_p.as<double>(), ncol, c.stream);
   a_s.copy_back(); a_p.copy_back();
   if (!c.async || a_c.staged || a_s.staged || a_p.staged) CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }

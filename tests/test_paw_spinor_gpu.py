@@ -92,3 +92,47 @@ def test_gemm_nonlop_entry_complex_dij_and_spinors(lib, nspinor):
                     nspinor, p.ntypat, 4, p.sij, sout, flat, vout)
     assert rel_err_per_band(vout, ro.reshape(flat.shape)) < 1e-11
     assert rel_err_per_band(sout, rs.reshape(flat.shape)) < 1e-11
+
+
+def test_apply_invovl_and_chebfiwf2_paw_spinors_vs_oracle(lib):
+    """PAW with nspinor = 2 through the solver side: apply_invovl on npw*nspinor blocks (S has no spin structure: every spinor
+    component is one column, m_invovl.F90:851-958) and ChebFi2-PAW (getBm1X = apply_invovl, B = S) against the oracle's chebfi_run
+    driven by getghc_paw_general and the oracle's apply_invovl."""
+    from oracle import xg as oxg, chebfi as och, invovl as oiv
+    from abinit_b200 import xg
+    nband = 6
+    p, enl, c = _problem(2, ndat=nband, seed=5)
+    vl = _vlocal(p, 4)
+    P = onl.prep_projectors(p.ffnl, p.ph3d, p.indlmn, p.nattyp, p.ucvol)
+    iv = oiv.make_invovl(P, p.sij, p.indlmn, p.nattyp, 1)
+    rows = 2 * p.npw
+
+    def apply_h(x):
+        g, s = ogh.getghc_paw_general(x.reshape(-1, 2, p.npw), vl, p.kg, p.ngfft, p.kinpw, P, enl, p.sij, p.indlmn, p.nattyp, p.atindx1 - 1,
+                                      nspinor=2, cplex_enl=2, sij_opt=1)
+        return g.reshape(-1, rows), s.reshape(-1, rows)
+
+    def bm1(ax):
+        s, _ = oiv.apply_invovl(P, iv, np.ascontiguousarray(ax.reshape(-1, p.npw)), 1)
+        return s.reshape(-1, rows)
+    h = ab.Hamiltonian(p.ngfft, p.natom, p.ntypat, p.lmnmax, p.indlmn, p.nattyp, p.atindx1, 1, p.ucvol)
+    h.set_nspinor(2)
+    h.load_spin_nvloc(vl, 4)
+    h.load_enl(enl, p.sij)
+    h.load_k(1, p.kgF, p.kinpw, p.ffnl, p.ph3d, me_g0=1)
+    x0 = np.ascontiguousarray(c.reshape(nband, rows))
+    # apply_invovl: C-ABI with the reference's argument list (nspinor = 2) vs the oracle, and S^-1 S = 1
+    sm1 = np.zeros_like(x0)
+    ab.apply_invovl(h, x0, sm1, None, p.npw, nband, nspinor=2)
+    assert rel_err_per_band(sm1, bm1(x0)) < 1e-10
+    _, sx = apply_h(sm1)
+    live = p.kinpw < 1e290
+    assert np.max(np.abs(sx.reshape(-1, p.npw)[:, live] - x0.reshape(-1, p.npw)[:, live])) < 1e-9 * np.max(np.abs(x0))
+    x_ref = x0.copy(); cg = x0.copy()
+    eig = np.zeros(nband); resid = np.zeros(nband)
+    for it in range(2):
+        w_ref, r_ref, x_ref = och.chebfi_run(apply_h, x_ref, oxg.SPACE_C, -1, p.ecut, nline=4, tolerance=1e-16, get_bm1x=bm1)
+        xg.chebfiwf2(cg, eig, None, None, h, nband, p.npw, 2, resid, 1e-16, p.ecut, 4, bandpp=3)
+        assert np.max(np.abs(eig - w_ref)) < 1e-9 * max(1.0, np.max(np.abs(w_ref))), (it, eig - w_ref)
+        assert np.max(np.abs(resid - r_ref) / (np.abs(r_ref) + 1e-12)) < 1e-5, (it, resid, r_ref)
+    h.destroy()
