@@ -87,6 +87,7 @@ void abi_b200_fourwf_set_tuning(const char* name, int value) {
   else if (k == "xh_order") t.xh_order = value;
   else if (k == "pipeline") ctx().pipeline = value != 0;
   else if (k == "nonlop_ozaki") ozaki_set_enabled(value);     // EXPERIMENTAL int8-sliced gemm_nonlop (ozaki.cu), default off
+  else if (k == "nonlop_rag") nonlop_set_rag(value);
   else if (k == "pipe_chunks") ctx().pipe_chunks = std::max(1, value);
   else if (k == "plane_ctas_per_sm") t.plane_ctas_per_sm = value;
   else if (k == "plane_split") t.plane_split = value;

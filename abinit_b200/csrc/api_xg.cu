@@ -665,7 +665,163 @@ void abi_b200_chebfiwf2_paral_(double* cg, double* eig, double* resid, abi_b200_
   a_cg.copy_back();
   CUDA_CHECK(cudaStreamSynchronize(st));
 }
+// build_pcon on the rows [lo, lo + nr) of a block with npw*nspinor rows (row-sharded layout)
+__global__ void k_build_pcon_rows(int npw, long long lo, int nr, const double* __restrict__ kinpw, double* __restrict__ pcon, double filter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nr) return;
+  const double k = kinpw[(lo + i) % npw];
+  if (k > filter) { pcon[i] = 0.0; return; }
+  const double num = 27 + k * (18 + k * (12 + 8 * k));
+  pcon[i] = num / (num + 16 * k * k * k * k);
+}
+
+// lobpcg_run with paral_kgb = 1, npband = ranks of the library communicator, one block of all bands
+// (src/48_diago/m_lobpcg2.F90:340-765): getAX_BX on the rank's own band block (band-sharded layout), everything else --
+// B-orthonormalisation, X / XW / XWP Rayleigh-Ritz, residuals, preconditioner -- on the rank's plane-wave rows with the Gram matrices
+// summed over the ranks and the small dense problems solved redundantly; per iteration one xgTransposer exchange out (W) and one
+// (PAW: two) back (AW, BW).  The scheme of abinit_b200/parallel.py:lobpcg_band_parallel with NCCL on the library stream.
+void abi_b200_lobpcgwf2_paral_(double* cg, double* eig, double* resid, abi_b200_ham_t** gs_hamk, int* nband, int* ncols_mine, int* npw,
+                               int* nspinor, double* tolwfr_diago, int* nline, int* bandpp) {
+  ensure_init();
+  NvtxRange nvtx("LOBPCG2");
+  Context& c = ctx();
+  cudaStream_t st = c.stream;
+  abi_b200_ham* h = *gs_hamk;
+  const CommState& cm = comm_state();
+  const int R = cm.nranks, n = *nband, nsp = *nspinor;
+  ABI_CHECK(nsp == h->nspinor, "lobpcgwf2_paral: nspinor differs from the Hamiltonian's (abi_b200_ham_set_nspinor)");
+  ABI_CHECK(*npw == h->npw && h->plan != nullptr, "lobpcgwf2_paral: npw differs from the k-point loaded in gs_hamk");
+  ABI_CHECK(!is_device_ptr(eig) && !is_device_ptr(resid), "lobpcgwf2_paral: eig, resid are host arrays");
+  const int np = *npw * nsp;
+  long long f, l, lo, hi;
+  block_range(n, R, cm.rank, &f, &l);
+  block_range(np, R, cm.rank, &lo, &hi);
+  const int ncols = (int)(l - f), nr = (int)(hi - lo);
+  ABI_CHECK(*ncols_mine == ncols, "lobpcgwf2_paral: cg does not hold this rank's band block (contiguous blocks, larger ones first)");
+  const bool paw = h->usepaw == 1;
+  const int space = space_of(h), me_g0_cols = me_g0_of(h);
+  const int me_g0 = space == SPACE_CR ? ((h->istwf_k == 2 && cm.rank == 0 && h->me_g0 == 1) ? 1 : 0) : -1;   // row 0 lives on rank 0
+  const int sub_space = space == SPACE_C ? SPACE_C : SPACE_R, sc = sub_cplex(space);
+  AsyncGuard g;
+  const size_t colr = 2 * (size_t)std::max(nr, 1);            // doubles per column in the row layout
+  const size_t blk_r = colr * n, blk_c = 2 * (size_t)np * std::max(ncols, 1);
+  DevArg a_cg(10, cg, sizeof(double) * 2 * (size_t)np * ncols, true);
+  double* XWP = g_cheb[4].get(3 * blk_r);
+  double* AXWP = g_cheb[0].get(3 * blk_r);
+  double* BXWP = paw ? g_cheb[1].get(3 * blk_r) : XWP;
+  CUDA_CHECK(cudaMemsetAsync(XWP, 0, sizeof(double) * 3 * blk_r, st));
+  CUDA_CHECK(cudaMemsetAsync(AXWP, 0, sizeof(double) * 3 * blk_r, st));
+  if (paw) CUDA_CHECK(cudaMemsetAsync(BXWP, 0, sizeof(double) * 3 * blk_r, st));
+  double* blocks[3] = {XWP, AXWP, BXWP};
+  const int nblocks = paw ? 3 : 2;
+  double* cols_in = g_cheb[2].get(blk_c);                     // band-sharded work blocks of getAX_BX
+  double* cols_a = g_cheb[3].get(blk_c);
+  double* cols_b = paw ? g_cheb[5].get(blk_c) : nullptr;
+  double* pack = g_par[0].get(blk_c);
+  const long long ldw3 = (3LL * n + 1) & ~1LL;
+  double* sub = g_par[2].get((size_t)2 * sc * ldw3 * 3 * n + (size_t)sc * ldw3 * n);   // A / B sub-space matrices + the c1 rotation block
+  double* d_pcon = g_par[1].get((size_t)nr + 8);
+  double* d_eig = g_small[0].get((size_t)4 * n);              // 3n eigenvalues + n residuals
+  double* d_res = d_eig + 3 * n;
+  if (nr) { k_build_pcon_rows<<<ceil_div(nr, 256), 256, 0, st>>>(*npw, lo, nr, h->d_kinpw, d_pcon, 1.7976931348623157e308 * 1.0e-11); CUDA_CHECK(cudaGetLastError()); }
+  double *X = XWP, *W = XWP + blk_r, *AX = AXWP, *AW = AXWP + blk_r, *BX = BXWP, *BW = BXWP + blk_r;
+
+  auto to_rows = [&](const double* cols, double* rows) {
+    if (R > 1) transpose_cols_to_rows(cols, rows, pack, np, n, st);
+    else CUDA_CHECK(cudaMemcpyAsync(rows, cols, sizeof(double) * blk_r, cudaMemcpyDeviceToDevice, st));
+  };
+  auto to_cols = [&](const double* rows, double* cols) {
+    if (R > 1) transpose_rows_to_cols(rows, cols, pack, np, n, st);
+    else CUDA_CHECK(cudaMemcpyAsync(cols, rows, sizeof(double) * blk_r, cudaMemcpyDeviceToDevice, st));
+  };
+  auto apply_h = [&](const double* src_rows, double* dst_rows, double* dst_b_rows) {
+    to_cols(src_rows, cols_in);
+    get_ax_bx(h, space, me_g0_cols, np, ncols, *bandpp, cols_in, cols_a, cols_b);
+    to_rows(cols_a, dst_rows);
+    if (paw) to_rows(cols_b, dst_b_rows);
+  };
+  auto zero_all = [&](int m) { for (int b = 0; b < nblocks; b++) xg_zero_im_g0(space, m, blocks[b], nr, me_g0, st); };
+  auto b_orthonormalize = [&](int m) -> int {
+    const long long ldw = (m + 1) & ~1LL;
+    CUDA_CHECK(cudaMemsetAsync(sub, 0, sizeof(double) * sc * ldw * m, st));
+    zero_all(m);
+    xg_gram(space, nr, m, m, XWP, nr, BXWP, nr, sub, ldw, me_g0, st);
+    comm_allreduce(sub, (size_t)sc * ldw * m, false, st);
+    const int info = xg_chol_inverse(sub_space, m, sub, ldw, st);
+    if (info != 0) return info;
+    for (int b = 0; b < nblocks; b++) xg_gemm_nn_upper(space, nr, m, m, blocks[b], nr, sub, ldw, blocks[b], nr, st);
+    return 0;
+  };
+  auto rayleigh_ritz = [&](int nvar) {
+    const int m = nvar * n;
+    const long long ldw = (m + 1) & ~1LL;
+    const size_t nsub = (size_t)sc * ldw * m;
+    double* subA = sub; double* subB = sub + nsub;
+    CUDA_CHECK(cudaMemsetAsync(sub, 0, sizeof(double) * 2 * nsub, st));
+    zero_all(m);
+    for (int v = 0; v < nvar; v++) {                          // upper block columns of [X W P]^H A [X W P] (and B)
+      xg_gram(space, nr, (v + 1) * n, n, XWP, nr, AXWP + (size_t)v * blk_r, nr, subA + (size_t)sc * ldw * v * n, ldw, me_g0, st);
+      if (nvar > 1) xg_gram(space, nr, (v + 1) * n, n, XWP, nr, BXWP + (size_t)v * blk_r, nr, subB + (size_t)sc * ldw * v * n, ldw, me_g0, st);
+    }
+    comm_allreduce(sub, (nvar > 1 ? 2 : 1) * nsub, false, st);
+    const int info = xg_hegvd(sub_space, m, subA, ldw, nvar > 1 ? subB : nullptr, ldw, d_eig, st);
+    ABI_CHECK(info == 0, "lobpcg: the sub-space eigenproblem failed");
+    double* c1 = nullptr; long long ldc1 = 0;
+    if (nvar > 1) {                                           // rows n..m of the first n eigenvectors -> K-padded (m - n) x n block
+      ldc1 = (m - n + 1) & ~1LL;
+      c1 = sub + 2 * nsub;
+      CUDA_CHECK(cudaMemsetAsync(c1, 0, sizeof(double) * sc * ldc1 * n, st));
+      CUDA_CHECK(cudaMemcpy2DAsync(c1, sizeof(double) * sc * ldc1, subA + (size_t)sc * n, sizeof(double) * sc * ldw, sizeof(double) * sc * (m - n), n,
+                                   cudaMemcpyDeviceToDevice, st));
+    }
+    for (int b = 0; b < nblocks; b++) {
+      double* blk = blocks[b];
+      xg_rotate(space, nr, n, n, blk, nr, subA, ldw, st);                                             // X <- X C(0:n)
+      if (nvar > 1) {
+        xg_gemm_nn(space, nr, m - n, n, blk + blk_r, nr, c1, ldc1, blk + 2 * blk_r, nr, st);          // P <- [W P] C(n:m)
+        xg_add(space, nr, n, blk, nr, blk + 2 * blk_r, nr, st);                                        // X += P
+      }
+    }
+  };
+  std::vector<double> r(n);
+  double min_res = 0.0, max_res = 0.0;
+  auto residuals = [&]() {
+    xg_colwise_cymax(space, nr, n, W, nr, d_eig, BX, nr, AX, nr, st);           // W = AX - eig BX (BX = X when norm-conserving)
+    xg_colwise_norm2(space, nr, n, W, nr, d_res, me_g0, st);
+    comm_allreduce(d_res, n, false, st);
+    xg_apply_diag(space, nr, n, W, nr, d_pcon, st);
+    CUDA_CHECK(cudaMemcpyAsync(r.data(), d_res, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    min_res = max_res = r[0];
+    for (int i = 0; i < n; i++) { min_res = std::min(min_res, r[i]); max_res = std::max(max_res, r[i]); }
+  };
+  to_rows(a_cg.as<double>(), X);
+  apply_h(X, AX, BX);
+  b_orthonormalize(n);
+  rayleigh_ritz(1);
+  bool compute_residu = true;
+  for (int iline = 1; iline <= *nline; iline++) {
+    residuals();
+    if (max_res < *tolwfr_diago) { compute_residu = false; break; }
+    apply_h(W, AW, BW);
+    bool use_xw = (iline == 1 || min_res < 1e-27);
+    if (!use_xw && b_orthonormalize(3 * n) != 0) use_xw = true;
+    if (use_xw) {
+      b_orthonormalize(2 * n);
+      for (int b = 0; b < nblocks; b++) CUDA_CHECK(cudaMemsetAsync(blocks[b] + 2 * blk_r, 0, sizeof(double) * blk_r, st));
+    }
+    rayleigh_ritz(use_xw ? 2 : 3);
+  }
+  if (compute_residu) residuals();
+  CUDA_CHECK(cudaMemcpyAsync(eig, d_eig, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  std::copy(r.begin(), r.end(), resid);
+  to_cols(X, cols_in);
+  CUDA_CHECK(cudaMemcpyAsync(a_cg.as<double>(), cols_in, sizeof(double) * 2 * (size_t)np * ncols, cudaMemcpyDeviceToDevice, st));
+  a_cg.copy_back();
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
 #endif   // ABI_EMU
+
 
 
 }  // extern "C"

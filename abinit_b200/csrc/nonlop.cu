@@ -16,6 +16,7 @@
 //  * opernla is K-long and output-small: split-K across CTAs with deterministic partial buffers; the reduction
 //    kernel fuses the x2 / G=0 fix-up, the projections store and the NC ekb scaling (opernlc).
 #include "nonlop.cuh"
+#include <type_traits>
 #include "fourwf.cuh"   // g_kernel_launches
 #include "context.cuh"
 #include <algorithm>
@@ -231,6 +232,8 @@ __global__ void __launch_bounds__(Cfg::WARPS_M * Cfg::WARPS_N * 32, Cfg::MINB) k
   __syncthreads();
   double a[2][FM], b[2][FN];
   const bool active = !RAG || n0 + wn < p.N;               // warp-uniform
+  // RAG: 8-column fragments of this warp that hold columns (warp-uniform): the DMMAs of the others are skipped
+  const int nfr = RAG ? min(FN, max(0, (p.N - n0 - wn + 7) >> 3)) : FN;
   if (active) ld_frags(As, Bs, 0, a[0], b[0]);
   for (int kt = 0; kt < nkt; kt++) {
     const double* as = As + (kt % STAGES) * A_STAGE;
@@ -247,10 +250,17 @@ __global__ void __launch_bounds__(Cfg::WARPS_M * Cfg::WARPS_N * 32, Cfg::MINB) k
         if (active) ld_frags(As + nk * A_STAGE, Bs + nk * B_STAGE, 0, a[(kk + 1) & 1], b[(kk + 1) & 1]);
       }
       if (active) {
+        // (predicated-off DMMAs still occupy the FP64 pipe -- measured: no gain -- so the fragment counts are separate branches)
+        auto mma = [&](auto nf) {
 #pragma unroll
-        for (int i = 0; i < FM; i++)
+          for (int j = 0; j < decltype(nf)::value; j++)
 #pragma unroll
-          for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[kk & 1][i], b[kk & 1][j]);
+            for (int i = 0; i < FM; i++) dmma884(acc[i][j][0], acc[i][j][1], a[kk & 1][i], b[kk & 1][j]);
+        };
+        if (!RAG || nfr == FN) mma(std::integral_constant<int, FN>());
+        else if (nfr * 2 > FN) mma(std::integral_constant<int, (3 * FN) / 4>());
+        else if (nfr * 4 > FN) mma(std::integral_constant<int, FN / 2>());
+        else mma(std::integral_constant<int, FN / 4>());
       }
     }
   }
@@ -708,6 +718,10 @@ void mkffnl_device(double* d_ffnl, int npw, int lmnmax, int ntypat, const int* d
 #endif
 }
 
+// developer knob (abi_b200_fourwf_set_tuning("nonlop_rag", mask)): ragged variants of bit 0: TN 128-wide, bit 1: TN 64-wide, bit 2: NN 64-wide
+int g_nonlop_rag = 7;
+void nonlop_set_rag(int mask) { g_nonlop_rag = mask; }
+
 template <bool TN, bool CPLX, class Cfg, bool RAG = false>
 static void launch_gemm(const GemmParams& p, int nblocks, cudaStream_t st) {
   auto kern = k_dgemm<TN, CPLX, Cfg, RAG>;
@@ -791,8 +805,12 @@ static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long lo
   p.C = part;
   ProfScope ps(prof_name);
   const int nb = tiles * nsplit;
-  const bool ragt = BN == 128 && p.tiles_n == 1 && Neff <= BN - 32;
-  if (ragt) { if (cplx) launch_gemm<true, true, TnCfg, true>(p, nb, st); else launch_gemm<true, false, TnCfg, true>(p, nb, st); }
+  // ragged single column tile: the variant that spreads column blocks over the SM sub-partitions and skips the DMMAs of empty
+  // 8-column fragments (cost follows the columns present, rounded up to 8)
+  // (32-column tiles stream P at the HBM rate whatever their DMMA count: no ragged variant there)
+  const bool ragt = p.tiles_n == 1 && Neff <= BN - 8 && M >= 4 * BM && BN >= 64 && (g_nonlop_rag & (BN == 128 ? 1 : 2));
+  if (ragt && BN == 128) { if (cplx) launch_gemm<true, true, TnCfg, true>(p, nb, st); else launch_gemm<true, false, TnCfg, true>(p, nb, st); }
+  else if (ragt) { if (cplx) launch_gemm<true, true, TnCfg64, true>(p, nb, st); else launch_gemm<true, false, TnCfg64, true>(p, nb, st); }
   else if (BN == 128) { if (cplx) launch_gemm<true, true, TnCfg>(p, nb, st); else launch_gemm<true, false, TnCfg>(p, nb, st); }
   else if (BN == 64) { if (cplx) launch_gemm<true, true, TnCfg64>(p, nb, st); else launch_gemm<true, false, TnCfg64>(p, nb, st); }
   else { if (cplx) launch_gemm<true, true, TnCfg32>(p, nb, st); else launch_gemm<true, false, TnCfg32>(p, nb, st); }
@@ -812,7 +830,10 @@ static void launch_nn(bool cplx, int M, int N, int K, const double* A, long long
   const int nb = p.tiles_m * p.tiles_n;
   // (no RAG variant here: the 64 x 128 tile has two warps per column block, which cannot cover the four sub-partitions of an SM --
   //  measured on B200, 76 columns: 20.2 ms against 18.9 ms for the plain kernel; the TN kernel gains 19 %)
+  //  the narrower tiles have four / eight warps per column block: there the ragged variant's fragment skipping pays)
+  const bool ragn = p.tiles_n == 1 && N <= BN - 8 && BN == 64 && M >= 4 * BM && (g_nonlop_rag & 4);
   if (BN == 128) { if (cplx) launch_gemm<false, true, NnCfg>(p, nb, st); else launch_gemm<false, false, NnCfg>(p, nb, st); }
+  else if (ragn) { if (cplx) launch_gemm<false, true, NnCfg64, true>(p, nb, st); else launch_gemm<false, false, NnCfg64, true>(p, nb, st); }
   else if (BN == 64) { if (cplx) launch_gemm<false, true, NnCfg64>(p, nb, st); else launch_gemm<false, false, NnCfg64>(p, nb, st); }
   else { if (cplx) launch_gemm<false, true, NnCfg32>(p, nb, st); else launch_gemm<false, false, NnCfg32>(p, nb, st); }
 }

@@ -19,6 +19,7 @@ struct OzakiP {
 };
 bool ozaki_enabled();
 void ozaki_set_enabled(int flag);
+void nonlop_set_rag(int mask);   // developer knob: which ragged GEMM variants may be used (nonlop.cu)
 
 // Projectors of one k-point, resident on the device as the real view of P(2, npw, nprojs):
 // a column-major (2*npw) x nprojs FP64 matrix (rows = re/im interleaved plane-wave coefficients).

@@ -32,7 +32,7 @@ SYMBOLS = [
     "abi_b200_chebfiwf2_", "abi_b200_lobpcgwf2_", "abi_b200_chebfi_rq_", "abi_b200_chebfi_core_", "abi_b200_cheb_oracle1_", "abi_b200_cheb_poly1_",
     "abi_b200_make_invovl_", "abi_b200_apply_invovl_",
     "abi_b200_comm_get_unique_id_", "abi_b200_comm_init_rank_", "abi_b200_comm_adopt_", "abi_b200_comm_destroy_", "abi_b200_xg_transpose_",
-    "abi_b200_chebfiwf2_paral_",
+    "abi_b200_chebfiwf2_paral_", "abi_b200_lobpcgwf2_paral_",
 ]
 
 
@@ -111,6 +111,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         lib.abi_b200_comm_adopt_.argtypes = [vp] * 3
         lib.abi_b200_xg_transpose_.argtypes = [vp] * 5
         lib.abi_b200_chebfiwf2_paral_.argtypes = [vp] * 11
+        lib.abi_b200_lobpcgwf2_paral_.argtypes = [vp] * 11
     if path is None:
         _LIB = lib
     return lib

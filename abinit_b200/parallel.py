@@ -145,6 +145,19 @@ def chebfi_band_parallel_native(gs_hamk, cg_cols, nband: int, ecut: float, nline
     return eig, res[:ncols]
 
 
+def lobpcg_band_parallel_native(gs_hamk, cg_cols, nband: int, nline: int, tolwfr_diago: float = 1e-30, bandpp: int = 128, group=None):
+    """lobpcg_band_parallel through the library's own driver (abi_b200_lobpcgwf2_paral_): returns (eig[nband], resid[nband])."""
+    import numpy as np
+    import torch
+    from . import xg
+    init_library_comm(group)
+    ncols, npw = int(cg_cols.shape[0]), int(cg_cols.shape[1])
+    eig = np.zeros(nband); res = np.zeros(nband)
+    torch.cuda.current_stream(cg_cols.device).synchronize()
+    xg.lobpcgwf2_paral(cg_cols, eig, res, gs_hamk, nband, ncols, npw, 1, float(tolwfr_diago), int(nline), bandpp=bandpp)
+    return eig, res
+
+
 def chebfi_band_parallel(gs_hamk, cg_cols, nband: int, ecut: float, nline: int, bandpp: int = 128, group=None):
     """chebfi_run with paral_kgb=1, npband = world size (src/48_diago/m_chebfi2.F90:466-735): every rank filters its own
     band block (no communication), the Rayleigh quotient extrema are reduced over ranks (:606-611), the blocks are

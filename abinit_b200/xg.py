@@ -147,3 +147,12 @@ def chebfiwf2_paral(cg, eig, resid, gs_hamk: Hamiltonian, nband, ncols_mine, npw
     bp = int(max(ncols_mine, 1) if bandpp is None else bandpp)
     L().abi_b200_chebfiwf2_paral_(_ptr(cg, _F, "cg"), _ptr(eig, _F, "eig"), _ptr(resid, _F, "resid"), C.byref(hp), _iref(nband),
                                   _iref(ncols_mine), _iref(npw), _iref(nspinor), _dref(ecut), _iref(nline), _iref(bp))
+
+
+def lobpcgwf2_paral(cg, eig, resid, gs_hamk: Hamiltonian, nband, ncols_mine, npw, nspinor, tolwfr_diago, nline, bandpp=None):
+    """lobpcgwf2 (one block of all bands) with paral_kgb = 1 over the ranks of the library communicator: cg holds this rank's band
+    block (in/out); eig and resid (nband, replicated) are host float64 arrays."""
+    hp = C.c_void_p(gs_hamk.h)
+    bp = int(max(ncols_mine, 1) if bandpp is None else bandpp)
+    L().abi_b200_lobpcgwf2_paral_(_ptr(cg, _F, "cg"), _ptr(eig, _F, "eig"), _ptr(resid, _F, "resid"), C.byref(hp), _iref(nband),
+                                  _iref(ncols_mine), _iref(npw), _iref(nspinor), _dref(tolwfr_diago), _iref(nline), _iref(bp))

@@ -260,6 +260,12 @@ void abi_b200_comm_destroy_(void);
 void abi_b200_xg_transpose_(int* to_rows, double* cols, double* lin, int* rows, int* nband);
 void abi_b200_chebfiwf2_paral_(double* cg, double* eig, double* resid, abi_b200_ham_t** gs_hamk, int* nband, int* ncols_mine,
                                int* npw, int* nspinor, double* ecut, int* nline, int* bandpp);
+/* lobpcg_run with paral_kgb = 1 on the same communicator (src/48_diago/m_lobpcg2.F90:340-765, one block of all bands, NC and PAW):
+ * getAX_BX on the rank's band block, B-orthonormalisation / Rayleigh-Ritz / residuals / preconditioner on the rank's plane-wave
+ * rows, Gram and residual sums over NCCL, one xgTransposer exchange out and one (PAW: two) back per iteration.
+ * cg: this rank's band block (in/out); eig(nband), resid(nband): host, replicated. */
+void abi_b200_lobpcgwf2_paral_(double* cg, double* eig, double* resid, abi_b200_ham_t** gs_hamk, int* nband, int* ncols_mine,
+                               int* npw, int* nspinor, double* tolwfr_diago, int* nline, int* bandpp);
 /* LOBPCG (src/48_diago/m_lobpcg2.F90:340-765 lobpcg_run) driven as lobpcgwf2 drives it (src/79_seqpar_mpi/m_lobpcgwf.F90:
  * 100-250): getAX_BX = fused getghc, preconditioner = build_pcon(kinpw) (:316-334), xg_Borthonormalize (Cholesky) and the
  * X / XW / XWP Rayleigh-Ritz of src/45_xgTools/m_xg_ortho_RR.F90:86-150, 251-571.  nblock_lobpcg blocks of

@@ -55,6 +55,13 @@ def main():
         lv_ok = np.max(np.abs(np.abs(cl) - np.abs(cgl1[f:l]))) < 1e-7
         print(f"rank {rank} istwf_k {istwf_k}: lobpcg eig {le_err:.2e} resid {lr_ok} vec {lv_ok}", flush=True)
         ok = ok and le_err < 1e-8 and lr_ok and lv_ok
+        cgn = torch.from_numpy(np.ascontiguousarray(p.cwavef[f:l]).view(np.float64).reshape(l - f, p.npw, 2)).cuda()
+        eign, resn = par.lobpcg_band_parallel_native(h, cgn, nband, 3, bandpp=4)
+        ne_err = float(np.max(np.abs(eign - eigl1))); nr_ok = np.max(np.abs(resn - resl1) / (np.abs(resl1) + 1e-12)) < 1e-4
+        cn = cgn.cpu().numpy(); cn = cn[..., 0] + 1j * cn[..., 1]
+        nv_ok = np.max(np.abs(np.abs(cn) - np.abs(cgl1[f:l]))) < 1e-7
+        print(f"rank {rank} istwf_k {istwf_k}: native lobpcg eig {ne_err:.2e} resid {nr_ok} vec {nv_ok}", flush=True)
+        ok = ok and ne_err < 1e-8 and nr_ok and nv_ok
         h.destroy()
     # PAW (B = S): S X in the Rayleigh quotients, apply_invovl in the filter, X^H S X in the Rayleigh-Ritz step, BX transposed too
     for istwf_k, kpt, nband in ((2, (0, 0, 0), 11), (1, (-.25, .5, 0), 10)):
@@ -89,6 +96,13 @@ def main():
         lv_ok = np.max(np.abs(np.abs(cl) - np.abs(cgl1[f:l]))) < 1e-7
         print(f"rank {rank} istwf_k {istwf_k} PAW: lobpcg eig {le_err:.2e} resid {lr_ok} vec {lv_ok}", flush=True)
         ok = ok and le_err < 1e-8 and lr_ok and lv_ok
+        cgn = torch.from_numpy(np.ascontiguousarray(p.cwavef[f:l]).view(np.float64).reshape(l - f, p.npw, 2)).cuda()
+        eign, resn = par.lobpcg_band_parallel_native(h, cgn, nband, 3, bandpp=4)
+        ne_err = float(np.max(np.abs(eign - eigl1))); nr_ok = np.max(np.abs(resn - resl1) / (np.abs(resl1) + 1e-12)) < 1e-4
+        cn = cgn.cpu().numpy(); cn = cn[..., 0] + 1j * cn[..., 1]
+        nv_ok = np.max(np.abs(np.abs(cn) - np.abs(cgl1[f:l]))) < 1e-7
+        print(f"rank {rank} istwf_k {istwf_k} PAW: native lobpcg eig {ne_err:.2e} resid {nr_ok} vec {nv_ok}", flush=True)
+        ok = ok and ne_err < 1e-8 and nr_ok and nv_ok
         h.destroy()
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)

@@ -114,3 +114,23 @@ def test_lobpcg_converges_to_dense_eigenvalues(lib):
     assert np.max(np.abs(eig[:6] - wd[:6])) < 1e-9
     assert np.max(resid[:6]) < 1e-16
     h.destroy()
+
+
+@pytest.mark.parametrize("istwf_k,kpt,usepaw", [(1, (-.25, .5, 0), 0), (2, (0, 0, 0), 0), (2, (0, 0, 0), 1)])
+def test_lobpcgwf2_paral_on_one_rank_equals_lobpcgwf2(lib, istwf_k, kpt, usepaw):
+    """The library's band-parallel LOBPCG driver (abi_b200_lobpcgwf2_paral_) on a one-rank communicator against the serial
+    lobpcgwf2 (one block); the 2-GPU comparison is tests/test_chebfi_mgpu.py."""
+    nband = 7
+    p = make_problem(7.0, (8.0, 9.0, 7.5), kpt, istwf_k, ndat=nband, natom_per_type=(2,), lmax_per_type=(1,), usepaw=usepaw,
+                     filter_shell=False)
+    h = _ham(p)
+    cg1 = p.cwavef.copy(); eig1 = np.zeros(nband); res1 = np.zeros(nband)
+    xg.lobpcgwf2(cg1, eig1, None, None, h, nband, p.npw, 1, res1, 1e-30, 3, bandpp=4)
+    xg.comm_init_rank(bytes(128), 1, 0)
+    cg = p.cwavef.copy(); eig = np.zeros(nband); res = np.zeros(nband)
+    xg.lobpcgwf2_paral(cg, eig, res, h, nband, nband, p.npw, 1, 1e-30, 3, bandpp=4)
+    xg.comm_destroy()
+    assert np.max(np.abs(eig - eig1)) < 1e-9
+    assert np.max(np.abs(res - res1) / (np.abs(res1) + 1e-12)) < 1e-4
+    assert np.max(np.abs(np.abs(cg) - np.abs(cg1))) < 1e-7
+    h.destroy()

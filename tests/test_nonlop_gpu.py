@@ -164,3 +164,21 @@ def test_initylmg_on_device_matches_oracle(lib, mpsang):
             s = np.sum(ylm[l * l:(l + 1) ** 2] ** 2, axis=0)
             nz = np.linalg.norm(gprimd @ (kg + np.asarray(kpt)[:, None]), axis=0) > 1e-10
             assert np.allclose(s[nz], (2 * l + 1) / (4 * np.pi), atol=1e-13)
+
+
+@pytest.mark.parametrize("istwf_k,kpt", [(2, (0, 0, 0)), (1, (.1, .2, .3))])
+@pytest.mark.parametrize("ndat", [3, 10, 19, 38, 76, 100])
+def test_ragged_band_blocks_with_many_projectors(lib, istwf_k, kpt, ndat):
+    """Band blocks that do not fill their column tile, on a projector count large enough (>= 2048) for the ragged GEMM variants
+    (column blocks spread over the SM sub-partitions, DMMAs of empty 8-column fragments skipped): choice 1 NC and PAW paw_opt 4."""
+    for usepaw in (0, 1):
+        p = make_problem(8.0, (8.0, 9.0, 7.5), kpt, istwf_k, ndat=ndat, natom_per_type=(70, 60), lmax_per_type=(2, 2), usepaw=usepaw, seed=ndat)
+        assert onl.count_nprojs(p.indlmn, p.nattyp) >= 2048
+        P = _setup(lib, p)
+        paw_opt = 4 if usepaw else 0
+        vout, sout, proj = _apply(p, 1, paw_opt, cpopt=0)
+        rv, rs, rgx = onl.gemm_nonlop(P, p.cwavef, p.enl, p.sij, p.indlmn, p.nattyp, p.atindx1 - 1, istwf_k, 1, paw_opt)
+        assert rel_err_per_band(vout, rv) < TOL
+        assert rel_err_per_band(_proj_as_complex(proj, 2 if istwf_k == 1 else 1), rgx) < TOL
+        if usepaw:
+            assert rel_err_per_band(sout, rs) < TOL

@@ -2,6 +2,7 @@
 namespace abi {
 void nonlop_release_all() {}
 void ozaki_set_enabled(int) {}
+void nonlop_set_rag(int) {}
 void xg_release_workspace() {}
 void chebfi_release_workspace() {}
 }

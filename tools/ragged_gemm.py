@@ -16,13 +16,15 @@ env = dict(rank=0, world=1, local=0, dev=dev, stream=stream, dist=None, barrier=
 w = bench.build_workload(args, 0)
 blk = bench.Block(args, env, w, 256, keep_host_p=False)
 api.set_async(True)
-for nd in (128, 76, 138, 10, 64, 200, 256):
-    blk.ndat = nd
-    cw, ghc = blk.cw[:nd], blk.ghc[:nd]
-    for _ in range(2):
-        blk.step(cw, ghc)
-    api.profile_enable(True)
-    for _ in range(3):
-        blk.step(cw, ghc)
-    prof = api.profile_collect(); api.profile_enable(False)
-    print(json.dumps({"ndat": nd, "ms": {k: round(v[0] / 3, 3) for k, v in prof.items() if k.startswith("dgemm")}}), flush=True)
+for rag in (0, 7):
+    api.set_tuning("nonlop_rag", rag)
+    for nd in (128, 100, 76, 48, 40, 24, 10):
+        blk.ndat = nd
+        cw, ghc = blk.cw[:nd], blk.ghc[:nd]
+        for _ in range(2):
+            blk.step(cw, ghc)
+        api.profile_enable(True)
+        for _ in range(3):
+            blk.step(cw, ghc)
+        prof = api.profile_collect(); api.profile_enable(False)
+        print(json.dumps({"nonlop_rag": rag, "ndat": nd, "ms": {k: round(v[0] / 3, 3) for k, v in prof.items() if k.startswith("dgemm")}}), flush=True)
