@@ -16,7 +16,7 @@ env = dict(rank=0, world=1, local=0, dev=dev, stream=stream, dist=None, barrier=
 w = bench.build_workload(args, 0)
 blk = bench.Block(args, env, w, 256, keep_host_p=False)
 api.set_async(True)
-for rag in (0, 7):
+for rag in (0, 15):
     api.set_tuning("nonlop_rag", rag)
     for nd in (128, 100, 76, 48, 40, 24, 10):
         blk.ndat = nd
