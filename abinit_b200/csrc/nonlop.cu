@@ -823,6 +823,7 @@ static void launch_nn(bool cplx, int M, int N, int K, const double* A, long long
   const int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128), BM = 64 * 128 / BN;
   // 65..104 columns on a large M: a full 64-wide pass plus a ragged / narrow pass over the rest costs less than one 128-wide
   // pass whose empty warp columns cannot be spread over the sub-partitions (two passes over A: 9.9 + 5.4 ms against 19.0 at 76 columns)
+  // (a 128 x 128 one-CTA-per-SM ragged NN tile was measured too: 15.2 ms at 76 columns, 18.6 at 100 -- slower than the split below)
   if (BN == 128 && N > 64 && N <= 104 && M >= 4 * BM && (g_nonlop_rag & 8)) {
     launch_nn(cplx, M, 64, K, A, lda, B, ldb, C, ldc, add, st, C2, kin, kin_filter, prof_name);
     const long long n0 = 64;

@@ -397,7 +397,15 @@ def run_fe2(args, env):
         h.load_spin(q["vlocal"], 1); h.load_enl(q["dij"], q["sij"]); h.load_k(1, q["kg"], q["kinpw"], None, None, me_g0=1)
         h.set_projectors(torch.from_numpy(q["P"]).to(dev), q["nprojs"])
         hams.append(h); probs.append(q)
-        cws.append(torch.from_numpy(q["c"]).to(dev)); ghcs.append(torch.zeros_like(cws[-1])); gscs.append(torch.zeros_like(cws[-1]))
+    # the wavefunction blocks of all (k, spin) pairs of this rank live in ONE array with per-pair offsets, like the reference's
+    # cg(2, mcg) with its icg offsets (src/79_seqpar_mpi/m_vtorho.F90:1035-1045): the blocks handed to getghc are views
+    sizes = [int(q["c"].size) for q in probs]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    cw_all = torch.empty(int(offs[-1]), dtype=torch.float64, device=dev); ghc_all = torch.zeros_like(cw_all); gsc_all = torch.zeros_like(cw_all)
+    for i, q in enumerate(probs):
+        cw_all[offs[i]:offs[i + 1]] = torch.from_numpy(q["c"].reshape(-1)).to(dev)
+        shp = q["c"].shape
+        cws.append(cw_all[offs[i]:offs[i + 1]].view(shp)); ghcs.append(ghc_all[offs[i]:offs[i + 1]].view(shp)); gscs.append(gsc_all[offs[i]:offs[i + 1]].view(shp))
     torch.cuda.synchronize()
     api.set_async(True)
 
@@ -456,18 +464,15 @@ def run_fe2(args, env):
     # end to end: pinned host blocks -> device, batch, results back to the host
     e2e = None
     if not args.no_e2e:
-        hc = [c.cpu().pin_memory() for c in cws]
-        hg = [torch.empty_like(x).pin_memory() for x in hc]; hs = [torch.empty_like(x).pin_memory() for x in hc]
+        hc = cw_all.cpu().pin_memory()                   # host cg / ghc / gsc arrays of the whole sweep: one copy each way per step
+        hg = torch.empty_like(hc).pin_memory(); hs = torch.empty_like(hc).pin_memory()
 
         def step_host():
             with torch.cuda.stream(stream):
-                for d, s in zip(cws, hc):
-                    d.copy_(s, non_blocking=True)
+                cw_all.copy_(hc, non_blocking=True)
                 step_dev()
-                for d, s in zip(hg, ghcs):
-                    d.copy_(s, non_blocking=True)
-                for d, s in zip(hs, gscs):
-                    d.copy_(s, non_blocking=True)
+                hg.copy_(ghc_all, non_blocking=True)
+                hs.copy_(gsc_all, non_blocking=True)
         for _ in range(3):
             step_host()
         barrier()

@@ -176,9 +176,14 @@ def test_ragged_band_blocks_with_many_projectors(lib, istwf_k, kpt, ndat):
         assert onl.count_nprojs(p.indlmn, p.nattyp) >= 2048
         P = _setup(lib, p)
         paw_opt = 4 if usepaw else 0
-        vout, sout, proj = _apply(p, 1, paw_opt, cpopt=0)
         rv, rs, rgx = onl.gemm_nonlop(P, p.cwavef, p.enl, p.sij, p.indlmn, p.nattyp, p.atindx1 - 1, istwf_k, 1, paw_opt)
-        assert rel_err_per_band(vout, rv) < TOL
-        assert rel_err_per_band(_proj_as_complex(proj, 2 if istwf_k == 1 else 1), rgx) < TOL
-        if usepaw:
-            assert rel_err_per_band(sout, rs) < TOL
+        for knob in (0, 15):                   # no ragged variant / the default set (developer knob nonlop_rag)
+            api.set_tuning("nonlop_rag", knob)
+            try:
+                vout, sout, proj = _apply(p, 1, paw_opt, cpopt=0)
+            finally:
+                api.set_tuning("nonlop_rag", 15)
+            assert rel_err_per_band(vout, rv) < TOL, knob
+            assert rel_err_per_band(_proj_as_complex(proj, 2 if istwf_k == 1 else 1), rgx) < TOL, knob
+            if usepaw:
+                assert rel_err_per_band(sout, rs) < TOL, knob

@@ -18,7 +18,7 @@ blk = bench.Block(args, env, w, 256, keep_host_p=False)
 api.set_async(True)
 for rag in (0, 15):
     api.set_tuning("nonlop_rag", rag)
-    for nd in (128, 100, 76, 48, 40, 24, 10):
+    for nd in (128, 112, 100, 76, 66, 48, 40, 24, 10):
         blk.ndat = nd
         cw, ghc = blk.cw[:nd], blk.ghc[:nd]
         for _ in range(2):
