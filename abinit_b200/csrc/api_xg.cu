@@ -101,8 +101,12 @@ struct ChebOpts {
 };
 
 // chebfi_set_ndeg_from_residu (m_chebfi2.F90:1131-1210), single band group (shift = 0); work = one block of scratch
+// band-parallel: `occ` points at the occupations of THIS rank's bands, `shift` = global index of its first band, `ntot` = all bands
+// (shift = xmpi_comm_rank(comm_cols) * bandpp, :1161); the caller takes the MAX over the ranks (:1203)
 int ndeg_from_residu(const ChebOpts& o, int space, int me_g0, int npw, int ncols, double lm, double lp, const double* occ,
-                     const std::vector<double>& div, int ndeg_max, const double* AX, const double* BX, double* work) {
+                     const std::vector<double>& div, int ndeg_max, const double* AX, const double* BX, double* work, int shift = 0,
+                     int ntot = -1) {
+  if (ntot < 0) ntot = ncols;
   cudaStream_t st = ctx().stream;
   double* d_eig = g_small[1].get((size_t)2 * ncols);
   double* d_res = d_eig + ncols;
@@ -120,7 +124,7 @@ int ndeg_from_residu(const ChebOpts& o, int space, int me_g0, int npw, int ncols
     const double occ_i = occ ? occ[i] : 1.0;
     if (o.nbdbuf == -101) r *= occ_i;                                              // xgBlock_apply_diag(residu, occ)
     const bool test1 = r < o.tolerance;
-    const bool test2 = (i + 1) > ncols - nbdbuf;
+    const bool test2 = (i + 1 + shift) > ntot - nbdbuf;
     const bool test3 = o.nbdbuf == -101 && occ_i < o.oracle_min_occ;
     int nd = 0;
     if (!(test1 || test2 || test3)) {
@@ -561,8 +565,9 @@ void abi_b200_xg_transpose_(int* to_rows, double* cols, double* lin, int* rows, 
   if (!ctx().async) CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
-void abi_b200_chebfiwf2_paral_(double* cg, double* eig, double* resid, abi_b200_ham_t** gs_hamk, int* nband, int* ncols_mine, int* npw,
-                               int* nspinor, double* ecut, int* nline, int* bandpp) {
+void abi_b200_chebfiwf2_paral_(double* cg, double* eig, double* occ, double* enl_out, double* resid, abi_b200_ham_t** gs_hamk, int* nband,
+                               int* ncols_mine, int* npw, int* nspinor, double* tolwfr_diago, double* ecut, int* nline, int* nbdbuf,
+                               int* chebfi_oracle, double* oracle_factor, double* oracle_min_occ, int* bandpp) {
   ensure_init();
   NvtxRange nvtx("CHEBFI2");
   Context& c = ctx();
@@ -605,7 +610,23 @@ void abi_b200_chebfiwf2_paral_(double* cg, double* eig, double* resid, abi_b200_
     maxeig = mm[0]; mineig = -mm[1];
   }
   const double lambda_minus = maxeig, lambda_plus = *ecut;
-  const int ndeg = std::min(cheb_oracle1(mineig, lambda_minus, lambda_plus, 1e-16, 40), *nline);
+  const int ndeg_max = cheb_oracle1(mineig, lambda_minus, lambda_plus, 1e-16, 40);
+  int ndeg = std::min(ndeg_max, *nline);
+  if (*chebfi_oracle > 0) {                                   // chebfi_set_ndeg_from_residu on my bands, MAX over the ranks (:1203)
+    ABI_CHECK(*nbdbuf >= 0 || (*nbdbuf == -101 && occ != nullptr), "Bad value of nbdbuf");
+    ChebOpts o{*tolwfr_diago, *ecut, *nline, *nbdbuf, *chebfi_oracle, *oracle_factor, *oracle_min_occ, *bandpp};
+    ndeg = ndeg_from_residu(o, space, me_g0, np, ncols, lambda_minus, lambda_plus, occ ? occ + f : nullptr, div, ndeg_max, AX, BX ? BX : X, Xn,
+                            (int)f, nb);
+    if (R > 1) {
+      double* d_nd = g_par[3].get(8);
+      double nd = ndeg;
+      CUDA_CHECK(cudaMemcpyAsync(d_nd, &nd, sizeof(double), cudaMemcpyHostToDevice, st));
+      comm_allreduce(d_nd, 1, true, st);
+      CUDA_CHECK(cudaMemcpyAsync(&nd, d_nd, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      ndeg = (int)nd;
+    }
+  }
   { NvtxRange nc("CHEBFI2_CORE"); cheb_core(h, space, me_g0, np, ncols, *bandpp, &X, AX, BX, &Xn, &Xp, lambda_minus, lambda_plus, ndeg, div); }
   // ---- Rayleigh-Ritz in the row-sharded layout (m_chebfi2.F90:687-705): all bands, my rows
   NvtxRange nrr("RAYLRITZ");
@@ -663,8 +684,10 @@ void abi_b200_chebfiwf2_paral_(double* cg, double* eig, double* resid, abi_b200_
   if (ncols) CUDA_CHECK(cudaMemcpyAsync(resid, d_res, sizeof(double) * ncols, cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaMemcpyAsync(a_cg.as<double>(), X, sizeof(double) * 2 * (size_t)np * ncols, cudaMemcpyDeviceToDevice, st));
   a_cg.copy_back();
+  if (!paw && enl_out && ncols) enl_per_band(h, ncols, nsp, *bandpp, X, enl_out, st);   // <psi|Vnl|psi> of my bands (m_chebfiwf.F90:289-316)
   CUDA_CHECK(cudaStreamSynchronize(st));
 }
+
 // build_pcon on the rows [lo, lo + nr) of a block with npw*nspinor rows (row-sharded layout)
 __global__ void k_build_pcon_rows(int npw, long long lo, int nr, const double* __restrict__ kinpw, double* __restrict__ pcon, double filter) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

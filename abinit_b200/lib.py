@@ -110,7 +110,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         lib.abi_b200_comm_init_rank_.argtypes = [vp] * 3
         lib.abi_b200_comm_adopt_.argtypes = [vp] * 3
         lib.abi_b200_xg_transpose_.argtypes = [vp] * 5
-        lib.abi_b200_chebfiwf2_paral_.argtypes = [vp] * 11
+        lib.abi_b200_chebfiwf2_paral_.argtypes = [vp] * 18
         lib.abi_b200_lobpcgwf2_paral_.argtypes = [vp] * 11
     if path is None:
         _LIB = lib

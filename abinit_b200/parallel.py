@@ -130,7 +130,9 @@ def init_library_comm(group=None):
     _LIB_COMM["world"] = world
 
 
-def chebfi_band_parallel_native(gs_hamk, cg_cols, nband: int, ecut: float, nline: int, bandpp: int = 128, group=None):
+def chebfi_band_parallel_native(gs_hamk, cg_cols, nband: int, ecut: float, nline: int, bandpp: int = 128, group=None, occ=None,
+                                tolwfr_diago: float = 1e-16, nbdbuf: int = 0, chebfi_oracle: int = 0, oracle_factor: float = 1e-2,
+                                oracle_min_occ: float = 1e-8, enl_out=None):
     """chebfi_band_parallel through the library's own driver (abi_b200_chebfiwf2_paral_, include/abinit_b200.h): same arguments
     and results; the all-to-all re-layouts, the Gram allreduce (overlapped with the second Gram product) and the MAX reduction
     run on the library stream without host synchronisation in between."""
@@ -141,7 +143,8 @@ def chebfi_band_parallel_native(gs_hamk, cg_cols, nband: int, ecut: float, nline
     ncols, npw = int(cg_cols.shape[0]), int(cg_cols.shape[1])
     eig = np.zeros(nband); res = np.zeros(max(ncols, 1))
     torch.cuda.current_stream(cg_cols.device).synchronize()
-    xg.chebfiwf2_paral(cg_cols, eig, res, gs_hamk, nband, ncols, npw, 1, float(ecut), int(nline), bandpp=bandpp)
+    xg.chebfiwf2_paral(cg_cols, eig, occ, enl_out, res, gs_hamk, nband, ncols, npw, 1, float(tolwfr_diago), float(ecut), int(nline),
+                       nbdbuf=nbdbuf, chebfi_oracle=chebfi_oracle, oracle_factor=oracle_factor, oracle_min_occ=oracle_min_occ, bandpp=bandpp)
     return eig, res[:ncols]
 
 

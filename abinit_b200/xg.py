@@ -140,13 +140,16 @@ def xg_transpose(to_rows: bool, cols, lin, rows, nband):
     L().abi_b200_xg_transpose_(_iref(1 if to_rows else 0), _ptr(cols), _ptr(lin), _iref(rows), _iref(nband))
 
 
-def chebfiwf2_paral(cg, eig, resid, gs_hamk: Hamiltonian, nband, ncols_mine, npw, nspinor, ecut, nline, bandpp=None):
-    """chebfiwf2 with paral_kgb = 1 over the ranks of the library communicator: cg holds this rank's band block (in/out), eig
-    (nband, replicated) and resid (ncols_mine) are host float64 arrays."""
+def chebfiwf2_paral(cg, eig, occ, enl_out, resid, gs_hamk: Hamiltonian, nband, ncols_mine, npw, nspinor, tolwfr_diago, ecut, nline,
+                    nbdbuf=0, chebfi_oracle=0, oracle_factor=1e-2, oracle_min_occ=1e-8, bandpp=None):
+    """chebfiwf2 with paral_kgb = 1 over the ranks of the library communicator: cg holds this rank's band block (in/out); eig and occ
+    (nband, replicated) and enl_out / resid (ncols_mine) are host float64 arrays; the dtset scalars as in chebfiwf2."""
     hp = C.c_void_p(gs_hamk.h)
     bp = int(max(ncols_mine, 1) if bandpp is None else bandpp)
-    L().abi_b200_chebfiwf2_paral_(_ptr(cg, _F, "cg"), _ptr(eig, _F, "eig"), _ptr(resid, _F, "resid"), C.byref(hp), _iref(nband),
-                                  _iref(ncols_mine), _iref(npw), _iref(nspinor), _dref(ecut), _iref(nline), _iref(bp))
+    L().abi_b200_chebfiwf2_paral_(_ptr(cg, _F, "cg"), _ptr(eig, _F, "eig"), _ptr(occ, _F, "occ"), _ptr(enl_out, _F, "enl_out"),
+                                  _ptr(resid, _F, "resid"), C.byref(hp), _iref(nband), _iref(ncols_mine), _iref(npw), _iref(nspinor),
+                                  _dref(tolwfr_diago), _dref(ecut), _iref(nline), _iref(nbdbuf), _iref(chebfi_oracle), _dref(oracle_factor),
+                                  _dref(oracle_min_occ), _iref(bp))
 
 
 def lobpcgwf2_paral(cg, eig, resid, gs_hamk: Hamiltonian, nband, ncols_mine, npw, nspinor, tolwfr_diago, nline, bandpp=None):

@@ -249,17 +249,21 @@ void abi_b200_chebfi_core_(abi_b200_ham_t** gs_hamk, int* ncols, int* bandpp, do
  *   xg_transpose       : xgTransposer_transpose on device blocks: to_rows = 1: cols(2, rows, my_ncols) -> lin(2, my_nrows, nband),
  *                        to_rows = 0 the inverse.  Bands and rows are distributed in contiguous blocks whose sizes differ by at
  *                        most one, the larger blocks on the lower ranks.
- *   chebfiwf2_paral    : cg(2, npw*nspinor*ncols_mine): this rank's band block (host or device, in/out); eig(nband): all
- *                        eigenvalues (host, replicated); resid(ncols_mine): residuals of the rank's bands (host).
- *                        chebfi_oracle = 0 (fixed degree nline, capped by cheb_oracle1 like the serial entry).  NC and PAW.
+ *   chebfiwf2_paral    : the argument list of abi_b200_chebfiwf2_ with nband = ALL bands and ncols_mine = this rank's:
+ *                        cg(2, npw*nspinor*ncols_mine): the rank's band block (host or device, in/out); eig(nband): all
+ *                        eigenvalues (host, replicated); occ(nband): all occupations (host, may be NULL when chebfi_oracle = 0);
+ *                        enl_out(ncols_mine) (NC only, may be NULL) and resid(ncols_mine): the rank's bands (host).
+ *                        chebfi_oracle 1 / 2: chebfi_set_ndeg_from_residu on the rank's bands (shift = its first band,
+ *                        m_chebfi2.F90:1161) and the MAX of the degrees over the ranks (:1203).  NC and PAW.
  * ---------------------------------------------------------------------------------------------------- */
 void abi_b200_comm_get_unique_id_(char* id128);
 void abi_b200_comm_init_rank_(const char* id128, int* nranks, int* rank);
 void abi_b200_comm_adopt_(void* nccl_comm, int* nranks, int* rank);
 void abi_b200_comm_destroy_(void);
 void abi_b200_xg_transpose_(int* to_rows, double* cols, double* lin, int* rows, int* nband);
-void abi_b200_chebfiwf2_paral_(double* cg, double* eig, double* resid, abi_b200_ham_t** gs_hamk, int* nband, int* ncols_mine,
-                               int* npw, int* nspinor, double* ecut, int* nline, int* bandpp);
+void abi_b200_chebfiwf2_paral_(double* cg, double* eig, double* occ, double* enl_out, double* resid, abi_b200_ham_t** gs_hamk,
+                               int* nband, int* ncols_mine, int* npw, int* nspinor, double* tolwfr_diago, double* ecut, int* nline,
+                               int* nbdbuf, int* chebfi_oracle, double* oracle_factor, double* oracle_min_occ, int* bandpp);
 /* lobpcg_run with paral_kgb = 1 on the same communicator (src/48_diago/m_lobpcg2.F90:340-765, one block of all bands, NC and PAW):
  * getAX_BX on the rank's band block, B-orthonormalisation / Rayleigh-Ritz / residuals / preconditioner on the rank's plane-wave
  * rows, Gram and residual sums over NCCL, one xgTransposer exchange out and one (PAW: two) back per iteration.

@@ -45,6 +45,15 @@ def main():
         nv_ok = np.max(np.abs(np.abs(cn) - np.abs(cg1[f:l]))) < 1e-8
         print(f"rank {rank} istwf_k {istwf_k}: native eig {ne_err:.2e} resid {nr_ok} vec {nv_ok}", flush=True)
         ok = ok and ne_err < 1e-8 and nr_ok and nv_ok
+        # oracle-driven degree (chebfi_oracle = 1 with a band buffer): per-rank degrees, MAX over the ranks
+        occ = np.where(np.arange(nband) < nband - 3, 1.0, 0.0)
+        cgo1 = p.cwavef.copy(); eigo1 = np.zeros(nband); reso1 = np.zeros(nband)
+        xg.chebfiwf2(cgo1, eigo1, occ, None, h, nband, p.npw, 1, reso1, 1e-16, p.ecut, 5, nbdbuf=2, chebfi_oracle=1, bandpp=4)
+        cgo = torch.from_numpy(np.ascontiguousarray(p.cwavef[f:l]).view(np.float64).reshape(l - f, p.npw, 2)).cuda()
+        eigo, _ = par.chebfi_band_parallel_native(h, cgo, nband, p.ecut, 5, bandpp=4, occ=occ, nbdbuf=2, chebfi_oracle=1)
+        oe_err = float(np.max(np.abs(eigo - eigo1)))
+        print(f"rank {rank} istwf_k {istwf_k}: native oracle=1 eig {oe_err:.2e}", flush=True)
+        ok = ok and oe_err < 1e-8
         # band-parallel LOBPCG (row-sharded linear algebra, Gram allreduce) vs the single-GPU lobpcgwf2
         cgl1 = p.cwavef.copy(); eigl1 = np.zeros(nband); resl1 = np.zeros(nband)
         xg.lobpcgwf2(cgl1, eigl1, None, None, h, nband, p.npw, 1, resl1, 1e-30, 3, bandpp=4)

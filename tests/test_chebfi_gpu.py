@@ -133,13 +133,22 @@ def test_chebfiwf2_paral_on_one_rank_equals_chebfiwf2(lib, istwf_k, kpt, usepaw)
         cg = p.cwavef.copy(); eig = np.zeros(nband); res = np.zeros(nband)
         if on_dev:
             d = torch.from_numpy(cg).cuda()
-            xg.chebfiwf2_paral(d, eig, res, h, nband, nband, p.npw, 1, p.ecut, 5, bandpp=4)
+            xg.chebfiwf2_paral(d, eig, None, None, res, h, nband, nband, p.npw, 1, 1e-16, p.ecut, 5, bandpp=4)
             cg = d.cpu().numpy()
         else:
-            xg.chebfiwf2_paral(cg, eig, res, h, nband, nband, p.npw, 1, p.ecut, 5, bandpp=4)
+            xg.chebfiwf2_paral(cg, eig, None, None, res, h, nband, nband, p.npw, 1, 1e-16, p.ecut, 5, bandpp=4)
         assert np.max(np.abs(eig - eig1)) < 1e-10
         assert np.max(np.abs(res - res1) / (np.abs(res1) + 1e-12)) < 1e-5
         assert np.max(np.abs(np.abs(cg) - np.abs(cg1))) < 1e-8
+    # oracle-driven degree (chebfi_oracle = 1, band buffer) and enl_out (NC) through the band-parallel entry == the serial entry
+    occ = np.where(np.arange(nband) < 6, 1.0, 0.0)
+    cga = p.cwavef.copy(); eiga = np.zeros(nband); resa = np.zeros(nband); enla = np.zeros(nband)
+    xg.chebfiwf2(cga, eiga, occ, None if usepaw else enla, h, nband, p.npw, 1, resa, 1e-16, p.ecut, 5, nbdbuf=2, chebfi_oracle=1, bandpp=4)
+    cgb = p.cwavef.copy(); eigb = np.zeros(nband); resb = np.zeros(nband); enlb = np.zeros(nband)
+    xg.chebfiwf2_paral(cgb, eigb, occ, None if usepaw else enlb, resb, h, nband, nband, p.npw, 1, 1e-16, p.ecut, 5, nbdbuf=2, chebfi_oracle=1,
+                       bandpp=4)
+    assert np.max(np.abs(eigb - eiga)) < 1e-10 and np.max(np.abs(np.abs(cgb) - np.abs(cga))) < 1e-8
+    assert usepaw or np.max(np.abs(enlb - enla)) < 1e-10
     a = torch.randn((nband, p.npw, 2), dtype=torch.float64, device="cuda"); b = torch.zeros_like(a); c = torch.zeros_like(a)
     xg.xg_transpose(True, a, b, p.npw, nband)
     xg.xg_transpose(False, c, b, p.npw, nband)
