@@ -511,7 +511,7 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
         fourwf_fused_opt2(*h->plan, h->vloc, a_c.as<double2>(), a_ghc.as<double2>(), nd, epi, c.stream);
       } else {
         // band chunks (even sizes keep the Gamma-point pairs together): H2D on the copy stream, fourwf behind an event
-        // (8 chunks: the exposed head of the pipeline is the H2D of the first chunk only)
+        // (16 chunks: the exposed head of the pipeline is the H2D of the first chunk only)
         const int nchunk = std::max(1, std::min(c.pipe_chunks, nd / 8));
         const int chunk = ceil_div(ceil_div(nd, nchunk), 2) * 2;
         for (int b0 = 0; b0 < nd; b0 += chunk) {

@@ -19,7 +19,7 @@ struct Context {
   cudaStream_t stream = 0;
   cudaStream_t copy_stream = 0;   // host<->device staging pipeline of getghc (H2D / D2H overlapped with compute)
   bool pipeline = true;
-  int pipe_chunks = 8;            // band chunks (H2D) / row slabs (D2H) of the pipelined host-array getghc
+  int pipe_chunks = 16;           // band chunks (H2D) / row slabs (D2H) of the pipelined host-array getghc (B200: e2e 2835 at 8, 2889 at 16 and 24)
   bool own_stream = false;
   bool async = false;
   int me_g0 = 1;

@@ -820,26 +820,41 @@ def run_block_workload(args, env):
                     "timing": "host clock between barrier + device synchronise on both sides, max over ranks (the call holds host syncs)",
                     "kernel_ms": {k: v[0] for k, v in prof_scf.items()}}
         del cg
-    # the same SCF-step-equivalent with LOBPCG (one block of all bands, nline LOBPCG iterations; single GPU only in this build)
+    # the same SCF-step-equivalent with LOBPCG (one block of all bands, nline LOBPCG iterations): lobpcgwf2 on one GPU, the library's
+    # band-parallel driver (abi_b200_lobpcgwf2_paral_) on several; start block seeded per GLOBAL band index like the ChebFi2 leg
     lobpcg_step = None
-    if world == 1 and extras:
-        from abinit_b200 import xg as xgm
+    if extras:
+        from abinit_b200 import xg as xgm, parallel as par
         api.set_async(False)
+        f, l = par.band_block(args.nband, world, rank)
         with torch.cuda.stream(stream):
-            gen = torch.Generator(device=dev).manual_seed(778)
             damp = torch.from_numpy(1.0 / (1.0 + np.minimum(w["kinpw"], 1e6))).to(dev)
-            cgl = torch.randn((args.nband, npw, 2), generator=gen, device=dev, dtype=torch.float64) * damp[None, :, None]
+            cg0 = torch.empty((l - f, npw, 2), device=dev, dtype=torch.float64)
+            for b in range(f, l):
+                gen = torch.Generator(device=dev).manual_seed(778000 + b)
+                cg0[b - f] = torch.randn((npw, 2), generator=gen, device=dev, dtype=torch.float64)
+            cg0 *= damp[None, :, None]
             if args.istwfk == 2:
-                cgl[:, 0, 1] = 0.0
+                cg0[:, 0, 1] = 0.0
             eigl = np.zeros(args.nband); resl = np.zeros(args.nband)
             tl = []
-            for it in range(2):
+            for it in range(2):                                   # second call timed, both from the same start block
+                cgl = cg0.clone()
                 barrier(); t0 = time.perf_counter()
-                xgm.lobpcgwf2(cgl, eigl, None, None, ham, args.nband, npw, 1, resl, 1e-30, args.nline, bandpp=ndat)
+                if world == 1:
+                    xgm.lobpcgwf2(cgl, eigl, None, None, ham, args.nband, npw, 1, resl, 1e-30, args.nline, bandpp=ndat)
+                else:
+                    eigl, resl = par.lobpcg_band_parallel_native(ham, cgl, args.nband, args.nline, bandpp=ndat)
                 barrier(); tl.append(time.perf_counter() - t0)
-        lobpcg_step = {"value": tl[-1], "unit": "s per LOBPCG call (one k-point, one block of all bands)", "nband": args.nband,
-                       "nline": args.nline, "eig_min_max": [float(eigl.min()), float(eigl.max())], "resid_max": float(resl.max())}
-        del cgl
+            dtl = torch.tensor([tl[-1]], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(dtl, op=dist.ReduceOp.MAX)
+        eigl = np.asarray(eigl); resl = np.asarray(resl)
+        lobpcg_step = {"value": float(dtl.item()), "unit": "s per LOBPCG call (one k-point, one block of all bands)", "nband": args.nband,
+                       "nline": args.nline, "bands_per_gpu": l - f, "driver": "lobpcgwf2" if world == 1 else "abi_b200_lobpcgwf2_paral_ (NCCL inside the library)",
+                       "eig_min_max": [float(eigl.min()), float(eigl.max())], "resid_max": float(resl.max()),
+                       "cross_n_invariant": {"eig_sum": float(np.sum(eigl)), "eig_first": [float(x) for x in eigl[:4]]}}
+        del cgl, cg0
         torch.cuda.empty_cache()
     # density build (the step after the solver): fourwf option 1 on the same band block, fused path
     density = None
