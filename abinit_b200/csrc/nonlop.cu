@@ -718,8 +718,8 @@ void mkffnl_device(double* d_ffnl, int npw, int lmnmax, int ntypat, const int* d
 #endif
 }
 
-// developer knob (abi_b200_fourwf_set_tuning("nonlop_rag", mask)): ragged variants of bit 0: TN 128-wide, bit 1: TN 64-wide, bit 2: NN 64-wide, bit 3: NN 65..104 columns as 64 + rest
-int g_nonlop_rag = 15;
+// developer knob (abi_b200_fourwf_set_tuning("nonlop_rag", mask)): ragged variants of bit 0: TN 128-wide, bit 1: TN 64-wide, bit 2: NN 64-wide, bit 3: NN 65..104 columns as 64 + rest, bit 4 / 5: TN / NN 32-wide (TN: no gain, off by default)
+int g_nonlop_rag = 47;
 void nonlop_set_rag(int mask) { g_nonlop_rag = mask; }
 
 template <bool TN, bool CPLX, class Cfg, bool RAG = false>
@@ -773,6 +773,8 @@ __global__ void __launch_bounds__(256) k_small_tn(GemmParams p) {
 // split-K TN GEMM into partial buffers; returns nsplit
 static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long long lda, const double* B, long long ldb,
                      double*& part, cudaStream_t st, const char* prof_name = "dgemm_tn_opernla") {
+  // (narrow blocks, Neff <= 32, on the ragged 64- or 128-wide tiles instead of the 512 x 32 one: measured 5.0 / 6.2 ms against 5.0-5.2
+  //  at 10 columns -- the narrow TN product is bound by its 128-byte-per-row access pattern (4.2 TB/s), not by DMMAs or tile shape)
   const int BN = Neff <= 32 ? 32 : (Neff <= 64 ? 64 : 128), BM = 128 * 128 / BN;
   GemmParams p{};
   p.M = M; p.N = Neff; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.add = nullptr; p.ldc = 0;
@@ -807,10 +809,12 @@ static int launch_tn(bool cplx, int M, int Neff, int K, const double* A, long lo
   const int nb = tiles * nsplit;
   // ragged single column tile: the variant that spreads column blocks over the SM sub-partitions and skips the DMMAs of empty
   // 8-column fragments (cost follows the columns present, rounded up to 8)
-  // (32-column tiles stream P at the HBM rate whatever their DMMA count: no ragged variant there)
-  const bool ragt = p.tiles_n == 1 && Neff <= BN - 8 && M >= 4 * BM && BN >= 64 && (g_nonlop_rag & (BN == 128 ? 1 : 2));
+  // (a 32-column tile issues 4.75 ms of DMMAs per pass over the Si-512 P against 3.3 ms of HBM time: with 8 or 16 columns present
+  //  the skipped fragments turn it from pipe-bound into HBM-bound)
+  const bool ragt = p.tiles_n == 1 && Neff <= BN - 8 && M >= 4 * BM && (g_nonlop_rag & (BN == 128 ? 1 : (BN == 64 ? 2 : 16)));
   if (ragt && BN == 128) { if (cplx) launch_gemm<true, true, TnCfg, true>(p, nb, st); else launch_gemm<true, false, TnCfg, true>(p, nb, st); }
-  else if (ragt) { if (cplx) launch_gemm<true, true, TnCfg64, true>(p, nb, st); else launch_gemm<true, false, TnCfg64, true>(p, nb, st); }
+  else if (ragt && BN == 64) { if (cplx) launch_gemm<true, true, TnCfg64, true>(p, nb, st); else launch_gemm<true, false, TnCfg64, true>(p, nb, st); }
+  else if (ragt) { if (cplx) launch_gemm<true, true, TnCfg32, true>(p, nb, st); else launch_gemm<true, false, TnCfg32, true>(p, nb, st); }
   else if (BN == 128) { if (cplx) launch_gemm<true, true, TnCfg>(p, nb, st); else launch_gemm<true, false, TnCfg>(p, nb, st); }
   else if (BN == 64) { if (cplx) launch_gemm<true, true, TnCfg64>(p, nb, st); else launch_gemm<true, false, TnCfg64>(p, nb, st); }
   else { if (cplx) launch_gemm<true, true, TnCfg32>(p, nb, st); else launch_gemm<true, false, TnCfg32>(p, nb, st); }
@@ -841,9 +845,10 @@ static void launch_nn(bool cplx, int M, int N, int K, const double* A, long long
   // (no RAG variant here: the 64 x 128 tile has two warps per column block, which cannot cover the four sub-partitions of an SM --
   //  measured on B200, 76 columns: 20.2 ms against 18.9 ms for the plain kernel; the TN kernel gains 19 %)
   //  the narrower tiles have four / eight warps per column block: there the ragged variant's fragment skipping pays)
-  const bool ragn = p.tiles_n == 1 && N <= BN - 8 && BN == 64 && M >= 4 * BM && (g_nonlop_rag & 4);
+  const bool ragn = p.tiles_n == 1 && N <= BN - 8 && BN <= 64 && M >= 4 * BM && (g_nonlop_rag & (BN == 64 ? 4 : 32));
   if (BN == 128) { if (cplx) launch_gemm<false, true, NnCfg>(p, nb, st); else launch_gemm<false, false, NnCfg>(p, nb, st); }
-  else if (ragn) { if (cplx) launch_gemm<false, true, NnCfg64, true>(p, nb, st); else launch_gemm<false, false, NnCfg64, true>(p, nb, st); }
+  else if (ragn && BN == 64) { if (cplx) launch_gemm<false, true, NnCfg64, true>(p, nb, st); else launch_gemm<false, false, NnCfg64, true>(p, nb, st); }
+  else if (ragn) { if (cplx) launch_gemm<false, true, NnCfg32, true>(p, nb, st); else launch_gemm<false, false, NnCfg32, true>(p, nb, st); }
   else if (BN == 64) { if (cplx) launch_gemm<false, true, NnCfg64>(p, nb, st); else launch_gemm<false, false, NnCfg64>(p, nb, st); }
   else { if (cplx) launch_gemm<false, true, NnCfg32>(p, nb, st); else launch_gemm<false, false, NnCfg32>(p, nb, st); }
 }

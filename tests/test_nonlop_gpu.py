@@ -177,12 +177,12 @@ def test_ragged_band_blocks_with_many_projectors(lib, istwf_k, kpt, ndat):
         P = _setup(lib, p)
         paw_opt = 4 if usepaw else 0
         rv, rs, rgx = onl.gemm_nonlop(P, p.cwavef, p.enl, p.sij, p.indlmn, p.nattyp, p.atindx1 - 1, istwf_k, 1, paw_opt)
-        for knob in (0, 15):                   # no ragged variant / the default set (developer knob nonlop_rag)
+        for knob in (0, 47, 63):               # no ragged variant / the default set / every variant (developer knob nonlop_rag)
             api.set_tuning("nonlop_rag", knob)
             try:
                 vout, sout, proj = _apply(p, 1, paw_opt, cpopt=0)
             finally:
-                api.set_tuning("nonlop_rag", 15)
+                api.set_tuning("nonlop_rag", 47)
             assert rel_err_per_band(vout, rv) < TOL, knob
             assert rel_err_per_band(_proj_as_complex(proj, 2 if istwf_k == 1 else 1), rgx) < TOL, knob
             if usepaw:

@@ -16,9 +16,9 @@ env = dict(rank=0, world=1, local=0, dev=dev, stream=stream, dist=None, barrier=
 w = bench.build_workload(args, 0)
 blk = bench.Block(args, env, w, 256, keep_host_p=False)
 api.set_async(True)
-for rag in (0, 15):
+for rag in (0, 47):
     api.set_tuning("nonlop_rag", rag)
-    for nd in (128, 112, 100, 76, 66, 48, 40, 24, 10):
+    for nd in (128, 100, 76, 48, 40, 24, 19, 10, 4):
         blk.ndat = nd
         cw, ghc = blk.cw[:nd], blk.ghc[:nd]
         for _ in range(2):
