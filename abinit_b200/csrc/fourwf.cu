@@ -46,6 +46,7 @@ FourwfTuning& fourwf_tuning() {
     if (const char* e = getenv("ABI_B200_FOURWF_PLANE_CFG")) t.plane_cfg = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_PLANE_CTAS")) t.plane_ctas_per_sm = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_PACK2")) t.pack2 = atoi(e);
+    if (const char* e = getenv("ABI_B200_FOURWF_HALF_CFG")) t.half_cfg = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_HALF")) t.half = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_XHALF")) t.xhalf = atoi(e);
     if (const char* e = getenv("ABI_B200_FOURWF_HALF_CFG")) t.half_cfg = atoi(e);

@@ -33,6 +33,8 @@ def run(ecut, L, kpt, istwfk, ndat, cplex, option, impl, ng=None):
     assert err < 1e-12
 if __name__ == "__main__":
     api.init(0)
+    if os.environ.get("HALF_CFG"):
+        api.set_tuning("half_cfg", int(os.environ["HALF_CFG"]))   # developer variants of the half-support plane stage
     for impl in (1, 2):
         run(6.0, 8.0, (.1, .2, .3), 1, 2, 1, 2, impl)
         run(6.0, 8.0, (0, 0, 0), 2, 3, 1, 2, impl)
