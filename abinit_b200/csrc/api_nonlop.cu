@@ -599,7 +599,7 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
 // Reference: the (k, spin) loop of src/79_seqpar_mpi/m_vtorho.F90:789-1045 around the eigensolver's getghc calls.
 // ------------------------------------------------------------------------------------------------------
 namespace {
-struct GraphEntry { int state = 0; cudaGraphExec_t exec = nullptr; };
+struct GraphEntry { int state = 0; cudaGraphExec_t exec = nullptr; cudaGraph_t graph = nullptr; };
 struct GraphKey {
   const void* h; unsigned epoch; const void* c; const void* g; const void* s; int ndat, sij, tc, lane;
   bool operator<(const GraphKey& o) const {
@@ -608,12 +608,29 @@ struct GraphKey {
 };
 std::map<GraphKey, GraphEntry>& graph_cache() { static std::map<GraphKey, GraphEntry> c; return c; }
 cudaEvent_t g_lane_ev[kMaxLanes + 1] = {};
+// One graph for a whole sweep: the per-call graphs as child nodes, chained per lane (8 parallel branches), built the first time
+// every call of a batch has its own graph and replayed with ONE launch while the batch (handles, epochs, arrays, order) is unchanged.
+struct SweepGraph { std::vector<GraphKey> keys; cudaGraphExec_t exec = nullptr; int seen = 0; };
+SweepGraph& sweep_graph() { static SweepGraph g; return g; }
+bool same_keys(const std::vector<GraphKey>& a, const std::vector<GraphKey>& b) {
+  if (a.size() != b.size()) return false;
+  for (size_t i = 0; i < a.size(); i++) if (a[i] < b[i] || b[i] < a[i]) return false;
+  return true;
+}
+void sweep_graph_drop() {
+  SweepGraph& g = sweep_graph();
+#ifndef ABI_EMU
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+#endif
+  g = SweepGraph();
+}
 }  // namespace
 
 void abi_b200_graphs_clear(void) {
 #ifndef ABI_EMU
-  for (auto& kv : graph_cache()) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (auto& kv : graph_cache()) { if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); if (kv.second.graph) cudaGraphDestroy(kv.second.graph); }
 #endif
+  sweep_graph_drop();
   graph_cache().clear();
 }
 
@@ -632,6 +649,20 @@ void abi_b200_getghc_batch_(int* nk, abi_b200_ham_t** hams, double** cwavef, dou
   const bool was_async = c.async;
   cudaStream_t main_stream = c.stream;
   const int nlanes = std::min(kMaxLanes, std::max(1, *nk));
+  // ---- whole-sweep graph: one launch for the batch when nothing changed since it was built
+  std::vector<GraphKey> keys;
+  if (*use_graphs && *nk > 1) {
+    keys.reserve(*nk);
+    for (int i = 0; i < *nk; i++)
+      keys.push_back(GraphKey{hams[i], hams[i]->epoch, cwavef[i], ghc[i], gsc ? gsc[i] : nullptr, *ndat, *sij_opt, *type_calc, i % nlanes});
+    SweepGraph& sg = sweep_graph();
+    if (sg.exec && same_keys(sg.keys, keys)) {
+      CUDA_CHECK(cudaGraphLaunch(sg.exec, main_stream));
+      c.fourwf_counter += 2LL * (*ndat) * (*nk); c.nonlop_counter += (long long)(*ndat) * (*nk); g_kernel_launches += *nk;
+      if (!c.async) CUDA_CHECK(cudaStreamSynchronize(main_stream));
+      return;
+    }
+  }
   for (int l = 0; l < nlanes; l++) {
     if (!c.lane_stream[l]) CUDA_CHECK(cudaStreamCreateWithFlags(&c.lane_stream[l], cudaStreamNonBlocking));
     if (!g_lane_ev[l]) CUDA_CHECK(cudaEventCreateWithFlags(&g_lane_ev[l], cudaEventDisableTiming));
@@ -666,7 +697,7 @@ void abi_b200_getghc_batch_(int* nk, abi_b200_ham_t** hams, double** cwavef, dou
       CUDA_CHECK(cudaStreamEndCapture(c.stream, &graph));
       c.force_scratch_clear = false;
       CUDA_CHECK(cudaGraphInstantiate(&ge.exec, graph, 0));
-      CUDA_CHECK(cudaGraphDestroy(graph));
+      ge.graph = graph;                        // kept: child node of the whole-sweep graph
       ge.state = 2;
       // the captured call did not run: undo its bookkeeping, the launch below redoes it
       c.fourwf_counter = fw0; c.nonlop_counter = nl0; g_kernel_launches = kl0;
@@ -683,6 +714,28 @@ void abi_b200_getghc_batch_(int* nk, abi_b200_ham_t** hams, double** cwavef, dou
   for (int l = 0; l < nlanes; l++) {
     CUDA_CHECK(cudaEventRecord(g_lane_ev[l], c.lane_stream[l]));
     CUDA_CHECK(cudaStreamWaitEvent(main_stream, g_lane_ev[l], 0));
+  }
+  // every call of this batch has its own graph now: compose them (third occurrence of the batch) for the following sweeps
+  if (!keys.empty()) {
+    bool all = true;
+    for (const GraphKey& k : keys) { auto it = graph_cache().find(k); if (it == graph_cache().end() || it->second.state != 2 || !it->second.graph) { all = false; break; } }
+    SweepGraph& sg = sweep_graph();
+    if (all && !(sg.exec && same_keys(sg.keys, keys))) {
+      sweep_graph_drop();
+      cudaGraph_t bg = nullptr;
+      CUDA_CHECK(cudaGraphCreate(&bg, 0));
+      std::vector<cudaGraphNode_t> prev(nlanes, nullptr);
+      for (int i = 0; i < *nk; i++) {
+        const int lane = i % nlanes;
+        cudaGraphNode_t node = nullptr;
+        CUDA_CHECK(cudaGraphAddChildGraphNode(&node, bg, prev[lane] ? &prev[lane] : nullptr, prev[lane] ? 1 : 0, graph_cache()[keys[i]].graph));
+        prev[lane] = node;
+      }
+      SweepGraph& ng = sweep_graph();
+      CUDA_CHECK(cudaGraphInstantiate(&ng.exec, bg, 0));
+      CUDA_CHECK(cudaGraphDestroy(bg));
+      ng.keys = keys;
+    }
   }
   if (!c.async) CUDA_CHECK(cudaStreamSynchronize(main_stream));
 #endif

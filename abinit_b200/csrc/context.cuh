@@ -11,7 +11,7 @@ struct Staging {             // grow-only device buffer used to mirror one host 
   void release();
 };
 
-constexpr int kMaxLanes = 8;    // concurrent streams of the batched small-system path (getghc_batch); lane 0 = the library stream
+constexpr int kMaxLanes = 32;   // concurrent streams of the batched small-system path (getghc_batch); lane 0 = the library stream
 
 struct Context {
   bool initialized = false;
