@@ -544,6 +544,7 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
   if (nonlocal) {
     NvtxRange nvtx_nl("NLOCPOT");                        // NVTX_GETGHC_NLOCPOT, m_getghc.F90:1042
     c.nonlop_counter += nd;
+    bool gsc_filtered = false;
     if (tc == 0) {
       NonlopFusion fuse;
       fuse.ghc = a_ghc.as<double>(); fuse.kinpw = h->d_kinpw; fuse.kin_filter = kin_filter;
@@ -552,6 +553,7 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
       gemm_nonlop_device(h->P, h->atoms, h->enl, 1, cpopt_here, paw_opt, h->me_g0, a_lam.as<double>(), nd, a_c.as<double>(),
                          a_gv.as<double>(), a_gsc.as<double>(), a_prj.as<double>(), c.stream, &fuse);
       if (h->atoms.nprojs == 0 || nd == 0) ghc_shipped = false;          // nothing was launched: plain copy below
+      gsc_filtered = fuse.gsc_filtered;
     } else {
       // type_calc == 2: non-local + kinetic added to the caller's ghc (m_getghc.F90:152)
       double* d_gv = a_gv.as<double>();
@@ -567,7 +569,7 @@ void abi_b200_getghc_(int* cpopt, double* cwavef, double* cwaveprj, double* ghc,
       CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
     }
-    if (*sij_opt == 1 && a_gsc.dev) {                                    // gsc = 0 where the kinetic filter strikes
+    if (*sij_opt == 1 && a_gsc.dev && !gsc_filtered) {                   // gsc = 0 where the kinetic filter strikes
       const int blocks = std::min(kNumSM * 8, (int)ceil_div<long long>((long long)npw * nd, 256));
       k_filter_only<<<blocks, 256, 0, c.stream>>>(a_gsc.as<double2>(), h->d_kinpw, npw, nd, kin_filter, false);
       CUDA_CHECK(cudaGetLastError());

@@ -1051,7 +1051,11 @@ void gemm_nonlop_device(const Projectors& P, const NonlopAtoms& at, const Nonlop
     // + vectin except for choice 7 (m_opernlb_gemm.F90:654-665)
     if (ozaki_enabled() && P.oz_stamp == P.stamp && !P.oz.failed)
       ozaki_expand(P.oz, zs, ldg, ndat, svectout, 0, nullptr, nullptr, 0.0, choice == 7 ? nullptr : vectin, st);
-    else
+    else if (fuse != nullptr && fuse->kinpw != nullptr) {     // getghc: gsc = 0 where the kinetic filter strikes, in the epilogue
+      launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zs, ldg, svectout, ldv, choice == 7 ? nullptr : vectin, st, nullptr, fuse->kinpw,
+                fuse->kin_filter);
+      fuse->gsc_filtered = true;
+    } else
     launch_nn(cplx, 2 * npw, ndat, nprojs, P.d_p, ldv, zs, ldg, svectout, ldv, choice == 7 ? nullptr : vectin, st);
   }
   if (choice == 1 && (paw_opt == 0 || paw_opt == 1 || paw_opt == 2 || paw_opt == 4)) {

@@ -92,6 +92,7 @@ struct NonlopFusion {
   int nslabs = 1;
   void (*after_slab)(void* user, int ipw_begin, int ipw_end) = nullptr;
   void* user = nullptr;
+  mutable bool gsc_filtered = false; // out: the kinetic filter was applied to svectout in the epilogue of its GEMM (one kernel less)
 };
 
 // gemm_nonlop, choice in {0,1,7}, signs=2, or choice=1, signs=1 (enlout(ndat) = <psi|Vnl|psi>, opernld).
