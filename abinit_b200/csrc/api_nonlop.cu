@@ -284,7 +284,7 @@ void abi_b200_ham_destroy(abi_b200_ham_t* h) {
 }
 
 void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_vloc, int n4, int n5, int n6) {
-  h->epoch++;
+  h->epoch = ++ham_epoch_counter();
   ensure_init();
   ABI_CHECK(n4 == h->ngfft[0] && n5 == h->ngfft[1] && n6 == h->ngfft[2],
             "FFT SIZE ERROR: when gpu mode is on the fft grid must not be augmented (n4,n5,n6 must equal n1,n2,n3)");
@@ -295,7 +295,7 @@ void abi_b200_ham_load_spin(abi_b200_ham_t* h, const double* vlocal, int cplex_v
 }
 
 void abi_b200_ham_set_nspinor(abi_b200_ham_t* h, int nspinor) {
-  h->epoch++;
+  h->epoch = ++ham_epoch_counter();
   ABI_CHECK(nspinor == 1 || nspinor == 2, "nspinor must be 1 or 2");
   // PAW spinors: D_ij comes as four complex blocks (abi_b200_ham_load_enl_spinor), m_opernlc_ylm_allwf.F90:660-737
   h->nspinor = nspinor;
@@ -312,7 +312,7 @@ __global__ void k_pack_vud(const double* __restrict__ v3, const double* __restri
 #endif
 
 void abi_b200_ham_load_spin_nvloc(abi_b200_ham_t* h, const double* vlocal, int nvloc, int n4, int n5, int n6) {
-  h->epoch++;
+  h->epoch = ++ham_epoch_counter();
   ensure_init();
   ABI_CHECK(nvloc == 1 || nvloc == 4, "nvloc must be 1 or 4");
   if (nvloc == 1) { abi_b200_ham_load_spin(h, vlocal, 1, n4, n5, n6); h->nvloc = 1; return; }
@@ -338,7 +338,7 @@ void abi_b200_ham_load_spin_nvloc(abi_b200_ham_t* h, const double* vlocal, int n
 }
 
 void abi_b200_ham_load_enl_spinor(abi_b200_ham_t* h, const double* enl, int dimenl1, int dimenl2, int nspinortot2, const double* sij) {
-  h->epoch++;
+  h->epoch = ++ham_epoch_counter();
   ensure_init();
   ABI_CHECK(nspinortot2 == 1 || nspinortot2 == 4, "load_enl: enl(dimenl1, dimenl2, nspinortot**2) needs nspinortot**2 = 1 or 4");
   const int lmn2 = h->lmnmax * (h->lmnmax + 1) / 2;
@@ -359,7 +359,7 @@ void abi_b200_ham_load_enl(abi_b200_ham_t* h, const double* enl, int dimenl1, in
 
 void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw, const double* ffnl,
                          int dimffnl, const double* ph3d, int matblk, int me_g0) {
-  h->epoch++;
+  h->epoch = ++ham_epoch_counter();
   ensure_init();
   Context& c = ctx();
   ABI_CHECK(!is_device_ptr(kg_k), "kg_k must be a host array");
@@ -384,7 +384,7 @@ void abi_b200_ham_load_k(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_
 
 void abi_b200_ham_load_k_xred(abi_b200_ham_t* h, int istwf_k, int npw, const int* kg_k, const double* kinpw, const double* ffnl,
                               int dimffnl, const double* kpt, const double* xred, int me_g0) {
-  h->epoch++;
+  h->epoch = ++ham_epoch_counter();
   ABI_CHECK(ffnl != nullptr && kpt != nullptr && xred != nullptr, "load_k_xred: ffnl, kpt and xred are required");
   abi_b200_ham_load_k(h, istwf_k, npw, kg_k, kinpw, nullptr, 0, nullptr, 0, me_g0);
   Context& c = ctx();
@@ -397,7 +397,7 @@ void abi_b200_ham_load_k_xred(abi_b200_ham_t* h, int istwf_k, int npw, const int
 }
 
 void abi_b200_ham_set_projectors(abi_b200_ham_t* h, const double* projs, int nprojs) {
-  h->epoch++;
+  h->epoch = ++ham_epoch_counter();
   ensure_init();
   ABI_CHECK(nprojs == h->atoms.nprojs, "set_projectors: nprojs differs from sum(nlmn*nattyp)");
   h->P.alloc(h->npw, nprojs, h->istwf_k);

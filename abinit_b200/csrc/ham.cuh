@@ -16,6 +16,8 @@ struct Invovl {
 };
 }  // namespace abi
 
+namespace abi { inline unsigned& ham_epoch_counter() { static unsigned c = 0; return c; } }
+
 struct abi_b200_ham {
   // (the members are abi:: types; the struct itself lives in the global namespace because the C header names it)
   int ngfft[18];
@@ -35,7 +37,10 @@ struct abi_b200_ham {
   std::shared_ptr<abi::FourwfPlan> plan_ref;   // keeps the plan alive whatever happens to the plan cache
   abi::FourwfPlan* plan = nullptr;
   double* d_gvnlxc = nullptr; size_t gvnlxc_cap = 0;
-  unsigned epoch = 0;                 // bumped by every load_* / set_*: invalidates the CUDA graphs captured for this handle
+  // bumped by every load_* / set_*: invalidates the CUDA graphs captured for this handle.  Values are drawn from ONE process-wide
+  // counter, so a handle allocated at the address of a destroyed one can never match the graph keys (handle, epoch, arrays) of its
+  // predecessor.
+  unsigned epoch = ++abi::ham_epoch_counter();
   abi::Invovl invovl;                 // built lazily by apply_invovl, dropped by load_k / load_enl / set_projectors
 };
 
