@@ -275,7 +275,7 @@ void abi_b200_lobpcgwf2_paral_(double* cg, double* eig, double* resid, abi_b200_
  * X / XW / XWP Rayleigh-Ritz of src/45_xgTools/m_xg_ortho_RR.F90:86-150, 251-571.  nblock_lobpcg blocks of
  * blockdim = nband / nblock_lobpcg bands (m_lobpcgwf.F90:133; lobpcg_orthoXwrtBlocks m_lobpcg2.F90:803-840 against the
  * finished blocks, final xg_Borthonormalize + xg_RayleighRitz over all bands :744-751); paral_kgb = 0 in this entry (the
- * band-parallel scheme is abi_b200_lobpcgwf2_paral_ below); dtset scalars flattened (tolwfr_diago, nline,
+ * band-parallel scheme is abi_b200_lobpcgwf2_paral_ above); dtset scalars flattened (tolwfr_diago, nline,
  * nblock_lobpcg, nbdbuf).  nspinor = 2 (NC): blocks have npw*nspinor rows, nspinor must match abi_b200_ham_set_nspinor.
  * cg in/out (host or device); eig, resid, occ (used when nbdbuf = -101), enl_out (NC, may be NULL): host arrays. */
 void abi_b200_lobpcgwf2_(double* cg, double* eig, double* occ, double* enl_out, abi_b200_ham_t** gs_hamk, int* nband,
